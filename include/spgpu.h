@@ -1,0 +1,222 @@
+/*
+ * spgpu.h -- C ABI of the B200-native prover backend for spartan-parallel's
+ * data-parallel R1CS proving path.
+ *
+ * The reference crate (scroll-tech/spartan-parallel, pure Rust) has no FFI seam;
+ * the seam is the set of method bodies listed below. A Rust `-sys` crate binds
+ * exactly these symbols; the python/ctypes mirror in
+ * spartan_parallel_b200/ binds the same ones.
+ *
+ * Conventions
+ *  - spg_fq is the reference's `Scalar`: four little-endian u64 limbs holding
+ *    a*2^256 mod q, fully reduced (src/scalar/ristretto255.rs:193-199). Every
+ *    scalar crossing this boundary, in either direction, is in that form.
+ *  - Every function returns 0 on success, a negative SPG_E* code otherwise;
+ *    spg_last_error() gives the message. The reference's prover asserts/panics
+ *    on bad shapes (e.g. src/r1csproof.rs:240-263); the Rust wrapper turns a
+ *    non-zero status into panic!(). There is no CPU fallback anywhere.
+ *  - Handles are opaque, own device memory, and are not thread-safe: one host
+ *    thread drives one context (the reference prover is single-threaded).
+ *  - Tables live on the device in NATURAL (p, q, w, x) order; the reference's
+ *    bit-reversed (p, q_rev, w, x_rev) storage (src/custom_dense_mlpoly.rs:67-111)
+ *    is an implementation detail of its top-binding loops and never crosses the ABI.
+ */
+#ifndef SPGPU_H
+#define SPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[4]; } spg_fq;
+
+typedef struct spg_ctx spg_ctx;       /* one device + stream + scratch */
+typedef struct spg_vec spg_vec;       /* device vector of spg_fq (DensePolynomial.Z) */
+typedef struct spg_r1cs spg_r1cs;     /* device copy of an R1CSInstance */
+typedef struct spg_witness spg_witness; /* one witness section (ProverWitnessSecInfo) */
+typedef struct spg_zmat spg_zmat;     /* z_mat[p][q][w][x] of R1CSProof::prove */
+typedef struct spg_sc1 spg_sc1;       /* phase-1 sumcheck state */
+typedef struct spg_sc2 spg_sc2;       /* phase-2 sumcheck state */
+typedef struct spg_cubic spg_cubic;   /* prove_cubic_batched state */
+typedef struct spg_gens spg_gens;     /* MultiCommitGens on the device */
+
+enum {
+  SPG_OK = 0,
+  SPG_EINVAL = -1,  /* bad shape / argument (reference: assert!) */
+  SPG_ECUDA = -2,   /* CUDA runtime error */
+  SPG_ENOMEM = -3,
+  SPG_ESTATE = -4   /* call out of order (e.g. round_bind before round_eval) */
+};
+
+const char *spg_last_error(void);
+int spg_version(void);
+
+/* ---------------------------------------------------------------- context */
+int spg_ctx_create(int device, spg_ctx **out);
+void spg_ctx_destroy(spg_ctx *ctx);
+int spg_ctx_sync(spg_ctx *ctx);
+/* number of kernel launches issued through this context so far */
+uint64_t spg_ctx_launch_count(const spg_ctx *ctx);
+/* cudaStream_t the context launches on (for CUDA-event timing by the caller) */
+void *spg_ctx_stream(const spg_ctx *ctx);
+/* pinned host allocation for fast uploads (optional convenience) */
+int spg_host_alloc(size_t bytes, void **out);
+void spg_host_free(void *p);
+
+/* ---------------------------------------------------------------- vectors
+ * DensePolynomial (src/dense_mlpoly.rs:19-24). */
+int spg_vec_alloc(spg_ctx *ctx, size_t n, spg_vec **out);
+int spg_vec_upload(spg_ctx *ctx, const spg_fq *host, size_t n, spg_vec **out);
+/* wrap caller-owned device memory (e.g. a torch tensor); not freed by spg_vec_free */
+int spg_vec_wrap(spg_ctx *ctx, void *device_ptr, size_t n, spg_vec **out);
+int spg_vec_download(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_fq *host);
+size_t spg_vec_len(const spg_vec *v);
+void *spg_vec_device_ptr(const spg_vec *v);
+void spg_vec_free(spg_vec *v);
+
+/* ---------------------------------------------------------------- field (a1)
+ * Scalar::{mul,add,sub,neg} elementwise, src/scalar/ristretto255.rs:690-763.
+ * op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 square(a), 5 to canonical integer (to_bytes) */
+int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_vec *out);
+/* Scalar::from_u512 / from_bytes_wide on n wide values (8 u64 each), :435-466 */
+int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec **out);
+
+/* ---------------------------------------------------------------- eq / dense MLE (a2, a3) */
+/* EqPolynomial::evals, src/dense_mlpoly.rs:76-92: out has 2^ell entries, MSB <-> r[0] */
+int spg_eq_evals(spg_ctx *ctx, const spg_fq *r, size_t ell, spg_vec **out);
+/* DensePolynomial::bound_poly_var_top / _bot, :267-275 / :350-358 (in place; len halves) */
+int spg_dense_bound_top(spg_ctx *ctx, spg_vec *v, const spg_fq *r);
+int spg_dense_bound_bot(spg_ctx *ctx, spg_vec *v, const spg_fq *r);
+/* DensePolynomial::evaluate, :361-367; r has log2(len) entries */
+int spg_dense_evaluate(spg_ctx *ctx, const spg_vec *v, const spg_fq *r, size_t ell, spg_fq *out);
+/* DensePolynomial::bound(L), :258-265: out[i] = sum_j L[j] * Z[j*R_size + i] */
+int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_size,
+                      spg_vec **out);
+/* DotProductProofLog::compute_dotproduct */
+int spg_dot(spg_ctx *ctx, const spg_vec *a, const spg_vec *b, spg_fq *out);
+
+/* ---------------------------------------------------------------- R1CS instance (a9, a10, a12)
+ * R1CSInstance::new, src/r1csinstance.rs:89-182. Matrices are COO triples
+ * (row, col, val) exactly as the reference stores them (src/sparse_mlpoly.rs:19-24);
+ * mat index m = 3*inst + {0:A, 1:B, 2:C}; nnz[m] entries each, concatenated. */
+int spg_r1cs_create(spg_ctx *ctx, size_t num_instances, size_t max_num_cons,
+                    const size_t *num_cons, size_t num_vars, const size_t *nnz,
+                    const uint32_t *rows, const uint32_t *cols, const spg_fq *vals,
+                    spg_r1cs **out);
+void spg_r1cs_destroy(spg_r1cs *inst);
+/* SparseMatPolynomial::multi_evaluate via R1CSInstance::multi_evaluate,
+ * src/r1csinstance.rs:583-595: out[3*num_instances] */
+int spg_r1cs_multi_evaluate(spg_ctx *ctx, const spg_r1cs *inst, const spg_fq *rx, size_t nrx,
+                            const spg_fq *ry, size_t nry, spg_fq *out);
+
+/* ---------------------------------------------------------------- witnesses and z_mat (a11)
+ * One ProverWitnessSecInfo (src/lib.rs): w_mat[p][q][i] flattened, poly_w[p] = w_mat[p].
+ * num_instances is 1 (single) or P; num_proofs[p] is 1 (short) or Q_p. */
+int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                       const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out);
+void spg_witness_destroy(spg_witness *w);
+/* poly_w[p] as a dense vector view (not owned by the caller) */
+int spg_witness_poly(spg_witness *w, size_t p, spg_vec **out);
+/* z_mat assembly, src/r1csproof.rs:278-293 */
+int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                   const size_t *num_inputs, size_t num_witness_secs,
+                   spg_witness *const *witness_secs, spg_zmat **out);
+void spg_zmat_destroy(spg_zmat *z);
+
+/* ---------------------------------------------------------------- phase-1 sumcheck (a4, a5, a9)
+ * ZKSumcheckInstanceProof::prove_cubic_with_additive_term_disjoint_rounds,
+ * src/sumcheck.rs:1067-1380, with comb = A*(B*C - D) (src/r1csproof.rs:100-104).
+ * create = multiply_vec_block (src/r1csinstance.rs:363-436) + the three eq tables
+ * (src/r1csproof.rs:305-322). num_cons is per proving instance (block_num_cons). */
+int spg_sc1_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
+                   const size_t *num_proofs, size_t max_num_proofs, const size_t *num_cons,
+                   size_t max_num_cons, size_t max_num_inputs, const spg_fq *tau_p,
+                   const spg_fq *tau_q, const spg_fq *tau_x, spg_sc1 **out);
+/* same, from caller-provided Az/Bz/Cz in natural ragged [p][q][x] order (tests, partial offload) */
+int spg_sc1_create_from_tables(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                               size_t max_num_proofs, const size_t *num_cons, size_t max_num_cons,
+                               const spg_fq *Az, const spg_fq *Bz, const spg_fq *Cz,
+                               const spg_fq *tau_p, const spg_fq *tau_q, const spg_fq *tau_x,
+                               spg_sc1 **out);
+size_t spg_sc1_num_rounds(const spg_sc1 *s);
+/* e = (eval_point_0, eval_point_2, eval_point_3) of the current round, :1166-1245 */
+int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]);
+/* bind the round's variable to r_j, :1265-1275 */
+int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r);
+/* (tau_claim, Az, Bz, Cz) after the last bind, :1372-1377 */
+int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]);
+/* copy the current Az/Bz/Cz tables back in natural ragged order (tests) */
+int spg_sc1_debug_tables(spg_sc1 *s, spg_fq *Az, spg_fq *Bz, spg_fq *Cz, size_t cap, size_t *n);
+void spg_sc1_destroy(spg_sc1 *s);
+
+/* ---------------------------------------------------------------- phase-2 sumcheck (a6, a10)
+ * ZKSumcheckInstanceProof::prove_cubic_disjoint_rounds, src/sumcheck.rs:788-1065,
+ * comb = A*B*C. create = ABC table (src/r1csproof.rs:431-465), Z_poly bound to rq
+ * (:469-479) and eq(rp) (:482). rx has log2(max_num_cons) entries (natural order,
+ * i.e. already reversed as at :413), rq_rev log2(max_num_proofs), rp log2(P'). */
+int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
+                   const size_t *num_proofs, size_t max_num_proofs, const size_t *num_inputs,
+                   size_t max_num_inputs, size_t num_witness_secs, const spg_fq *rx,
+                   const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
+                   const spg_fq *r_C, spg_sc2 **out);
+size_t spg_sc2_num_rounds(const spg_sc2 *s);
+int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]);
+int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r);
+/* (eq claim, ABC claim, Z claim), :1058-1062 */
+int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]);
+void spg_sc2_destroy(spg_sc2 *s);
+
+/* ---------------------------------------------------------------- product trees (a13, a14, a7)
+ * ProductCircuit::new, src/product_tree.rs:36-56: builds all layers of one circuit on
+ * the device. layer k (0 = leaves) has left/right halves of length len/2^(k+1). */
+typedef struct spg_prodtree spg_prodtree;
+int spg_prodtree_build(spg_ctx *ctx, const spg_vec *leaves, spg_prodtree **out);
+size_t spg_prodtree_num_layers(const spg_prodtree *t);
+int spg_prodtree_layer(spg_prodtree *t, size_t layer, spg_vec **left, spg_vec **right);
+/* ProductCircuit::evaluate, :58-63 */
+int spg_prodtree_evaluate(spg_ctx *ctx, spg_prodtree *t, spg_fq *out);
+void spg_prodtree_destroy(spg_prodtree *t);
+
+/* SumcheckInstanceProof::prove_cubic_batched, src/sumcheck.rs:264-434, comb = A*B*C.
+ * npar (A_i, B_i) pairs share C_par; nseq (A, B, C) triples. Tables are consumed
+ * (bound in place). */
+int spg_cubic_create(spg_ctx *ctx, size_t npar, spg_vec *const *A_par, spg_vec *const *B_par,
+                     spg_vec *C_par, size_t nseq, spg_vec *const *A_seq, spg_vec *const *B_seq,
+                     spg_vec *const *C_seq, const spg_fq *coeffs, spg_cubic **out);
+int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]);
+int spg_cubic_round_bind(spg_cubic *s, const spg_fq *r);
+/* claims: A_par[npar], B_par[npar], C_par, A_seq[nseq], B_seq[nseq], C_seq[nseq] */
+int spg_cubic_final(spg_cubic *s, spg_fq *claims);
+void spg_cubic_destroy(spg_cubic *s);
+
+/* ---------------------------------------------------------------- sparse-poly memory check (a15)
+ * Layers::build_hash_layer, src/sparse_mlpoly.rs:612-687:
+ *   out[i] = ts[i]*gamma^2 + val[i]*gamma + addr[i] - tau   (hash_func at :623-626)
+ * addr/ts given as u64 integers (converted like DensePolynomial::from_usize), val as scalars. */
+int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const uint64_t *ts,
+                   size_t n, const spg_fq *gamma, const spg_fq *tau, int ts_plus_one,
+                   spg_vec **out);
+/* AddrTimestamps::deref_mem, :255-264: out[i] = mem[addr[i]] */
+int spg_deref(spg_ctx *ctx, const uint64_t *addr, size_t n, const spg_vec *mem, spg_vec **out);
+
+/* ---------------------------------------------------------------- commitments (a16)
+ * MultiCommitGens::new is host-side setup (src/commitments.rs:15-33); the caller
+ * passes the n+1 generators as compressed ristretto points (G[0..n], h). */
+int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, spg_gens **out);
+void spg_gens_destroy(spg_gens *g);
+/* DensePolynomial::commit with zero blinds, src/dense_mlpoly.rs:199-239:
+ * out = L_size compressed row commitments (32 bytes each). */
+int spg_poly_commit(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size,
+                    uint8_t *out_compressed);
+/* Commitments::commit for a batch of short vectors sharing the bases (sumcheck
+ * round polynomials etc.): out[i] = sum_j s[i*len+j] G[j] + blind[i] h */
+int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, size_t len,
+                     const spg_fq *blinds, size_t count, uint8_t *out_compressed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPGPU_H */

@@ -1,0 +1,20 @@
+"""B200-native prover backend for spartan-parallel's data-parallel R1CS proving path.
+
+The product is ``libspgpu.so`` (hand-written sm_100a CUDA kernels behind the C ABI
+of ``include/spgpu.h``); this package is the thin host-side mirror of the reference
+interface used by the tests and the benchmark. It never imports ``oracle``.
+"""
+from ._lib import LIB_PATH, SpgError, declared_symbols  # noqa: F401
+from .api import (  # noqa: F401
+    MODE_P,
+    MODE_Q,
+    MODE_W,
+    MODE_X,
+    Context,
+    DensePolynomial,
+    EqPolynomial,
+    SumcheckPhase1,
+    dot,
+    from_u512,
+    vec_op,
+)

@@ -1,0 +1,241 @@
+"""Host-side mirror of the reference interface for the accelerated path.
+
+Names follow the reference crate (scroll-tech/spartan-parallel): ``EqPolynomial``,
+``DensePolynomial``, ``R1CSInstance``, the two disjoint-round sumcheck provers and
+``prove_cubic_batched``. Scalars are numpy ``uint64[..., 4]`` arrays holding the
+reference's Montgomery limbs (src/scalar/ristretto255.rs:193-199). Every call goes
+through the C ABI in include/spgpu.h; nothing here computes field arithmetic on
+the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SpgError, check
+
+MODE_P, MODE_Q, MODE_W, MODE_X = 1, 2, 3, 4
+
+
+def _fq(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.shape[-1] != 4:
+        raise ValueError(f"scalar arrays must have a trailing axis of 4 limbs, got {a.shape}")
+    return a
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _sz(v) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(v, dtype=np.uint64).reshape(-1))
+
+
+class Context:
+    """One device + stream (spg_ctx). The reference prover is single-threaded; so is this."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.lib()
+        h = C.c_void_p()
+        check(self.L.spg_ctx_create(device, C.byref(h)), "spg_ctx_create")
+        self.h = h
+        self.device = device
+
+    def sync(self):
+        check(self.L.spg_ctx_sync(self.h), "spg_ctx_sync")
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.spg_ctx_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.spg_ctx_stream(self.h) or 0)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.spg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DensePolynomial:
+    """Device-resident DensePolynomial (src/dense_mlpoly.rs:19-24)."""
+
+    def __init__(self, ctx: Context, handle, owner=None):
+        self.ctx, self.h, self._owner = ctx, handle, owner
+
+    @classmethod
+    def new(cls, ctx: Context, Z) -> "DensePolynomial":
+        Z = _fq(Z).reshape(-1, 4)
+        n = Z.shape[0]
+        n2 = 1 if n == 0 else 1 << (n - 1).bit_length()
+        if n2 != n:  # DensePolynomial::new zero-pads to a power of two (:152-161)
+            Z = np.concatenate([Z, np.zeros((n2 - n, 4), dtype=np.uint64)])
+        h = C.c_void_p()
+        check(ctx.L.spg_vec_upload(ctx.h, _ptr(Z), Z.shape[0], C.byref(h)), "spg_vec_upload")
+        return cls(ctx, h)
+
+    @classmethod
+    def wrap(cls, ctx: Context, device_ptr: int, n: int, owner=None) -> "DensePolynomial":
+        h = C.c_void_p()
+        check(ctx.L.spg_vec_wrap(ctx.h, C.c_void_p(device_ptr), n, C.byref(h)), "spg_vec_wrap")
+        return cls(ctx, h, owner)
+
+    @classmethod
+    def empty(cls, ctx: Context, n: int) -> "DensePolynomial":
+        h = C.c_void_p()
+        check(ctx.L.spg_vec_alloc(ctx.h, n, C.byref(h)), "spg_vec_alloc")
+        return cls(ctx, h)
+
+    def __len__(self):
+        return int(self.ctx.L.spg_vec_len(self.h))
+
+    def len(self):
+        return len(self)
+
+    def get_num_vars(self):
+        return len(self).bit_length() - 1
+
+    @property
+    def device_ptr(self) -> int:
+        return int(self.ctx.L.spg_vec_device_ptr(self.h) or 0)
+
+    def to_host(self) -> np.ndarray:
+        out = np.empty((len(self), 4), dtype=np.uint64)
+        check(self.ctx.L.spg_vec_download(self.ctx.h, self.h, 0, len(self), _ptr(out)), "spg_vec_download")
+        return out
+
+    def bound_poly_var_top(self, r):
+        check(self.ctx.L.spg_dense_bound_top(self.ctx.h, self.h, _ptr(_fq(r))), "spg_dense_bound_top")
+
+    def bound_poly_var_bot(self, r):
+        check(self.ctx.L.spg_dense_bound_bot(self.ctx.h, self.h, _ptr(_fq(r))), "spg_dense_bound_bot")
+
+    def evaluate(self, r) -> np.ndarray:
+        r = _fq(np.asarray(r, dtype=np.uint64).reshape(-1, 4))
+        out = np.empty(4, dtype=np.uint64)
+        check(self.ctx.L.spg_dense_evaluate(self.ctx.h, self.h, _ptr(r), r.shape[0], _ptr(out)), "spg_dense_evaluate")
+        return out
+
+    def bound(self, L) -> "DensePolynomial":
+        L = _fq(L).reshape(-1, 4)
+        h = C.c_void_p()
+        check(self.ctx.L.spg_dense_bound_L(self.ctx.h, self.h, _ptr(L), L.shape[0], C.byref(h)), "spg_dense_bound_L")
+        return DensePolynomial(self.ctx, h)
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_vec_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def vec_op(ctx: Context, op: str, a: DensePolynomial, b: DensePolynomial | None = None) -> DensePolynomial:
+    """Scalar::{mul,add,sub,neg,square,to_bytes} elementwise on the device."""
+    code = {"mul": 0, "add": 1, "sub": 2, "neg": 3, "square": 4, "to_canonical": 5}[op]
+    out = DensePolynomial.empty(ctx, len(a))
+    check(ctx.L.spg_fq_vec_op(ctx.h, code, a.h, b.h if b is not None else None, out.h), "spg_fq_vec_op")
+    return out
+
+
+def from_u512(ctx: Context, wide) -> DensePolynomial:
+    wide = np.ascontiguousarray(wide, dtype=np.uint64)
+    assert wide.shape[-1] == 8
+    h = C.c_void_p()
+    check(ctx.L.spg_fq_from_u512(ctx.h, _ptr(wide), wide.size // 8, C.byref(h)), "spg_fq_from_u512")
+    return DensePolynomial(ctx, h)
+
+
+def dot(ctx: Context, a: DensePolynomial, b: DensePolynomial) -> np.ndarray:
+    out = np.empty(4, dtype=np.uint64)
+    check(ctx.L.spg_dot(ctx.h, a.h, b.h, _ptr(out)), "spg_dot")
+    return out
+
+
+class EqPolynomial:
+    """EqPolynomial (src/dense_mlpoly.rs:60-131)."""
+
+    def __init__(self, ctx: Context, r):
+        self.ctx = ctx
+        self.r = _fq(np.asarray(r, dtype=np.uint64).reshape(-1, 4))
+
+    def evals(self) -> DensePolynomial:
+        h = C.c_void_p()
+        check(self.ctx.L.spg_eq_evals(self.ctx.h, _ptr(self.r), self.r.shape[0], C.byref(h)), "spg_eq_evals")
+        return DensePolynomial(self.ctx, h)
+
+    @staticmethod
+    def compute_factored_lens(ell: int):
+        return ell // 2, ell - ell // 2
+
+    def compute_factored_evals(self):
+        left, _ = self.compute_factored_lens(self.r.shape[0])
+        return EqPolynomial(self.ctx, self.r[:left]).evals(), EqPolynomial(self.ctx, self.r[left:]).evals()
+
+
+class SumcheckPhase1:
+    """Device loops of prove_cubic_with_additive_term_disjoint_rounds (src/sumcheck.rs:1067-1380)."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx, self.h = ctx, handle
+
+    @classmethod
+    def from_tables(cls, ctx: Context, num_proofs, max_num_proofs, num_cons, max_num_cons, Az, Bz, Cz, tau_p, tau_q, tau_x):
+        npf, nc = _sz(num_proofs), _sz(num_cons)
+        h = C.c_void_p()
+        tp, tq, tx = (_fq(np.asarray(t, dtype=np.uint64).reshape(-1, 4)) for t in (tau_p, tau_q, tau_x))
+        check(ctx.L.spg_sc1_create_from_tables(ctx.h, len(npf), _ptr(npf), max_num_proofs, _ptr(nc), max_num_cons,
+                                               _ptr(_fq(Az)), _ptr(_fq(Bz)), _ptr(_fq(Cz)), _ptr(tp), _ptr(tq), _ptr(tx),
+                                               C.byref(h)), "spg_sc1_create_from_tables")
+        return cls(ctx, h)
+
+    @property
+    def num_rounds(self) -> int:
+        return int(self.ctx.L.spg_sc1_num_rounds(self.h))
+
+    def round_eval(self) -> np.ndarray:
+        out = np.empty((3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc1_round_eval(self.h, _ptr(out)), "spg_sc1_round_eval")
+        return out
+
+    def round_bind(self, r):
+        check(self.ctx.L.spg_sc1_round_bind(self.h, _ptr(_fq(r))), "spg_sc1_round_bind")
+
+    def final(self) -> np.ndarray:
+        out = np.empty((4, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc1_final(self.h, _ptr(out)), "spg_sc1_final")
+        return out
+
+    def debug_tables(self):
+        n = C.c_size_t()
+        check(self.ctx.L.spg_sc1_debug_tables(self.h, None, None, None, 0, C.byref(n)), "spg_sc1_debug_tables")
+        out = [np.empty((n.value, 4), dtype=np.uint64) for _ in range(3)]
+        check(self.ctx.L.spg_sc1_debug_tables(self.h, _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), n.value, C.byref(n)),
+              "spg_sc1_debug_tables")
+        return out
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_sc1_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

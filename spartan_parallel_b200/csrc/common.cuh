@@ -1,0 +1,129 @@
+// Shared host-side plumbing for libspgpu: context, device vectors, error handling,
+// launch accounting and the small reductions every sumcheck round ends with.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/spgpu.h"
+#include "fq.cuh"
+#include "host_fq.h"
+
+namespace spg {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define SPG_CUDA(expr)                                                       \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) return spg::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define SPG_CHECK(cond, ...)      \
+  do {                            \
+    if (!(cond)) {                \
+      spg::set_error(__VA_ARGS__); \
+      return SPG_EINVAL;          \
+    }                             \
+  } while (0)
+
+#define SPG_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != SPG_OK) return _rc; \
+  } while (0)
+
+static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline size_t next_pow2(size_t n) {
+  size_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+static inline unsigned log2u(size_t n) {
+  unsigned l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+
+}  // namespace spg
+
+// ---------------------------------------------------------------- handles
+struct spg_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  // per-block partial sums of the round kernels, and the 3-scalar result slot
+  spg::fq *d_partials = nullptr;
+  size_t partial_cap = 0;  // in fq
+  spg::fq *h_result = nullptr;  // pinned + mapped
+  spg::fq *d_result = nullptr;  // device alias of h_result
+  // small staging for scalar arguments
+  spg::fq *d_scalars = nullptr;  // device scratch, 64 fq
+};
+
+struct spg_vec {
+  spg_ctx *ctx = nullptr;
+  spg::fq *d = nullptr;
+  size_t n = 0;      // logical length
+  size_t cap = 0;    // allocated length
+  bool owned = true;
+};
+
+namespace spg {
+
+// launch bookkeeping: every kernel goes through this so gpu_launches is exact
+#define SPG_LAUNCH(ctx, kernel, grid, block, smem, ...)                       \
+  do {                                                                        \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \
+    (ctx)->launches++;                                                        \
+    SPG_CUDA(cudaGetLastError());                                             \
+  } while (0)
+
+int ensure_partials(spg_ctx *ctx, size_t n_fq);
+int vec_new(spg_ctx *ctx, size_t n, spg_vec **out);
+
+// grid sizing: persistent-style grids in multiples of the SM count
+static inline int grid_for(const spg_ctx *ctx, size_t items, int block, int max_waves = 8) {
+  size_t blocks = (items + block - 1) / block;
+  size_t cap = (size_t)ctx->sm_count * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks == 0) blocks = 1;
+  return (int)blocks;
+}
+
+// sum `count` groups of `width` scalars laid out [block][width] into out[width]
+int reduce_partials(spg_ctx *ctx, const fq *partials, size_t nblocks, int width, fq *d_out);
+// fetch `width` scalars from the mapped result slot after a stream sync
+int fetch_result(spg_ctx *ctx, int width, spg_fq *out);
+
+// block-level modular sum of `W` accumulators; thread 0 of the block gets the result
+template <int W>
+__device__ __forceinline__ void block_sum(fq (&acc)[W], fq *smem /* [W * 32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < W; k++) acc[k] = fq_warp_sum(acc[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < W; k++) smem[k * 32 + warp] = acc[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+      fq v = lane < nwarps ? smem[k * 32 + lane] : fq_zero();
+      acc[k] = fq_warp_sum(v);
+    }
+  }
+}
+
+}  // namespace spg

@@ -1,0 +1,196 @@
+// Context, device vectors, error reporting and the shared reduction kernels.
+#include "common.cuh"
+
+namespace spg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return e == cudaErrorMemoryAllocation ? SPG_ENOMEM : SPG_ECUDA;
+}
+
+int ensure_partials(spg_ctx *ctx, size_t n_fq) {
+  if (ctx->partial_cap >= n_fq) return SPG_OK;
+  if (ctx->d_partials) SPG_CUDA(cudaFree(ctx->d_partials));
+  ctx->d_partials = nullptr;
+  ctx->partial_cap = 0;
+  SPG_CUDA(cudaMalloc(&ctx->d_partials, n_fq * sizeof(fq)));
+  ctx->partial_cap = n_fq;
+  return SPG_OK;
+}
+
+int vec_new(spg_ctx *ctx, size_t n, spg_vec **out) {
+  spg_vec *v = new (std::nothrow) spg_vec();
+  if (!v) return SPG_ENOMEM;
+  v->ctx = ctx;
+  v->n = v->cap = n;
+  cudaError_t e = cudaMalloc(&v->d, (n ? n : 1) * sizeof(fq));
+  if (e != cudaSuccess) {
+    delete v;
+    return cuda_fail(e, "cudaMalloc(vec)", __FILE__, __LINE__);
+  }
+  *out = v;
+  return SPG_OK;
+}
+
+// one block: sums partials[b*width + k] over b for each k < width (width <= 8)
+__global__ void k_reduce_partials(const fq *__restrict__ partials, size_t nblocks, int width,
+                                  fq *__restrict__ out) {
+  __shared__ fq sm[32];
+  for (int k = 0; k < width; k++) {
+    fq acc = fq_zero();
+    for (size_t b = threadIdx.x; b < nblocks; b += blockDim.x)
+      acc = fq_add(acc, partials[b * width + k]);
+    acc = fq_warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      fq v = threadIdx.x < ((blockDim.x + 31) >> 5) ? sm[threadIdx.x] : fq_zero();
+      v = fq_warp_sum(v);
+      if (threadIdx.x == 0) out[k] = v;
+    }
+    __syncthreads();
+  }
+}
+
+int reduce_partials(spg_ctx *ctx, const fq *partials, size_t nblocks, int width, fq *d_out) {
+  int threads = nblocks >= 256 ? 256 : (nblocks > 32 ? 128 : 32);
+  SPG_LAUNCH(ctx, k_reduce_partials, 1, threads, 0, partials, nblocks, width, d_out);
+  return SPG_OK;
+}
+
+int fetch_result(spg_ctx *ctx, int width, spg_fq *out) {
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, ctx->h_result, sizeof(spg_fq) * width);
+  return SPG_OK;
+}
+
+}  // namespace spg
+
+using namespace spg;
+
+extern "C" {
+
+const char *spg_last_error(void) { return g_err; }
+int spg_version(void) { return 100; }
+
+int spg_ctx_create(int device, spg_ctx **out) {
+  SPG_CHECK(out != nullptr, "spg_ctx_create: out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_error("spg_ctx_create: no CUDA device available (%s); this backend has no CPU fallback",
+              cudaGetErrorString(e));
+    return SPG_ECUDA;
+  }
+  SPG_CHECK(device >= 0 && device < count, "spg_ctx_create: device %d out of range (%d devices)",
+            device, count);
+  SPG_CUDA(cudaSetDevice(device));
+  spg_ctx *ctx = new (std::nothrow) spg_ctx();
+  if (!ctx) return SPG_ENOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  SPG_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  SPG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  SPG_CUDA(cudaHostAlloc(&ctx->h_result, 64 * sizeof(fq), cudaHostAllocMapped));
+  SPG_CUDA(cudaHostGetDevicePointer(&ctx->d_result, ctx->h_result, 0));
+  SPG_CUDA(cudaMalloc(&ctx->d_scalars, 64 * sizeof(fq)));
+  int rc = ensure_partials(ctx, (size_t)ctx->sm_count * 16 * 8);
+  if (rc != SPG_OK) return rc;
+  *out = ctx;
+  return SPG_OK;
+}
+
+void spg_ctx_destroy(spg_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int spg_ctx_sync(spg_ctx *ctx) {
+  SPG_CHECK(ctx, "null ctx");
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}
+
+uint64_t spg_ctx_launch_count(const spg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *spg_ctx_stream(const spg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int spg_host_alloc(size_t bytes, void **out) {
+  SPG_CHECK(out, "null out");
+  SPG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+  return SPG_OK;
+}
+void spg_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+int spg_vec_alloc(spg_ctx *ctx, size_t n, spg_vec **out) {
+  SPG_CHECK(ctx && out, "spg_vec_alloc: null argument");
+  return vec_new(ctx, n, out);
+}
+
+int spg_vec_upload(spg_ctx *ctx, const spg_fq *host, size_t n, spg_vec **out) {
+  SPG_CHECK(ctx && out && (host || n == 0), "spg_vec_upload: null argument");
+  spg_vec *v = nullptr;
+  SPG_TRY(vec_new(ctx, n, &v));
+  if (n) {
+    cudaError_t e = cudaMemcpyAsync(v->d, host, n * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      spg_vec_free(v);
+      return cuda_fail(e, "upload", __FILE__, __LINE__);
+    }
+  }
+  *out = v;
+  return SPG_OK;
+}
+
+int spg_vec_wrap(spg_ctx *ctx, void *device_ptr, size_t n, spg_vec **out) {
+  SPG_CHECK(ctx && out && device_ptr, "spg_vec_wrap: null argument");
+  SPG_CHECK(((uintptr_t)device_ptr & 31) == 0, "spg_vec_wrap: pointer must be 32-byte aligned");
+  spg_vec *v = new (std::nothrow) spg_vec();
+  if (!v) return SPG_ENOMEM;
+  v->ctx = ctx;
+  v->d = (fq *)device_ptr;
+  v->n = v->cap = n;
+  v->owned = false;
+  *out = v;
+  return SPG_OK;
+}
+
+int spg_vec_download(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_fq *host) {
+  SPG_CHECK(ctx && v && (host || n == 0), "spg_vec_download: null argument");
+  SPG_CHECK(offset + n <= v->n, "spg_vec_download: range [%zu, %zu) exceeds length %zu", offset,
+            offset + n, v->n);
+  if (n) {
+    SPG_CUDA(cudaMemcpyAsync(host, v->d + offset, n * sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return SPG_OK;
+}
+
+size_t spg_vec_len(const spg_vec *v) { return v ? v->n : 0; }
+void *spg_vec_device_ptr(const spg_vec *v) { return v ? (void *)v->d : nullptr; }
+
+void spg_vec_free(spg_vec *v) {
+  if (!v) return;
+  if (v->owned && v->d) cudaFree(v->d);
+  delete v;
+}
+
+}  // extern "C"

@@ -1,0 +1,341 @@
+// Elementwise field ops, EqPolynomial expansion and DensePolynomial kernels.
+//   reference: src/scalar/ristretto255.rs, src/dense_mlpoly.rs:60-131, 258-367
+// All of these are one-pass streams over 32-byte scalars (LDG.256 / STG.256), so
+// they are HBM-bound except for the modmul-heavy reductions.
+#include "common.cuh"
+
+namespace spg {
+
+// ---------------------------------------------------------------- elementwise
+template <int OP>
+__global__ void k_vec_op(const fq *__restrict__ a, const fq *__restrict__ b, fq *__restrict__ out,
+                         size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fq x = fq_load(a + i);
+    fq r;
+    if (OP == 0) r = fq_mul(x, fq_load(b + i));
+    else if (OP == 1) r = fq_add(x, fq_load(b + i));
+    else if (OP == 2) r = fq_sub(x, fq_load(b + i));
+    else if (OP == 3) r = fq_neg(x);
+    else if (OP == 4) r = fq_sqr(x);
+    else r = fq_from_mont(x);
+    fq_store(out + i, r);
+  }
+}
+
+// Scalar::from_u512: d0*R2 + d1*R3
+__global__ void k_from_u512(const uint32_t *__restrict__ wide, fq *__restrict__ out, size_t n) {
+  fq R2, R3;
+  R2.v[0] = 0x449c0f01u; R2.v[1] = 0xa40611e3u; R2.v[2] = 0x68859347u; R2.v[3] = 0xd00e1ba7u;
+  R2.v[4] = 0x17f5be65u; R2.v[5] = 0xceec73d2u; R2.v[6] = 0x7c309a3du; R2.v[7] = 0x0399411bu;
+  R3.v[0] = 0x7b83a2dbu; R3.v[1] = 0x2a9e4968u; R3.v[2] = 0xaef7f3ecu; R3.v[3] = 0x278324e6u;
+  R3.v[4] = 0x04ec5b65u; R3.v[5] = 0x8065dc6cu; R3.v[6] = 0x3599cec7u; R3.v[7] = 0x0e530b77u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fq d0, d1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      d0.v[k] = wide[i * 16 + k];
+      d1.v[k] = wide[i * 16 + 8 + k];
+    }
+    // d0, d1 are arbitrary 256-bit values: the Montgomery product stays below 2q
+    // as long as the other operand is canonical (ristretto255.rs:455-461)
+    fq x = fq_canon(fq_mul_lazy(R2, d0));
+    fq y = fq_canon(fq_mul_lazy(R3, d1));
+    fq_store(out + i, fq_add(x, y));
+  }
+}
+
+// ---------------------------------------------------------------- eq expansion
+// One doubling step of EqPolynomial::evals (dense_mlpoly.rs:81-90):
+//   out[2i+1] = prev[i]*r, out[2i] = prev[i] - out[2i+1]
+__global__ void k_eq_expand(const fq *__restrict__ prev, fq *__restrict__ out, size_t n, fq r) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fq s = fq_load(prev + i);
+    fq hi = fq_mul(s, r);
+    fq lo = fq_sub(s, hi);
+    fq_store(out + 2 * i, lo);
+    fq_store(out + 2 * i + 1, hi);
+  }
+}
+
+// The first levels (up to 2^LV entries) in one block through shared memory.
+template <int LV>
+__global__ void k_eq_expand_small(const fq *__restrict__ r, int ell, fq *__restrict__ out) {
+  __shared__ fq buf[2][1 << LV];
+  if (threadIdx.x == 0) buf[0][0] = fq_one();
+  __syncthreads();
+  int cur = 0;
+  for (int j = 0; j < ell; j++) {
+    size_t n = (size_t)1 << j;
+    fq rj = r[j];
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      fq s = buf[cur][i];
+      fq hi = fq_mul(s, rj);
+      buf[cur ^ 1][2 * i + 1] = hi;
+      buf[cur ^ 1][2 * i] = fq_sub(s, hi);
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  size_t n = (size_t)1 << ell;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = buf[cur][i];
+}
+
+constexpr int EQ_SMALL_LV = 9;
+
+// evals of eq(r, .) with MSB <-> r[0]; r on device (ell scalars). out has 2^ell entries.
+// scratch must hold 2^(ell-1) entries when ell > EQ_SMALL_LV.
+int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch) {
+  int small = (int)(ell < (size_t)EQ_SMALL_LV ? ell : EQ_SMALL_LV);
+  if (ell <= (size_t)EQ_SMALL_LV) {
+    SPG_LAUNCH(ctx, k_eq_expand_small<EQ_SMALL_LV>, 1, 256, 0, d_r, small, out);
+    return SPG_OK;
+  }
+  // ping-pong so that the last level lands in `out`
+  size_t remaining = ell - small;
+  fq *bufs[2] = {out, scratch};
+  int which = (remaining % 2 == 0) ? 0 : 1;
+  SPG_LAUNCH(ctx, k_eq_expand_small<EQ_SMALL_LV>, 1, 256, 0, d_r, small, bufs[which]);
+  for (size_t j = small; j < ell; j++) {
+    size_t n = (size_t)1 << j;
+    fq rj;
+    memcpy(&rj, &h_r[j], sizeof(fq));
+    SPG_LAUNCH(ctx, k_eq_expand, grid_for(ctx, n, 256), 256, 0, bufs[which], bufs[which ^ 1], n, rj);
+    which ^= 1;
+  }
+  return SPG_OK;
+}
+
+// ---------------------------------------------------------------- dense bind
+// top: Z[i] += r*(Z[i+n]-Z[i]); bot: Z[i] = Z[2i] + r*(Z[2i+1]-Z[2i]) (out of place)
+__global__ void k_bound_top(fq *__restrict__ Z, size_t n, fq r) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fq lo = fq_load(Z + i), hi = fq_load(Z + i + n);
+    fq_store(Z + i, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+  }
+}
+
+__global__ void k_bound_bot(const fq *__restrict__ Z, fq *__restrict__ out, size_t n, fq r) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    fq lo = fq_load(Z + 2 * i), hi = fq_load(Z + 2 * i + 1);
+    fq_store(out + i, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+  }
+}
+
+// ---------------------------------------------------------------- reductions
+// partial[b] = sum over the block's elements of a[i]*b[i]
+__global__ void k_dot(const fq *__restrict__ a, const fq *__restrict__ b, size_t n,
+                      fq *__restrict__ partials) {
+  __shared__ fq sm[32];
+  fq acc[1] = {fq_zero()};
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    acc[0] = fq_add(acc[0], fq_mul(fq_load_stream(a + i), fq_load_stream(b + i)));
+  block_sum<1>(acc, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+}
+
+// DensePolynomial::evaluate without materialising the 2^ell chi table:
+//   Z(r) = sum_j L[j] * sum_i R[i] * Z[j*Rs + i], L = eq(r_hi), R = eq(r_lo).
+// One block handles `chunk` consecutive elements of one row j.
+__global__ void k_eval_rows(const fq *__restrict__ Z, const fq *__restrict__ L,
+                            const fq *__restrict__ R, size_t Rs, size_t chunk, size_t chunks_per_row,
+                            fq *__restrict__ partials) {
+  __shared__ fq sm[32];
+  size_t j = blockIdx.x / chunks_per_row, c = blockIdx.x % chunks_per_row;
+  size_t base = c * chunk;
+  fq acc[1] = {fq_zero()};
+  for (size_t i = base + threadIdx.x; i < base + chunk && i < Rs; i += blockDim.x)
+    acc[0] = fq_add(acc[0], fq_mul(fq_load_stream(Z + j * Rs + i), fq_load(R + i)));
+  block_sum<1>(acc, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = fq_mul(acc[0], L[j]);
+}
+
+// bound(L): partial[y][i] = sum_{j in slab y} L[j] * Z[j*Rs + i]
+__global__ void k_bound_L_partial(const fq *__restrict__ Z, const fq *__restrict__ L, size_t Ls,
+                                  size_t Rs, size_t slab, fq *__restrict__ partial) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Rs) return;
+  size_t j0 = (size_t)blockIdx.y * slab, j1 = j0 + slab < Ls ? j0 + slab : Ls;
+  fq acc = fq_zero();
+  for (size_t j = j0; j < j1; j++) acc = fq_add(acc, fq_mul(L[j], fq_load_stream(Z + j * Rs + i)));
+  fq_store(partial + (size_t)blockIdx.y * Rs + i, acc);
+}
+
+__global__ void k_sum_slabs(const fq *__restrict__ partial, size_t nslabs, size_t Rs,
+                            fq *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Rs) return;
+  fq acc = fq_zero();
+  for (size_t y = 0; y < nslabs; y++) acc = fq_add(acc, fq_load(partial + y * Rs + i));
+  fq_store(out + i, acc);
+}
+
+int dense_evaluate_device(spg_ctx *ctx, const fq *Z, size_t n, const spg_fq *r, size_t ell, fq *d_out) {
+  // split r = (r_hi | r_lo) like compute_factored_lens (dense_mlpoly.rs:118-120)
+  size_t left = ell / 2, right = ell - left;
+  size_t Ls = (size_t)1 << left, Rs = (size_t)1 << right;
+  fq *tabs = nullptr, *d_r = nullptr;
+  SPG_CUDA(cudaMalloc(&tabs, (Ls + Rs + Rs) * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&d_r, (ell ? ell : 1) * sizeof(fq)));
+  SPG_CUDA(cudaMemcpyAsync(d_r, r, ell * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  fq *dL = tabs, *dR = tabs + Ls, *scratch = tabs + Ls + Rs;
+  int rc = eq_evals_device(ctx, d_r, r, left, dL, scratch);
+  if (rc == SPG_OK) rc = eq_evals_device(ctx, d_r + left, r + left, right, dR, scratch);
+  if (rc == SPG_OK) {
+    size_t chunk = Rs < 2048 ? Rs : 2048;
+    size_t cpr = (Rs + chunk - 1) / chunk;
+    size_t nblocks = Ls * cpr;
+    rc = ensure_partials(ctx, nblocks);
+    if (rc == SPG_OK) {
+      int threads = chunk >= 256 ? 256 : 64;
+      k_eval_rows<<<(unsigned)nblocks, threads, 0, ctx->stream>>>(Z, dL, dR, Rs, chunk, cpr, ctx->d_partials);
+      ctx->launches++;
+      rc = reduce_partials(ctx, ctx->d_partials, nblocks, 1, d_out);
+    }
+  }
+  (void)n;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(tabs);
+  cudaFree(d_r);
+  return rc;
+}
+
+}  // namespace spg
+
+using namespace spg;
+
+extern "C" {
+
+int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_vec *out) {
+  SPG_CHECK(ctx && a && out, "spg_fq_vec_op: null argument");
+  SPG_CHECK(op >= 0 && op <= 5, "spg_fq_vec_op: unknown op %d", op);
+  bool binary = op <= 2;
+  SPG_CHECK(!binary || (b && b->n == a->n), "spg_fq_vec_op: operand length mismatch");
+  SPG_CHECK(out->n == a->n, "spg_fq_vec_op: output length mismatch");
+  size_t n = a->n;
+  if (n == 0) return SPG_OK;
+  int grid = grid_for(ctx, n, 256);
+  const fq *pb = b ? b->d : a->d;
+  switch (op) {
+    case 0: SPG_LAUNCH(ctx, k_vec_op<0>, grid, 256, 0, a->d, pb, out->d, n); break;
+    case 1: SPG_LAUNCH(ctx, k_vec_op<1>, grid, 256, 0, a->d, pb, out->d, n); break;
+    case 2: SPG_LAUNCH(ctx, k_vec_op<2>, grid, 256, 0, a->d, pb, out->d, n); break;
+    case 3: SPG_LAUNCH(ctx, k_vec_op<3>, grid, 256, 0, a->d, pb, out->d, n); break;
+    case 4: SPG_LAUNCH(ctx, k_vec_op<4>, grid, 256, 0, a->d, pb, out->d, n); break;
+    default: SPG_LAUNCH(ctx, k_vec_op<5>, grid, 256, 0, a->d, pb, out->d, n); break;
+  }
+  return SPG_OK;
+}
+
+int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec **out) {
+  SPG_CHECK(ctx && out && (host_wide || n == 0), "spg_fq_from_u512: null argument");
+  spg_vec *v = nullptr;
+  SPG_TRY(vec_new(ctx, n, &v));
+  if (n) {
+    uint32_t *d_wide = nullptr;
+    SPG_CUDA(cudaMalloc(&d_wide, n * 64));
+    SPG_CUDA(cudaMemcpyAsync(d_wide, host_wide, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_LAUNCH(ctx, k_from_u512, grid_for(ctx, n, 256), 256, 0, d_wide, v->d, n);
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SPG_CUDA(cudaFree(d_wide));
+  }
+  *out = v;
+  return SPG_OK;
+}
+
+int spg_eq_evals(spg_ctx *ctx, const spg_fq *r, size_t ell, spg_vec **out) {
+  SPG_CHECK(ctx && out && (r || ell == 0), "spg_eq_evals: null argument");
+  SPG_CHECK(ell <= 34, "spg_eq_evals: ell = %zu too large", ell);
+  size_t n = (size_t)1 << ell;
+  spg_vec *v = nullptr;
+  SPG_TRY(vec_new(ctx, n, &v));
+  fq *d_r = nullptr, *scratch = nullptr;
+  SPG_CUDA(cudaMalloc(&d_r, (ell ? ell : 1) * sizeof(fq)));
+  SPG_CUDA(cudaMemcpyAsync(d_r, r, ell * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  if (ell > (size_t)EQ_SMALL_LV) SPG_CUDA(cudaMalloc(&scratch, (n / 2) * sizeof(fq)));
+  int rc = eq_evals_device(ctx, d_r, r, ell, v->d, scratch);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_r);
+  if (scratch) cudaFree(scratch);
+  if (rc != SPG_OK) {
+    spg_vec_free(v);
+    return rc;
+  }
+  *out = v;
+  return SPG_OK;
+}
+
+int spg_dense_bound_top(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
+  SPG_CHECK(ctx && v && r, "spg_dense_bound_top: null argument");
+  SPG_CHECK(v->n >= 2 && is_pow2(v->n), "spg_dense_bound_top: length %zu is not a power of two >= 2", v->n);
+  size_t n = v->n / 2;
+  fq rr;
+  memcpy(&rr, r, sizeof rr);
+  SPG_LAUNCH(ctx, k_bound_top, grid_for(ctx, n, 256), 256, 0, v->d, n, rr);
+  v->n = n;
+  return SPG_OK;
+}
+
+int spg_dense_bound_bot(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
+  SPG_CHECK(ctx && v && r, "spg_dense_bound_bot: null argument");
+  SPG_CHECK(v->n >= 2 && is_pow2(v->n), "spg_dense_bound_bot: length %zu is not a power of two >= 2", v->n);
+  SPG_CHECK(v->owned, "spg_dense_bound_bot: vector must be library-owned");
+  size_t n = v->n / 2;
+  fq rr;
+  memcpy(&rr, r, sizeof rr);
+  fq *tmp = nullptr;
+  SPG_CUDA(cudaMalloc(&tmp, n * sizeof(fq)));
+  SPG_LAUNCH(ctx, k_bound_bot, grid_for(ctx, n, 256), 256, 0, v->d, tmp, n, rr);
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  SPG_CUDA(cudaFree(v->d));
+  v->d = tmp;
+  v->n = v->cap = n;
+  return SPG_OK;
+}
+
+int spg_dense_evaluate(spg_ctx *ctx, const spg_vec *v, const spg_fq *r, size_t ell, spg_fq *out) {
+  SPG_CHECK(ctx && v && out && (r || ell == 0), "spg_dense_evaluate: null argument");
+  SPG_CHECK(v->n == ((size_t)1 << ell), "spg_dense_evaluate: len %zu != 2^%zu", v->n, ell);
+  SPG_TRY(dense_evaluate_device(ctx, v->d, v->n, r, ell, ctx->d_result));
+  return fetch_result(ctx, 1, out);
+}
+
+int spg_dot(spg_ctx *ctx, const spg_vec *a, const spg_vec *b, spg_fq *out) {
+  SPG_CHECK(ctx && a && b && out, "spg_dot: null argument");
+  SPG_CHECK(a->n == b->n, "spg_dot: length mismatch");
+  int grid = grid_for(ctx, a->n, 256, 4);
+  SPG_TRY(ensure_partials(ctx, grid));
+  SPG_LAUNCH(ctx, k_dot, grid, 256, 0, a->d, b->d, a->n, ctx->d_partials);
+  SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 1, ctx->d_result));
+  return fetch_result(ctx, 1, out);
+}
+
+int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_size, spg_vec **out) {
+  SPG_CHECK(ctx && v && L && out, "spg_dense_bound_L: null argument");
+  SPG_CHECK(L_size && v->n % L_size == 0, "spg_dense_bound_L: L_size %zu does not divide len %zu", L_size, v->n);
+  size_t Rs = v->n / L_size;
+  spg_vec *o = nullptr;
+  SPG_TRY(vec_new(ctx, Rs, &o));
+  size_t slab = 64;
+  size_t nslabs = (L_size + slab - 1) / slab;
+  fq *dL = nullptr, *partial = nullptr;
+  SPG_CUDA(cudaMalloc(&dL, L_size * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&partial, nslabs * Rs * sizeof(fq)));
+  SPG_CUDA(cudaMemcpyAsync(dL, L, L_size * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((unsigned)((Rs + 127) / 128), (unsigned)nslabs);
+  SPG_LAUNCH(ctx, k_bound_L_partial, grid, 128, 0, v->d, dL, L_size, Rs, slab, partial);
+  SPG_LAUNCH(ctx, k_sum_slabs, (unsigned)((Rs + 127) / 128), 128, 0, partial, nslabs, Rs, o->d);
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dL);
+  cudaFree(partial);
+  *out = o;
+  return SPG_OK;
+}
+
+}  // extern "C"

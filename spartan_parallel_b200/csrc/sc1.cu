@@ -1,0 +1,611 @@
+// Phase-1 sumcheck of R1CSProof::prove:
+//   ZKSumcheckInstanceProof::prove_cubic_with_additive_term_disjoint_rounds
+//   (/root/reference/src/sumcheck.rs:1067-1380), comb = A*(B*C - D)
+//   over DensePolynomialPqx tables (/root/reference/src/custom_dense_mlpoly.rs).
+// The transcript / ZK glue of that function stays on the host; this file owns the
+// two hot loops: round evaluation (:1166-1245) and binding (:1265-1275).
+// See rounds.cuh for the device layout and the eq factorisation.
+#include "rounds.cuh"
+
+namespace spg {
+
+int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch);
+__global__ void k_eq_expand(const fq *__restrict__ prev, fq *__restrict__ out, size_t n, fq r);
+
+#ifndef SPG_RB
+#define SPG_RB 256
+#endif
+#ifndef SPG_MINB
+#define SPG_MINB 1
+#endif
+constexpr int RB = SPG_RB;  // threads per block of the round kernels
+
+// ---------------------------------------------------------------- round evaluation
+// One work item = one (lo, hi) pair of adjacent scalars (or a single scalar of an
+// exhausted row). 192 B read per item, 7 modmul.
+template <int COMB>
+__global__ void __launch_bounds__(RB, SPG_MINB)
+k_pair_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
+            const Seg *__restrict__ segs, int nseg, unsigned long long total_items,
+            const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
+  __shared__ fq sm[3 * 32];
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
+       item += (unsigned long long)gridDim.x * RB) {
+    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
+    Seg sg = segs[s];
+    unsigned long long local = item - sg.item_start;
+    fq a0, a1, b0, b1, c0, c1, w;
+    if (sg.log_len >= 1) {
+      unsigned int hl = sg.log_len - 1;
+      unsigned long long row = local >> hl, i = local & ((1ull << hl) - 1);
+      unsigned long long idx = sg.in_off + 2 * local;
+      a0 = fq_load_stream(T0 + idx); a1 = fq_load_stream(T0 + idx + 1);
+      b0 = fq_load_stream(T1 + idx); b1 = fq_load_stream(T1 + idx + 1);
+      c0 = fq_load_stream(T2 + idx); c1 = fq_load_stream(T2 + idx + 1);
+      w = fq_mul(fq_load(RW + sg.rw_off + row), fq_load(S + i));
+    } else {
+      unsigned long long idx = sg.in_off + local;
+      a0 = fq_load_stream(T0 + idx); b0 = fq_load_stream(T1 + idx); c0 = fq_load_stream(T2 + idx);
+      a1 = b1 = c1 = fq_zero();
+      w = fq_mul(fq_load(RW + sg.rw_off + local), fq_load(S));
+    }
+    comb_accumulate<COMB>(acc, w, a0, a1, b0, b1, c0, c1);
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+// bind: out = lo + r*(hi - lo); 192 B read + 96 B written per item, 3 modmul
+__global__ void __launch_bounds__(RB, SPG_MINB)
+k_pair_bind(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
+            fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2,
+            const Seg *__restrict__ segs, int nseg, unsigned long long total_items, fq r) {
+  for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
+       item += (unsigned long long)gridDim.x * RB) {
+    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
+    Seg sg = segs[s];
+    unsigned long long local = item - sg.item_start;
+    unsigned long long o = sg.out_off + local;
+    if (sg.log_len >= 1) {
+      unsigned long long idx = sg.in_off + 2 * local;
+      fq lo = fq_load_stream(T0 + idx), hi = fq_load_stream(T0 + idx + 1);
+      fq_store(O0 + o, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+      lo = fq_load_stream(T1 + idx); hi = fq_load_stream(T1 + idx + 1);
+      fq_store(O1 + o, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+      lo = fq_load_stream(T2 + idx); hi = fq_load_stream(T2 + idx + 1);
+      fq_store(O2 + o, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+    } else {
+      unsigned long long idx = sg.in_off + local;
+      fq lo = fq_load_stream(T0 + idx);
+      fq_store(O0 + o, fq_sub(lo, fq_mul(r, lo)));
+      lo = fq_load_stream(T1 + idx);
+      fq_store(O1 + o, fq_sub(lo, fq_mul(r, lo)));
+      lo = fq_load_stream(T2 + idx);
+      fq_store(O2 + o, fq_sub(lo, fq_mul(r, lo)));
+    }
+  }
+}
+
+// fused bind_j + eval_{j+1}: one item = four adjacent input scalars per table ->
+// two bound scalars (written) -> one (lo, hi) pair of the next round.
+// 384 B read + 192 B written per item, 6 + 7 modmul. Requires log_len >= 2.
+template <int COMB>
+__global__ void __launch_bounds__(RB, SPG_MINB)
+k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
+                 fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2,
+                 const Seg *__restrict__ segs, int nseg, unsigned long long total_items, fq r,
+                 const fq *__restrict__ RW, const fq *__restrict__ Snext, fq *__restrict__ partials) {
+  __shared__ fq sm[3 * 32];
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
+       item += (unsigned long long)gridDim.x * RB) {
+    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
+    Seg sg = segs[s];
+    unsigned long long local = item - sg.item_start;
+    unsigned int ql = sg.log_len - 2;
+    unsigned long long row = local >> ql, i = local & ((1ull << ql) - 1);
+    unsigned long long idx = sg.in_off + 4 * local, o = sg.out_off + 2 * local;
+    fq lo, hi, a0, a1, b0, b1, c0, c1;
+    lo = fq_load_stream(T0 + idx); hi = fq_load_stream(T0 + idx + 1);
+    a0 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = fq_load_stream(T0 + idx + 2); hi = fq_load_stream(T0 + idx + 3);
+    a1 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    fq_store(O0 + o, a0); fq_store(O0 + o + 1, a1);
+    lo = fq_load_stream(T1 + idx); hi = fq_load_stream(T1 + idx + 1);
+    b0 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = fq_load_stream(T1 + idx + 2); hi = fq_load_stream(T1 + idx + 3);
+    b1 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    fq_store(O1 + o, b0); fq_store(O1 + o + 1, b1);
+    lo = fq_load_stream(T2 + idx); hi = fq_load_stream(T2 + idx + 1);
+    c0 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = fq_load_stream(T2 + idx + 2); hi = fq_load_stream(T2 + idx + 3);
+    c1 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    fq_store(O2 + o, c0); fq_store(O2 + o + 1, c1);
+    fq w = fq_mul(fq_load(RW + sg.rw_off + row), fq_load(Snext + i));
+    comb_accumulate<COMB>(acc, w, a0, a1, b0, b1, c0, c1);
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+// ---------------------------------------------------------------- p rounds (tiny)
+// tables hold one scalar per instance, zero padded to P'. MODE_P binds the TOP bit
+// of p (no reversal): pairs (p, p + half). sumcheck.rs:1186-1245 with mode P.
+__global__ void k_p_eval(const fq *__restrict__ Ap, const fq *__restrict__ T0,
+                         const fq *__restrict__ T1, const fq *__restrict__ T2, size_t half,
+                         size_t limit, fq *__restrict__ out) {
+  __shared__ fq sm[3 * 32];
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t p = threadIdx.x; p < limit; p += blockDim.x) {
+    fq A0 = Ap[p], A1 = Ap[p + half], A2, A3;
+    line23(A0, A1, A2, A3);
+    fq a0 = T0[p], a1 = T0[p + half], b0 = T1[p], b1 = T1[p + half], c0 = T2[p], c1 = T2[p + half];
+    fq a2, a3, b2, b3, c2, c3;
+    line23(a0, a1, a2, a3);
+    line23(b0, b1, b2, b3);
+    line23(c0, c1, c2, c3);
+    acc[0] = fq_add(acc[0], fq_mul(A0, fq_sub(fq_mul(a0, b0), c0)));
+    acc[1] = fq_add(acc[1], fq_mul(A2, fq_sub(fq_mul(a2, b2), c2)));
+    acc[2] = fq_add(acc[2], fq_mul(A3, fq_sub(fq_mul(a3, b3), c3)));
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    out[0] = acc[0];
+    out[1] = acc[1];
+    out[2] = acc[2];
+  }
+}
+
+__global__ void k_p_bind(fq *__restrict__ Ap, fq *__restrict__ T0, fq *__restrict__ T1,
+                         fq *__restrict__ T2, size_t half, fq r) {
+  for (size_t p = threadIdx.x; p < half; p += blockDim.x) {
+    fq lo = Ap[p], hi = Ap[p + half];
+    Ap[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = T0[p]; hi = T0[p + half];
+    T0[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = T1[p]; hi = T1[p + half];
+    T1[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = T2[p]; hi = T2[p + half];
+    T2[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+  }
+}
+
+// RW[off_p + q] = Ap[p] * Eq_nat[q]
+__global__ void k_row_weights(const fq *__restrict__ Ap, const fq *__restrict__ Eq,
+                              const unsigned long long *__restrict__ rw_off,
+                              const unsigned int *__restrict__ Qp, int P, fq *__restrict__ RW) {
+  int p = blockIdx.y;
+  if (p >= P) return;
+  fq ap = Ap[p];
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < Qp[p]; q += gridDim.x * blockDim.x)
+    RW[rw_off[p] + q] = fq_mul(ap, Eq[q]);
+}
+
+// suffix eq tables for LSB-first binding: level m (2^m entries) lives at buf + 2^m,
+//   level_m[2i + b] = level_{m-1}[i] * eq(tau[n - m], b),  level_0 = [1]
+// so level m is the eq table of tau[n-m .. n-1] with index bit k <-> tau[n-m+k].
+int build_suffix_tables(spg_ctx *ctx, const std::vector<hfq> &tau, size_t max_level, fq *buf) {
+  fq one_h;
+  hfq one = hfq_one();
+  memcpy(&one_h, &one, sizeof one_h);
+  SPG_CUDA(cudaMemcpyAsync(buf + 1, &one_h, sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  size_t n = tau.size();
+  for (size_t m = 1; m <= max_level; m++) {
+    fq r;
+    memcpy(&r, &tau[n - m], sizeof r);
+    size_t cnt = (size_t)1 << (m - 1);
+    SPG_LAUNCH(ctx, k_eq_expand, grid_for(ctx, cnt, 256), 256, 0, buf + cnt, buf + 2 * cnt, cnt, r);
+  }
+  return SPG_OK;
+}
+
+}  // namespace spg
+
+using namespace spg;
+
+struct spg_sc1 {
+  spg_ctx *ctx = nullptr;
+  size_t P = 0, Pp = 1;  // instances, padded to a power of two
+  size_t nx = 0, nq = 0, np = 0;
+  std::vector<size_t> Q, X;
+  std::vector<hfq> tau_p, tau_q, tau_x;
+  fq *tab[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  size_t cap[2] = {0, 0};
+  int cur = 0;
+  fq *Sx = nullptr, *Sq = nullptr, *Ap = nullptr, *RWx = nullptr;
+  Seg *d_segs = nullptr;
+  unsigned long long *d_rw_off = nullptr;
+  unsigned int *d_Qp = nullptr;
+  std::vector<Seg> segs;
+  std::vector<unsigned> loglen;  // current log row length per instance
+  size_t round = 0;
+  bool evaluated = false;
+  bool have_cached = false;  // raw device sums for the current round already in h_cached
+  hfq cached[3];
+  hfq cx, cq;    // prod eq(tau_k, r_k) over the bound x / q variables
+  size_t p_len = 1;  // current instance_len during the p rounds
+  bool fuse = true;
+  bool p_ready = false;
+};
+
+namespace {
+
+int phase_of(const spg_sc1 *s, size_t round) {
+  if (round < s->nx) return 0;
+  if (round < s->nx + s->nq) return 1;
+  return 2;
+}
+
+// segments for the current phase; item counts for pair kernels (div = 1) or quad kernels (div = 2)
+void build_segs(spg_sc1 *s, int phase, int quad, unsigned long long *total_items,
+                unsigned long long *out_total) {
+  unsigned long long in_off = 0, out_off = 0, items = 0, rw = 0;
+  s->segs.resize(s->P);
+  for (size_t p = 0; p < s->P; p++) {
+    Seg &g = s->segs[p];
+    unsigned ll = s->loglen[p];
+    unsigned long long rows = phase == 0 ? s->Q[p] : 1;
+    g.in_off = in_off;
+    g.out_off = out_off;
+    g.item_start = items;
+    g.log_len = ll;
+    g.n_rows = (unsigned)rows;
+    g.rw_off = (unsigned)rw;
+    g.pad = 0;
+    unsigned long long in_sz = rows << ll;
+    unsigned long long out_sz = ll >= 1 ? in_sz >> 1 : in_sz;
+    unsigned long long it = quad ? (in_sz >> 2) : out_sz;
+    in_off += in_sz;
+    out_off += out_sz;
+    items += it;
+    rw += rows;
+  }
+  *total_items = items;
+  *out_total = out_off;
+}
+
+int upload_segs(spg_sc1 *s) {
+  SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice,
+                           s->ctx->stream));
+  return SPG_OK;
+}
+
+const fq *s_table(const spg_sc1 *s, int phase, size_t level) {
+  const fq *base = phase == 0 ? s->Sx : s->Sq;
+  return base + ((size_t)1 << level);
+}
+
+// rounds already bound inside the current phase
+size_t phase_round(const spg_sc1 *s, size_t round) {
+  int ph = phase_of(s, round);
+  return ph == 0 ? round : (ph == 1 ? round - s->nx : round - s->nx - s->nq);
+}
+
+int sc1_alloc_common(spg_ctx *ctx, size_t P, const size_t *num_proofs, size_t max_num_proofs,
+                     const size_t *num_cons, size_t max_num_cons, const spg_fq *tau_p,
+                     const spg_fq *tau_q, const spg_fq *tau_x, spg_sc1 **out) {
+  SPG_CHECK(ctx && out && num_proofs && num_cons, "spg_sc1_create: null argument");
+  SPG_CHECK(P >= 1, "spg_sc1_create: num_instances must be >= 1");
+  SPG_CHECK(is_pow2(max_num_proofs) && is_pow2(max_num_cons),
+            "spg_sc1_create: max_num_proofs / max_num_cons must be powers of two");
+  for (size_t p = 0; p < P; p++) {
+    SPG_CHECK(is_pow2(num_proofs[p]) && num_proofs[p] <= max_num_proofs,
+              "spg_sc1_create: num_proofs[%zu] = %zu is not a power of two <= %zu", p, num_proofs[p],
+              max_num_proofs);
+    SPG_CHECK(is_pow2(num_cons[p]) && num_cons[p] <= max_num_cons,
+              "spg_sc1_create: num_cons[%zu] = %zu is not a power of two <= %zu", p, num_cons[p],
+              max_num_cons);
+  }
+  spg_sc1 *s = new (std::nothrow) spg_sc1();
+  if (!s) return SPG_ENOMEM;
+  s->ctx = ctx;
+  s->P = P;
+  s->Pp = next_pow2(P);
+  s->nx = log2u(max_num_cons);
+  s->nq = log2u(max_num_proofs);
+  s->np = log2u(s->Pp);
+  SPG_CHECK((s->np == 0 || tau_p) && (s->nq == 0 || tau_q) && (s->nx == 0 || tau_x),
+            "spg_sc1_create: null tau");
+  s->Q.assign(num_proofs, num_proofs + P);
+  s->X.assign(num_cons, num_cons + P);
+  for (size_t i = 0; i < s->np; i++) s->tau_p.push_back(hfq_from(tau_p[i]));
+  for (size_t i = 0; i < s->nq; i++) s->tau_q.push_back(hfq_from(tau_q[i]));
+  for (size_t i = 0; i < s->nx; i++) s->tau_x.push_back(hfq_from(tau_x[i]));
+  size_t N = 0, rows = 0;
+  for (size_t p = 0; p < P; p++) {
+    N += s->Q[p] * s->X[p];
+    rows += s->Q[p];
+  }
+  size_t N1 = 0;  // size after the first bind: exhausted rows (length 1) do not shrink
+  for (size_t p = 0; p < P; p++) {
+    size_t len = s->nx ? s->X[p] : s->Q[p], rws = s->nx ? s->Q[p] : 1;
+    N1 += rws * (len > 1 ? len / 2 : 1);
+  }
+  s->cap[0] = N > s->Pp ? N : s->Pp;
+  s->cap[1] = N1 > s->Pp ? N1 : s->Pp;
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 3; k++) SPG_CUDA(cudaMalloc(&s->tab[b][k], s->cap[b] * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&s->Sx, ((size_t)2 << s->nx) * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&s->Sq, ((size_t)2 << s->nq) * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&s->Ap, s->Pp * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&s->RWx, rows * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&s->d_segs, P * sizeof(Seg)));
+  SPG_CUDA(cudaMalloc(&s->d_rw_off, P * sizeof(unsigned long long)));
+  SPG_CUDA(cudaMalloc(&s->d_Qp, P * sizeof(unsigned int)));
+  s->cx = hfq_one();
+  s->cq = hfq_one();
+  s->p_len = s->Pp;
+  s->loglen.resize(P);
+  for (size_t p = 0; p < P; p++) s->loglen[p] = s->nx ? log2u(s->X[p]) : log2u(s->Q[p]);
+  *out = s;
+  return SPG_OK;
+}
+
+// eq tables + row weights (src/r1csproof.rs:305-312 and the Ap*Aq products of sumcheck.rs:1186)
+int sc1_build_weights(spg_sc1 *s) {
+  spg_ctx *ctx = s->ctx;
+  // Ap = eq(tau_p).evals() in the reference's order (p is never bit-reversed)
+  {
+    fq *d_r = nullptr, *scratch = nullptr;
+    std::vector<spg_fq> hr(s->np ? s->np : 1);
+    for (size_t i = 0; i < s->np; i++) hr[i] = hfq_to(s->tau_p[i]);
+    SPG_CUDA(cudaMalloc(&d_r, hr.size() * sizeof(fq)));
+    SPG_CUDA(cudaMalloc(&scratch, s->Pp * sizeof(fq)));
+    SPG_CUDA(cudaMemcpyAsync(d_r, hr.data(), s->np * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = eq_evals_device(ctx, d_r, hr.data(), s->np, s->Ap, scratch);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_r);
+    cudaFree(scratch);
+    SPG_TRY(rc);
+  }
+  SPG_TRY(build_suffix_tables(ctx, s->tau_x, s->nx, s->Sx));
+  SPG_TRY(build_suffix_tables(ctx, s->tau_q, s->nq, s->Sq));
+  std::vector<unsigned long long> rw_off(s->P);
+  std::vector<unsigned int> Qp(s->P);
+  unsigned long long rw = 0;
+  unsigned int maxQ = 1;
+  for (size_t p = 0; p < s->P; p++) {
+    rw_off[p] = rw;
+    Qp[p] = (unsigned)s->Q[p];
+    rw += s->Q[p];
+    if (Qp[p] > maxQ) maxQ = Qp[p];
+  }
+  SPG_CUDA(cudaMemcpyAsync(s->d_rw_off, rw_off.data(), s->P * sizeof(unsigned long long),
+                           cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(s->d_Qp, Qp.data(), s->P * sizeof(unsigned int), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  dim3 grid((maxQ + 127) / 128, (unsigned)s->P);
+  SPG_LAUNCH(ctx, k_row_weights, grid, 128, 0, s->Ap, s->Sq + ((size_t)1 << s->nq), s->d_rw_off,
+             s->d_Qp, (int)s->P, s->RWx);
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}
+
+// after the last q round every table holds one scalar per instance: pad to P' with zeros
+int sc1_enter_p_phase(spg_sc1 *s) {
+  if (s->p_ready) return SPG_OK;
+  if (s->Pp > s->P)
+    for (int k = 0; k < 3; k++)
+      SPG_CUDA(cudaMemsetAsync(s->tab[s->cur][k] + s->P, 0, (s->Pp - s->P) * sizeof(fq), s->ctx->stream));
+  s->p_ready = true;
+  return SPG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spg_sc1_create_from_tables(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                               size_t max_num_proofs, const size_t *num_cons, size_t max_num_cons,
+                               const spg_fq *Az, const spg_fq *Bz, const spg_fq *Cz,
+                               const spg_fq *tau_p, const spg_fq *tau_q, const spg_fq *tau_x,
+                               spg_sc1 **out) {
+  SPG_CHECK(Az && Bz && Cz, "spg_sc1_create_from_tables: null table");
+  spg_sc1 *s = nullptr;
+  SPG_TRY(sc1_alloc_common(ctx, num_instances, num_proofs, max_num_proofs, num_cons, max_num_cons,
+                           tau_p, tau_q, tau_x, &s));
+  size_t N = 0;
+  for (size_t p = 0; p < s->P; p++) N += s->Q[p] * s->X[p];
+  const spg_fq *src[3] = {Az, Bz, Cz};
+  for (int k = 0; k < 3; k++) {
+    cudaError_t e = cudaMemcpyAsync(s->tab[0][k], src[k], N * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      spg_sc1_destroy(s);
+      return cuda_fail(e, "table upload", __FILE__, __LINE__);
+    }
+  }
+  int rc = sc1_build_weights(s);
+  if (rc != SPG_OK) {
+    spg_sc1_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return SPG_OK;
+}
+
+size_t spg_sc1_num_rounds(const spg_sc1 *s) { return s ? s->nx + s->nq + s->np : 0; }
+
+int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
+  SPG_CHECK(s && e, "spg_sc1_round_eval: null argument");
+  if (s->round >= spg_sc1_num_rounds(s)) {
+    set_error("spg_sc1_round_eval: all %zu rounds are done", spg_sc1_num_rounds(s));
+    return SPG_ESTATE;
+  }
+  if (s->evaluated) {
+    set_error("spg_sc1_round_eval: round %zu already evaluated; call round_bind", s->round);
+    return SPG_ESTATE;
+  }
+  spg_ctx *ctx = s->ctx;
+  int phase = phase_of(s, s->round);
+  size_t j = phase_round(s, s->round);
+  hfq raw[3];
+  if (phase == 2) {
+    SPG_TRY(sc1_enter_p_phase(s));
+    size_t half = s->p_len / 2;
+    size_t limit = half < s->P ? half : s->P;
+    SPG_LAUNCH(ctx, k_p_eval, 1, 128, 0, s->Ap, s->tab[s->cur][0], s->tab[s->cur][1],
+               s->tab[s->cur][2], half, limit, ctx->d_result);
+    spg_fq tmp[3];
+    SPG_TRY(fetch_result(ctx, 3, tmp));
+    hfq c = hfq_mul(s->cx, s->cq);
+    for (int t = 0; t < 3; t++) e[t] = hfq_to(hfq_mul(c, hfq_from(tmp[t])));
+    s->evaluated = true;
+    return SPG_OK;
+  }
+  if (s->have_cached) {
+    for (int t = 0; t < 3; t++) raw[t] = s->cached[t];
+    s->have_cached = false;
+  } else {
+    unsigned long long items = 0, out_total = 0;
+    build_segs(s, phase, 0, &items, &out_total);
+    SPG_TRY(upload_segs(s));
+    size_t n_phase = phase == 0 ? s->nx : s->nq;
+    const fq *S = s_table(s, phase, n_phase - j - 1);
+    const fq *RW = phase == 0 ? s->RWx : s->Ap;
+    int grid = grid_for(ctx, items, RB, 4);
+    SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+    SPG_LAUNCH(ctx, k_pair_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
+               s->tab[s->cur][2], s->d_segs, (int)s->P, items, RW, S, ctx->d_partials);
+    SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
+    spg_fq tmp[3];
+    SPG_TRY(fetch_result(ctx, 3, tmp));
+    for (int t = 0; t < 3; t++) raw[t] = hfq_from(tmp[t]);
+  }
+  // scalar prefix and the active variable's eq line, left to the host by the kernels
+  hfq line[3];
+  const hfq &tau = phase == 0 ? s->tau_x[j] : s->tau_q[j];
+  hfq_eq_line_023(tau, line);
+  hfq c = phase == 0 ? s->cx : hfq_mul(s->cx, s->cq);
+  for (int t = 0; t < 3; t++) e[t] = hfq_to(hfq_mul(hfq_mul(c, line[t]), raw[t]));
+  s->evaluated = true;
+  return SPG_OK;
+}
+
+int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
+  SPG_CHECK(s && r, "spg_sc1_round_bind: null argument");
+  if (!s->evaluated) {
+    set_error("spg_sc1_round_bind: round %zu has not been evaluated", s->round);
+    return SPG_ESTATE;
+  }
+  spg_ctx *ctx = s->ctx;
+  int phase = phase_of(s, s->round);
+  size_t j = phase_round(s, s->round);
+  fq rr;
+  memcpy(&rr, r, sizeof rr);
+  hfq rh = hfq_from(*r);
+  if (phase == 2) {
+    size_t half = s->p_len / 2;
+    SPG_LAUNCH(ctx, k_p_bind, 1, 128, 0, s->Ap, s->tab[s->cur][0], s->tab[s->cur][1],
+               s->tab[s->cur][2], half, rr);
+    s->p_len = half;
+  } else {
+    size_t n_phase = phase == 0 ? s->nx : s->nq;
+    bool next_same = j + 1 < n_phase;
+    unsigned minlen = 64;
+    for (size_t p = 0; p < s->P; p++) minlen = s->loglen[p] < minlen ? s->loglen[p] : minlen;
+    int nxt = s->cur ^ 1;
+    unsigned long long items = 0, out_total = 0;
+    if (s->fuse && next_same && minlen >= 2) {
+      build_segs(s, phase, 1, &items, &out_total);
+      SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
+      SPG_TRY(upload_segs(s));
+      const fq *Snext = s_table(s, phase, n_phase - j - 2);
+      const fq *RW = phase == 0 ? s->RWx : s->Ap;
+      int grid = grid_for(ctx, items, RB, 4);
+      SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+      SPG_LAUNCH(ctx, k_quad_bind_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
+                 s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs,
+                 (int)s->P, items, rr, RW, Snext, ctx->d_partials);
+      SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
+      spg_fq tmp[3];
+      SPG_TRY(fetch_result(ctx, 3, tmp));
+      for (int t = 0; t < 3; t++) s->cached[t] = hfq_from(tmp[t]);
+      s->have_cached = true;
+    } else {
+      build_segs(s, phase, 0, &items, &out_total);
+      SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
+      SPG_TRY(upload_segs(s));
+      SPG_LAUNCH(ctx, k_pair_bind, grid_for(ctx, items, RB, 8), RB, 0, s->tab[s->cur][0],
+                 s->tab[s->cur][1], s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1],
+                 s->tab[nxt][2], s->d_segs, (int)s->P, items, rr);
+    }
+    s->cur = nxt;
+    for (size_t p = 0; p < s->P; p++)
+      if (s->loglen[p] > 0) s->loglen[p]--;
+    const hfq &tau = phase == 0 ? s->tau_x[j] : s->tau_q[j];
+    if (phase == 0) s->cx = hfq_mul(s->cx, hfq_eq1(tau, rh));
+    else s->cq = hfq_mul(s->cq, hfq_eq1(tau, rh));
+    // x rounds done: rows of the q phase are whole instances
+    if (phase == 0 && j + 1 == s->nx)
+      for (size_t p = 0; p < s->P; p++) s->loglen[p] = log2u(s->Q[p]);
+  }
+  s->round++;
+  s->evaluated = false;
+  return SPG_OK;
+}
+
+int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
+  SPG_CHECK(s && claims, "spg_sc1_final: null argument");
+  if (s->round != spg_sc1_num_rounds(s)) {
+    set_error("spg_sc1_final: %zu of %zu rounds bound", s->round, spg_sc1_num_rounds(s));
+    return SPG_ESTATE;
+  }
+  spg_ctx *ctx = s->ctx;
+  // with zero q rounds the x phase never re-keys the segments; everything is length one anyway
+  fq h[4];
+  SPG_CUDA(cudaMemcpyAsync(&h[0], s->Ap, sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
+  for (int k = 0; k < 3; k++)
+    SPG_CUDA(cudaMemcpyAsync(&h[1 + k], s->tab[s->cur][k], sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  hfq ap;
+  memcpy(&ap, &h[0], sizeof ap);
+  claims[0] = hfq_to(hfq_mul(hfq_mul(ap, s->cq), s->cx));
+  for (int k = 0; k < 3; k++) memcpy(&claims[1 + k], &h[1 + k], sizeof(spg_fq));
+  return SPG_OK;
+}
+
+int spg_sc1_debug_tables(spg_sc1 *s, spg_fq *Az, spg_fq *Bz, spg_fq *Cz, size_t cap, size_t *n) {
+  SPG_CHECK(s && n, "spg_sc1_debug_tables: null argument");
+  size_t total = 0;
+  int phase = s->round < spg_sc1_num_rounds(s) ? phase_of(s, s->round) : 2;
+  if (phase == 2) total = s->p_len < s->P ? s->p_len : s->P;
+  else
+    for (size_t p = 0; p < s->P; p++) total += ((phase == 0 ? s->Q[p] : 1) << s->loglen[p]);
+  *n = total;
+  if (!Az) return SPG_OK;
+  SPG_CHECK(cap >= total, "spg_sc1_debug_tables: capacity %zu < %zu", cap, total);
+  spg_fq *dst[3] = {Az, Bz, Cz};
+  for (int k = 0; k < 3; k++)
+    SPG_CUDA(cudaMemcpyAsync(dst[k], s->tab[s->cur][k], total * sizeof(fq), cudaMemcpyDeviceToHost,
+                             s->ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return SPG_OK;
+}
+
+void spg_sc1_destroy(spg_sc1 *s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 3; k++)
+      if (s->tab[b][k]) cudaFree(s->tab[b][k]);
+  if (s->Sx) cudaFree(s->Sx);
+  if (s->Sq) cudaFree(s->Sq);
+  if (s->Ap) cudaFree(s->Ap);
+  if (s->RWx) cudaFree(s->RWx);
+  if (s->d_segs) cudaFree(s->d_segs);
+  if (s->d_rw_off) cudaFree(s->d_rw_off);
+  if (s->d_Qp) cudaFree(s->d_Qp);
+  delete s;
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+"""GPU parity for the phase-1 sumcheck loops (spg_sc1_*) against the oracle's
+restatement of sumcheck.rs:1067-1380. Every round polynomial evaluation and every
+final claim must be bit-identical."""
+import numpy as np
+import pytest
+
+from oracle import cbind as O
+from tests.helpers import drive_sc1_oracle, log2, rand_scalars
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import spartan_parallel_b200 as sp
+
+    return sp.Context(0)
+
+
+CASES = [
+    # (num_proofs, num_cons)
+    ([1], [1]),
+    ([1], [2]),
+    ([1], [16]),
+    ([4], [1]),
+    ([4], [1024]),          # BASELINE config C1 shape
+    ([2, 1], [8, 8]),
+    ([8, 4, 4, 1, 1], [64, 32, 64, 2, 1]),   # ragged in q and x, P = 5 -> P' = 8
+    ([64, 16, 16, 4, 1], [256, 256, 128, 256, 64]),  # C4-like
+    ([1, 1, 1], [4, 4, 4]),
+]
+
+
+@pytest.mark.parametrize("num_proofs,num_cons", CASES)
+@pytest.mark.parametrize("fuse", [True])
+def test_sc1_rounds_bit_exact(ctx, num_proofs, num_cons, fuse):
+    import spartan_parallel_b200 as sp
+
+    P = len(num_proofs)
+    max_q, max_x = max(num_proofs), max(num_cons)
+    Pp = 1 if P == 1 else 1 << (P - 1).bit_length()
+    N = sum(q * x for q, x in zip(num_proofs, num_cons))
+    seed = 1000 + 17 * N + P
+    Az, Bz, Cz = rand_scalars(N, seed), rand_scalars(N, seed + 1), rand_scalars(N, seed + 2)
+    tau_p, tau_q, tau_x = rand_scalars(max(log2(Pp), 1), seed + 3)[: log2(Pp)], rand_scalars(max(log2(max_q), 1), seed + 4)[: log2(max_q)], rand_scalars(max(log2(max_x), 1), seed + 5)[: log2(max_x)]
+    rounds = log2(Pp) + log2(max_q) + log2(max_x)
+    ch = rand_scalars(max(rounds, 1), seed + 6)
+    want_evals, want_final = drive_sc1_oracle(num_proofs, max_q, num_cons, max_x, Az, Bz, Cz, tau_p, tau_q, tau_x, ch)
+
+    sc = sp.SumcheckPhase1.from_tables(ctx, num_proofs, max_q, num_cons, max_x, Az, Bz, Cz, tau_p, tau_q, tau_x)
+    assert sc.num_rounds == rounds
+    for j in range(rounds):
+        got = sc.round_eval()
+        assert np.array_equal(got, want_evals[j]), f"round {j} evals differ"
+        sc.round_bind(ch[j])
+    assert np.array_equal(sc.final(), want_final)
+
+
+def test_sc1_state_errors(ctx):
+    import spartan_parallel_b200 as sp
+
+    Az = rand_scalars(8, 1)
+    tau = rand_scalars(3, 2)
+    sc = sp.SumcheckPhase1.from_tables(ctx, [1], 1, [8], 8, Az, Az, Az, tau[:0], tau[:0], tau)
+    with pytest.raises(sp.SpgError):
+        sc.round_bind(tau[0])  # bind before eval
+    sc.round_eval()
+    with pytest.raises(sp.SpgError):
+        sc.round_eval()  # eval twice
+    with pytest.raises(sp.SpgError):
+        sc.final()  # not all rounds bound
+    with pytest.raises(sp.SpgError):
+        sp.SumcheckPhase1.from_tables(ctx, [3], 4, [8], 8, Az, Az, Az, tau[:0], tau[:2], tau)  # non power of two

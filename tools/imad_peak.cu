@@ -1,0 +1,149 @@
+// Integer-pipe roofline microbenchmark for B200:
+//   (a) IMAD.WIDE.U32 issue rate with independent accumulators,
+//   (b) carry-chained IMAD.WIDE.U32.X (mad.lo.cc / madc.hi.cc pairs),
+//   (c) in-register 256-bit Montgomery products/s with the library's fq_mul_lazy / fq_mul.
+// Prints one JSON object. Build: make tools ; run on the GPU box.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../spartan_parallel_b200/csrc/fq.cuh"
+using namespace spg;
+
+template <int ILP>
+__global__ void k_imad_wide(unsigned long long *out, unsigned int a, unsigned int b, int iters) {
+  unsigned long long acc[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; i++) acc[i] = threadIdx.x + i;
+  unsigned int x = a + threadIdx.x, y = b;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++)
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(x), "r"(y));
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) s ^= acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// 8-wide carry chain per step, 4 independent chains
+__global__ void k_imad_carry(unsigned int *out, unsigned int a, unsigned int b, int iters) {
+  unsigned int t[4][9];
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 9; i++) t[c][i] = threadIdx.x + i + c;
+  unsigned int x0 = a + threadIdx.x, x1 = a ^ 0x1234567u, x2 = a * 3u, x3 = a + 77u, y = b;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      asm volatile(
+          "mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+          "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+          "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+          "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+          "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+          "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+          "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+          "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+          "addc.u32        %8, %8, 0;\n\t"
+          : "+r"(t[c][0]), "+r"(t[c][1]), "+r"(t[c][2]), "+r"(t[c][3]), "+r"(t[c][4]), "+r"(t[c][5]),
+            "+r"(t[c][6]), "+r"(t[c][7]), "+r"(t[c][8])
+          : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(y));
+  }
+  unsigned int s = 0;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int i = 0; i < 9; i++) s ^= t[c][i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int ILP, bool CANON>
+__global__ void k_modmul(fq *out, fq seed, int iters) {
+  fq x[ILP], y = seed;
+#pragma unroll
+  for (int i = 0; i < ILP; i++) {
+    x[i] = seed;
+    x[i].v[0] ^= (threadIdx.x + 131 * i);
+    x[i].v[7] &= 0x0fffffffu;
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < ILP; i++) x[i] = CANON ? fq_mul(x[i], y) : fq_mul_lazy(x[i], y);
+  }
+  fq s = x[0];
+#pragma unroll
+  for (int i = 1; i < ILP; i++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) s.v[k] ^= x[i].v[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename F>
+static float time_ms(F f) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  f();
+  f();
+  cudaDeviceSynchronize();
+  cudaEventRecord(a);
+  for (int i = 0; i < 5; i++) f();
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms / 5;
+}
+
+int main() {
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, 0);
+  int sms = prop.multiProcessorCount;
+  void *buf;
+  cudaMalloc(&buf, (size_t)sms * 8 * 1024 * 32);
+  const int iters = 2048;
+  fq seed;
+  for (int i = 0; i < 8; i++) seed.v[i] = 0x9e3779b9u * (i + 1);
+  seed.v[7] &= 0x0fffffffu;
+  printf("{\"sms\": %d", sms);
+  {
+    int blocks = sms * 8, threads = 256;
+    float ms = time_ms([&] { k_imad_wide<8><<<blocks, threads>>>((unsigned long long *)buf, 3, 5, iters); });
+    double ops = (double)blocks * threads * iters * 8;
+    printf(", \"imad_wide_per_s\": %.4g, \"imad_wide_per_clk_per_sm_at_1965\": %.2f", ops / (ms * 1e-3),
+           ops / (ms * 1e-3) / sms / 1.965e9);
+  }
+  {
+    int blocks = sms * 8, threads = 256;
+    float ms = time_ms([&] { k_imad_carry<<<blocks, threads>>>((unsigned int *)buf, 3, 5, iters); });
+    double ops = (double)blocks * threads * iters * 4 * 4;  // wide mads (pairs)
+    printf(", \"imad_wide_carry_per_s\": %.4g", ops / (ms * 1e-3));
+  }
+  for (int threads : {128, 256, 512}) {
+    int blocks = sms * (2048 / threads);
+    float ms = time_ms([&] { k_modmul<2, false><<<blocks, threads>>>((fq *)buf, seed, iters / 8); });
+    double ops = (double)blocks * threads * (iters / 8) * 2;
+    printf(", \"modmul_lazy_ilp2_t%d_per_s\": %.4g", threads, ops / (ms * 1e-3));
+  }
+  {
+    int threads = 256, blocks = sms * 8;
+    float ms = time_ms([&] { k_modmul<1, false><<<blocks, threads>>>((fq *)buf, seed, iters / 8); });
+    double ops = (double)blocks * threads * (iters / 8);
+    printf(", \"modmul_lazy_ilp1_per_s\": %.4g", ops / (ms * 1e-3));
+    ms = time_ms([&] { k_modmul<2, true><<<blocks, threads>>>((fq *)buf, seed, iters / 8); });
+    ops = (double)blocks * threads * (iters / 8) * 2;
+    printf(", \"modmul_canon_ilp2_per_s\": %.4g", ops / (ms * 1e-3));
+    // low occupancy: 2 warps per SMSP, like a 150-register kernel
+    blocks = sms;
+    ms = time_ms([&] { k_modmul<2, false><<<blocks, 256>>>((fq *)buf, seed, iters / 8); });
+    ops = (double)blocks * 256 * (iters / 8) * 2;
+    printf(", \"modmul_lazy_ilp2_8warps_per_sm_per_s\": %.4g", ops / (ms * 1e-3));
+    ms = time_ms([&] { k_modmul<4, false><<<blocks, 256>>>((fq *)buf, seed, iters / 8); });
+    ops = (double)blocks * 256 * (iters / 8) * 4;
+    printf(", \"modmul_lazy_ilp4_8warps_per_sm_per_s\": %.4g", ops / (ms * 1e-3));
+  }
+  cudaError_t e = cudaDeviceSynchronize();
+  printf(", \"cuda_status\": \"%s\"}\n", cudaGetErrorString(e));
+  return e != cudaSuccess;
+}
