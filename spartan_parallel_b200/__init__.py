@@ -13,8 +13,13 @@ from .api import (  # noqa: F401
     Context,
     DensePolynomial,
     EqPolynomial,
+    ProverWitnessSecInfo,
+    R1CSInstance,
     SumcheckPhase1,
+    SumcheckPhase2,
+    ZMat,
     dot,
     from_u512,
+    sumcheck_phase1,
     vec_op,
 )

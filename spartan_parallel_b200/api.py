@@ -239,3 +239,172 @@ class SumcheckPhase1:
             self.free()
         except Exception:
             pass
+
+
+class R1CSInstance:
+    """Device copy of R1CSInstance (src/r1csinstance.rs:19-31, ::new :89-182).
+
+    ``A_list``/``B_list``/``C_list``: per instance, (rows, cols, vals) COO arrays --
+    the reference's ``Vec<(usize, usize, Scalar)>`` in struct-of-arrays form."""
+
+    def __init__(self, ctx: Context, num_instances, max_num_cons, num_cons, num_vars, A_list, B_list, C_list):
+        assert len(A_list) == len(B_list) == len(C_list) == num_instances
+        self.ctx = ctx
+        self.num_instances, self.max_num_cons, self.num_vars = num_instances, max_num_cons, num_vars
+        self.num_cons = list(num_cons)
+        rows, cols, vals, nnz = [], [], [], []
+        for i in range(num_instances):
+            for M in (A_list[i], B_list[i], C_list[i]):
+                r, c, v = M
+                rows.append(np.asarray(r, dtype=np.uint32))
+                cols.append(np.asarray(c, dtype=np.uint32))
+                vals.append(_fq(v).reshape(-1, 4))
+                nnz.append(len(r))
+        rows = np.ascontiguousarray(np.concatenate(rows)) if rows else np.zeros(0, np.uint32)
+        cols = np.ascontiguousarray(np.concatenate(cols)) if cols else np.zeros(0, np.uint32)
+        vals = np.ascontiguousarray(np.concatenate(vals)) if vals else np.zeros((0, 4), np.uint64)
+        h = C.c_void_p()
+        check(ctx.L.spg_r1cs_create(ctx.h, num_instances, max_num_cons, _ptr(_sz(num_cons)), num_vars, _ptr(_sz(nnz)),
+                                    _ptr(rows), _ptr(cols), _ptr(vals), C.byref(h)), "spg_r1cs_create")
+        self.h = h
+
+    def get_num_instances(self):
+        return self.num_instances
+
+    def get_num_cons(self):
+        return self.max_num_cons
+
+    def get_inst_num_cons(self):
+        return self.num_cons
+
+    def multi_evaluate(self, rx, ry) -> np.ndarray:
+        """R1CSInstance::multi_evaluate (src/r1csinstance.rs:583-595)."""
+        rx = _fq(np.asarray(rx, dtype=np.uint64).reshape(-1, 4))
+        ry = _fq(np.asarray(ry, dtype=np.uint64).reshape(-1, 4))
+        out = np.empty((3 * self.num_instances, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_r1cs_multi_evaluate(self.ctx.h, self.h, _ptr(rx), rx.shape[0], _ptr(ry), ry.shape[0], _ptr(out)),
+              "spg_r1cs_multi_evaluate")
+        return out
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_r1cs_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ProverWitnessSecInfo:
+    """One witness section (src/lib.rs ProverWitnessSecInfo): ``w_mat`` flattened
+    [p][q][i]; ``num_proofs[p]`` is 1 for a short section; one instance for a single one."""
+
+    def __init__(self, ctx: Context, num_proofs, num_inputs, w_mat):
+        self.ctx = ctx
+        self.num_proofs, self.num_inputs = list(num_proofs), list(num_inputs)
+        w = _fq(w_mat).reshape(-1, 4)
+        assert w.shape[0] == sum(a * b for a, b in zip(self.num_proofs, self.num_inputs))
+        h = C.c_void_p()
+        check(ctx.L.spg_witness_upload(ctx.h, len(self.num_proofs), _ptr(_sz(num_proofs)), _ptr(_sz(num_inputs)), _ptr(w),
+                                       C.byref(h)), "spg_witness_upload")
+        self.h = h
+
+    def poly_w(self, p: int) -> DensePolynomial:
+        h = C.c_void_p()
+        check(self.ctx.L.spg_witness_poly(self.h, p, C.byref(h)), "spg_witness_poly")
+        d = DensePolynomial(self.ctx, h, owner=self)
+        d.free = lambda: None  # view owned by the witness handle
+        return d
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_witness_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ZMat:
+    """z_mat of R1CSProof::prove (src/r1csproof.rs:278-293), device resident."""
+
+    def __init__(self, ctx: Context, num_proofs, num_inputs, witness_secs: Sequence[ProverWitnessSecInfo]):
+        self.ctx = ctx
+        self.num_proofs, self.num_inputs = list(num_proofs), list(num_inputs)
+        self.witness_secs = list(witness_secs)
+        arr = (C.c_void_p * len(witness_secs))(*[w.h for w in witness_secs])
+        h = C.c_void_p()
+        check(ctx.L.spg_zmat_build(ctx.h, len(self.num_proofs), _ptr(_sz(num_proofs)), _ptr(_sz(num_inputs)),
+                                   len(witness_secs), arr, C.byref(h)), "spg_zmat_build")
+        self.h = h
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_zmat_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def sumcheck_phase1(ctx: Context, inst: R1CSInstance, z: ZMat, num_proofs, max_num_proofs, num_cons, max_num_cons,
+                    max_num_inputs, tau_p, tau_q, tau_x) -> SumcheckPhase1:
+    """multiply_vec_block + eq tables, ready for the phase-1 rounds (src/r1csproof.rs:305-343)."""
+    npf, nc = _sz(num_proofs), _sz(num_cons)
+    tp, tq, tx = (_fq(np.asarray(t, dtype=np.uint64).reshape(-1, 4)) for t in (tau_p, tau_q, tau_x))
+    h = C.c_void_p()
+    check(ctx.L.spg_sc1_create(ctx.h, inst.h, z.h, len(npf), _ptr(npf), max_num_proofs, _ptr(nc), max_num_cons,
+                               max_num_inputs, _ptr(tp), _ptr(tq), _ptr(tx), C.byref(h)), "spg_sc1_create")
+    return SumcheckPhase1(ctx, h)
+
+
+class SumcheckPhase2:
+    """Device loops of prove_cubic_disjoint_rounds (src/sumcheck.rs:788-1065)."""
+
+    def __init__(self, ctx: Context, inst: R1CSInstance, z: ZMat, num_proofs, max_num_proofs, num_inputs, max_num_inputs,
+                 num_witness_secs, rx, rq_rev, rp, r_A, r_B, r_C):
+        self.ctx = ctx
+        npf, nin = _sz(num_proofs), _sz(num_inputs)
+        a = [_fq(np.asarray(t, dtype=np.uint64).reshape(-1, 4)) for t in (rx, rq_rev, rp)]
+        h = C.c_void_p()
+        check(ctx.L.spg_sc2_create(ctx.h, inst.h, z.h, len(npf), _ptr(npf), max_num_proofs, _ptr(nin), max_num_inputs,
+                                   num_witness_secs, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(_fq(r_A)), _ptr(_fq(r_B)),
+                                   _ptr(_fq(r_C)), C.byref(h)), "spg_sc2_create")
+        self.h = h
+
+    @property
+    def num_rounds(self) -> int:
+        return int(self.ctx.L.spg_sc2_num_rounds(self.h))
+
+    def round_eval(self) -> np.ndarray:
+        out = np.empty((3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc2_round_eval(self.h, _ptr(out)), "spg_sc2_round_eval")
+        return out
+
+    def round_bind(self, r):
+        check(self.ctx.L.spg_sc2_round_bind(self.h, _ptr(_fq(r))), "spg_sc2_round_bind")
+
+    def final(self) -> np.ndarray:
+        out = np.empty((3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc2_final(self.h, _ptr(out)), "spg_sc2_final")
+        return out
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_sc2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -6,6 +6,7 @@
 // two hot loops: round evaluation (:1166-1245) and binding (:1265-1275).
 // See rounds.cuh for the device layout and the eq factorisation.
 #include "rounds.cuh"
+#include "r1cs.cuh"
 
 namespace spg {
 
@@ -425,6 +426,27 @@ int spg_sc1_create_from_tables(spg_ctx *ctx, size_t num_instances, const size_t 
     }
   }
   int rc = sc1_build_weights(s);
+  if (rc != SPG_OK) {
+    spg_sc1_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return SPG_OK;
+}
+
+int spg_sc1_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
+                   const size_t *num_proofs, size_t max_num_proofs, const size_t *num_cons,
+                   size_t max_num_cons, size_t max_num_inputs, const spg_fq *tau_p,
+                   const spg_fq *tau_q, const spg_fq *tau_x, spg_sc1 **out) {
+  SPG_CHECK(inst && z, "spg_sc1_create: null instance / z_mat");
+  SPG_CHECK(max_num_cons == inst->max_num_cons, "spg_sc1_create: max_num_cons %zu != instance's %zu",
+            max_num_cons, inst->max_num_cons);
+  spg_sc1 *s = nullptr;
+  SPG_TRY(sc1_alloc_common(ctx, num_instances, num_proofs, max_num_proofs, num_cons, max_num_cons,
+                           tau_p, tau_q, tau_x, &s));
+  int rc = r1cs_multiply_vec_block(ctx, inst, z, num_instances, num_proofs, num_cons, max_num_inputs,
+                                   s->tab[0][0], s->tab[0][1], s->tab[0][2]);
+  if (rc == SPG_OK) rc = sc1_build_weights(s);
   if (rc != SPG_OK) {
     spg_sc1_destroy(s);
     return rc;

@@ -1,0 +1,485 @@
+// Phase-2 sumcheck of R1CSProof::prove:
+//   ZKSumcheckInstanceProof::prove_cubic_disjoint_rounds
+//   (/root/reference/src/sumcheck.rs:788-1065), comb = A*B*C with
+//   A = eq(rp, p), B = ABC(p | 0, w, y), C = Z bound to rq (p, w, y).
+// create also owns the three table builders that precede it in R1CSProof::prove:
+//   ABC table (src/r1csproof.rs:431-465), Z_poly.bound_poly_vars_rq (:469-479) and
+//   eq(rp) (:482).
+// Rounds: y (low bit first, natural order = adjacent pairs) -> w (top bit first;
+// tables are re-laid out once in bit-reversed w so the pairs are adjacent again)
+// -> p (top bit first, tiny).
+#include "r1cs.cuh"
+#include "rounds.cuh"
+
+namespace spg {
+
+int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch);
+int build_suffix_tables(spg_ctx *ctx, const std::vector<hfq> &tau, size_t max_level, fq *buf);
+
+constexpr int RB2 = 128;
+
+// Z_rq[p][w][y] = sum_q E[q] * Z[p][q][w][y]; E = LSB-first eq table of rq_rev, whose
+// entries q < Q_p already carry the (1 - r) factors of the rounds after instance p ran
+// out of proofs (bound_poly_q, custom_dense_mlpoly.rs:222-244).
+__global__ void k_z_bind_rq(const fq *__restrict__ Z, const fq *__restrict__ E, size_t Q, size_t WY,
+                            fq *__restrict__ out) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < WY;
+       t += (size_t)gridDim.x * blockDim.x) {
+    fq acc = fq_zero();
+    for (size_t q = 0; q < Q; q++) acc = fq_add(acc, fq_mul(fq_load(E + q), fq_load_stream(Z + q * WY + t)));
+    fq_store(out + t, acc);
+  }
+}
+
+// one (lo, hi) pair per item; weight = A[p] (constant in the bound variable)
+__global__ void __launch_bounds__(RB2)
+k2_pair_eval(const fq *__restrict__ B, const fq *__restrict__ C, const Seg *__restrict__ segs, int nseg,
+             unsigned long long total_items, const fq *__restrict__ A, fq *__restrict__ partials) {
+  __shared__ fq sm[3 * 32];
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (unsigned long long item = (unsigned long long)blockIdx.x * RB2 + threadIdx.x; item < total_items;
+       item += (unsigned long long)gridDim.x * RB2) {
+    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
+    Seg sg = segs[s];
+    unsigned long long local = item - sg.item_start;
+    fq b0, b1, c0, c1;
+    if (sg.log_len >= 1) {
+      unsigned long long idx = sg.in_off + 2 * local;
+      b0 = fq_load_stream(B + idx); b1 = fq_load_stream(B + idx + 1);
+      c0 = fq_load_stream(C + idx); c1 = fq_load_stream(C + idx + 1);
+    } else {
+      unsigned long long idx = sg.in_off + local;
+      b0 = fq_load_stream(B + idx); c0 = fq_load_stream(C + idx);
+      b1 = c1 = fq_zero();
+    }
+    comb_accumulate<2>(acc, fq_load(A + sg.rw_off), b0, b1, c0, c1, c0, c1);
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+__global__ void __launch_bounds__(RB2)
+k2_pair_bind(const fq *__restrict__ B, const fq *__restrict__ C, fq *__restrict__ OB, fq *__restrict__ OC,
+             const Seg *__restrict__ segs, int nseg, unsigned long long total_items, fq r) {
+  for (unsigned long long item = (unsigned long long)blockIdx.x * RB2 + threadIdx.x; item < total_items;
+       item += (unsigned long long)gridDim.x * RB2) {
+    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
+    Seg sg = segs[s];
+    unsigned long long local = item - sg.item_start;
+    unsigned long long o = sg.out_off + local;
+    if (sg.log_len >= 1) {
+      unsigned long long idx = sg.in_off + 2 * local;
+      fq lo = fq_load_stream(B + idx), hi = fq_load_stream(B + idx + 1);
+      fq_store(OB + o, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+      lo = fq_load_stream(C + idx); hi = fq_load_stream(C + idx + 1);
+      fq_store(OC + o, fq_add(lo, fq_mul(r, fq_sub(hi, lo))));
+    } else {
+      unsigned long long idx = sg.in_off + local;
+      fq lo = fq_load_stream(B + idx);
+      fq_store(OB + o, fq_sub(lo, fq_mul(r, lo)));
+      lo = fq_load_stream(C + idx);
+      fq_store(OC + o, fq_sub(lo, fq_mul(r, lo)));
+    }
+  }
+}
+
+// fused bind_j + eval_{j+1}; needs log_len >= 2 everywhere
+__global__ void __launch_bounds__(RB2)
+k2_quad_bind_eval(const fq *__restrict__ B, const fq *__restrict__ C, fq *__restrict__ OB,
+                  fq *__restrict__ OC, const Seg *__restrict__ segs, int nseg,
+                  unsigned long long total_items, fq r, const fq *__restrict__ A,
+                  fq *__restrict__ partials) {
+  __shared__ fq sm[3 * 32];
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (unsigned long long item = (unsigned long long)blockIdx.x * RB2 + threadIdx.x; item < total_items;
+       item += (unsigned long long)gridDim.x * RB2) {
+    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
+    Seg sg = segs[s];
+    unsigned long long local = item - sg.item_start;
+    unsigned long long idx = sg.in_off + 4 * local, o = sg.out_off + 2 * local;
+    fq lo, hi, b0, b1, c0, c1;
+    lo = fq_load_stream(B + idx); hi = fq_load_stream(B + idx + 1);
+    b0 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = fq_load_stream(B + idx + 2); hi = fq_load_stream(B + idx + 3);
+    b1 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    fq_store(OB + o, b0); fq_store(OB + o + 1, b1);
+    lo = fq_load_stream(C + idx); hi = fq_load_stream(C + idx + 1);
+    c0 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = fq_load_stream(C + idx + 2); hi = fq_load_stream(C + idx + 3);
+    c1 = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    fq_store(OC + o, c0); fq_store(OC + o + 1, c1);
+    comb_accumulate<2>(acc, fq_load(A + sg.rw_off), b0, b1, c0, c1, c0, c1);
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 3 + 0] = acc[0];
+    partials[blockIdx.x * 3 + 1] = acc[1];
+    partials[blockIdx.x * 3 + 2] = acc[2];
+  }
+}
+
+// [p][w] (W per instance) -> [p][bitrev(w)] with W' slots, zero padded
+__global__ void k2_w_relayout(const fq *__restrict__ in, fq *__restrict__ out, size_t P, size_t W,
+                              unsigned int logWp) {
+  size_t Wp = (size_t)1 << logWp;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < P * Wp;
+       t += (size_t)gridDim.x * blockDim.x) {
+    size_t p = t >> logWp, slot = t & (Wp - 1);
+    size_t w = logWp ? (__brev((unsigned int)slot) >> (32 - logWp)) : 0;
+    out[t] = w < W ? in[p * W + w] : fq_zero();
+  }
+}
+
+__global__ void k2_p_eval(const fq *__restrict__ A, const fq *__restrict__ B, const fq *__restrict__ C,
+                          size_t half, size_t limit, fq *__restrict__ out) {
+  __shared__ fq sm[3 * 32];
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t p = threadIdx.x; p < limit; p += blockDim.x) {
+    fq a0 = A[p], a1 = A[p + half], b0 = B[p], b1 = B[p + half], c0 = C[p], c1 = C[p + half];
+    fq a2, a3, b2, b3, c2, c3;
+    line23(a0, a1, a2, a3);
+    line23(b0, b1, b2, b3);
+    line23(c0, c1, c2, c3);
+    acc[0] = fq_add(acc[0], fq_mul(fq_mul(a0, b0), c0));
+    acc[1] = fq_add(acc[1], fq_mul(fq_mul(a2, b2), c2));
+    acc[2] = fq_add(acc[2], fq_mul(fq_mul(a3, b3), c3));
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    out[0] = acc[0];
+    out[1] = acc[1];
+    out[2] = acc[2];
+  }
+}
+
+__global__ void k2_p_bind(fq *__restrict__ A, fq *__restrict__ B, fq *__restrict__ C, size_t half, fq r) {
+  for (size_t p = threadIdx.x; p < half; p += blockDim.x) {
+    fq lo = A[p], hi = A[p + half];
+    A[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = B[p]; hi = B[p + half];
+    B[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+    lo = C[p]; hi = C[p + half];
+    C[p] = fq_add(lo, fq_mul(r, fq_sub(hi, lo)));
+  }
+}
+
+// replicate entry 0 into [1, n)
+__global__ void k2_replicate(fq *__restrict__ v, size_t n) {
+  fq x = v[0];
+  for (size_t i = 1 + threadIdx.x; i < n; i += blockDim.x) v[i] = x;
+}
+
+}  // namespace spg
+
+using namespace spg;
+
+struct spg_sc2 {
+  spg_ctx *ctx = nullptr;
+  size_t P = 0, Pp = 1, W = 0, Wp = 1;
+  size_t ny = 0, nw = 0, np = 0;
+  bool single_inst = false;
+  std::vector<size_t> Y;
+  fq *tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [buffer][B, C]
+  size_t cap = 0;
+  int cur = 0;
+  fq *A = nullptr;  // eq(rp), P' entries
+  Seg *d_segs = nullptr;
+  std::vector<Seg> segs;
+  std::vector<unsigned> loglen;
+  size_t round = 0;
+  bool evaluated = false, have_cached = false;
+  spg_fq cached[3];
+  size_t p_len = 1;
+  bool w_ready = false, p_ready = false;
+};
+
+namespace {
+
+int phase2_of(const spg_sc2 *s, size_t round) {
+  if (round < s->ny) return 0;
+  if (round < s->ny + s->nw) return 1;
+  return 2;
+}
+
+void build_segs2(spg_sc2 *s, int phase, int quad, unsigned long long *items_out, unsigned long long *out_total) {
+  unsigned long long in_off = 0, out_off = 0, items = 0;
+  s->segs.resize(s->P);
+  for (size_t p = 0; p < s->P; p++) {
+    Seg &g = s->segs[p];
+    unsigned ll = s->loglen[p];
+    unsigned long long rows = phase == 0 ? s->W : 1;
+    g.in_off = in_off;
+    g.out_off = out_off;
+    g.item_start = items;
+    g.log_len = ll;
+    g.n_rows = (unsigned)rows;
+    g.rw_off = (unsigned)p;
+    g.pad = 0;
+    unsigned long long in_sz = rows << ll;
+    unsigned long long out_sz = ll >= 1 ? in_sz >> 1 : in_sz;
+    in_off += in_sz;
+    out_off += out_sz;
+    items += quad ? (in_sz >> 2) : out_sz;
+  }
+  *items_out = items;
+  *out_total = out_off;
+}
+
+// y rounds finished: [p][w] -> [p][bitrev w] padded to W'
+int enter_w_phase(spg_sc2 *s) {
+  if (s->w_ready) return SPG_OK;
+  spg_ctx *ctx = s->ctx;
+  int nxt = s->cur ^ 1;
+  unsigned logWp = log2u(s->Wp);
+  for (int k = 0; k < 2; k++)
+    SPG_LAUNCH(ctx, k2_w_relayout, grid_for(ctx, s->P * s->Wp, 128), 128, 0, s->tab[s->cur][k],
+               s->tab[nxt][k], s->P, s->W, logWp);
+  s->cur = nxt;
+  for (size_t p = 0; p < s->P; p++) s->loglen[p] = logWp;
+  s->w_ready = true;
+  return SPG_OK;
+}
+
+int enter_p_phase(spg_sc2 *s) {
+  if (s->p_ready) return SPG_OK;
+  spg_ctx *ctx = s->ctx;
+  if (s->Pp > s->P) {
+    // C (and B for distinct instances) are zero beyond the last instance; a shared
+    // instance (single_inst) has the same ABC for every p of the padded cube and is
+    // not bound in MODE_P (sumcheck.rs:965-967): keeping P' identical copies is equivalent.
+    SPG_CUDA(cudaMemsetAsync(s->tab[s->cur][1] + s->P, 0, (s->Pp - s->P) * sizeof(fq), ctx->stream));
+    if (s->single_inst) SPG_LAUNCH(ctx, k2_replicate, 1, 64, 0, s->tab[s->cur][0], s->Pp);
+    else SPG_CUDA(cudaMemsetAsync(s->tab[s->cur][0] + s->P, 0, (s->Pp - s->P) * sizeof(fq), ctx->stream));
+  }
+  s->p_ready = true;
+  return SPG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
+                   const size_t *num_proofs, size_t max_num_proofs, const size_t *num_inputs,
+                   size_t max_num_inputs, size_t num_witness_secs, const spg_fq *rx,
+                   const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
+                   const spg_fq *r_C, spg_sc2 **out) {
+  SPG_CHECK(ctx && inst && z && out && num_proofs && num_inputs && r_A && r_B && r_C,
+            "spg_sc2_create: null argument");
+  size_t P = num_instances;
+  SPG_CHECK(P >= 1 && z->P == P && z->W == num_witness_secs, "spg_sc2_create: z_mat shape mismatch");
+  SPG_CHECK(inst->num_instances == 1 || inst->num_instances == P,
+            "spg_sc2_create: instance has %zu blocks, proving %zu", inst->num_instances, P);
+  SPG_CHECK(is_pow2(max_num_proofs) && is_pow2(max_num_inputs), "spg_sc2_create: maxima must be powers of two");
+  // compute_eval_table_sparse_disjoint_rounds asserts W' * Y_max == num_vars (r1csinstance.rs:500)
+  SPG_CHECK(next_pow2(num_witness_secs) * max_num_inputs == inst->num_vars,
+            "spg_sc2_create: next_pow2(num_witness_secs) * max_num_inputs = %zu != num_vars = %zu",
+            next_pow2(num_witness_secs) * max_num_inputs, inst->num_vars);
+  bool single = inst->num_instances == 1 && P > 1;
+  for (size_t p = 0; p < P; p++) {
+    SPG_CHECK(z->num_proofs[p] == num_proofs[p] && z->num_inputs[p] == num_inputs[p],
+              "spg_sc2_create: z_mat shape mismatch at instance %zu", p);
+    SPG_CHECK(is_pow2(num_inputs[p]) && num_inputs[p] <= max_num_inputs, "spg_sc2_create: bad num_inputs[%zu]", p);
+    SPG_CHECK(!single || num_inputs[p] == num_inputs[0],
+              "spg_sc2_create: a shared instance requires equal num_inputs (got %zu vs %zu)", num_inputs[p], num_inputs[0]);
+  }
+  spg_sc2 *s = new (std::nothrow) spg_sc2();
+  if (!s) return SPG_ENOMEM;
+  s->ctx = ctx;
+  s->P = P;
+  s->Pp = next_pow2(P);
+  s->W = num_witness_secs;
+  s->Wp = next_pow2(num_witness_secs);
+  s->ny = log2u(max_num_inputs);
+  s->nw = log2u(s->Wp);
+  s->np = log2u(s->Pp);
+  s->single_inst = single;
+  s->Y.assign(num_inputs, num_inputs + P);
+  s->p_len = s->Pp;
+  size_t nq = log2u(max_num_proofs), nx = log2u(inst->max_num_cons);
+  SPG_CHECK((nx == 0 || rx) && (nq == 0 || rq_rev) && (s->np == 0 || rp), "spg_sc2_create: null challenge vector");
+  size_t total = 0;
+  std::vector<size_t> off(P);
+  for (size_t p = 0; p < P; p++) {
+    off[p] = total;
+    total += s->W * s->Y[p];
+  }
+  s->cap = std::max(std::max(total, P * s->Wp), s->Pp);
+  int rc = SPG_OK;
+  auto fail = [&](int code) {
+    spg_sc2_destroy(s);
+    return code;
+  };
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 2; k++)
+      if (cudaMalloc(&s->tab[b][k], s->cap * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 tables", __FILE__, __LINE__));
+  if (cudaMalloc(&s->A, s->Pp * sizeof(fq)) != cudaSuccess || cudaMalloc(&s->d_segs, P * sizeof(Seg)) != cudaSuccess)
+    return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 aux", __FILE__, __LINE__));
+
+  // scratch: eq(rx) table, suffix tables of rq_rev, challenge staging
+  size_t X = inst->max_num_cons;
+  fq *scr = nullptr;
+  size_t XS = X > s->Pp ? X : s->Pp;  // eq expansion scratch
+  size_t scr_n = X + XS + ((size_t)2 << nq) + s->Pp + nx + s->np + 8;
+  if (cudaMalloc(&scr, scr_n * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 scratch", __FILE__, __LINE__));
+  fq *evals_rx = scr, *eq_scratch = scr + X, *Sq = scr + X + XS, *d_r = Sq + ((size_t)2 << nq) + s->Pp;
+  do {
+    // evals_rx = EqPolynomial::new(rx).evals()  (src/r1csproof.rs:433)
+    if (nx && (rc = cudaMemcpyAsync(d_r, rx, nx * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) { rc = cuda_fail((cudaError_t)rc, "rx upload", __FILE__, __LINE__); break; }
+    if ((rc = eq_evals_device(ctx, d_r, rx, nx, evals_rx, eq_scratch)) != SPG_OK) break;
+    // ABC table straight into B's buffer; a shared instance is expanded to one copy per p
+    {
+      std::vector<size_t> ncols(inst->num_instances), ooff(inst->num_instances);
+      for (size_t p = 0; p < inst->num_instances; p++) {
+        ncols[p] = s->Y[p];
+        ooff[p] = off[p];
+      }
+      if ((rc = r1cs_abc_table(ctx, inst, evals_rx, s->W, max_num_inputs, ncols.data(), ooff.data(), r_A, r_B, r_C, s->tab[0][0])) != SPG_OK) break;
+      if (single)
+        for (size_t p = 1; p < P; p++)
+          if (cudaMemcpyAsync(s->tab[0][0] + off[p], s->tab[0][0], s->W * s->Y[0] * sizeof(fq), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "ABC replicate", __FILE__, __LINE__); break; }
+      if (rc != SPG_OK) break;
+    }
+    // Z bound to rq: LSB-first eq table of rq_rev (full level = nq)
+    {
+      std::vector<hfq> tq(nq);
+      for (size_t i = 0; i < nq; i++) tq[i] = hfq_from(rq_rev[i]);
+      if ((rc = build_suffix_tables(ctx, tq, nq, Sq)) != SPG_OK) break;
+      const fq *E = Sq + ((size_t)1 << nq);
+      for (size_t p = 0; p < P; p++) {
+        size_t WY = s->W * s->Y[p];
+        k_z_bind_rq<<<grid_for(ctx, WY, 128), 128, 0, ctx->stream>>>(z->d + z->off[p], E, num_proofs[p], WY, s->tab[0][1] + off[p]);
+        ctx->launches++;
+      }
+      if (cudaGetLastError() != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "k_z_bind_rq", __FILE__, __LINE__); break; }
+    }
+    // A = EqPolynomial::new(rp).evals()
+    if (s->np && cudaMemcpyAsync(d_r, rp, s->np * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "rp upload", __FILE__, __LINE__); break; }
+    if ((rc = eq_evals_device(ctx, d_r, rp, s->np, s->A, eq_scratch)) != SPG_OK) break;
+  } while (0);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(scr);
+  if (rc != SPG_OK) return fail(rc);
+  s->loglen.resize(P);
+  for (size_t p = 0; p < P; p++) s->loglen[p] = log2u(s->Y[p]);
+  *out = s;
+  return SPG_OK;
+}
+
+size_t spg_sc2_num_rounds(const spg_sc2 *s) { return s ? s->ny + s->nw + s->np : 0; }
+
+int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]) {
+  SPG_CHECK(s && e, "spg_sc2_round_eval: null argument");
+  if (s->round >= spg_sc2_num_rounds(s)) {
+    set_error("spg_sc2_round_eval: all rounds are done");
+    return SPG_ESTATE;
+  }
+  if (s->evaluated) {
+    set_error("spg_sc2_round_eval: round %zu already evaluated; call round_bind", s->round);
+    return SPG_ESTATE;
+  }
+  spg_ctx *ctx = s->ctx;
+  int phase = phase2_of(s, s->round);
+  if (phase >= 1) SPG_TRY(enter_w_phase(s));
+  if (phase == 2) {
+    SPG_TRY(enter_p_phase(s));
+    size_t half = s->p_len / 2;
+    size_t limit = half < s->P ? half : s->P;
+    SPG_LAUNCH(ctx, k2_p_eval, 1, 128, 0, s->A, s->tab[s->cur][0], s->tab[s->cur][1], half, limit, ctx->d_result);
+    SPG_TRY(fetch_result(ctx, 3, e));
+  } else if (s->have_cached) {
+    memcpy(e, s->cached, sizeof s->cached);
+    s->have_cached = false;
+  } else {
+    unsigned long long items = 0, out_total = 0;
+    build_segs2(s, phase, 0, &items, &out_total);
+    SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+    int grid = grid_for(ctx, items, RB2, 4);
+    SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+    SPG_LAUNCH(ctx, k2_pair_eval, grid, RB2, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->d_segs, (int)s->P,
+               items, s->A, ctx->d_partials);
+    SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
+    SPG_TRY(fetch_result(ctx, 3, e));
+  }
+  s->evaluated = true;
+  return SPG_OK;
+}
+
+int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r) {
+  SPG_CHECK(s && r, "spg_sc2_round_bind: null argument");
+  if (!s->evaluated) {
+    set_error("spg_sc2_round_bind: round %zu has not been evaluated", s->round);
+    return SPG_ESTATE;
+  }
+  spg_ctx *ctx = s->ctx;
+  int phase = phase2_of(s, s->round);
+  fq rr;
+  memcpy(&rr, r, sizeof rr);
+  if (phase == 2) {
+    size_t half = s->p_len / 2;
+    SPG_LAUNCH(ctx, k2_p_bind, 1, 128, 0, s->A, s->tab[s->cur][0], s->tab[s->cur][1], half, rr);
+    s->p_len = half;
+  } else {
+    size_t j = phase == 0 ? s->round : s->round - s->ny;
+    size_t n_phase = phase == 0 ? s->ny : s->nw;
+    bool next_same = j + 1 < n_phase;
+    unsigned minlen = 64;
+    for (size_t p = 0; p < s->P; p++) minlen = s->loglen[p] < minlen ? s->loglen[p] : minlen;
+    int nxt = s->cur ^ 1;
+    unsigned long long items = 0, out_total = 0;
+    if (next_same && minlen >= 2) {
+      build_segs2(s, phase, 1, &items, &out_total);
+      SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+      int grid = grid_for(ctx, items, RB2, 4);
+      SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+      SPG_LAUNCH(ctx, k2_quad_bind_eval, grid, RB2, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[nxt][0],
+                 s->tab[nxt][1], s->d_segs, (int)s->P, items, rr, s->A, ctx->d_partials);
+      SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
+      SPG_TRY(fetch_result(ctx, 3, s->cached));
+      s->have_cached = true;
+    } else {
+      build_segs2(s, phase, 0, &items, &out_total);
+      SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
+      SPG_LAUNCH(ctx, k2_pair_bind, grid_for(ctx, items, RB2, 8), RB2, 0, s->tab[s->cur][0], s->tab[s->cur][1],
+                 s->tab[nxt][0], s->tab[nxt][1], s->d_segs, (int)s->P, items, rr);
+    }
+    s->cur = nxt;
+    for (size_t p = 0; p < s->P; p++)
+      if (s->loglen[p] > 0) s->loglen[p]--;
+  }
+  s->round++;
+  s->evaluated = false;
+  return SPG_OK;
+}
+
+int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]) {
+  SPG_CHECK(s && claims, "spg_sc2_final: null argument");
+  if (s->round != spg_sc2_num_rounds(s)) {
+    set_error("spg_sc2_final: %zu of %zu rounds bound", s->round, spg_sc2_num_rounds(s));
+    return SPG_ESTATE;
+  }
+  SPG_TRY(enter_w_phase(s));
+  spg_ctx *ctx = s->ctx;
+  SPG_CUDA(cudaMemcpyAsync(&claims[0], s->A, sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(&claims[1], s->tab[s->cur][0], sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(&claims[2], s->tab[s->cur][1], sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}
+
+void spg_sc2_destroy(spg_sc2 *s) {
+  if (!s) return;
+  cudaStreamSynchronize(s->ctx->stream);
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 2; k++)
+      if (s->tab[b][k]) cudaFree(s->tab[b][k]);
+  if (s->A) cudaFree(s->A);
+  if (s->d_segs) cudaFree(s->d_segs);
+  delete s;
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""GPU parity for the R1CSProof::prove table pipeline through the C ABI:
+z_mat assembly, multiply_vec_block (SpMV), phase-1 rounds, ABC table, Z bound to rq,
+phase-2 rounds -- against oracle.r1cs.prove_tables with the same injected challenges.
+Bit-exact at every round."""
+import numpy as np
+import pytest
+
+from oracle import cbind as O
+from oracle import r1cs as R
+from tests.helpers import log2, rand_scalars, random_instance, random_witness_secs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import spartan_parallel_b200 as sp
+
+    return sp.Context(0)
+
+
+def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2):
+    import spartan_parallel_b200 as sp
+
+    A = [inst.mats[3 * i] for i in range(inst.num_instances)]
+    B = [inst.mats[3 * i + 1] for i in range(inst.num_instances)]
+    Cm = [inst.mats[3 * i + 2] for i in range(inst.num_instances)]
+    dinst = sp.R1CSInstance(ctx, inst.num_instances, inst.max_num_cons, inst.num_cons, inst.num_vars, A, B, Cm)
+    dsecs = []
+    for ws in secs:
+        nq = [len(ws.w_mat[p]) for p in range(len(ws.w_mat))]
+        flat = np.concatenate([np.concatenate(ws.w_mat[p]) for p in range(len(ws.w_mat))])
+        dsecs.append(sp.ProverWitnessSecInfo(ctx, nq, ws.num_inputs, flat))
+    z = sp.ZMat(ctx, num_proofs, num_inputs, dsecs)
+    block_cons = [inst.num_cons[0]] * P if inst.num_instances == 1 else inst.num_cons
+    sc1 = sp.sumcheck_phase1(ctx, dinst, z, num_proofs, max_q, block_cons, inst.max_num_cons, max_y, tau_p, tau_q, tau_x)
+    e1 = []
+    for j in range(sc1.num_rounds):
+        e1.append(sc1.round_eval())
+        sc1.round_bind(ch1[j])
+    c1 = sc1.final()
+    nx, nq_ = log2(inst.max_num_cons), log2(max_q)
+    r = np.asarray(ch1).reshape(-1, 4)
+    rx = r[:nx][::-1].copy()
+    rq_rev, rp = r[nx:nx + nq_], r[nx + nq_:]
+    sc2 = sp.SumcheckPhase2(ctx, dinst, z, num_proofs, max_q, num_inputs, max_y, len(secs), rx, rq_rev, rp, *r_abc)
+    e2 = []
+    for j in range(sc2.num_rounds):
+        e2.append(sc2.round_eval())
+        sc2.round_bind(ch2[j])
+    c2 = sc2.final()
+    return e1, c1, e2, c2, dinst, dsecs
+
+
+def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed):
+    max_q = max(num_proofs)
+    Pp = 1 if P == 1 else 1 << (P - 1).bit_length()
+    W = len(secs)
+    Wp = 1 if W == 1 else 1 << (W - 1).bit_length()
+    np_, nq, nx, ny, nw = log2(Pp), log2(max_q), log2(inst.max_num_cons), log2(max_y), log2(Wp)
+    big = rand_scalars(64, seed)
+    tau_p, tau_q, tau_x = big[:np_], big[8:8 + nq], big[16:16 + nx]
+    ch1 = rand_scalars(max(np_ + nq + nx, 1), seed + 1)
+    ch2 = rand_scalars(max(np_ + nw + ny, 1), seed + 2)
+    r_abc = rand_scalars(3, seed + 3)
+    want = R.prove_tables(inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
+    e1, c1, e2, c2, dinst, _ = gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
+    assert len(e1) == len(want.evals1) and len(e2) == len(want.evals2)
+    for j, (g, w) in enumerate(zip(e1, want.evals1)):
+        assert np.array_equal(g, w), f"phase 1 round {j}"
+    assert np.array_equal(c1, want.claims1)
+    for j, (g, w) in enumerate(zip(e2, want.evals2)):
+        assert np.array_equal(g, w), f"phase 2 round {j}"
+    assert np.array_equal(c2, want.claims2)
+    return dinst, want
+
+
+def test_c1_synthetic(ctx):
+    """BASELINE config C1: X = 2^10, Q = 4, one instance, sections (u, v)."""
+    X, Q = 1 << 10, 4
+    inst = R.synthetic_instance(X)
+    secs = R.synthetic_witness(X, [Q], seed=11)
+    dinst, want = run_case(ctx, inst, 1, [Q], [X], X, secs, seed=100)
+    # a satisfying witness makes the phase-1 claim vanish at every round-0 point
+    assert np.array_equal(want.evals1[0][0], O.ZERO)
+
+
+def test_synthetic_non_unit_coefficients(ctx):
+    X, Q = 1 << 6, 8
+    inst = R.synthetic_instance(X, unit=False, seed=3)
+    secs = R.synthetic_witness(X, [Q], seed=12)
+    run_case(ctx, inst, 1, [Q], [X], X, secs, seed=101)
+
+
+def test_three_distinct_instances(ctx):
+    P, X = 3, 1 << 7
+    inst = R.synthetic_instance(X, num_instances=P, unit=False, seed=5)
+    secs = R.synthetic_witness(X, [4, 2, 2], seed=13)
+    run_case(ctx, inst, P, [4, 2, 2], [X] * P, X, secs, seed=102)
+
+
+def test_shared_instance_single_inst(ctx):
+    """One R1CS instance shared by P proving instances (perm-root call site, src/lib.rs:2472)."""
+    P, X = 3, 1 << 5
+    inst = R.synthetic_instance(X)
+    secs = R.synthetic_witness(X, [4, 4, 1], seed=14)
+    run_case(ctx, inst, P, [4, 4, 1], [X] * P, X, secs, seed=103)
+
+
+def test_c4_heterogeneous(ctx):
+    """BASELINE config C4 shape: P = 5, Q_p = {64,16,16,4,1}, W = 5 with a single section,
+    ragged num_inputs and num_cons."""
+    P, W, Ymax = 5, 5, 1 << 6
+    num_proofs = [16, 8, 8, 4, 1]
+    num_cons = [128, 64, 128, 32, 16]
+    Y = [64, 64, 32, 64, 16]
+    inst = random_instance(P, num_cons, W, Ymax, Y, nnz=150, seed=21)
+    kinds = ["full", "single", "full", "short", "full"]
+    sec_inputs = [Y, [32] * P, [64, 128, 16, 64, 16], [8] * P, [8] * P]
+    secs = random_witness_secs(P, num_proofs, W, sec_inputs, kinds, seed=22)
+    run_case(ctx, inst, P, num_proofs, Y, Ymax, secs, seed=104)
+
+
+def test_multi_evaluate(ctx):
+    inst = random_instance(2, [32, 16], 3, 16, [16, 8], nnz=90, seed=31)
+    import spartan_parallel_b200 as sp
+
+    A = [inst.mats[3 * i] for i in range(2)]
+    B = [inst.mats[3 * i + 1] for i in range(2)]
+    Cm = [inst.mats[3 * i + 2] for i in range(2)]
+    d = sp.R1CSInstance(ctx, 2, 32, [32, 16], inst.num_vars, A, B, Cm)
+    rx, ry = rand_scalars(5, 1), rand_scalars(log2(inst.num_vars), 2)
+    got = d.multi_evaluate(rx, ry)
+    trx, try_ = O.eq_evals(rx), O.eq_evals(ry)
+    for m in range(6):
+        rows, cols, vals = inst.mats[m]
+        assert np.array_equal(got[m], O.sparse_evaluate_with_tables(rows, cols, vals, trx, try_)), m
+
+
+def test_witness_poly_evaluate(ctx):
+    """polyeval step (src/r1csproof.rs:534-573): poly_w[p].evaluate(rq_short ++ ry_short)."""
+    import spartan_parallel_b200 as sp
+
+    Q, Y = 8, 32
+    w = rand_scalars(Q * Y, 5)
+    sec = sp.ProverWitnessSecInfo(ctx, [Q], [Y], w)
+    r = rand_scalars(8, 6)
+    assert np.array_equal(sec.poly_w(0).evaluate(r), O.dense_evaluate(w, r))
+
+
+def test_bad_shapes_rejected(ctx):
+    import spartan_parallel_b200 as sp
+
+    inst = R.synthetic_instance(8)
+    with pytest.raises(sp.SpgError):
+        sp.R1CSInstance(ctx, 1, 12, [8], 16, [inst.mats[0]], [inst.mats[1]], [inst.mats[2]])  # not a power of two
+    bad = (inst.mats[0][0], (inst.mats[0][1] + 100).astype(np.uint32), inst.mats[0][2])
+    with pytest.raises(sp.SpgError):
+        sp.R1CSInstance(ctx, 1, 8, [8], 16, [bad], [inst.mats[1]], [inst.mats[2]])  # column out of range
