@@ -60,6 +60,12 @@ void spg_ctx_destroy(spg_ctx *ctx);
 int spg_ctx_sync(spg_ctx *ctx);
 /* number of kernel launches issued through this context so far */
 uint64_t spg_ctx_launch_count(const spg_ctx *ctx);
+/* Per-kernel timing with CUDA events recorded on the launching stream. Between begin
+ * and end every launch is bracketed by an event pair; end writes a JSON array
+ * [{"kernel", "launches", "total_ms", "units", "max_ms", "max_units"}] where "units" is
+ * the algorithmic byte count the launcher declared for the kernel (0 if none). */
+int spg_ctx_profile_begin(spg_ctx *ctx);
+int spg_ctx_profile_end(spg_ctx *ctx, char *out_json, size_t cap);
 /* cudaStream_t the context launches on (for CUDA-event timing by the caller) */
 void *spg_ctx_stream(const spg_ctx *ctx);
 /* pinned host allocation for fast uploads (optional convenience) */

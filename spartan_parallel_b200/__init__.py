@@ -11,15 +11,19 @@ from .api import (  # noqa: F401
     MODE_W,
     MODE_X,
     Context,
+    CubicBatched,
     DensePolynomial,
     EqPolynomial,
+    ProductCircuit,
     ProverWitnessSecInfo,
     R1CSInstance,
     SumcheckPhase1,
     SumcheckPhase2,
     ZMat,
+    deref,
     dot,
     from_u512,
+    hash_layer,
     sumcheck_phase1,
     vec_op,
 )

@@ -58,6 +58,8 @@ def _proto(L):
     sigs = {
         "spg_ctx_create": [INT, PP],
         "spg_ctx_sync": [P],
+        "spg_ctx_profile_begin": [P],
+        "spg_ctx_profile_end": [P, P, SZ],
         "spg_host_alloc": [SZ, PP],
         "spg_vec_alloc": [P, SZ, PP],
         "spg_vec_upload": [P, P, SZ, PP],

@@ -48,6 +48,16 @@ class Context:
     def sync(self):
         check(self.L.spg_ctx_sync(self.h), "spg_ctx_sync")
 
+    def profile_begin(self):
+        check(self.L.spg_ctx_profile_begin(self.h), "spg_ctx_profile_begin")
+
+    def profile_end(self) -> list:
+        import json
+
+        buf = C.create_string_buffer(1 << 16)
+        check(self.L.spg_ctx_profile_end(self.h, buf, len(buf)), "spg_ctx_profile_end")
+        return json.loads(buf.value.decode())
+
     @property
     def launches(self) -> int:
         return int(self.L.spg_ctx_launch_count(self.h))
@@ -408,3 +418,103 @@ class SumcheckPhase2:
             self.free()
         except Exception:
             pass
+
+
+class ProductCircuit:
+    """ProductCircuit (src/product_tree.rs:11-64), all layers device resident."""
+
+    def __init__(self, ctx: Context, poly: DensePolynomial):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(ctx.L.spg_prodtree_build(ctx.h, poly.h, C.byref(h)), "spg_prodtree_build")
+        self.h = h
+
+    @property
+    def num_layers(self) -> int:
+        return int(self.ctx.L.spg_prodtree_num_layers(self.h))
+
+    def layer(self, k: int):
+        """(left_vec[k], right_vec[k]) as views."""
+        l, r = C.c_void_p(), C.c_void_p()
+        check(self.ctx.L.spg_prodtree_layer(self.h, k, C.byref(l), C.byref(r)), "spg_prodtree_layer")
+        out = []
+        for hh in (l, r):
+            d = DensePolynomial(self.ctx, hh, owner=self)
+            d.free = lambda: None
+            out.append(d)
+        return out
+
+    def evaluate(self) -> np.ndarray:
+        out = np.empty(4, dtype=np.uint64)
+        check(self.ctx.L.spg_prodtree_evaluate(self.ctx.h, self.h, _ptr(out)), "spg_prodtree_evaluate")
+        return out
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_prodtree_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CubicBatched:
+    """Device loops of SumcheckInstanceProof::prove_cubic_batched (src/sumcheck.rs:264-434)."""
+
+    def __init__(self, ctx: Context, A_par, B_par, C_par, A_seq, B_seq, C_seq, coeffs):
+        self.ctx = ctx
+        self._keep = (A_par, B_par, C_par, A_seq, B_seq, C_seq)
+        arr = lambda vs: (C.c_void_p * max(len(vs), 1))(*[v.h for v in vs])
+        h = C.c_void_p()
+        co = _fq(coeffs).reshape(-1, 4)
+        check(ctx.L.spg_cubic_create(ctx.h, len(A_par), arr(A_par), arr(B_par), C_par.h if C_par is not None else None,
+                                     len(A_seq), arr(A_seq), arr(B_seq), arr(C_seq), _ptr(co), C.byref(h)), "spg_cubic_create")
+        self.h = h
+        self.n_claims = 2 * len(A_par) + (1 if A_par else 0) + 3 * len(A_seq)
+
+    def round_eval(self) -> np.ndarray:
+        out = np.empty((3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_cubic_round_eval(self.h, _ptr(out)), "spg_cubic_round_eval")
+        return out
+
+    def round_bind(self, r):
+        check(self.ctx.L.spg_cubic_round_bind(self.h, _ptr(_fq(r))), "spg_cubic_round_bind")
+
+    def final(self) -> np.ndarray:
+        out = np.empty((self.n_claims, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_cubic_final(self.h, _ptr(out)), "spg_cubic_final")
+        return out
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_cubic_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def hash_layer(ctx: Context, addr, val: DensePolynomial, ts, gamma, tau, ts_plus_one=False) -> DensePolynomial:
+    """One vector of Layers::build_hash_layer (src/sparse_mlpoly.rs:612-687):
+    ts*gamma^2 + val*gamma + addr - tau; addr=None means the cell index, ts=None means 0."""
+    n = len(val)
+    a = None if addr is None else np.ascontiguousarray(addr, dtype=np.uint64)
+    t = None if ts is None else np.ascontiguousarray(ts, dtype=np.uint64)
+    h = C.c_void_p()
+    check(ctx.L.spg_hash_layer(ctx.h, _ptr(a), val.h, _ptr(t), n, _ptr(_fq(gamma)), _ptr(_fq(tau)), int(ts_plus_one),
+                               C.byref(h)), "spg_hash_layer")
+    return DensePolynomial(ctx, h)
+
+
+def deref(ctx: Context, addr, mem: DensePolynomial) -> DensePolynomial:
+    """AddrTimestamps::deref_mem (src/sparse_mlpoly.rs:255-264)."""
+    a = np.ascontiguousarray(addr, dtype=np.uint64)
+    h = C.c_void_p()
+    check(ctx.L.spg_deref(ctx.h, _ptr(a), len(a), mem.h, C.byref(h)), "spg_deref")
+    return DensePolynomial(ctx, h)

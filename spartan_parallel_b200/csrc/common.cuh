@@ -68,6 +68,16 @@ struct spg_ctx {
   spg::fq *d_result = nullptr;  // device alias of h_result
   // small staging for scalar arguments
   spg::fq *d_scalars = nullptr;  // device scratch, 64 fq
+  // optional per-kernel timing with CUDA events on the launching stream
+  bool profiling = false;
+  struct ProfRec {
+    const char *name;
+    cudaEvent_t a, b;
+    double units;  // caller-defined work units of the launch (bytes, items ...)
+  };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  double next_units = 0;  // set by the launcher just before SPG_LAUNCH
 };
 
 struct spg_vec {
@@ -83,11 +93,16 @@ namespace spg {
 // launch bookkeeping: every kernel goes through this so gpu_launches is exact
 #define SPG_LAUNCH(ctx, kernel, grid, block, smem, ...)                       \
   do {                                                                        \
+    cudaEvent_t _ea = nullptr, _eb = nullptr;                                 \
+    if ((ctx)->profiling) spg::prof_begin((ctx), #kernel, &_ea, &_eb);        \
     kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);          \
+    if (_eb) cudaEventRecord(_eb, (ctx)->stream);                             \
     (ctx)->launches++;                                                        \
+    (ctx)->next_units = 0;                                                    \
     SPG_CUDA(cudaGetLastError());                                             \
   } while (0)
 
+void prof_begin(spg_ctx *ctx, const char *name, cudaEvent_t *a, cudaEvent_t *b);
 int ensure_partials(spg_ctx *ctx, size_t n_fq);
 int vec_new(spg_ctx *ctx, size_t n, spg_vec **out);
 

@@ -17,6 +17,23 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   return e == cudaErrorMemoryAllocation ? SPG_ENOMEM : SPG_ECUDA;
 }
 
+void prof_begin(spg_ctx *ctx, const char *name, cudaEvent_t *a, cudaEvent_t *b) {
+  auto get = [&]() {
+    cudaEvent_t e = nullptr;
+    if (!ctx->ev_pool.empty()) {
+      e = ctx->ev_pool.back();
+      ctx->ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  };
+  *a = get();
+  *b = get();
+  cudaEventRecord(*a, ctx->stream);
+  ctx->prof.push_back(spg_ctx::ProfRec{name, *a, *b, ctx->next_units});
+}
+
 int ensure_partials(spg_ctx *ctx, size_t n_fq) {
   if (ctx->partial_cap >= n_fq) return SPG_OK;
   if (ctx->d_partials) SPG_CUDA(cudaFree(ctx->d_partials));
@@ -128,6 +145,64 @@ int spg_ctx_sync(spg_ctx *ctx) {
 }
 
 uint64_t spg_ctx_launch_count(const spg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int spg_ctx_profile_begin(spg_ctx *ctx) {
+  SPG_CHECK(ctx, "null ctx");
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto &r : ctx->prof) {
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  ctx->profiling = true;
+  return SPG_OK;
+}
+
+int spg_ctx_profile_end(spg_ctx *ctx, char *out, size_t cap) {
+  SPG_CHECK(ctx && out && cap > 2, "spg_ctx_profile_end: bad buffer");
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->profiling = false;
+  struct Agg {
+    const char *name;
+    double ms, units, max_ms, max_units;
+    size_t n;
+  };
+  std::vector<Agg> aggs;
+  for (auto &r : ctx->prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Agg *g = nullptr;
+    for (auto &a : aggs)
+      if (a.name == r.name || strcmp(a.name, r.name) == 0) g = &a;
+    if (!g) {
+      aggs.push_back(Agg{r.name, 0, 0, 0, 0, 0});
+      g = &aggs.back();
+    }
+    g->ms += ms;
+    g->units += r.units;
+    g->n++;
+    if (ms > g->max_ms) {
+      g->max_ms = ms;
+      g->max_units = r.units;
+    }
+    ctx->ev_pool.push_back(r.a);
+    ctx->ev_pool.push_back(r.b);
+  }
+  ctx->prof.clear();
+  std::string js = "[";
+  char buf[512];
+  for (size_t i = 0; i < aggs.size(); i++) {
+    snprintf(buf, sizeof buf,
+             "%s{\"kernel\": \"%s\", \"launches\": %zu, \"total_ms\": %.6f, \"units\": %.6g, "
+             "\"max_ms\": %.6f, \"max_units\": %.6g}",
+             i ? ", " : "", aggs[i].name, aggs[i].n, aggs[i].ms, aggs[i].units, aggs[i].max_ms, aggs[i].max_units);
+    js += buf;
+  }
+  js += "]";
+  SPG_CHECK(js.size() + 1 <= cap, "spg_ctx_profile_end: buffer too small (%zu needed)", js.size() + 1);
+  memcpy(out, js.c_str(), js.size() + 1);
+  return SPG_OK;
+}
 void *spg_ctx_stream(const spg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int spg_host_alloc(size_t bytes, void **out) {

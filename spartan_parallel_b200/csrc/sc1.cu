@@ -496,6 +496,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
     const fq *RW = phase == 0 ? s->RWx : s->Ap;
     int grid = grid_for(ctx, items, RB, 4);
     SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+    ctx->next_units = 192.0 * (double)items;  // 2 scalars x 3 tables read per pair
     SPG_LAUNCH(ctx, k_pair_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
                s->tab[s->cur][2], s->d_segs, (int)s->P, items, RW, S, ctx->d_partials);
     SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
@@ -545,6 +546,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       const fq *RW = phase == 0 ? s->RWx : s->Ap;
       int grid = grid_for(ctx, items, RB, 4);
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+      ctx->next_units = 576.0 * (double)items;  // 4 read + 2 written scalars x 3 tables per item
       SPG_LAUNCH(ctx, k_quad_bind_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
                  s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs,
                  (int)s->P, items, rr, RW, Snext, ctx->d_partials);
@@ -557,6 +559,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       build_segs(s, phase, 0, &items, &out_total);
       SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
       SPG_TRY(upload_segs(s));
+      ctx->next_units = 288.0 * (double)items;
       SPG_LAUNCH(ctx, k_pair_bind, grid_for(ctx, items, RB, 8), RB, 0, s->tab[s->cur][0],
                  s->tab[s->cur][1], s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1],
                  s->tab[nxt][2], s->d_segs, (int)s->P, items, rr);
