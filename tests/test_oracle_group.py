@@ -144,11 +144,16 @@ def test_edwards_arithmetic_against_libsodium_ed25519():
         x, y = pt.X * zi % G.P, pt.Y * zi % G.P
         return (y | ((x & 1) << 255)).to_bytes(32, "little")
 
+    # the Ed25519 base point (y = 4/5, x even); its ristretto encoding is the RFC's generator
+    by = 4 * pow(5, -1, G.P) % G.P
+    bx = 15112221349535400772501151409588531511454012693041857206046113283949847762202
+    B = G.Point(bx, by, 1, bx * by)
+    assert B.compress() == G.BASEPOINT_COMPRESSED and B == G.BASEPOINT
     rng = random.Random(9)
     pts = []
     for _ in range(8):
         k = rng.randrange(1, G.L)
-        mine = G.BASEPOINT.mul(k)
+        mine = B.mul(k)
         assert ed_encode(mine) == nacl.crypto_scalarmult_ed25519_base_noclamp(k.to_bytes(32, "little"))
         pts.append(mine)
     for a, c in zip(pts[:-1], pts[1:]):
