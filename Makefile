@@ -1,7 +1,7 @@
 # Builds libspgpu.so (CUDA kernels + C ABI) for sm_100a, in-tree.
 NVCC ?= /usr/local/cuda/bin/nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas --expt-relaxed-constexpr
 PKG := spartan_parallel_b200
 SRC := $(wildcard $(PKG)/csrc/*.cu)
 OBJ := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(SRC))

@@ -14,6 +14,7 @@ from .api import (  # noqa: F401
     CubicBatched,
     DensePolynomial,
     EqPolynomial,
+    MultiCommitGens,
     ProductCircuit,
     ProverWitnessSecInfo,
     R1CSInstance,

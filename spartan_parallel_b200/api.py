@@ -518,3 +518,48 @@ def deref(ctx: Context, addr, mem: DensePolynomial) -> DensePolynomial:
     h = C.c_void_p()
     check(ctx.L.spg_deref(ctx.h, _ptr(a), len(a), mem.h, C.byref(h)), "spg_deref")
     return DensePolynomial(ctx, h)
+
+
+class MultiCommitGens:
+    """Device copy of MultiCommitGens (src/commitments.rs:8-67). Generator derivation
+    (SHAKE256 -> from_uniform_bytes) is one-off host setup; the caller passes the n + 1
+    compressed ristretto points G[0..n], h."""
+
+    def __init__(self, ctx: Context, compressed: bytes):
+        assert len(compressed) % 32 == 0 and len(compressed) >= 64
+        self.ctx = ctx
+        self.n = len(compressed) // 32 - 1
+        buf = np.frombuffer(bytes(compressed), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        check(ctx.L.spg_gens_upload(ctx.h, _ptr(buf), self.n + 1, C.byref(h)), "spg_gens_upload")
+        self.h = h
+
+    def commit_poly(self, poly: DensePolynomial, L_size: int | None = None) -> list:
+        """DensePolynomial::commit with zero blinds (src/dense_mlpoly.rs:214-239): L_size
+        compressed row commitments."""
+        if L_size is None:
+            L_size = 1 << (poly.get_num_vars() // 2)
+        out = np.empty(32 * L_size, dtype=np.uint8)
+        check(self.ctx.L.spg_poly_commit(self.ctx.h, self.h, poly.h, L_size, _ptr(out)), "spg_poly_commit")
+        return [out[32 * i: 32 * (i + 1)].tobytes() for i in range(L_size)]
+
+    def commit_batch(self, scalars, blinds=None) -> list:
+        """Commitments::commit for `count` vectors of equal length sharing these generators."""
+        s = _fq(scalars)
+        assert s.ndim == 3
+        count, length = s.shape[0], s.shape[1]
+        b = None if blinds is None else _fq(blinds).reshape(count, 4)
+        out = np.empty(32 * count, dtype=np.uint8)
+        check(self.ctx.L.spg_commit_batch(self.ctx.h, self.h, _ptr(s), length, _ptr(b), count, _ptr(out)), "spg_commit_batch")
+        return [out[32 * i: 32 * (i + 1)].tobytes() for i in range(count)]
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_gens_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
