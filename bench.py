@@ -137,22 +137,40 @@ def run_gpu(args):
     u_pin, v_pin = hu.numpy().view(np.uint64), hv.numpy().view(np.uint64)
     A, B, Cm = synthetic_matrices(X, ONE)
     inst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A], [B], [Cm])
-    tau_q, tau_x = challenges(rng, nq), challenges(rng, nx)
-    ch1, ch2 = challenges(rng, nx + nq), challenges(rng, 1 + nx)
-    r_abc = challenges(rng, 3)
+    # challenges are common to all ranks (in production they come from rank 0's transcript)
+    crng = np.random.default_rng(0xC4A11E46E)
+    ng = log2(world)
+    tau_q, tau_x = challenges(crng, nq + ng), challenges(crng, nx)
+    ch1, ch2 = challenges(crng, nx + nq + ng), challenges(crng, 1 + nx)
+    r_abc = challenges(crng, 3)
     setup_s = time.time() - t_setup
+    from spartan_parallel_b200 import parallel
+
+    comm = parallel.TorchComm(device=torch.device("cuda", local)) if world > 1 else parallel.LocalComm()
 
     def one_pass(secs):
         """The hot path for one batch: everything R1CSProof::prove does on tables."""
         z = sp.ZMat(ctx, [Q], [X], secs)
-        sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
-        for j in range(sc1.num_rounds):
-            sc1.round_eval()
-            sc1.round_bind(ch1[j])
-        c1 = sc1.final()
-        sc1.free()
         rx = ch1[:nx][::-1].copy()
-        sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[nx:nx + nq], ch1[:0], r_abc[0], r_abc[1], r_abc[2])
+        if world == 1:
+            sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
+            for j in range(sc1.num_rounds):
+                sc1.round_eval()
+                sc1.round_bind(ch1[j])
+            c1 = sc1.final()
+            sc1.free()
+            sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[nx:nx + nq], ch1[:0], r_abc[0], r_abc[1], r_abc[2])
+        else:
+            # one proof over Q * world proofs: shards exchange 3 scalars per round, then one
+            # all-gather of the rq-bound Z table; phase 2 (independent of Q) runs replicated
+            sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, tau_q, tau_x)
+            for j in range(sc1.num_rounds):
+                sc1.round_eval()
+                sc1.round_bind(ch1[j])
+            c1 = sc1.final()
+            sc1.engine.free()
+            zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q)
+            sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
         for j in range(sc2.num_rounds):
             sc2.round_eval()
             sc2.round_bind(ch2[j])
@@ -261,12 +279,12 @@ def run_gpu(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u256 (F_q, 8x32-bit Montgomery limbs)", "data": "synthetic",
         "config": {"workload": f"data-parallel R1CS batch, X=2^{args.log_x} constraints x Q={Q} proofs per GPU, P=1 instance, W=2 sections (BASELINE configs[4] shape)",
-                   "constraints_per_step": total_units, "sharding": "independent proof shards per rank, no data-path collective",
+                   "constraints_per_step": total_units, "sharding": ("single GPU" if world == 1 else f"one batch of {Q * world} proofs sharded by proof index over {world} ranks: per-round all-gather of 3 scalars per rank + one all-gather of the rq-bound Z table (NCCL)"),
                    "l2": "inputs (>= 4 GiB/step) exceed the 126 MB L2; no flush needed",
                    "challenges": "precomputed per-round challenges; one host round trip (96 B out, 32 B in) per round is inside the timed region",
                    "phases": "z_mat + SpMV + phase-1 rounds + ABC/Z tables + phase-2 rounds"},
         "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(2 * N * 32), "d2h_bytes_per_step": int(96 * (2 * nx + nq + 1) + 7 * 32)},
+                "h2d_bytes_per_step": int(2 * N * 32), "d2h_bytes_per_step": int(96 * (2 * nx + nq + ng + 1) + 7 * 32)},
         "gpu_launches": int(launches), "wall_ms_per_step": wall_dev / args.steps,
         "prove_time_s": step_ms * 1e-3, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s,

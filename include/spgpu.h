@@ -90,6 +90,14 @@ int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_
 /* Scalar::from_u512 / from_bytes_wide on n wide values (8 u64 each), :435-466 */
 int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec **out);
 
+/* Host-side scalar helpers (no device involved) for the glue around sharded proving:
+ * out[k] = sum_i in[i*width + k]  (Scalar::add) */
+int spg_fq_host_sum(const spg_fq *in, size_t count, size_t width, spg_fq *out);
+int spg_fq_host_mul(const spg_fq *a, const spg_fq *b, spg_fq *out);
+/* prod_k eq(tau[k], bit_k(index)), k < nbits: the eq weight of a shard index when the
+ * variable is bound low bit first */
+int spg_fq_host_eq_weight(const spg_fq *tau, size_t nbits, uint64_t index, spg_fq *out);
+
 /* ---------------------------------------------------------------- eq / dense MLE (a2, a3) */
 /* EqPolynomial::evals, src/dense_mlpoly.rs:76-92: out has 2^ell entries, MSB <-> r[0] */
 int spg_eq_evals(spg_ctx *ctx, const spg_fq *r, size_t ell, spg_vec **out);
@@ -147,6 +155,10 @@ int spg_sc1_create_from_tables(spg_ctx *ctx, size_t num_instances, const size_t 
                                const spg_fq *Az, const spg_fq *Bz, const spg_fq *Cz,
                                const spg_fq *tau_p, const spg_fq *tau_q, const spg_fq *tau_x,
                                spg_sc1 **out);
+/* Multiply every round evaluation and the eq claim by a constant. A shard of the proof
+ * axis (multi-GPU) carries the eq factor of the proof bits it does not hold; the tail
+ * rounds after a gather carry the eq products already bound on the shards. */
+int spg_sc1_set_scale(spg_sc1 *s, const spg_fq *c);
 size_t spg_sc1_num_rounds(const spg_sc1 *s);
 /* e = (eval_point_0, eval_point_2, eval_point_3) of the current round, :1166-1245 */
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]);
@@ -168,6 +180,17 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
                    size_t max_num_inputs, size_t num_witness_secs, const spg_fq *rx,
                    const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
                    const spg_fq *r_C, spg_sc2 **out);
+/* The same, from a Z table already bound to rq (natural [p][w][y], sum_p W*num_inputs[p]
+ * scalars). Used when the proof axis is sharded: every rank binds its shard with
+ * spg_zmat_bind_rq, the partial tables are summed (Scalar::add) and phase 2 runs once. */
+int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *zrq, size_t num_instances,
+                            const size_t *num_inputs, size_t max_num_inputs, size_t num_witness_secs,
+                            const spg_fq *rx, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
+                            const spg_fq *r_C, spg_sc2 **out);
+/* Z_poly.bound_poly_vars_rq (src/r1csproof.rs:478, src/custom_dense_mlpoly.rs:222-244, 300-304)
+ * on its own: out[p][w][y] = scale * sum_q eq_lsb(rq_rev, q) z[p][q][w][y]; scale may be NULL (= 1). */
+int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
+                     spg_vec *out);
 size_t spg_sc2_num_rounds(const spg_sc2 *s);
 int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]);
 int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r);

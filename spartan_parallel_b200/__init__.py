@@ -25,6 +25,10 @@ from .api import (  # noqa: F401
     dot,
     from_u512,
     hash_layer,
+    host_eq_weight,
+    host_mul,
+    host_sum,
     sumcheck_phase1,
     vec_op,
+    zmat_bind_rq,
 )

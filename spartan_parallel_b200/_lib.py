@@ -80,11 +80,17 @@ def _proto(L):
         "spg_zmat_build": [P, SZ, P, P, SZ, P, PP],
         "spg_sc1_create": [P, P, P, SZ, P, SZ, P, SZ, SZ, P, P, P, PP],
         "spg_sc1_create_from_tables": [P, SZ, P, SZ, P, SZ, P, P, P, P, P, P, PP],
+        "spg_sc1_set_scale": [P, P],
+        "spg_fq_host_sum": [P, SZ, SZ, P],
+        "spg_fq_host_mul": [P, P, P],
+        "spg_fq_host_eq_weight": [P, SZ, C.c_uint64, P],
         "spg_sc1_round_eval": [P, P],
         "spg_sc1_round_bind": [P, P],
         "spg_sc1_final": [P, P],
         "spg_sc1_debug_tables": [P, P, P, P, SZ, P],
         "spg_sc2_create": [P, P, P, SZ, P, SZ, P, SZ, SZ, P, P, P, P, P, P, PP],
+        "spg_sc2_create_from_zrq": [P, P, P, SZ, P, SZ, SZ, P, P, P, P, P, PP],
+        "spg_zmat_bind_rq": [P, P, P, SZ, P, P],
         "spg_sc2_round_eval": [P, P],
         "spg_sc2_round_bind": [P, P],
         "spg_sc2_final": [P, P],

@@ -18,6 +18,8 @@ from . import _lib
 from ._lib import SpgError, check
 
 MODE_P, MODE_Q, MODE_W, MODE_X = 1, 2, 3, 4
+# Scalar::one() = R mod q (src/scalar/ristretto255.rs:307-312)
+ONE = np.array([0xD6EC31748D98951D, 0xC6EF5BF4737DCF70, 0xFFFFFFFFFFFFFFFE, 0x0FFFFFFFFFFFFFFF], dtype=np.uint64)
 
 
 def _fq(a) -> np.ndarray:
@@ -218,6 +220,10 @@ class SumcheckPhase1:
     def num_rounds(self) -> int:
         return int(self.ctx.L.spg_sc1_num_rounds(self.h))
 
+    def set_scale(self, c):
+        """Multiply every evaluation and the eq claim by c (shards of the proof axis)."""
+        check(self.ctx.L.spg_sc1_set_scale(self.h, _ptr(_fq(c))), "spg_sc1_set_scale")
+
     def round_eval(self) -> np.ndarray:
         out = np.empty((3, 4), dtype=np.uint64)
         check(self.ctx.L.spg_sc1_round_eval(self.h, _ptr(out)), "spg_sc1_round_eval")
@@ -377,8 +383,57 @@ def sumcheck_phase1(ctx: Context, inst: R1CSInstance, z: ZMat, num_proofs, max_n
     return SumcheckPhase1(ctx, h)
 
 
+def host_sum(vals) -> np.ndarray:
+    """Scalar::add over axis 0 of a (count, width, 4) array, on the host side of the ABI."""
+    v = _fq(vals)
+    if v.ndim == 2:
+        v = v.reshape(v.shape[0], 1, 4)
+    out = np.empty((v.shape[1], 4), dtype=np.uint64)
+    check(_lib.lib().spg_fq_host_sum(_ptr(v), v.shape[0], v.shape[1], _ptr(out)), "spg_fq_host_sum")
+    return out
+
+
+def host_mul(a, b) -> np.ndarray:
+    out = np.empty(4, dtype=np.uint64)
+    check(_lib.lib().spg_fq_host_mul(_ptr(_fq(a)), _ptr(_fq(b)), _ptr(out)), "spg_fq_host_mul")
+    return out
+
+
+def host_eq_weight(tau, index: int) -> np.ndarray:
+    """prod_k eq(tau[k], bit_k(index)): eq weight of a shard index (low bit first)."""
+    t = _fq(np.asarray(tau, dtype=np.uint64).reshape(-1, 4))
+    out = np.empty(4, dtype=np.uint64)
+    check(_lib.lib().spg_fq_host_eq_weight(_ptr(t), t.shape[0], C.c_uint64(index), _ptr(out)), "spg_fq_host_eq_weight")
+    return out
+
+
+def zmat_bind_rq(ctx: Context, z: "ZMat", rq_rev, scale=None, out: DensePolynomial | None = None) -> DensePolynomial:
+    """Z_poly.bound_poly_vars_rq on its own (src/r1csproof.rs:478); natural [p][w][y] output."""
+    rq = _fq(np.asarray(rq_rev, dtype=np.uint64).reshape(-1, 4))
+    total = sum(len(z.witness_secs) * y for y in z.num_inputs)
+    if out is None:
+        out = DensePolynomial.empty(ctx, total)
+    sc = None if scale is None else _fq(scale)
+    check(ctx.L.spg_zmat_bind_rq(ctx.h, z.h, _ptr(rq), rq.shape[0], _ptr(sc), out.h), "spg_zmat_bind_rq")
+    return out
+
+
 class SumcheckPhase2:
     """Device loops of prove_cubic_disjoint_rounds (src/sumcheck.rs:788-1065)."""
+
+    @classmethod
+    def from_zrq(cls, ctx: Context, inst: R1CSInstance, zrq: DensePolynomial, num_inputs, max_num_inputs,
+                 num_witness_secs, rx, rp, r_A, r_B, r_C):
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        nin = _sz(num_inputs)
+        a = [_fq(np.asarray(t, dtype=np.uint64).reshape(-1, 4)) for t in (rx, rp)]
+        h = C.c_void_p()
+        check(ctx.L.spg_sc2_create_from_zrq(ctx.h, inst.h, zrq.h, len(nin), _ptr(nin), max_num_inputs, num_witness_secs,
+                                            _ptr(a[0]), _ptr(a[1]), _ptr(_fq(r_A)), _ptr(_fq(r_B)), _ptr(_fq(r_C)),
+                                            C.byref(h)), "spg_sc2_create_from_zrq")
+        self.h = h
+        return self
 
     def __init__(self, ctx: Context, inst: R1CSInstance, z: ZMat, num_proofs, max_num_proofs, num_inputs, max_num_inputs,
                  num_witness_secs, rx, rq_rev, rp, r_A, r_B, r_C):

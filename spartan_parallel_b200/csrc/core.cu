@@ -205,6 +205,33 @@ int spg_ctx_profile_end(spg_ctx *ctx, char *out, size_t cap) {
 }
 void *spg_ctx_stream(const spg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+int spg_fq_host_sum(const spg_fq *in, size_t count, size_t width, spg_fq *out) {
+  SPG_CHECK(in && out, "spg_fq_host_sum: null argument");
+  for (size_t k = 0; k < width; k++) {
+    hfq acc = hfq_zero();
+    for (size_t i = 0; i < count; i++) acc = hfq_add(acc, hfq_from(in[i * width + k]));
+    out[k] = hfq_to(acc);
+  }
+  return SPG_OK;
+}
+
+int spg_fq_host_mul(const spg_fq *a, const spg_fq *b, spg_fq *out) {
+  SPG_CHECK(a && b && out, "spg_fq_host_mul: null argument");
+  *out = hfq_to(hfq_mul(hfq_from(*a), hfq_from(*b)));
+  return SPG_OK;
+}
+
+int spg_fq_host_eq_weight(const spg_fq *tau, size_t nbits, uint64_t index, spg_fq *out) {
+  SPG_CHECK((tau || nbits == 0) && out, "spg_fq_host_eq_weight: null argument");
+  hfq acc = hfq_one(), one = hfq_one();
+  for (size_t k = 0; k < nbits; k++) {
+    hfq t = hfq_from(tau[k]);
+    acc = hfq_mul(acc, ((index >> k) & 1) ? t : hfq_sub(one, t));
+  }
+  *out = hfq_to(acc);
+  return SPG_OK;
+}
+
 int spg_host_alloc(size_t bytes, void **out) {
   SPG_CHECK(out, "null out");
   SPG_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));

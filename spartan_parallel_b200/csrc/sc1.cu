@@ -234,6 +234,7 @@ struct spg_sc1 {
   bool have_cached = false;  // raw device sums for the current round already in h_cached
   hfq cached[3];
   hfq cx, cq;    // prod eq(tau_k, r_k) over the bound x / q variables
+  hfq scale;     // external factor on every evaluation (spg_sc1_set_scale); one by default
   size_t p_len = 1;  // current instance_len during the p rounds
   bool fuse = true;
   bool p_ready = false;
@@ -345,6 +346,7 @@ int sc1_alloc_common(spg_ctx *ctx, size_t P, const size_t *num_proofs, size_t ma
   SPG_CUDA(cudaMalloc(&s->d_Qp, P * sizeof(unsigned int)));
   s->cx = hfq_one();
   s->cq = hfq_one();
+  s->scale = hfq_one();
   s->p_len = s->Pp;
   s->loglen.resize(P);
   for (size_t p = 0; p < P; p++) s->loglen[p] = s->nx ? log2u(s->X[p]) : log2u(s->Q[p]);
@@ -455,6 +457,12 @@ int spg_sc1_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
   return SPG_OK;
 }
 
+int spg_sc1_set_scale(spg_sc1 *s, const spg_fq *c) {
+  SPG_CHECK(s && c, "spg_sc1_set_scale: null argument");
+  s->scale = hfq_from(*c);
+  return SPG_OK;
+}
+
 size_t spg_sc1_num_rounds(const spg_sc1 *s) { return s ? s->nx + s->nq + s->np : 0; }
 
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
@@ -479,7 +487,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
                s->tab[s->cur][2], half, limit, ctx->d_result);
     spg_fq tmp[3];
     SPG_TRY(fetch_result(ctx, 3, tmp));
-    hfq c = hfq_mul(s->cx, s->cq);
+    hfq c = hfq_mul(hfq_mul(s->cx, s->cq), s->scale);
     for (int t = 0; t < 3; t++) e[t] = hfq_to(hfq_mul(c, hfq_from(tmp[t])));
     s->evaluated = true;
     return SPG_OK;
@@ -508,7 +516,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
   hfq line[3];
   const hfq &tau = phase == 0 ? s->tau_x[j] : s->tau_q[j];
   hfq_eq_line_023(tau, line);
-  hfq c = phase == 0 ? s->cx : hfq_mul(s->cx, s->cq);
+  hfq c = hfq_mul(phase == 0 ? s->cx : hfq_mul(s->cx, s->cq), s->scale);
   for (int t = 0; t < 3; t++) e[t] = hfq_to(hfq_mul(hfq_mul(c, line[t]), raw[t]));
   s->evaluated = true;
   return SPG_OK;
@@ -594,7 +602,7 @@ int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   hfq ap;
   memcpy(&ap, &h[0], sizeof ap);
-  claims[0] = hfq_to(hfq_mul(hfq_mul(ap, s->cq), s->cx));
+  claims[0] = hfq_to(hfq_mul(hfq_mul(hfq_mul(ap, s->cq), s->cx), s->scale));
   for (int k = 0; k < 3; k++) memcpy(&claims[1 + k], &h[1 + k], sizeof(spg_fq));
   return SPG_OK;
 }

@@ -168,6 +168,11 @@ __global__ void k2_p_bind(fq *__restrict__ A, fq *__restrict__ B, fq *__restrict
 }
 
 // replicate entry 0 into [1, n)
+__global__ void k_scale_vec(fq *__restrict__ v, size_t n, fq c) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    v[i] = fq_mul(v[i], c);
+}
+
 __global__ void k2_replicate(fq *__restrict__ v, size_t n) {
   fq x = v[0];
   for (size_t i = 1 + threadIdx.x; i < n; i += blockDim.x) v[i] = x;
@@ -261,17 +266,47 @@ int enter_p_phase(spg_sc2 *s) {
 
 }  // namespace
 
-extern "C" {
+// Z_rq[p][w][y] for every instance, written at dst + off[p]; scale multiplies the eq table
+static int z_bind_rq_all(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
+                         fq *dst, const std::vector<size_t> &off) {
+  fq *Sq = nullptr;
+  SPG_CUDA(cudaMalloc(&Sq, ((size_t)2 << nq) * sizeof(fq)));
+  std::vector<hfq> tq(nq);
+  for (size_t i = 0; i < nq; i++) tq[i] = hfq_from(rq_rev[i]);
+  int rc = build_suffix_tables(ctx, tq, nq, Sq);
+  fq *E = Sq + ((size_t)1 << nq);
+  if (rc == SPG_OK && scale) {
+    fq sc;
+    memcpy(&sc, scale, 32);
+    k_scale_vec<<<grid_for(ctx, (size_t)1 << nq, 128), 128, 0, ctx->stream>>>(E, (size_t)1 << nq, sc);
+    ctx->launches++;
+  }
+  for (size_t p = 0; rc == SPG_OK && p < z->P; p++) {
+    size_t WY = z->W * z->num_inputs[p];
+    if (z->num_proofs[p] > ((size_t)1 << nq)) {
+      set_error("z_bind_rq: instance %zu has %zu proofs but only %zu challenges", p, z->num_proofs[p], nq);
+      rc = SPG_EINVAL;
+      break;
+    }
+    ctx->next_units = 32.0 * (double)WY * (double)(z->num_proofs[p] + 1);
+    k_z_bind_rq<<<grid_for(ctx, WY, 128), 128, 0, ctx->stream>>>(z->d + z->off[p], E, z->num_proofs[p], WY, dst + off[p]);
+    ctx->launches++;
+  }
+  if (rc == SPG_OK && cudaGetLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "k_z_bind_rq", __FILE__, __LINE__);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(Sq);
+  return rc;
+}
 
-int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
-                   const size_t *num_proofs, size_t max_num_proofs, const size_t *num_inputs,
-                   size_t max_num_inputs, size_t num_witness_secs, const spg_fq *rx,
-                   const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
-                   const spg_fq *r_C, spg_sc2 **out) {
-  SPG_CHECK(ctx && inst && z && out && num_proofs && num_inputs && r_A && r_B && r_C,
-            "spg_sc2_create: null argument");
+static int sc2_build(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, const spg_vec *zrq,
+                     size_t num_instances, const size_t *num_proofs, size_t max_num_proofs,
+                     const size_t *num_inputs, size_t max_num_inputs, size_t num_witness_secs,
+                     const spg_fq *rx, const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A,
+                     const spg_fq *r_B, const spg_fq *r_C, spg_sc2 **out) {
+  SPG_CHECK(ctx && inst && (z || zrq) && out && num_inputs && r_A && r_B && r_C, "spg_sc2_create: null argument");
   size_t P = num_instances;
-  SPG_CHECK(P >= 1 && z->P == P && z->W == num_witness_secs, "spg_sc2_create: z_mat shape mismatch");
+  SPG_CHECK(P >= 1, "spg_sc2_create: need at least one instance");
+  if (z) SPG_CHECK(num_proofs && z->P == P && z->W == num_witness_secs, "spg_sc2_create: z_mat shape mismatch");
   SPG_CHECK(inst->num_instances == 1 || inst->num_instances == P,
             "spg_sc2_create: instance has %zu blocks, proving %zu", inst->num_instances, P);
   SPG_CHECK(is_pow2(max_num_proofs) && is_pow2(max_num_inputs), "spg_sc2_create: maxima must be powers of two");
@@ -281,8 +316,9 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
             next_pow2(num_witness_secs) * max_num_inputs, inst->num_vars);
   bool single = inst->num_instances == 1 && P > 1;
   for (size_t p = 0; p < P; p++) {
-    SPG_CHECK(z->num_proofs[p] == num_proofs[p] && z->num_inputs[p] == num_inputs[p],
-              "spg_sc2_create: z_mat shape mismatch at instance %zu", p);
+    if (z)
+      SPG_CHECK(z->num_proofs[p] == num_proofs[p] && z->num_inputs[p] == num_inputs[p],
+                "spg_sc2_create: z_mat shape mismatch at instance %zu", p);
     SPG_CHECK(is_pow2(num_inputs[p]) && num_inputs[p] <= max_num_inputs, "spg_sc2_create: bad num_inputs[%zu]", p);
     SPG_CHECK(!single || num_inputs[p] == num_inputs[0],
               "spg_sc2_create: a shared instance requires equal num_inputs (got %zu vs %zu)", num_inputs[p], num_inputs[0]);
@@ -301,7 +337,7 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
   s->Y.assign(num_inputs, num_inputs + P);
   s->p_len = s->Pp;
   size_t nq = log2u(max_num_proofs), nx = log2u(inst->max_num_cons);
-  SPG_CHECK((nx == 0 || rx) && (nq == 0 || rq_rev) && (s->np == 0 || rp), "spg_sc2_create: null challenge vector");
+  SPG_CHECK((nx == 0 || rx) && (nq == 0 || rq_rev || zrq) && (s->np == 0 || rp), "spg_sc2_create: null challenge vector");
   size_t total = 0;
   std::vector<size_t> off(P);
   for (size_t p = 0; p < P; p++) {
@@ -324,6 +360,7 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
   size_t X = inst->max_num_cons;
   fq *scr = nullptr;
   size_t XS = X > s->Pp ? X : s->Pp;  // eq expansion scratch
+  if (zrq) SPG_CHECK(zrq->n == total, "spg_sc2_create: Z_rq has %zu entries, expected %zu", zrq->n, total);
   size_t scr_n = X + XS + ((size_t)2 << nq) + s->Pp + nx + s->np + 8;
   if (cudaMalloc(&scr, scr_n * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 scratch", __FILE__, __LINE__));
   fq *evals_rx = scr, *eq_scratch = scr + X, *Sq = scr + X + XS, *d_r = Sq + ((size_t)2 << nq) + s->Pp;
@@ -344,18 +381,11 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
           if (cudaMemcpyAsync(s->tab[0][0] + off[p], s->tab[0][0], s->W * s->Y[0] * sizeof(fq), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "ABC replicate", __FILE__, __LINE__); break; }
       if (rc != SPG_OK) break;
     }
-    // Z bound to rq: LSB-first eq table of rq_rev (full level = nq)
-    {
-      std::vector<hfq> tq(nq);
-      for (size_t i = 0; i < nq; i++) tq[i] = hfq_from(rq_rev[i]);
-      if ((rc = build_suffix_tables(ctx, tq, nq, Sq)) != SPG_OK) break;
-      const fq *E = Sq + ((size_t)1 << nq);
-      for (size_t p = 0; p < P; p++) {
-        size_t WY = s->W * s->Y[p];
-        k_z_bind_rq<<<grid_for(ctx, WY, 128), 128, 0, ctx->stream>>>(z->d + z->off[p], E, num_proofs[p], WY, s->tab[0][1] + off[p]);
-        ctx->launches++;
-      }
-      if (cudaGetLastError() != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "k_z_bind_rq", __FILE__, __LINE__); break; }
+    // C = Z bound to rq (computed here, or handed in already summed over the proof shards)
+    if (zrq) {
+      if (cudaMemcpyAsync(s->tab[0][1], zrq->d, total * sizeof(fq), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "Z_rq copy", __FILE__, __LINE__); break; }
+    } else {
+      if ((rc = z_bind_rq_all(ctx, z, rq_rev, nq, nullptr, s->tab[0][1], off)) != SPG_OK) break;
     }
     // A = EqPolynomial::new(rp).evals()
     if (s->np && cudaMemcpyAsync(d_r, rp, s->np * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "rp upload", __FILE__, __LINE__); break; }
@@ -368,6 +398,40 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
   for (size_t p = 0; p < P; p++) s->loglen[p] = log2u(s->Y[p]);
   *out = s;
   return SPG_OK;
+}
+
+extern "C" {
+
+int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
+                   const size_t *num_proofs, size_t max_num_proofs, const size_t *num_inputs,
+                   size_t max_num_inputs, size_t num_witness_secs, const spg_fq *rx,
+                   const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
+                   const spg_fq *r_C, spg_sc2 **out) {
+  SPG_CHECK(z, "spg_sc2_create: null z_mat");
+  return sc2_build(ctx, inst, z, nullptr, num_instances, num_proofs, max_num_proofs, num_inputs, max_num_inputs,
+                   num_witness_secs, rx, rq_rev, rp, r_A, r_B, r_C, out);
+}
+
+int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *zrq, size_t num_instances,
+                            const size_t *num_inputs, size_t max_num_inputs, size_t num_witness_secs,
+                            const spg_fq *rx, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
+                            const spg_fq *r_C, spg_sc2 **out) {
+  SPG_CHECK(zrq, "spg_sc2_create_from_zrq: null Z_rq");
+  return sc2_build(ctx, inst, nullptr, zrq, num_instances, nullptr, 1, num_inputs, max_num_inputs, num_witness_secs,
+                   rx, nullptr, rp, r_A, r_B, r_C, out);
+}
+
+int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
+                     spg_vec *out) {
+  SPG_CHECK(ctx && z && out && (rq_rev || nq == 0), "spg_zmat_bind_rq: null argument");
+  std::vector<size_t> off(z->P);
+  size_t total = 0;
+  for (size_t p = 0; p < z->P; p++) {
+    off[p] = total;
+    total += z->W * z->num_inputs[p];
+  }
+  SPG_CHECK(out->n == total, "spg_zmat_bind_rq: output has %zu entries, expected %zu", out->n, total);
+  return z_bind_rq_all(ctx, z, rq_rev, nq, scale, out->d, off);
 }
 
 size_t spg_sc2_num_rounds(const spg_sc2 *s) { return s ? s->ny + s->nw + s->np : 0; }

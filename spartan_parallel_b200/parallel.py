@@ -1,0 +1,157 @@
+"""Sharding of the proof axis across GPUs (one process per GPU, torch.distributed).
+
+The protocol-level data parallelism of spartan-parallel is the proof index q: tables are
+independent per proof up to the per-round sum. A rank owns the contiguous block of
+proofs q = rank * Q_local + q_local, i.e. the HIGH bits of q are the rank. Because the
+sumcheck binds q low bit first (the reference stores q bit-reversed and binds the top,
+src/custom_dense_mlpoly.rs:83-99, 222-244), the x rounds and the first log2(Q_local) q
+rounds never pair scalars of different ranks: each rank runs the unchanged single-GPU
+kernels on its shard, scaled by the eq weight of its rank bits, and the only exchange
+per round is 3 scalars per rank (all-gather, then Scalar::add on the host -- NCCL has
+no modular reduction). After the local rounds every table is one scalar per rank; those
+are gathered and the last log2(G) rounds run on a G-entry table.
+
+Phase 2 needs Z bound to rq: sum over all proofs -> every rank binds its shard
+(spg_zmat_bind_rq with its rank weight), the partial (W * Y)-scalar tables are
+all-gathered once and added, and phase 2 (independent of Q) runs replicated.
+
+The per-rank engine is injected so that the CPU tests can drive the same logic with the
+oracle standing in for the device (tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def log2(n: int) -> int:
+    return n.bit_length() - 1
+
+
+class TorchComm:
+    """all_gather of small uint64 arrays over torch.distributed (nccl or gloo)."""
+
+    def __init__(self, device=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.rank = dist.get_rank()
+        self.world = dist.get_world_size()
+        self.device = device
+
+    def all_gather(self, arr: np.ndarray) -> np.ndarray:
+        import torch
+
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int64).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        outs = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(outs, t)
+        return np.stack([o.cpu().numpy().view(np.uint64).reshape(arr.shape) for o in outs])
+
+    def all_gather_device(self, tensor):
+        import torch
+
+        outs = [torch.empty_like(tensor) for _ in range(self.world)]
+        self.dist.all_gather(outs, tensor)
+        return outs
+
+
+class LocalComm:
+    """Single-process stand-in (world = 1)."""
+
+    rank, world = 0, 1
+
+    def all_gather(self, arr):
+        return np.stack([arr])
+
+
+class ShardedPhase1:
+    """Phase-1 sumcheck of one instance whose Q = Q_local * world proofs are sharded.
+
+    ``make_engine(tau_q_local)`` returns the rank-local prover (an object with
+    round_eval / round_bind / final / set_scale: ``api.SumcheckPhase1`` on a GPU);
+    ``make_tail(Az, Bz, Cz, tau_q_high)`` builds the prover for the gathered G-entry
+    tables."""
+
+    def __init__(self, comm, Q_local: int, X: int, tau_q, tau_x, make_engine, make_tail):
+        self.comm = comm
+        G = comm.world
+        assert G & (G - 1) == 0, "world size must be a power of two"
+        self.nx, self.nql, self.ng = log2(X), log2(Q_local), log2(G)
+        tau_q = np.asarray(tau_q, dtype=np.uint64).reshape(-1, 4)
+        assert tau_q.shape[0] == self.nql + self.ng
+        self.tau_q_high = tau_q[self.nql:]
+        self.engine = make_engine(tau_q[: self.nql])
+        self.engine.set_scale(api.host_eq_weight(self.tau_q_high, comm.rank))
+        self.make_tail = make_tail
+        self.tail = None
+        self.round = 0
+        self.num_rounds = self.nx + self.nql + self.ng
+
+    def round_eval(self) -> np.ndarray:
+        if self.round < self.nx + self.nql:
+            part = self.engine.round_eval()
+            return api.host_sum(self.comm.all_gather(part))
+        return self._tail().round_eval()
+
+    def round_bind(self, r):
+        if self.round < self.nx + self.nql:
+            self.engine.round_bind(r)
+        else:
+            self._tail().round_bind(r)
+        self.round += 1
+
+    def _tail(self):
+        if self.tail is None:
+            # one scalar per table per rank; the bound eq products are identical on all ranks
+            self.engine.set_scale(api.ONE)
+            claims = self.engine.final()
+            allc = self.comm.all_gather(claims)  # (G, 4, 4)
+            self.tail = self.make_tail(allc[:, 1].copy(), allc[:, 2].copy(), allc[:, 3].copy(), self.tau_q_high)
+            self.tail.set_scale(claims[0])
+        return self.tail
+
+    def final(self) -> np.ndarray:
+        return self._tail().final()
+
+
+def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x) -> ShardedPhase1:
+    """ShardedPhase1 on this rank's GPU."""
+    empty = np.zeros((0, 4), dtype=np.uint64)
+
+    def make_engine(tau_q_local):
+        return api.sumcheck_phase1(ctx, inst, z, [Q_local], Q_local, [X], X, max_num_inputs, empty, tau_q_local, tau_x)
+
+    def make_tail(Az, Bz, Cz, tau_high):
+        G = Az.shape[0]
+        return api.SumcheckPhase1.from_tables(ctx, [G], G, [1], 1, Az, Bz, Cz, empty, tau_high, empty)
+
+    return ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)
+
+
+def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local):
+    """Z bound to rq over all shards: local bind scaled by the rank's eq weight, one
+    all-gather of the partial tables (device tensors over NCCL), modular sum on the device."""
+    import torch
+
+    rq_rev = np.asarray(rq_rev, dtype=np.uint64).reshape(-1, 4)
+    nql = log2(Q_local)
+    total = sum(len(z.witness_secs) * y for y in z.num_inputs)
+    dev = torch.device("cuda", ctx.device)
+    mine = torch.empty((total, 4), dtype=torch.int64, device=dev)
+    out = api.DensePolynomial.wrap(ctx, mine.data_ptr(), total, owner=mine)
+    api.zmat_bind_rq(ctx, z, rq_rev[:nql], api.host_eq_weight(rq_rev[nql:], comm.rank), out)
+    ctx.sync()
+    if comm.world == 1:
+        return out
+    parts = comm.all_gather_device(mine)
+    torch.cuda.synchronize()
+    acc = api.DensePolynomial.wrap(ctx, parts[0].data_ptr(), total, owner=parts[0])
+    for t in parts[1:]:
+        nxt = api.DensePolynomial.wrap(ctx, t.data_ptr(), total, owner=t)
+        acc2 = api.vec_op(ctx, "add", acc, nxt)
+        acc = acc2
+    ctx.sync()
+    return acc
