@@ -103,6 +103,16 @@ namespace spg {
   } while (0)
 
 void prof_begin(spg_ctx *ctx, const char *name, cudaEvent_t *a, cudaEvent_t *b);
+
+// stream-ordered allocation from the device's default pool (kept warm: the release
+// threshold is raised in spg_ctx_create), so per-proof tables cost no cudaMalloc/cudaFree
+template <typename T>
+static inline cudaError_t dev_alloc(spg_ctx *ctx, T **p, size_t bytes) {
+  return cudaMallocAsync((void **)p, bytes ? bytes : 32, ctx->stream);
+}
+static inline void dev_free(spg_ctx *ctx, void *p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
 int ensure_partials(spg_ctx *ctx, size_t n_fq);
 int vec_new(spg_ctx *ctx, size_t n, spg_vec **out);
 

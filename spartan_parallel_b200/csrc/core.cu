@@ -49,10 +49,10 @@ int vec_new(spg_ctx *ctx, size_t n, spg_vec **out) {
   if (!v) return SPG_ENOMEM;
   v->ctx = ctx;
   v->n = v->cap = n;
-  cudaError_t e = cudaMalloc(&v->d, (n ? n : 1) * sizeof(fq));
+  cudaError_t e = dev_alloc(ctx, &v->d, n * sizeof(fq));
   if (e != cudaSuccess) {
     delete v;
-    return cuda_fail(e, "cudaMalloc(vec)", __FILE__, __LINE__);
+    return cuda_fail(e, "cudaMallocAsync(vec)", __FILE__, __LINE__);
   }
   *out = v;
   return SPG_OK;
@@ -118,6 +118,12 @@ int spg_ctx_create(int device, spg_ctx **out) {
   SPG_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   SPG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    SPG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    SPG_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   SPG_CUDA(cudaHostAlloc(&ctx->h_result, 64 * sizeof(fq), cudaHostAllocMapped));
   SPG_CUDA(cudaHostGetDevicePointer(&ctx->d_result, ctx->h_result, 0));
   SPG_CUDA(cudaMalloc(&ctx->d_scalars, 64 * sizeof(fq)));
@@ -291,7 +297,7 @@ void *spg_vec_device_ptr(const spg_vec *v) { return v ? (void *)v->d : nullptr; 
 
 void spg_vec_free(spg_vec *v) {
   if (!v) return;
-  if (v->owned && v->d) cudaFree(v->d);
+  if (v->owned && v->d) dev_free(v->ctx, v->d);
   delete v;
 }
 

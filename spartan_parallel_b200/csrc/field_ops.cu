@@ -290,10 +290,9 @@ int spg_dense_bound_bot(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
   fq rr;
   memcpy(&rr, r, sizeof rr);
   fq *tmp = nullptr;
-  SPG_CUDA(cudaMalloc(&tmp, n * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &tmp, n * sizeof(fq)));
   SPG_LAUNCH(ctx, k_bound_bot, grid_for(ctx, n, 256), 256, 0, v->d, tmp, n, rr);
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  SPG_CUDA(cudaFree(v->d));
+  dev_free(ctx, v->d);
   v->d = tmp;
   v->n = v->cap = n;
   return SPG_OK;

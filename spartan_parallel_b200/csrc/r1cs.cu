@@ -326,7 +326,7 @@ int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_pro
     tot += num_proofs[p] * num_inputs[p];
   }
   w->total = tot;
-  cudaError_t e = cudaMalloc(&w->d, tot * sizeof(fq));
+  cudaError_t e = dev_alloc(ctx, &w->d, tot * sizeof(fq));
   if (e == cudaSuccess) e = cudaMemcpyAsync(w->d, host_w_mat, tot * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
@@ -342,7 +342,7 @@ void spg_witness_destroy(spg_witness *w) {
   if (!w) return;
   for (spg_vec *v : w->views)
     if (v) spg_vec_free(v);
-  if (w->d) cudaFree(w->d);
+  if (w->d) dev_free(w->ctx, w->d);
   delete w;
 }
 
@@ -388,7 +388,7 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
     tot += num_proofs[p] * num_witness_secs * num_inputs[p];
   }
   z->total = tot;
-  cudaError_t e = cudaMalloc(&z->d, (tot ? tot : 1) * sizeof(fq));
+  cudaError_t e = dev_alloc(ctx, &z->d, tot * sizeof(fq));
   if (e != cudaSuccess) {
     delete z;
     return cuda_fail(e, "cudaMalloc(z_mat)", __FILE__, __LINE__);
@@ -417,7 +417,7 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
 
 void spg_zmat_destroy(spg_zmat *z) {
   if (!z) return;
-  if (z->d) cudaFree(z->d);
+  if (z->d) dev_free(z->ctx, z->d);
   delete z;
 }
 

@@ -336,14 +336,14 @@ int sc1_alloc_common(spg_ctx *ctx, size_t P, const size_t *num_proofs, size_t ma
   s->cap[0] = N > s->Pp ? N : s->Pp;
   s->cap[1] = N1 > s->Pp ? N1 : s->Pp;
   for (int b = 0; b < 2; b++)
-    for (int k = 0; k < 3; k++) SPG_CUDA(cudaMalloc(&s->tab[b][k], s->cap[b] * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&s->Sx, ((size_t)2 << s->nx) * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&s->Sq, ((size_t)2 << s->nq) * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&s->Ap, s->Pp * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&s->RWx, rows * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&s->d_segs, P * sizeof(Seg)));
-  SPG_CUDA(cudaMalloc(&s->d_rw_off, P * sizeof(unsigned long long)));
-  SPG_CUDA(cudaMalloc(&s->d_Qp, P * sizeof(unsigned int)));
+    for (int k = 0; k < 3; k++) SPG_CUDA(dev_alloc(ctx, &s->tab[b][k], s->cap[b] * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &s->Sx, ((size_t)2 << s->nx) * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &s->Sq, ((size_t)2 << s->nq) * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &s->Ap, s->Pp * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &s->RWx, rows * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &s->d_segs, P * sizeof(Seg)));
+  SPG_CUDA(dev_alloc(ctx, &s->d_rw_off, P * sizeof(unsigned long long)));
+  SPG_CUDA(dev_alloc(ctx, &s->d_Qp, P * sizeof(unsigned int)));
   s->cx = hfq_one();
   s->cq = hfq_one();
   s->scale = hfq_one();
@@ -362,13 +362,13 @@ int sc1_build_weights(spg_sc1 *s) {
     fq *d_r = nullptr, *scratch = nullptr;
     std::vector<spg_fq> hr(s->np ? s->np : 1);
     for (size_t i = 0; i < s->np; i++) hr[i] = hfq_to(s->tau_p[i]);
-    SPG_CUDA(cudaMalloc(&d_r, hr.size() * sizeof(fq)));
-    SPG_CUDA(cudaMalloc(&scratch, s->Pp * sizeof(fq)));
+    SPG_CUDA(dev_alloc(ctx, &d_r, hr.size() * sizeof(fq)));
+    SPG_CUDA(dev_alloc(ctx, &scratch, s->Pp * sizeof(fq)));
     SPG_CUDA(cudaMemcpyAsync(d_r, hr.data(), s->np * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
     int rc = eq_evals_device(ctx, d_r, hr.data(), s->np, s->Ap, scratch);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_r);
-    cudaFree(scratch);
+    cudaStreamSynchronize(ctx->stream);  // hr (host) is read by the upload above
+    dev_free(ctx, d_r);
+    dev_free(ctx, scratch);
     SPG_TRY(rc);
   }
   SPG_TRY(build_suffix_tables(ctx, s->tau_x, s->nx, s->Sx));
@@ -627,17 +627,15 @@ int spg_sc1_debug_tables(spg_sc1 *s, spg_fq *Az, spg_fq *Bz, spg_fq *Cz, size_t 
 
 void spg_sc1_destroy(spg_sc1 *s) {
   if (!s) return;
-  cudaStreamSynchronize(s->ctx->stream);
   for (int b = 0; b < 2; b++)
-    for (int k = 0; k < 3; k++)
-      if (s->tab[b][k]) cudaFree(s->tab[b][k]);
-  if (s->Sx) cudaFree(s->Sx);
-  if (s->Sq) cudaFree(s->Sq);
-  if (s->Ap) cudaFree(s->Ap);
-  if (s->RWx) cudaFree(s->RWx);
-  if (s->d_segs) cudaFree(s->d_segs);
-  if (s->d_rw_off) cudaFree(s->d_rw_off);
-  if (s->d_Qp) cudaFree(s->d_Qp);
+    for (int k = 0; k < 3; k++) dev_free(s->ctx, s->tab[b][k]);
+  dev_free(s->ctx, s->Sx);
+  dev_free(s->ctx, s->Sq);
+  dev_free(s->ctx, s->Ap);
+  dev_free(s->ctx, s->RWx);
+  dev_free(s->ctx, s->d_segs);
+  dev_free(s->ctx, s->d_rw_off);
+  dev_free(s->ctx, s->d_Qp);
   delete s;
 }
 

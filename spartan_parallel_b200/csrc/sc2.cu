@@ -270,7 +270,7 @@ int enter_p_phase(spg_sc2 *s) {
 static int z_bind_rq_all(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
                          fq *dst, const std::vector<size_t> &off) {
   fq *Sq = nullptr;
-  SPG_CUDA(cudaMalloc(&Sq, ((size_t)2 << nq) * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &Sq, ((size_t)2 << nq) * sizeof(fq)));
   std::vector<hfq> tq(nq);
   for (size_t i = 0; i < nq; i++) tq[i] = hfq_from(rq_rev[i]);
   int rc = build_suffix_tables(ctx, tq, nq, Sq);
@@ -293,8 +293,7 @@ static int z_bind_rq_all(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, 
     ctx->launches++;
   }
   if (rc == SPG_OK && cudaGetLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "k_z_bind_rq", __FILE__, __LINE__);
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(Sq);
+  dev_free(ctx, Sq);
   return rc;
 }
 
@@ -352,8 +351,8 @@ static int sc2_build(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, cons
   };
   for (int b = 0; b < 2; b++)
     for (int k = 0; k < 2; k++)
-      if (cudaMalloc(&s->tab[b][k], s->cap * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 tables", __FILE__, __LINE__));
-  if (cudaMalloc(&s->A, s->Pp * sizeof(fq)) != cudaSuccess || cudaMalloc(&s->d_segs, P * sizeof(Seg)) != cudaSuccess)
+      if (dev_alloc(ctx, &s->tab[b][k], s->cap * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 tables", __FILE__, __LINE__));
+  if (dev_alloc(ctx, &s->A, s->Pp * sizeof(fq)) != cudaSuccess || dev_alloc(ctx, &s->d_segs, P * sizeof(Seg)) != cudaSuccess)
     return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 aux", __FILE__, __LINE__));
 
   // scratch: eq(rx) table, suffix tables of rq_rev, challenge staging
@@ -362,7 +361,7 @@ static int sc2_build(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, cons
   size_t XS = X > s->Pp ? X : s->Pp;  // eq expansion scratch
   if (zrq) SPG_CHECK(zrq->n == total, "spg_sc2_create: Z_rq has %zu entries, expected %zu", zrq->n, total);
   size_t scr_n = X + XS + ((size_t)2 << nq) + s->Pp + nx + s->np + 8;
-  if (cudaMalloc(&scr, scr_n * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 scratch", __FILE__, __LINE__));
+  if (dev_alloc(ctx, &scr, scr_n * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 scratch", __FILE__, __LINE__));
   fq *evals_rx = scr, *eq_scratch = scr + X, *Sq = scr + X + XS, *d_r = Sq + ((size_t)2 << nq) + s->Pp;
   do {
     // evals_rx = EqPolynomial::new(rx).evals()  (src/r1csproof.rs:433)
@@ -392,7 +391,7 @@ static int sc2_build(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, cons
     if ((rc = eq_evals_device(ctx, d_r, rp, s->np, s->A, eq_scratch)) != SPG_OK) break;
   } while (0);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(scr);
+  dev_free(ctx, scr);
   if (rc != SPG_OK) return fail(rc);
   s->loglen.resize(P);
   for (size_t p = 0; p < P; p++) s->loglen[p] = log2u(s->Y[p]);
@@ -537,12 +536,10 @@ int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]) {
 
 void spg_sc2_destroy(spg_sc2 *s) {
   if (!s) return;
-  cudaStreamSynchronize(s->ctx->stream);
   for (int b = 0; b < 2; b++)
-    for (int k = 0; k < 2; k++)
-      if (s->tab[b][k]) cudaFree(s->tab[b][k]);
-  if (s->A) cudaFree(s->A);
-  if (s->d_segs) cudaFree(s->d_segs);
+    for (int k = 0; k < 2; k++) dev_free(s->ctx, s->tab[b][k]);
+  dev_free(s->ctx, s->A);
+  dev_free(s->ctx, s->d_segs);
   delete s;
 }
 

@@ -20,6 +20,8 @@ oracle standing in for the device (tests/test_sharding_gloo.py).
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import api
@@ -56,6 +58,66 @@ class TorchComm:
         outs = [torch.empty_like(tensor) for _ in range(self.world)]
         self.dist.all_gather(outs, tensor)
         return outs
+
+
+class ShmComm(TorchComm):
+    """Per-round exchange through a POSIX shared-memory mailbox.
+
+    The 3 round evaluations land in pinned HOST memory on every rank (the host needs them
+    for the transcript), and all ranks of one box share that host: exchanging 96 bytes per
+    rank through shared memory costs a few microseconds, against ~100 us for staging them
+    back to the device for an NCCL all-gather. Bulk device tables still go over NCCL
+    (all_gather_device). Slots are double-buffered by call parity: a rank can run at most
+    one call ahead of the slowest reader."""
+
+    SLOT = 4096
+
+    def __init__(self, device=None):
+        super().__init__(device)
+        from multiprocessing import shared_memory
+
+        self.calls = 0
+        name = f"spg_mbox_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        size = 2 * self.world * (self.SLOT + 64)
+        if self.rank == 0:
+            try:
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=size)
+            self.shm.buf[:size] = bytes(size)
+        self.dist.barrier()
+        if self.rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.dist.barrier()
+        words = np.ndarray((2, self.world, (self.SLOT + 64) // 8), dtype=np.uint64, buffer=self.shm.buf)
+        self.seq = words[:, :, 0]
+        self.data = words[:, :, 8:]
+
+    def all_gather(self, arr: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1)
+        assert a.size * 8 <= self.SLOT
+        self.calls += 1
+        b = self.calls & 1
+        self.data[b, self.rank, : a.size] = a
+        self.seq[b, self.rank] = self.calls
+        out = np.empty((self.world,) + arr.shape, dtype=np.uint64)
+        for r in range(self.world):
+            while self.seq[b, r] != self.calls:
+                pass
+            out[r] = self.data[b, r, : a.size].reshape(arr.shape)
+        return out
+
+    def close(self):
+        try:
+            self.dist.barrier()
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
 
 
 class LocalComm:

@@ -51,7 +51,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, Q_local, X):
+def _worker(rank, world, port, Q_local, X, use_shm=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -73,7 +73,7 @@ def _worker(rank, world, port, Q_local, X):
         want_final = full.final()
         # sharded: this rank owns proofs [rank * Q_local, (rank + 1) * Q_local)
         lo, hi = rank * Q_local * X, (rank + 1) * Q_local * X
-        comm = parallel.TorchComm()
+        comm = parallel.ShmComm() if use_shm else parallel.TorchComm()
 
         def make_engine(tau_q_local):
             return OracleEngine(mk_sc1(nx, log2(Q_local), Q_local, X, Az[lo:hi], Bz[lo:hi], Cz[lo:hi], tau_q_local, tau_x))
@@ -108,6 +108,8 @@ def _worker(rank, world, port, Q_local, X):
             part = O.vec_add(part, O.vec_mul(np.tile(O.mul(El[ql], wgt), (WY, 1)), Zfull[rank * Q_local + ql]))
         allp = comm.all_gather(part)
         assert np.array_equal(sp.host_sum(allp), wantZ)
+        if use_shm:
+            comm.close()
     finally:
         dist.destroy_process_group()
 
@@ -115,3 +117,7 @@ def _worker(rank, world, port, Q_local, X):
 @pytest.mark.parametrize("world,Q_local,X", [(2, 4, 8), (4, 2, 4), (2, 1, 16)])
 def test_sharded_phase1_matches_unsharded(world, Q_local, X):
     mp.spawn(_worker, args=(world, _free_port(), Q_local, X), nprocs=world, join=True)
+
+
+def test_shared_memory_mailbox():
+    mp.spawn(_worker, args=(2, _free_port(), 2, 8, True), nprocs=2, join=True)
