@@ -8,7 +8,14 @@ OBJ := $(patsubst $(PKG)/csrc/%.cu,build/%.o,$(SRC))
 HDR := $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.h) include/spgpu.h
 LIB := $(PKG)/libspgpu.so
 
-all: $(LIB)
+HOSTLIB := $(PKG)/libspghost.so
+HOSTSRC := $(wildcard $(PKG)/host/*.cpp) $(wildcard $(PKG)/host/*.hpp)
+
+all: $(LIB) $(HOSTLIB)
+
+# C++ mirror of the reference's transcript-side host code, above the C ABI
+$(HOSTLIB): $(HOSTSRC) $(PKG)/csrc/ed25519.cuh $(PKG)/csrc/host_fq.h include/spgpu.h $(LIB)
+	g++ -O2 -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o $@ $(PKG)/host/capi.cpp -L$(PKG) -lspgpu -Wl,-rpath,'$$ORIGIN'
 
 build/%.o: $(PKG)/csrc/%.cu $(HDR)
 	@mkdir -p build
@@ -27,6 +34,6 @@ build/imad_peak: tools/imad_peak.cu $(PKG)/csrc/fq.cuh
 	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ $<
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(HOSTLIB)
 
 .PHONY: all clean oracle tools

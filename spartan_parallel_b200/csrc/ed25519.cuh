@@ -337,3 +337,39 @@ __host__ __device__ inline bool ristretto_decompress(const uint8_t in[32], ge *o
 }
 
 }  // namespace spg
+
+namespace spg {
+
+// RFC 9496 4.3.4 MAP (one half of the element derivation / dalek's elligator_ristretto_flavor)
+__host__ __device__ inline ge ristretto_map(const fe &t) {
+  fe one = fe_one();
+  fe r = fe_mul(fe_sqrt_m1(), fe_sq(t));
+  fe u = fe_mul(fe_add(r, one), fe_one_minus_d_sq());
+  fe v = fe_mul(fe_sub(fe_neg(one), fe_mul(r, fe_d())), fe_add(r, fe_d()));
+  fe s;
+  bool was_square = fe_sqrt_ratio_m1(u, v, &s);
+  fe s_prime = fe_neg(fe_abs(fe_mul(s, t)));
+  if (!was_square) s = s_prime;
+  fe c = was_square ? fe_neg(one) : r;
+  fe N = fe_sub(fe_mul(fe_mul(c, fe_sub(r, one)), fe_d_minus_one_sq()), v);
+  fe ss = fe_sq(s);
+  fe w0 = fe_mul(fe_add(s, s), v);
+  fe w1 = fe_mul(N, fe_sqrt_ad_minus_one());
+  fe w2 = fe_sub(one, ss);
+  fe w3 = fe_add(one, ss);
+  ge p;
+  p.X = fe_mul(w0, w3);
+  p.Y = fe_mul(w2, w1);
+  p.Z = fe_mul(w1, w3);
+  p.T = fe_mul(w0, w2);
+  return p;
+}
+
+// RistrettoPoint::from_uniform_bytes (used by MultiCommitGens::new, src/commitments.rs:23-27)
+__host__ __device__ inline ge ristretto_from_uniform_bytes(const uint8_t b[64]) {
+  ge p1 = ristretto_map(fe_frombytes(b));       // fe_frombytes masks bit 255
+  ge p2 = ristretto_map(fe_frombytes(b + 32));
+  return ge_add(p1, ge_to_cached(p2));
+}
+
+}  // namespace spg

@@ -1,0 +1,88 @@
+"""ctypes binding of libspghost.so: the C++ mirror of the reference's transcript-side host
+code (merlin transcript, RandomTape, sigma protocols, UniPoly, ZK sumcheck glue, opening
+proofs, bincode layout). In production this layer is the unmodified Rust crate; see
+INTEGRATION.md. It drives the device exclusively through the C ABI of libspgpu.so."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._lib import SpgError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_LIB_PATH = os.path.join(_HERE, "libspghost.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(HOST_LIB_PATH):
+            raise SpgError(f"{HOST_LIB_PATH} is missing: build it with `make`")
+        from . import _lib as dev
+
+        dev.lib()  # libspgpu.so first (libspghost links against it)
+        L = C.CDLL(HOST_LIB_PATH)
+        L.sph_last_error.restype = C.c_char_p
+        L.sph_free.argtypes = [C.c_void_p]
+        L.sph_free.restype = None
+        L.sph_gens_derive.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p]
+        L.sph_transcript_kat.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p]
+        L.sph_r1cs_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                     C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise SpgError(f"{what}: {lib().sph_last_error().decode('utf-8', 'replace')}")
+
+
+def gens_derive(label: bytes, n: int) -> bytes:
+    """MultiCommitGens::new(n, label) (src/commitments.rs:15-33) as n + 1 compressed points."""
+    out = np.empty(32 * (n + 1), dtype=np.uint8)
+    _check(lib().sph_gens_derive(label, n, out.ctypes.data_as(C.c_void_p)), "sph_gens_derive")
+    return out.tobytes()
+
+
+def transcript_kat(label: bytes, l: bytes, m: bytes, c: bytes, n: int) -> bytes:
+    out = np.empty(n, dtype=np.uint8)
+    lib().sph_transcript_kat(label, l, m, c, n, out.ctypes.data_as(C.c_void_p))
+    return out.tobytes()
+
+
+def _sz(v):
+    return np.ascontiguousarray(np.asarray(v, dtype=np.uint64).reshape(-1))
+
+
+def r1cs_prove(ctx, inst, witness_secs, num_proofs, max_num_proofs, num_inputs, max_num_inputs, transcript_label: bytes,
+               gens_label: bytes, tape_seed, gens_num_vars: int):
+    """R1CSProof::prove (src/r1csproof.rs:210-685) with a caller-seeded RandomTape.
+    Returns (proof bytes in bincode layout, [rp, rq_rev, rx, rw ++ ry])."""
+    P = len(num_proofs)
+    secs = (C.c_void_p * len(witness_secs))(*[w.h for w in witness_secs])
+    sec_ni = _sz([len(w.num_proofs) for w in witness_secs])
+    sec_np = _sz([q for w in witness_secs for q in w.num_proofs])
+    sec_nin = _sz([y for w in witness_secs for y in w.num_inputs])
+    seed = np.ascontiguousarray(tape_seed, dtype=np.uint64)
+    out_bytes, out_len = C.c_void_p(), C.c_size_t()
+    ch = np.zeros((256, 4), dtype=np.uint64)
+    counts = np.zeros(4, dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    npf, nin, inc = _sz(num_proofs), _sz(num_inputs), _sz(inst.num_cons)
+    _check(lib().sph_r1cs_prove(ctx.h, transcript_label, gens_label, p(seed), P, max_num_proofs, p(npf), max_num_inputs, p(nin),
+                                len(witness_secs), secs, p(sec_ni), p(sec_np), p(sec_nin), inst.h, inst.num_instances,
+                                inst.max_num_cons, p(inc), gens_num_vars, C.byref(out_bytes), C.byref(out_len), p(ch), p(counts)),
+           "sph_r1cs_prove")
+    proof = C.string_at(out_bytes, out_len.value)
+    lib().sph_free(out_bytes)
+    outs, pos = [], 0
+    for c in counts:
+        outs.append(ch[pos:pos + int(c)].copy())
+        pos += int(c)
+    return proof, outs

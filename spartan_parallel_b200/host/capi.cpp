@@ -1,0 +1,84 @@
+// C entry points of libspghost.so: the C++ host mirror of the reference's transcript-side
+// prover (what stays in Rust in production), driving libspgpu.so through its C ABI.
+#include <cstdlib>
+
+#include "protocol.hpp"
+
+using namespace sph;
+
+static thread_local std::string g_err;
+
+extern "C" {
+
+const char *sph_last_error(void) { return g_err.c_str(); }
+
+void sph_free(void *p) { free(p); }
+
+// MultiCommitGens::new(n, label).compressed(): n + 1 points (G[0..n], h), 32 bytes each
+int sph_gens_derive(const char *label, size_t n, uint8_t *out) {
+  try {
+    MultiCommitGens g(n, label);
+    std::vector<uint8_t> c = g.compressed();
+    memcpy(out, c.data(), c.size());
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// merlin check vector helper: Transcript::new(label); append_message(l, m); challenge_bytes(c, n)
+int sph_transcript_kat(const char *label, const char *l, const char *m, const char *c, size_t n, uint8_t *out) {
+  Transcript t(label);
+  t.append_message(l, m);
+  t.challenge_bytes(c, out, n);
+  return 0;
+}
+
+// R1CSProof::prove (src/r1csproof.rs:210-685). The caller owns the device handles.
+//   sec_*: per witness section: number of instances, then num_proofs / num_inputs per instance (flattened)
+//   out_bytes / out_len: bincode layout of the proof (malloc'ed; free with sph_free)
+//   out_challenges: rp | rq_rev | rx | rw ++ ry as Montgomery scalars; out_counts[4] their lengths
+int sph_r1cs_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_label, const uint64_t tape_seed[4],
+                   size_t num_instances, size_t max_num_proofs, const size_t *num_proofs, size_t max_num_inputs,
+                   const size_t *num_inputs, size_t num_witness_secs, spg_witness *const *secs,
+                   const size_t *sec_num_instances, const size_t *sec_num_proofs, const size_t *sec_num_inputs,
+                   const spg_r1cs *inst, size_t inst_num_instances, size_t inst_max_num_cons, const size_t *inst_num_cons,
+                   size_t gens_num_vars, uint8_t **out_bytes, size_t *out_len, spg_fq *out_challenges, size_t out_counts[4]) {
+  try {
+    std::vector<WitnessSec> ws;
+    size_t k = 0;
+    for (size_t i = 0; i < num_witness_secs; i++) {
+      WitnessSec w;
+      w.dev = secs[i];
+      for (size_t p = 0; p < sec_num_instances[i]; p++, k++) {
+        w.num_proofs.push_back(sec_num_proofs[k]);
+        w.num_inputs.push_back(sec_num_inputs[k]);
+      }
+      ws.push_back(w);
+    }
+    R1CSGens gens(gens_label, gens_num_vars);  // sized for the largest committed polynomial
+    ProofTranscript t(transcript_label);
+    hfq seed{{tape_seed[0], tape_seed[1], tape_seed[2], tape_seed[3]}};
+    RandomTape tape("proof", Scalar(seed));
+    R1CSProofOut o = r1cs_prove(ctx, num_instances, max_num_proofs, std::vector<size_t>(num_proofs, num_proofs + num_instances),
+                                max_num_inputs, std::vector<size_t>(num_inputs, num_inputs + num_instances), ws, inst,
+                                inst_num_instances, inst_max_num_cons,
+                                std::vector<size_t>(inst_num_cons, inst_num_cons + inst_num_instances), gens, t, tape);
+    *out_len = o.bytes.size();
+    *out_bytes = (uint8_t *)malloc(o.bytes.size());
+    memcpy(*out_bytes, o.bytes.data(), o.bytes.size());
+    size_t pos = 0;
+    const std::vector<Scalar> *vs[4] = {&o.rp, &o.rq_rev, &o.rx, &o.rw_ry};
+    for (int i = 0; i < 4; i++) {
+      out_counts[i] = vs[i]->size();
+      for (auto &s : *vs[i]) out_challenges[pos++] = s.to_fq();
+    }
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,672 @@
+// C++ mirror of the transcript-side code of R1CSProof::prove, driving the device through
+// the C ABI (include/spgpu.h). Everything here is what the Rust host keeps doing in
+// production (sigma protocols, UniPoly, ZK sumcheck glue, opening proofs, serialization);
+// the table work is delegated to libspgpu.
+//   reference: src/unipoly.rs, src/nizk/mod.rs, src/nizk/bullet.rs,
+//              src/sumcheck.rs:788-1380 (ZK glue), src/dense_mlpoly.rs:861-960,
+//              src/r1csproof.rs:210-685
+#pragma once
+#include <map>
+
+#include "../../include/spgpu.h"
+#include "group.hpp"
+
+namespace sph {
+
+inline void check(int rc, const char *what) {
+  if (rc != SPG_OK) throw std::runtime_error(std::string(what) + ": " + spg_last_error());
+}
+inline size_t log2z(size_t n) {
+  size_t l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+inline size_t next_pow2(size_t n) {
+  size_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+// ---------------------------------------------------------------- serialization (bincode 1.x,
+// default options: fixed-width little-endian integers, u64 length prefix for Vec, none for
+// arrays/tuples; Scalar = its four Montgomery limbs, CompressedRistretto = 32 bytes)
+struct Writer {
+  std::vector<uint8_t> out;
+  void u64(uint64_t x) {
+    for (int i = 0; i < 8; i++) out.push_back((uint8_t)(x >> (8 * i)));
+  }
+  void scalar(const Scalar &s) {
+    for (int i = 0; i < 4; i++) u64(s.v.l[i]);
+  }
+  void point(const Compressed &c) { out.insert(out.end(), c.b, c.b + 32); }
+  void scalars(const std::vector<Scalar> &v) {
+    u64(v.size());
+    for (auto &s : v) scalar(s);
+  }
+  void points(const std::vector<Compressed> &v) {
+    u64(v.size());
+    for (auto &p : v) point(p);
+  }
+};
+
+// ---------------------------------------------------------------- UniPoly (src/unipoly.rs:22-93)
+struct UniPoly {
+  std::vector<Scalar> coeffs;  // lowest degree first
+  static UniPoly from_evals(const std::vector<Scalar> &e) {
+    // (2_usize).to_scalar() sums ones (src/scalar/mod.rs:10-15): same value as from_u64
+    Scalar two_inv = Scalar::from_u64(2).invert();
+    UniPoly p;
+    if (e.size() == 3) {
+      Scalar c = e[0];
+      Scalar a = two_inv * (e[2] - e[1] - e[1] + c);
+      Scalar b = e[1] - c - a;
+      p.coeffs = {c, b, a};
+    } else if (e.size() == 4) {
+      Scalar six_inv = Scalar::from_u64(6).invert();
+      Scalar d = e[0];
+      Scalar a = six_inv * (e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0]);
+      Scalar b = two_inv * (e[0] + e[0] - e[1] - e[1] - e[1] - e[1] - e[1] + e[2] + e[2] + e[2] + e[2] - e[3]);
+      Scalar c = e[1] - d - a - b;
+      p.coeffs = {d, c, b, a};
+    } else {
+      throw std::runtime_error("UniPoly::from_evals: degree must be 2 or 3");
+    }
+    return p;
+  }
+  size_t degree() const { return coeffs.size() - 1; }
+  Scalar evaluate(const Scalar &r) const {
+    Scalar eval = coeffs[0], power = r;
+    for (size_t i = 1; i < coeffs.size(); i++) {
+      eval += power * coeffs[i];
+      power *= r;
+    }
+    return eval;
+  }
+  Point commit(const MultiCommitGens &g, const Scalar &blind) const { return sph::commit(coeffs, blind, g); }
+};
+
+// ---------------------------------------------------------------- sigma protocols (src/nizk/mod.rs)
+struct KnowledgeProof {
+  Compressed alpha;
+  Scalar z1, z2;
+  static std::pair<KnowledgeProof, Compressed> prove(const MultiCommitGens &g, ProofTranscript &t, RandomTape &tape,
+                                                     const Scalar &x, const Scalar &r) {
+    t.append_protocol_name("knowledge proof");
+    Scalar t1 = tape.random_scalar("t1"), t2 = tape.random_scalar("t2");
+    Compressed C = commit(x, r, g).compress();
+    t.append_point("C", C);
+    KnowledgeProof p;
+    p.alpha = commit(t1, t2, g).compress();
+    t.append_point("alpha", p.alpha);
+    Scalar c = t.challenge_scalar("c");
+    p.z1 = x * c + t1;
+    p.z2 = r * c + t2;
+    return {p, C};
+  }
+  void write(Writer &w) const {
+    w.point(alpha);
+    w.scalar(z1);
+    w.scalar(z2);
+  }
+};
+
+struct EqualityProof {
+  Compressed alpha;
+  Scalar z;
+  static EqualityProof prove(const MultiCommitGens &g, ProofTranscript &t, RandomTape &tape, const Scalar &v1,
+                             const Scalar &s1, const Scalar &v2, const Scalar &s2) {
+    t.append_protocol_name("equality proof");
+    Scalar r = tape.random_scalar("r");
+    t.append_point("C1", commit(v1, s1, g).compress());
+    t.append_point("C2", commit(v2, s2, g).compress());
+    EqualityProof p;
+    p.alpha = (g.h * r).compress();
+    t.append_point("alpha", p.alpha);
+    Scalar c = t.challenge_scalar("c");
+    p.z = c * (s1 - s2) + r;
+    return p;
+  }
+  void write(Writer &w) const {
+    w.point(alpha);
+    w.scalar(z);
+  }
+};
+
+struct ProductProof {
+  Compressed alpha, beta, delta;
+  Scalar z[5];
+  struct Out {
+    Compressed X, Y, Z;
+  };
+  static std::pair<ProductProof, Out> prove(const MultiCommitGens &g, ProofTranscript &t, RandomTape &tape,
+                                            const Scalar &x, const Scalar &rX, const Scalar &y, const Scalar &rY,
+                                            const Scalar &z, const Scalar &rZ) {
+    t.append_protocol_name("product proof");
+    Scalar b1 = tape.random_scalar("b1"), b2 = tape.random_scalar("b2"), b3 = tape.random_scalar("b3"),
+           b4 = tape.random_scalar("b4"), b5 = tape.random_scalar("b5");
+    Out o;
+    o.X = commit(x, rX, g).compress();
+    t.append_point("X", o.X);
+    o.Y = commit(y, rY, g).compress();
+    t.append_point("Y", o.Y);
+    o.Z = commit(z, rZ, g).compress();
+    t.append_point("Z", o.Z);
+    ProductProof p;
+    p.alpha = commit(b1, b2, g).compress();
+    t.append_point("alpha", p.alpha);
+    p.beta = commit(b3, b4, g).compress();
+    t.append_point("beta", p.beta);
+    MultiCommitGens gX;
+    gX.n = 1;
+    gX.G = {Point::decompress(o.X)};
+    gX.h = g.h;
+    p.delta = commit(b3, b5, gX).compress();
+    t.append_point("delta", p.delta);
+    Scalar c = t.challenge_scalar("c");
+    p.z[0] = b1 + c * x;
+    p.z[1] = b2 + c * rX;
+    p.z[2] = b3 + c * y;
+    p.z[3] = b4 + c * rY;
+    p.z[4] = b5 + c * (rZ - rX * y);
+    return {p, o};
+  }
+  void write(Writer &w) const {
+    w.point(alpha);
+    w.point(beta);
+    w.point(delta);
+    for (int i = 0; i < 5; i++) w.scalar(z[i]);
+  }
+};
+
+struct DotProductProof {
+  Compressed delta, beta;
+  std::vector<Scalar> z;
+  Scalar z_delta, z_beta;
+  static Scalar dot(const std::vector<Scalar> &a, const std::vector<Scalar> &b) {
+    Scalar acc;
+    for (size_t i = 0; i < a.size(); i++) acc += a[i] * b[i];
+    return acc;
+  }
+  static DotProductProof prove(const MultiCommitGens &g1, const MultiCommitGens &gn, ProofTranscript &t, RandomTape &tape,
+                               const std::vector<Scalar> &x, const Scalar &blind_x, const std::vector<Scalar> &a,
+                               const Scalar &y, const Scalar &blind_y) {
+    t.append_protocol_name("dot product proof");
+    size_t n = x.size();
+    std::vector<Scalar> d = tape.random_vector("d_vec", n);
+    Scalar r_delta = tape.random_scalar("r_delta"), r_beta = tape.random_scalar("r_beta");
+    t.append_point("Cx", commit(x, blind_x, gn).compress());
+    t.append_point("Cy", commit(y, blind_y, g1).compress());
+    t.append_scalars("a", a);
+    DotProductProof p;
+    p.delta = commit(d, r_delta, gn).compress();
+    t.append_point("delta", p.delta);
+    p.beta = commit(dot(a, d), r_beta, g1).compress();
+    t.append_point("beta", p.beta);
+    Scalar c = t.challenge_scalar("c");
+    for (size_t i = 0; i < n; i++) p.z.push_back(c * x[i] + d[i]);
+    p.z_delta = c * blind_x + r_delta;
+    p.z_beta = c * blind_y + r_beta;
+    return p;
+  }
+  void write(Writer &w) const {
+    w.point(delta);
+    w.point(beta);
+    w.scalars(z);
+    w.scalar(z_delta);
+    w.scalar(z_beta);
+  }
+};
+
+// ---------------------------------------------------------------- bullet reduction (src/nizk/bullet.rs:32-132)
+struct BulletReductionProof {
+  std::vector<Compressed> L_vec, R_vec;
+  struct Out {
+    Scalar a, b, blind_fin;
+    Point G;
+  };
+  static std::pair<BulletReductionProof, Out> prove(ProofTranscript &t, const Point &Q, std::vector<Point> G, const Point &H,
+                                                    std::vector<Scalar> a, std::vector<Scalar> b, const Scalar &blind,
+                                                    const std::vector<std::pair<Scalar, Scalar>> &blinds) {
+    size_t n = G.size();
+    BulletReductionProof p;
+    Scalar blind_fin = blind;
+    size_t round = 0;
+    while (n != 1) {
+      n /= 2;
+      Scalar c_L, c_R;
+      for (size_t i = 0; i < n; i++) {
+        c_L += a[i] * b[n + i];
+        c_R += a[n + i] * b[i];
+      }
+      const Scalar &blind_L = blinds[round].first, &blind_R = blinds[round].second;
+      round++;
+      Point L = Q * c_L + H * blind_L, R = Q * c_R + H * blind_R;
+      for (size_t i = 0; i < n; i++) {
+        if (!(a[i] == Scalar::zero())) L = L + G[n + i] * a[i];
+        if (!(a[n + i] == Scalar::zero())) R = R + G[i] * a[n + i];
+      }
+      Compressed Lc = L.compress(), Rc = R.compress();
+      t.append_point("L", Lc);
+      t.append_point("R", Rc);
+      Scalar u = t.challenge_scalar("u");
+      Scalar u_inv = u.invert();
+      for (size_t i = 0; i < n; i++) {
+        a[i] = a[i] * u + u_inv * a[n + i];
+        b[i] = b[i] * u_inv + u * b[n + i];
+        G[i] = G[i] * u_inv + G[n + i] * u;
+      }
+      blind_fin = blind_fin + blind_L * u * u + blind_R * u_inv * u_inv;
+      p.L_vec.push_back(Lc);
+      p.R_vec.push_back(Rc);
+    }
+    Out o{a[0], b[0], blind_fin, G[0]};
+    return {p, o};
+  }
+  void write(Writer &w) const {
+    w.points(L_vec);
+    w.points(R_vec);
+  }
+};
+
+// DotProductProofGens (src/nizk/mod.rs:406-418)
+struct DotProductProofGens {
+  size_t n = 0;
+  MultiCommitGens gens_n, gens_1;
+  DotProductProofGens() {}
+  DotProductProofGens(size_t n_, const std::string &label) : n(n_) {
+    auto pr = MultiCommitGens(n + 1, label).split_at(n);
+    gens_n = pr.first;
+    gens_1 = pr.second;
+  }
+};
+
+// DotProductProofLog (src/nizk/mod.rs:420-523)
+struct DotProductProofLog {
+  BulletReductionProof bullet;
+  Compressed delta, beta;
+  Scalar z1, z2;
+  static DotProductProofLog prove(const DotProductProofGens &gens, ProofTranscript &t, RandomTape &tape,
+                                  const std::vector<Scalar> &x, const Scalar &blind_x, const std::vector<Scalar> &a,
+                                  const Scalar &y, const Scalar &blind_y) {
+    t.append_protocol_name("dot product proof (log)");
+    size_t n = x.size();
+    if (gens.n < n) throw std::runtime_error("DotProductProofLog: not enough generators");
+    Scalar d = tape.random_scalar("d");
+    Scalar r_delta = tape.random_scalar("r_delta");
+    Scalar r_beta = tape.random_scalar("r_delta");  // sic: the reference reuses the label (nizk/mod.rs:454)
+    size_t lg = log2z(n);
+    std::vector<Scalar> v1 = tape.random_vector("blinds_vec_1", 2 * lg), v2 = tape.random_vector("blinds_vec_2", 2 * lg);
+    std::vector<std::pair<Scalar, Scalar>> blinds;
+    for (size_t i = 0; i < v1.size(); i++) blinds.push_back({v1[i], v2[i]});
+    MultiCommitGens gn = gens.gens_n;
+    t.append_point("Cx", commit(x, blind_x, gn).compress());
+    t.append_point("Cy", commit(y, blind_y, gens.gens_1).compress());
+    t.append_scalars("a", a);
+    Scalar r = t.challenge_scalar("r");
+    MultiCommitGens g1s = gens.gens_1.scale(r);
+    Scalar blind_Gamma = blind_x + r * blind_y;
+    std::vector<Point> G(gn.G.begin(), gn.G.begin() + n);
+    auto br = BulletReductionProof::prove(t, g1s.G[0], G, gn.h, x, a, blind_Gamma, blinds);
+    const auto &o = br.second;
+    Scalar y_hat = o.a * o.b;
+    DotProductProofLog p;
+    p.bullet = br.first;
+    MultiCommitGens ghat;
+    ghat.n = 1;
+    ghat.G = {o.G};
+    ghat.h = gens.gens_1.h;
+    p.delta = commit(d, r_delta, ghat).compress();
+    t.append_point("delta", p.delta);
+    p.beta = commit(d, r_beta, g1s).compress();
+    t.append_point("beta", p.beta);
+    Scalar c = t.challenge_scalar("c");
+    p.z1 = d + c * y_hat;
+    p.z2 = o.b * (c * o.blind_fin + r_beta) + r_delta;
+    return p;
+  }
+  void write(Writer &w) const {
+    bullet.write(w);
+    w.point(delta);
+    w.point(beta);
+    w.scalar(z1);
+    w.scalar(z2);
+  }
+};
+
+// ---------------------------------------------------------------- generators (src/r1csproof.rs:45-80)
+struct R1CSGens {
+  MultiCommitGens sc_gens_1, sc_gens_3, sc_gens_4;
+  DotProductProofGens pc;
+  R1CSGens(const std::string &label, size_t num_vars) {
+    size_t ell = log2z(num_vars);
+    size_t right = ell - ell / 2;
+    pc = DotProductProofGens((size_t)1 << right, label);
+    sc_gens_1 = pc.gens_1;
+    sc_gens_3 = MultiCommitGens(3, label);
+    sc_gens_4 = MultiCommitGens(4, label);
+  }
+};
+
+// ---------------------------------------------------------------- ZK sumcheck glue
+struct ZKSumcheckProof {
+  std::vector<Compressed> comm_polys, comm_evals;
+  std::vector<DotProductProof> proofs;
+  void write(Writer &w) const {
+    w.points(comm_polys);
+    w.points(comm_evals);
+    w.u64(proofs.size());
+    for (auto &p : proofs) p.write(w);
+  }
+};
+
+// One loop for both disjoint-round provers (src/sumcheck.rs:1104-1367 == :816-1054): the only
+// difference is where (e0, e2, e3) come from and what is bound, i.e. the two callbacks.
+template <typename Eval, typename Bind>
+ZKSumcheckProof zk_sumcheck(const Scalar &claim, const Scalar &blind_claim, size_t num_rounds, Eval eval, Bind bind,
+                            const MultiCommitGens &g1, const MultiCommitGens &gn, ProofTranscript &t, RandomTape &tape,
+                            std::vector<Scalar> *r_out, Scalar *blind_out) {
+  std::vector<Scalar> blinds_poly = tape.random_vector("blinds_poly", num_rounds);
+  std::vector<Scalar> blinds_evals = tape.random_vector("blinds_evals", num_rounds);
+  Scalar claim_per_round = claim;
+  Compressed comm_claim_per_round = commit(claim_per_round, blind_claim, g1).compress();
+  ZKSumcheckProof pr;
+  for (size_t j = 0; j < num_rounds; j++) {
+    spg_fq e[3];
+    eval(e);
+    Scalar e0 = Scalar::from_fq(e[0]);
+    UniPoly poly = UniPoly::from_evals({e0, claim_per_round - e0, Scalar::from_fq(e[1]), Scalar::from_fq(e[2])});
+    Compressed comm_poly = poly.commit(gn, blinds_poly[j]).compress();
+    t.append_point("comm_poly", comm_poly);
+    pr.comm_polys.push_back(comm_poly);
+    Scalar r_j = t.challenge_scalar("challenge_nextround");
+    spg_fq rj = r_j.to_fq();
+    bind(&rj);
+    Scalar ev = poly.evaluate(r_j);
+    Compressed comm_eval = commit(ev, blinds_evals[j], g1).compress();
+    t.append_point("comm_claim_per_round", comm_claim_per_round);
+    t.append_point("comm_eval", comm_eval);
+    std::vector<Scalar> w = t.challenge_vector("combine_two_claims_to_one", 2);
+    Scalar target = w[0] * claim_per_round + w[1] * ev;
+    const Scalar &blind_sc = j == 0 ? blind_claim : blinds_evals[j - 1];
+    Scalar blind = w[0] * blind_sc + w[1] * blinds_evals[j];
+    // a = w0 * (2,1,1,1) + w1 * (1, r, r^2, r^3)
+    size_t deg = poly.degree();
+    std::vector<Scalar> a_sc(deg + 1, Scalar::one()), a_ev(deg + 1, Scalar::one()), a;
+    a_sc[0] += Scalar::one();
+    for (size_t k = 1; k <= deg; k++) a_ev[k] = a_ev[k - 1] * r_j;
+    for (size_t k = 0; k <= deg; k++) a.push_back(w[0] * a_sc[k] + w[1] * a_ev[k]);
+    pr.proofs.push_back(DotProductProof::prove(g1, gn, t, tape, poly.coeffs, blinds_poly[j], a, target, blind));
+    claim_per_round = ev;
+    comm_claim_per_round = comm_eval;
+    r_out->push_back(r_j);
+    pr.comm_evals.push_back(comm_eval);
+  }
+  *blind_out = blinds_evals[num_rounds - 1];
+  return pr;
+}
+
+// ---------------------------------------------------------------- witnesses
+struct WitnessSec {  // ProverWitnessSecInfo
+  std::vector<size_t> num_proofs, num_inputs;  // per instance of this section
+  spg_witness *dev = nullptr;
+};
+
+// ---------------------------------------------------------------- PolyEvalProof (src/dense_mlpoly.rs:861-960)
+struct PolyRef {
+  spg_witness *w;
+  size_t p;
+  size_t num_proofs, num_inputs;
+};
+
+inline std::vector<Scalar> eq_evals_host(const std::vector<Scalar> &r) {  // EqPolynomial::evals
+  std::vector<Scalar> ev((size_t)1 << r.size(), Scalar::one());
+  size_t size = 1;
+  for (size_t j = 0; j < r.size(); j++) {
+    size *= 2;
+    for (size_t i = size - 1;; i -= 2) {
+      Scalar s = ev[i / 2];
+      ev[i] = s * r[j];
+      ev[i - 1] = s - ev[i];
+      if (i == 1) break;
+    }
+  }
+  return ev;
+}
+
+inline std::vector<DotProductProofLog> prove_batched_instances_disjoint_rounds(
+    spg_ctx *ctx, const std::vector<PolyRef> &polys, const std::vector<Scalar> &rq, const std::vector<Scalar> &ry,
+    const std::vector<Scalar> &Zr, const DotProductProofGens &gens, ProofTranscript &t, RandomTape &tape) {
+  t.append_protocol_name("polynomial evaluation proof");
+  std::map<std::pair<size_t, size_t>, size_t> index_map;
+  std::vector<std::vector<Scalar>> LZ_list, L_list, R_list;
+  std::vector<Scalar> Zc_list;
+  Scalar c_base = t.challenge_scalar("challenge_c");
+  Scalar c = Scalar::one();
+  auto bound = [&](const PolyRef &pr, const std::vector<Scalar> &L) {
+    spg_vec *pv = nullptr, *out = nullptr;
+    check(spg_witness_poly(pr.w, pr.p, &pv), "spg_witness_poly");
+    std::vector<spg_fq> Lf;
+    for (auto &s : L) Lf.push_back(s.to_fq());
+    check(spg_dense_bound_L(ctx, pv, Lf.data(), Lf.size(), &out), "spg_dense_bound_L");
+    size_t n = spg_vec_len(out);
+    std::vector<spg_fq> h(n);
+    check(spg_vec_download(ctx, out, 0, n, h.data()), "spg_vec_download");
+    spg_vec_free(out);
+    std::vector<Scalar> r;
+    for (auto &x : h) r.push_back(Scalar::from_fq(x));
+    return r;
+  };
+  for (size_t i = 0; i < polys.size(); i++) {
+    auto key = std::make_pair(polys[i].num_proofs, polys[i].num_inputs);
+    auto it = index_map.find(key);
+    if (it != index_map.end()) {
+      c *= c_base;
+      size_t idx = it->second;
+      std::vector<Scalar> LZ = bound(polys[i], L_list[idx]);
+      for (size_t j = 0; j < LZ.size(); j++) LZ_list[idx][j] = LZ_list[idx][j] + c * LZ[j];
+      Zc_list[idx] += c * Zr[i];
+    } else {
+      index_map[key] = LZ_list.size();
+      Zc_list.push_back(Zr[i]);
+      size_t nvq = log2z(key.first), nvy = log2z(key.second);
+      std::vector<Scalar> r(rq.end() - nvq, rq.end());
+      if (nvy >= ry.size()) {
+        r.insert(r.end(), nvy - ry.size(), Scalar::zero());
+        r.insert(r.end(), ry.begin(), ry.end());
+      } else {
+        r.insert(r.end(), ry.end() - nvy, ry.end());
+      }
+      size_t left = r.size() / 2;
+      std::vector<Scalar> L = eq_evals_host(std::vector<Scalar>(r.begin(), r.begin() + left));
+      std::vector<Scalar> R = eq_evals_host(std::vector<Scalar>(r.begin() + left, r.end()));
+      LZ_list.push_back(bound(polys[i], L));
+      L_list.push_back(L);
+      R_list.push_back(R);
+    }
+  }
+  std::vector<DotProductProofLog> proofs;
+  for (size_t i = 0; i < LZ_list.size(); i++)
+    proofs.push_back(DotProductProofLog::prove(gens, t, tape, LZ_list[i], Scalar::zero(), R_list[i], Zc_list[i], Scalar::zero()));
+  return proofs;
+}
+
+// ---------------------------------------------------------------- R1CSProof::prove (src/r1csproof.rs:210-685)
+struct R1CSProofOut {
+  std::vector<uint8_t> bytes;                 // bincode layout of R1CSProof (src/r1csproof.rs:25-43)
+  std::vector<Scalar> rp, rq_rev, rx, rw_ry;  // the returned challenge vectors (:683)
+};
+
+inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_num_proofs,
+                               const std::vector<size_t> &num_proofs, size_t max_num_inputs,
+                               const std::vector<size_t> &num_inputs, const std::vector<WitnessSec> &secs,
+                               const spg_r1cs *inst, size_t inst_num_instances, size_t inst_max_num_cons,
+                               const std::vector<size_t> &inst_num_cons, const R1CSGens &gens, ProofTranscript &t,
+                               RandomTape &tape) {
+  t.append_protocol_name("R1CS proof");
+  size_t W = secs.size();
+  size_t P = num_instances;
+  size_t num_cons = inst_max_num_cons;
+  std::vector<size_t> block_num_cons = inst_num_instances == 1 ? std::vector<size_t>(P, inst_num_cons[0]) : inst_num_cons;
+  // z_mat on the device (:278-293)
+  std::vector<spg_witness *> wptr;
+  for (auto &s : secs) wptr.push_back(s.dev);
+  spg_zmat *z = nullptr;
+  check(spg_zmat_build(ctx, P, num_proofs.data(), num_inputs.data(), W, wptr.data(), &z), "spg_zmat_build");
+  size_t nrp = log2z(next_pow2(P)), nrq = log2z(max_num_proofs), nrx = log2z(num_cons), nrw = log2z(next_pow2(W)),
+         nry = log2z(max_num_inputs);
+  std::vector<Scalar> tau_p = t.challenge_vector("challenge_tau_p", nrp);
+  std::vector<Scalar> tau_q = t.challenge_vector("challenge_tau_q", nrq);
+  std::vector<Scalar> tau_x = t.challenge_vector("challenge_tau_x", nrx);
+  auto fqv = [](const std::vector<Scalar> &v) {
+    std::vector<spg_fq> o;
+    for (auto &s : v) o.push_back(s.to_fq());
+    if (o.empty()) o.push_back(spg_fq{{0, 0, 0, 0}});
+    return o;
+  };
+  // PHASE 1 (:313-343)
+  spg_sc1 *sc1 = nullptr;
+  check(spg_sc1_create(ctx, inst, z, P, num_proofs.data(), max_num_proofs, block_num_cons.data(), num_cons,
+                       max_num_inputs, fqv(tau_p).data(), fqv(tau_q).data(), fqv(tau_x).data(), &sc1),
+        "spg_sc1_create");
+  std::vector<Scalar> r1;
+  Scalar blind_claim_postsc1;
+  ZKSumcheckProof sc_proof_phase1 = zk_sumcheck(
+      Scalar::zero(), Scalar::zero(), nrx + nrq + nrp, [&](spg_fq *e) { check(spg_sc1_round_eval(sc1, e), "spg_sc1_round_eval"); },
+      [&](const spg_fq *r) { check(spg_sc1_round_bind(sc1, r), "spg_sc1_round_bind"); }, gens.sc_gens_1, gens.sc_gens_4, t,
+      tape, &r1, &blind_claim_postsc1);
+  spg_fq claims1[4];
+  check(spg_sc1_final(sc1, claims1), "spg_sc1_final");
+  spg_sc1_destroy(sc1);
+  Scalar tau_claim = Scalar::from_fq(claims1[0]), Az_claim = Scalar::from_fq(claims1[1]),
+         Bz_claim = Scalar::from_fq(claims1[2]), Cz_claim = Scalar::from_fq(claims1[3]);
+  Scalar Az_blind = tape.random_scalar("Az_blind"), Bz_blind = tape.random_scalar("Bz_blind"),
+         Cz_blind = tape.random_scalar("Cz_blind"), prod_Az_Bz_blind = tape.random_scalar("prod_Az_Bz_blind");
+  auto pok = KnowledgeProof::prove(gens.sc_gens_1, t, tape, Cz_claim, Cz_blind);
+  Compressed comm_Cz_claim = pok.second;
+  Scalar prod = Az_claim * Bz_claim;
+  auto pp = ProductProof::prove(gens.sc_gens_1, t, tape, Az_claim, Az_blind, Bz_claim, Bz_blind, prod, prod_Az_Bz_blind);
+  Compressed comm_Az_claim = pp.second.X, comm_Bz_claim = pp.second.Y, comm_prod = pp.second.Z;
+  t.append_point("comm_Az_claim", comm_Az_claim);
+  t.append_point("comm_Bz_claim", comm_Bz_claim);
+  t.append_point("comm_Cz_claim", comm_Cz_claim);
+  t.append_point("comm_prod_Az_Bz_claims", comm_prod);
+  Scalar blind_expected_claim_postsc1 = tau_claim * (prod_Az_Bz_blind - Cz_blind);
+  Scalar claim_post_phase1 = (Az_claim * Bz_claim - Cz_claim) * tau_claim;
+  EqualityProof proof_eq_sc_phase1 = EqualityProof::prove(gens.sc_gens_1, t, tape, claim_post_phase1,
+                                                          blind_expected_claim_postsc1, claim_post_phase1, blind_claim_postsc1);
+  // split r1 into rx_rev | rq_rev | rp (:410-416)
+  std::vector<Scalar> rx_rev(r1.begin(), r1.begin() + nrx), rq_rev(r1.begin() + nrx, r1.begin() + nrx + nrq),
+      rp(r1.begin() + nrx + nrq, r1.end());
+  std::vector<Scalar> rx(rx_rev.rbegin(), rx_rev.rend()), rq(rq_rev.rbegin(), rq_rev.rend());
+  // PHASE 2 (:421-501)
+  Scalar r_A = t.challenge_scalar("challenge_Az"), r_B = t.challenge_scalar("challenge_Bz"), r_C = t.challenge_scalar("challenge_Cz");
+  Scalar claim_phase2 = r_A * Az_claim + r_B * Bz_claim + r_C * Cz_claim;
+  Scalar blind_claim_phase2 = r_A * Az_blind + r_B * Bz_blind + r_C * Cz_blind;
+  spg_sc2 *sc2 = nullptr;
+  spg_fq fA = r_A.to_fq(), fB = r_B.to_fq(), fC = r_C.to_fq();
+  check(spg_sc2_create(ctx, inst, z, P, num_proofs.data(), max_num_proofs, num_inputs.data(), max_num_inputs, W,
+                       fqv(rx).data(), fqv(rq_rev).data(), fqv(rp).data(), &fA, &fB, &fC, &sc2),
+        "spg_sc2_create");
+  std::vector<Scalar> r2;
+  Scalar blind_claim_postsc2;
+  ZKSumcheckProof sc_proof_phase2 = zk_sumcheck(
+      claim_phase2, blind_claim_phase2, nry + nrw + nrp, [&](spg_fq *e) { check(spg_sc2_round_eval(sc2, e), "spg_sc2_round_eval"); },
+      [&](const spg_fq *r) { check(spg_sc2_round_bind(sc2, r), "spg_sc2_round_bind"); }, gens.sc_gens_1, gens.sc_gens_4, t,
+      tape, &r2, &blind_claim_postsc2);
+  spg_fq claims2[3];
+  check(spg_sc2_final(sc2, claims2), "spg_sc2_final");
+  spg_sc2_destroy(sc2);
+  spg_zmat_destroy(z);
+  std::vector<Scalar> ry_rev(r2.begin(), r2.begin() + nry), rw(r2.begin() + nry, r2.begin() + nry + nrw),
+      rp2(r2.begin() + nry + nrw, r2.end());
+  std::vector<Scalar> ry(ry_rev.rbegin(), ry_rev.rend());
+  // POLYEVAL (:518-586)
+  std::vector<Scalar> ry_factors(nry + 1, Scalar::one());
+  for (size_t i = 0; i < nry; i++) ry_factors[i + 1] = ry_factors[i] * (Scalar::one() - ry[i]);
+  std::vector<PolyRef> poly_list;
+  std::vector<Scalar> Zr_list;
+  std::vector<std::vector<Scalar>> eval_vars_at_ry_list(W);
+  std::vector<std::vector<Compressed>> comm_vars_at_ry_list(W);
+  for (size_t i = 0; i < W; i++) {
+    const WitnessSec &w = secs[i];
+    for (size_t p = 0; p < w.num_proofs.size(); p++) {
+      size_t wq = w.num_proofs[p], wy = w.num_inputs[p];
+      poly_list.push_back(PolyRef{w.dev, p, wq, wy});
+      std::vector<Scalar> r(rq.end() - log2z(wq), rq.end());
+      if (wy >= max_num_inputs) {
+        r.insert(r.end(), log2z(wy) - log2z(max_num_inputs), Scalar::zero());
+        r.insert(r.end(), ry.begin(), ry.end());
+      } else {
+        r.insert(r.end(), ry.end() - log2z(wy), ry.end());
+      }
+      spg_vec *pv = nullptr;
+      check(spg_witness_poly(w.dev, p, &pv), "spg_witness_poly");
+      spg_fq ev;
+      check(spg_dense_evaluate(ctx, pv, fqv(r).data(), r.size(), &ev), "spg_dense_evaluate");
+      Scalar e = Scalar::from_fq(ev);
+      Zr_list.push_back(e);
+      eval_vars_at_ry_list[i].push_back(wy >= max_num_inputs ? e : e * ry_factors[nry - log2z(wy)]);
+      comm_vars_at_ry_list[i].push_back(commit(e, Scalar::zero(), gens.pc.gens_1).compress());
+    }
+  }
+  std::vector<DotProductProofLog> proof_eval_vars =
+      prove_batched_instances_disjoint_rounds(ctx, poly_list, rq, ry, Zr_list, gens.pc, t, tape);
+  // combine per instance (:588-638)
+  size_t Wp = next_pow2(W);
+  if (Wp > 8) throw std::runtime_error("Unsupported num_witness_secs");  // the reference panics (:629-631)
+  std::vector<Scalar> prefix(Wp);
+  for (size_t k = 0; k < Wp; k++) {
+    Scalar acc = Scalar::one();
+    for (size_t b = 0; b < nrw; b++) acc = acc * (((k >> (nrw - 1 - b)) & 1) ? rw[b] : Scalar::one() - rw[b]);
+    prefix[k] = acc;
+  }
+  std::vector<Scalar> eval_vars_comb_list;
+  for (size_t p = 0; p < P; p++) {
+    Scalar comb;
+    for (size_t i = 0; i < W; i++) {
+      size_t wp = secs[i].num_proofs.size() == 1 ? 0 : p;
+      comb = comb + prefix[i] * eval_vars_at_ry_list[i][wp];
+    }
+    for (size_t q = 0; q < nrq - log2z(num_proofs[p]); q++) comb *= Scalar::one() - rq[q];
+    eval_vars_comb_list.push_back(comb);
+  }
+  // poly_vars.evaluate(rp): DensePolynomial::new pads with zeros (:641-642)
+  eval_vars_comb_list.resize(next_pow2(P), Scalar::zero());
+  std::vector<Scalar> eqp = eq_evals_host(rp2);
+  Scalar eval_vars_at_ry;
+  for (size_t i = 0; i < eqp.size(); i++) eval_vars_at_ry += eqp[i] * eval_vars_comb_list[i];
+  Compressed comm_vars_at_ry = commit(eval_vars_at_ry, Scalar::zero(), gens.pc.gens_1).compress();
+  Scalar claim_post_phase2 = Scalar::from_fq(claims2[0]) * Scalar::from_fq(claims2[1]) * Scalar::from_fq(claims2[2]);
+  EqualityProof proof_eq_sc_phase2 =
+      EqualityProof::prove(gens.pc.gens_1, t, tape, claim_post_phase2, Scalar::zero(), claim_post_phase2, blind_claim_postsc2);
+  // serialize in field order (:25-43)
+  Writer w;
+  sc_proof_phase1.write(w);
+  w.point(comm_Az_claim);
+  w.point(comm_Bz_claim);
+  w.point(comm_Cz_claim);
+  w.point(comm_prod);
+  pok.first.write(w);
+  pp.first.write(w);
+  proof_eq_sc_phase1.write(w);
+  sc_proof_phase2.write(w);
+  // the reference pre-sizes the list to W and then pushes one more empty Vec per section
+  // (src/r1csproof.rs:532-538), so the serialized list has 2W entries, the last W empty
+  w.u64(2 * comm_vars_at_ry_list.size());
+  for (auto &v : comm_vars_at_ry_list) w.points(v);
+  for (size_t i = 0; i < comm_vars_at_ry_list.size(); i++) w.u64(0);
+  w.point(comm_vars_at_ry);
+  w.u64(proof_eval_vars.size());
+  for (auto &p : proof_eval_vars) p.write(w);
+  proof_eq_sc_phase2.write(w);
+  R1CSProofOut out;
+  out.bytes = w.out;
+  out.rp = rp2;
+  out.rq_rev = rq_rev;
+  out.rx = rx;
+  out.rw_ry = rw;
+  out.rw_ry.insert(out.rw_ry.end(), ry.begin(), ry.end());
+  return out;
+}
+
+}  // namespace sph

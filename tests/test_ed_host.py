@@ -58,3 +58,14 @@ def test_invalid_encodings_rejected(harness):
 
     out = run(harness, [f"dec {x}" for x in RFC_BAD] + [f"dec {x}" for x in RFC_MULTIPLES])
     assert out == ["invalid"] * len(RFC_BAD) + ["ok"] * len(RFC_MULTIPLES)
+
+
+def test_from_uniform_bytes(harness):
+    import hashlib
+
+    rng = random.Random(3)
+    blobs = [hashlib.sha512(b"Ristretto is traditionally a short shot of espresso coffee").digest()]
+    blobs += [rng.getrandbits(512).to_bytes(64, "little") for _ in range(20)]
+    out = run(harness, [f"uni {b[:32].hex()} {b[32:].hex()}" for b in blobs])
+    assert out == [G.from_uniform_bytes(b).compress().hex() for b in blobs]
+    assert out[0] == "3066f82a1a747d45120d1740f14358531a8f04bbffe6a819f86dfe50f44a0a46"

@@ -6,6 +6,7 @@
 //   smul <scalar hex32 LE> <point compressed hex32>  -> compressed k*P   (or "invalid")
 //   add  <p> <q>                    -> compressed p+q
 //   dec  <p>                        -> "ok" / "invalid"
+//   uni  <lo hex32> <hi hex32>      -> compressed from_uniform_bytes(lo || hi)
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -28,6 +29,16 @@ int main() {
   while (std::cin >> op >> a) {
     uint8_t x[32], y[32], o[32];
     unhex(a, x);
+    if (op == "uni") {  // 64 uniform bytes given as two hex32 words
+      std::cin >> b;
+      uint8_t u[64];
+      unhex(a, u);
+      unhex(b, u + 32);
+      ge p = ristretto_from_uniform_bytes(u);
+      ristretto_compress(p, o);
+      std::cout << hex(o) << "\n";
+      continue;
+    }
     if (op == "dec") {
       ge p;
       std::cout << (ristretto_decompress(x, &p) ? "ok" : "invalid") << "\n";
