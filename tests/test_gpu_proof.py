@@ -91,4 +91,4 @@ def test_c1_baseline_config(ctx):
     inst = R.synthetic_instance(X)
     secs = R.synthetic_witness(X, [Q], seed=8)
     blob = run_case(ctx, inst, 1, [Q], [X], X, secs, seed=9, verify=False)
-    assert len(blob) > 10000
+    assert len(blob) > 8000
