@@ -134,7 +134,8 @@ int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_pro
 void spg_witness_destroy(spg_witness *w);
 /* poly_w[p] as a dense vector view (not owned by the caller) */
 int spg_witness_poly(spg_witness *w, size_t p, spg_vec **out);
-/* z_mat assembly, src/r1csproof.rs:278-293 */
+/* z_mat assembly, src/r1csproof.rs:278-293. The z_mat is a VIEW over the witness sections
+ * (nothing is copied): the witness handles must outlive it. */
 int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
                    const size_t *num_inputs, size_t num_witness_secs,
                    spg_witness *const *witness_secs, spg_zmat **out);

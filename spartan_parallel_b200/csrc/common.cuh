@@ -68,6 +68,7 @@ struct spg_ctx {
   spg::fq *d_result = nullptr;  // device alias of h_result
   // small staging for scalar arguments
   spg::fq *d_scalars = nullptr;  // device scratch, 64 fq
+  spg::fq *d_stage = nullptr;    // first-stage output of large reductions
   // optional per-kernel timing with CUDA events on the launching stream
   bool profiling = false;
   struct ProfRec {

@@ -78,7 +78,34 @@ __global__ void k_reduce_partials(const fq *__restrict__ partials, size_t nblock
   }
 }
 
+// stage 1 of a large reduction: block b sums rows b, b + gridDim.x, ... into out[b*width + k]
+__global__ void k_reduce_stage(const fq *__restrict__ partials, size_t nblocks, int width, fq *__restrict__ out) {
+  __shared__ fq sm[32];
+  for (int k = 0; k < width; k++) {
+    fq acc = fq_zero();
+    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += (size_t)gridDim.x * blockDim.x)
+      acc = fq_add(acc, fq_load(partials + b * width + k));
+    acc = fq_warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      fq v = threadIdx.x < ((blockDim.x + 31) >> 5) ? sm[threadIdx.x] : fq_zero();
+      v = fq_warp_sum(v);
+      if (threadIdx.x == 0) out[(size_t)blockIdx.x * width + k] = v;
+    }
+    __syncthreads();
+  }
+}
+
 int reduce_partials(spg_ctx *ctx, const fq *partials, size_t nblocks, int width, fq *d_out) {
+  if (nblocks > 4096) {
+    // two stages: 64 blocks fold the partial sums into the reserved tail of d_scalars' sibling buffer
+    const int stage_blocks = 64;
+    if (!ctx->d_stage) SPG_CUDA(cudaMalloc(&ctx->d_stage, (size_t)stage_blocks * 8 * sizeof(fq)));
+    SPG_LAUNCH(ctx, k_reduce_stage, stage_blocks, 256, 0, partials, nblocks, width, ctx->d_stage);
+    partials = ctx->d_stage;
+    nblocks = stage_blocks;
+  }
   int threads = nblocks >= 256 ? 256 : (nblocks > 32 ? 128 : 32);
   SPG_LAUNCH(ctx, k_reduce_partials, 1, threads, 0, partials, nblocks, width, d_out);
   return SPG_OK;
@@ -139,6 +166,7 @@ void spg_ctx_destroy(spg_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -17,33 +17,32 @@ struct CsxView {
   const fq *val;
 };
 
-__device__ __forceinline__ fq spmv_row(const CsxView &M, unsigned int x, const fq *__restrict__ zq,
-                                       unsigned int log_ymax, size_t Yp) {
+__device__ __forceinline__ fq spmv_row(const CsxView &M, unsigned int x, const SecView *__restrict__ secs,
+                                       size_t q, unsigned int log_ymax) {
   fq acc = fq_zero();
   for (uint32_t e = M.ptr[x]; e < M.ptr[x + 1]; e++) {
     uint32_t c = M.idx[e];
     bool unit = c & UNIT_FLAG;
     c &= ~UNIT_FLAG;
     size_t w = c >> log_ymax, y = c & ((1u << log_ymax) - 1);
-    fq zz = fq_load(zq + w * Yp + y);
+    fq zz = z_load(secs[w], q, y);
     acc = fq_add(acc, unit ? zz : fq_mul(fq_load(M.val + e), zz));
   }
   return acc;
 }
 
 // thread t = q * X + x computes row x of A, B, C against z[p][q]
-__global__ void k_spmv3(CsxView A, CsxView B, CsxView C, const fq *__restrict__ z, size_t Q,
-                        unsigned int log_x, size_t W, size_t Yp, unsigned int log_ymax,
+__global__ void k_spmv3(CsxView A, CsxView B, CsxView C, const SecView *__restrict__ secs, size_t Q,
+                        unsigned int log_x, unsigned int log_ymax,
                         fq *__restrict__ outA, fq *__restrict__ outB, fq *__restrict__ outC) {
   size_t total = Q << log_x;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
     size_t q = t >> log_x;
     unsigned int x = (unsigned int)(t & (((size_t)1 << log_x) - 1));
-    const fq *zq = z + q * W * Yp;
-    fq_store(outA + t, spmv_row(A, x, zq, log_ymax, Yp));
-    fq_store(outB + t, spmv_row(B, x, zq, log_ymax, Yp));
-    fq_store(outC + t, spmv_row(C, x, zq, log_ymax, Yp));
+    fq_store(outA + t, spmv_row(A, x, secs, q, log_ymax));
+    fq_store(outB + t, spmv_row(B, x, secs, q, log_ymax));
+    fq_store(outC + t, spmv_row(C, x, secs, q, log_ymax));
   }
 }
 
@@ -89,19 +88,6 @@ __global__ void k_sparse_eval(const uint32_t *__restrict__ row, const uint32_t *
   }
   block_sum<1>(acc, sm);
   if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
-}
-
-// z_mat[p][q][w][i] = i < copy ? w_mat[p_w][q_w][i] : 0   (src/r1csproof.rs:282-290)
-__global__ void k_zmat_fill(const fq *__restrict__ src, size_t src_ni, size_t src_q_stride, size_t copy,
-                            fq *__restrict__ dst, size_t Q, size_t W, size_t w, size_t Yp) {
-  size_t total = Q * Yp;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (size_t)gridDim.x * blockDim.x) {
-    size_t q = t / Yp, i = t % Yp;
-    fq v = i < copy ? fq_load(src + q * src_q_stride + i) : fq_zero();
-    (void)src_ni;
-    fq_store(dst + (q * W + w) * Yp + i, v);
-  }
 }
 
 // ---------------------------------------------------------------- host helpers
@@ -173,9 +159,10 @@ int r1cs_multiply_vec_block(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *
                     "multiply_vec_block: column %u exceeds num_inputs[%zu] = %zu", c, p, Yp);
     }
     size_t items = num_proofs[p] * num_cons[p];
+    ctx->next_units = 32.0 * (double)items * 3.0 * 2.0;  // >= one z read + one write per (row, q, matrix)
     SPG_LAUNCH(ctx, k_spmv3, grid_for(ctx, items, 256), 256, 0, view(inst->by_row[3 * pi]),
-               view(inst->by_row[3 * pi + 1]), view(inst->by_row[3 * pi + 2]), z->d + z->off[p],
-               num_proofs[p], log2u(num_cons[p]), z->W, Yp, log_ymax, Az + off, Bz + off, Cz + off);
+               view(inst->by_row[3 * pi + 1]), view(inst->by_row[3 * pi + 2]), z->views + p * z->W,
+               num_proofs[p], log2u(num_cons[p]), log_ymax, Az + off, Bz + off, Cz + off);
     off += items;
   }
   return SPG_OK;
@@ -382,34 +369,23 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
   z->W = num_witness_secs;
   z->num_proofs.assign(num_proofs, num_proofs + num_instances);
   z->num_inputs.assign(num_inputs, num_inputs + num_instances);
-  size_t tot = 0;
-  for (size_t p = 0; p < num_instances; p++) {
-    z->off.push_back(tot);
-    tot += num_proofs[p] * num_witness_secs * num_inputs[p];
-  }
-  z->total = tot;
-  cudaError_t e = dev_alloc(ctx, &z->d, tot * sizeof(fq));
-  if (e != cudaSuccess) {
-    delete z;
-    return cuda_fail(e, "cudaMalloc(z_mat)", __FILE__, __LINE__);
-  }
+  std::vector<SecView> hv(num_instances * num_witness_secs);
   for (size_t p = 0; p < num_instances; p++)
     for (size_t w = 0; w < num_witness_secs; w++) {
       const spg_witness *ws = witness_secs[w];
       size_t pw = ws->num_instances == 1 ? 0 : p;
       size_t ni = ws->num_inputs[pw];
-      size_t qstride = ws->num_proofs[pw] == 1 ? 0 : ni;
-      size_t copy = ni < num_inputs[p] ? ni : num_inputs[p];
-      size_t items = num_proofs[p] * num_inputs[p];
-      k_zmat_fill<<<grid_for(ctx, items, 256), 256, 0, ctx->stream>>>(ws->d + ws->off[pw], ni, qstride, copy,
-                                                                     z->d + z->off[p], num_proofs[p],
-                                                                     num_witness_secs, w, num_inputs[p]);
-      ctx->launches++;
+      SecView &v = hv[p * num_witness_secs + w];
+      v.ptr = ws->d + ws->off[pw];
+      v.q_stride = ws->num_proofs[pw] == 1 ? 0 : ni;
+      v.copy = ni < num_inputs[p] ? ni : num_inputs[p];
     }
-  e = cudaGetLastError();
+  cudaError_t e = dev_alloc(ctx, &z->views, hv.size() * sizeof(SecView));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(z->views, hv.data(), hv.size() * sizeof(SecView), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     spg_zmat_destroy(z);
-    return cuda_fail(e, "k_zmat_fill", __FILE__, __LINE__);
+    return cuda_fail(e, "z_mat views", __FILE__, __LINE__);
   }
   *out = z;
   return SPG_OK;
@@ -417,7 +393,7 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
 
 void spg_zmat_destroy(spg_zmat *z) {
   if (!z) return;
-  if (z->d) dev_free(z->ctx, z->d);
+  if (z->views) dev_free(z->ctx, z->views);
   delete z;
 }
 

@@ -18,6 +18,19 @@ struct Csx {
 
 constexpr uint32_t UNIT_FLAG = 0x80000000u;
 
+// z_mat[p][q][w][y] is never materialised: it is a view over the witness sections,
+//   z[p][q][w][y] = y < copy ? ptr[q * q_stride + y] : 0      (src/r1csproof.rs:282-290)
+// with q_stride = 0 for a short section (one row shared by every proof).
+struct SecView {
+  const fq *ptr;
+  unsigned long long q_stride;
+  unsigned long long copy;
+};
+
+__device__ __forceinline__ fq z_load(const SecView &v, size_t q, size_t y) {
+  return y < v.copy ? fq_load(v.ptr + q * v.q_stride + y) : fq_zero();
+}
+
 }  // namespace spg
 
 struct spg_r1cs {
@@ -41,9 +54,8 @@ struct spg_witness {
 struct spg_zmat {
   spg_ctx *ctx = nullptr;
   size_t P = 0, W = 0;
-  std::vector<size_t> num_proofs, num_inputs, off;  // off[p]: first scalar of z_mat[p]
-  spg::fq *d = nullptr;
-  size_t total = 0;
+  std::vector<size_t> num_proofs, num_inputs;
+  spg::SecView *views = nullptr;  // device array [P][W]; the witness handles must outlive the z_mat
 };
 
 namespace spg {

@@ -32,7 +32,7 @@ struct Seg {
   unsigned int log_len;           // log2(row_len)
   unsigned int n_rows;
   unsigned int rw_off;            // first row weight of the segment
-  unsigned int pad;
+  unsigned int log_tiles;         // tile kernels: log2(tiles per row); item_start counts tiles
 };
 
 __device__ __forceinline__ int find_seg(const Seg *__restrict__ segs, int nseg, unsigned long long item) {

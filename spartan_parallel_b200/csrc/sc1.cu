@@ -13,8 +13,10 @@ namespace spg {
 int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch);
 __global__ void k_eq_expand(const fq *__restrict__ prev, fq *__restrict__ out, size_t n, fq r);
 
+// 128-thread blocks: the round kernels need ~160 registers, so three 128-thread blocks
+// (12 warps) fit an SM where a single 256-thread block (8 warps) would (measured +13 %)
 #ifndef SPG_RB
-#define SPG_RB 256
+#define SPG_RB 128
 #endif
 #ifndef SPG_MINB
 #define SPG_MINB 1
@@ -138,6 +140,86 @@ k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq 
   }
 }
 
+// ---------------------------------------------------------------- row-tiled fast path
+// One block = one tile of one row, so the row weight RW[row] is applied once per block
+// (after the block reduction) instead of once per item, and all arithmetic between the
+// loads and the stores runs in the lazy range [0, 2q).
+//   FUSED = 0: evaluation only, points t = 0, 1, 2 (first round: also yields the true claim)
+//   FUSED = 1: bind with r, then evaluate the bound pair at t = 0, 2. The round polynomial is
+//              l_j(t) * G(t) with G quadratic, so G(0), G(2) and the running claim determine
+//              it (the host side solves for G(1), G(3); exact field arithmetic, see
+//              spg_sc1_round_eval).
+constexpr int ROWS_LOG_TILE = 10;  // 1024 items per tile = 8 per thread at 128 threads
+
+template <int FUSED>
+__global__ void __launch_bounds__(RB, SPG_MINB)
+k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
+       fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
+       int nseg, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
+  constexpr int NE = FUSED ? 2 : 3;
+  __shared__ fq sm[NE * 32];
+  unsigned long long tile = blockIdx.x;
+  int si = nseg == 1 ? 0 : find_seg(segs, nseg, tile);
+  Seg sg = segs[si];
+  unsigned long long tl = tile - sg.item_start;
+  unsigned long long row = tl >> sg.log_tiles, tr = tl & ((1ull << sg.log_tiles) - 1);
+  unsigned int li = sg.log_len - (FUSED ? 2 : 1);
+  unsigned long long items_row = 1ull << li, tile_items = items_row >> sg.log_tiles;
+  unsigned long long base = tr * tile_items;
+  fq acc[NE];
+#pragma unroll
+  for (int k = 0; k < NE; k++) acc[k] = fq_zero();
+  for (unsigned long long it = base + threadIdx.x; it < base + tile_items; it += RB) {
+    unsigned long long local = row * items_row + it;
+    fq a0, a1, b0, b1, c0, c1;
+    if (FUSED) {
+      unsigned long long idx = sg.in_off + 4 * local, o = sg.out_off + 2 * local;
+      fq lo, hi;
+      lo = fq_load_stream(T0 + idx); hi = fq_load_stream(T0 + idx + 1);
+      a0 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
+      lo = fq_load_stream(T0 + idx + 2); hi = fq_load_stream(T0 + idx + 3);
+      a1 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
+      a0 = fq_canon(a0); a1 = fq_canon(a1);
+      fq_store(O0 + o, a0); fq_store(O0 + o + 1, a1);
+      lo = fq_load_stream(T1 + idx); hi = fq_load_stream(T1 + idx + 1);
+      b0 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
+      lo = fq_load_stream(T1 + idx + 2); hi = fq_load_stream(T1 + idx + 3);
+      b1 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
+      b0 = fq_canon(b0); b1 = fq_canon(b1);
+      fq_store(O1 + o, b0); fq_store(O1 + o + 1, b1);
+      lo = fq_load_stream(T2 + idx); hi = fq_load_stream(T2 + idx + 1);
+      c0 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
+      lo = fq_load_stream(T2 + idx + 2); hi = fq_load_stream(T2 + idx + 3);
+      c1 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
+      c0 = fq_canon(c0); c1 = fq_canon(c1);
+      fq_store(O2 + o, c0); fq_store(O2 + o + 1, c1);
+    } else {
+      unsigned long long idx = sg.in_off + 2 * local;
+      a0 = fq_load_stream(T0 + idx); a1 = fq_load_stream(T0 + idx + 1);
+      b0 = fq_load_stream(T1 + idx); b1 = fq_load_stream(T1 + idx + 1);
+      c0 = fq_load_stream(T2 + idx); c1 = fq_load_stream(T2 + idx + 1);
+    }
+    fq w = fq_load(S + it);
+    // t = 0
+    acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a0, b0), c0)));
+    if (!FUSED)  // t = 1
+      acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a1, b1), c1)));
+    // t = 2: 2*hi - lo
+    fq a2 = fq_add_lazy(a1, fq_sub_lazy(a1, a0));
+    fq b2 = fq_add_lazy(b1, fq_sub_lazy(b1, b0));
+    fq c2 = fq_add_lazy(c1, fq_sub_lazy(c1, c0));
+    acc[NE - 1] = fq_add_lazy(acc[NE - 1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a2, b2), c2)));
+  }
+#pragma unroll
+  for (int k = 0; k < NE; k++) acc[k] = fq_canon(acc[k]);
+  block_sum<NE>(acc, sm);
+  if (threadIdx.x == 0) {
+    fq rw = RW[sg.rw_off + row];
+#pragma unroll
+    for (int k = 0; k < NE; k++) partials[(unsigned long long)blockIdx.x * NE + k] = fq_mul(rw, acc[k]);
+  }
+}
+
 // ---------------------------------------------------------------- p rounds (tiny)
 // tables hold one scalar per instance, zero padded to P'. MODE_P binds the TOP bit
 // of p (no reversal): pairs (p, p + half). sumcheck.rs:1186-1245 with mode P.
@@ -231,8 +313,15 @@ struct spg_sc1 {
   std::vector<unsigned> loglen;  // current log row length per instance
   size_t round = 0;
   bool evaluated = false;
-  bool have_cached = false;  // raw device sums for the current round already in h_cached
+  // raw device sums for the current round, produced by the fused bind+eval of the previous
+  // bind: 0 = none, 3 = sums at t = 0, 2, 3, 2 = sums at t = 0, 2 (needs the running claim)
+  int cached_kind = 0;
   hfq cached[3];
+  // the true running claim s_{j-1}(r_{j-1}) (= e(0) + e(1) of the current round), maintained
+  // from the evaluations this object itself produced: exact for any input tables
+  bool claim_known = false;
+  hfq claim;
+  hfq last_e[3];
   hfq cx, cq;    // prod eq(tau_k, r_k) over the bound x / q variables
   hfq scale;     // external factor on every evaluation (spg_sc1_set_scale); one by default
   size_t p_len = 1;  // current instance_len during the p rounds
@@ -263,7 +352,7 @@ void build_segs(spg_sc1 *s, int phase, int quad, unsigned long long *total_items
     g.log_len = ll;
     g.n_rows = (unsigned)rows;
     g.rw_off = (unsigned)rw;
-    g.pad = 0;
+    g.log_tiles = 0;
     unsigned long long in_sz = rows << ll;
     unsigned long long out_sz = ll >= 1 ? in_sz >> 1 : in_sz;
     unsigned long long it = quad ? (in_sz >> 2) : out_sz;
@@ -465,6 +554,55 @@ int spg_sc1_set_scale(spg_sc1 *s, const spg_fq *c) {
 
 size_t spg_sc1_num_rounds(const spg_sc1 *s) { return s ? s->nx + s->nq + s->np : 0; }
 
+namespace {
+
+// segments for the row-tiled kernels: item_start counts tiles
+void build_tile_segs(spg_sc1 *s, int phase, int fused, unsigned long long *tiles_out, unsigned long long *out_total) {
+  unsigned long long in_off = 0, out_off = 0, tiles = 0, rw = 0;
+  s->segs.resize(s->P);
+  for (size_t p = 0; p < s->P; p++) {
+    Seg &g = s->segs[p];
+    unsigned ll = s->loglen[p];
+    unsigned long long rows = phase == 0 ? s->Q[p] : 1;
+    unsigned li = ll - (fused ? 2 : 1);
+    unsigned lt = li > (unsigned)ROWS_LOG_TILE ? li - ROWS_LOG_TILE : 0;
+    g.in_off = in_off;
+    g.out_off = out_off;
+    g.item_start = tiles;
+    g.log_len = ll;
+    g.n_rows = (unsigned)rows;
+    g.rw_off = (unsigned)rw;
+    g.log_tiles = lt;
+    in_off += rows << ll;
+    out_off += (rows << ll) >> 1;
+    tiles += rows << lt;
+    rw += rows;
+  }
+  *tiles_out = tiles;
+  *out_total = out_off;
+}
+
+// the tiled kernels need every row to hold at least one item per thread of a block
+bool rows_eligible(const spg_sc1 *s, int fused) {
+  unsigned need = (fused ? 2 : 1) + 7;
+  for (size_t p = 0; p < s->P; p++)
+    if (s->loglen[p] < need) return false;
+  return true;
+}
+
+// value at r of the cubic through (0, e0), (1, e1), (2, e2), (3, e3)  (UniPoly::from_evals + evaluate)
+hfq cubic_at(const hfq &e0, const hfq &e1, const hfq &e2, const hfq &e3, const hfq &r) {
+  static const hfq two_inv = hfq_invert(hfq_from_u64(2)), six_inv = hfq_invert(hfq_from_u64(6));
+  hfq three_e1 = hfq_add(hfq_add(e1, e1), e1), three_e2 = hfq_add(hfq_add(e2, e2), e2);
+  hfq a = hfq_mul(six_inv, hfq_sub(hfq_add(hfq_sub(e3, three_e2), three_e1), e0));
+  hfq five_e1 = hfq_add(hfq_add(three_e1, e1), e1), four_e2 = hfq_add(three_e2, e2);
+  hfq b = hfq_mul(two_inv, hfq_sub(hfq_add(hfq_sub(hfq_add(e0, e0), five_e1), four_e2), e3));
+  hfq c = hfq_sub(hfq_sub(hfq_sub(e1, e0), a), b);
+  return hfq_add(e0, hfq_mul(r, hfq_add(c, hfq_mul(r, hfq_add(b, hfq_mul(r, a))))));
+}
+
+}  // namespace
+
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
   SPG_CHECK(s && e, "spg_sc1_round_eval: null argument");
   if (s->round >= spg_sc1_num_rounds(s)) {
@@ -478,7 +616,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
   spg_ctx *ctx = s->ctx;
   int phase = phase_of(s, s->round);
   size_t j = phase_round(s, s->round);
-  hfq raw[3];
+  hfq ev[3];  // e(0), e(2), e(3)
   if (phase == 2) {
     SPG_TRY(sc1_enter_p_phase(s));
     size_t half = s->p_len / 2;
@@ -488,36 +626,79 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
     spg_fq tmp[3];
     SPG_TRY(fetch_result(ctx, 3, tmp));
     hfq c = hfq_mul(hfq_mul(s->cx, s->cq), s->scale);
-    for (int t = 0; t < 3; t++) e[t] = hfq_to(hfq_mul(c, hfq_from(tmp[t])));
-    s->evaluated = true;
-    return SPG_OK;
-  }
-  if (s->have_cached) {
-    for (int t = 0; t < 3; t++) raw[t] = s->cached[t];
-    s->have_cached = false;
+    for (int t = 0; t < 3; t++) ev[t] = hfq_mul(c, hfq_from(tmp[t]));
   } else {
-    unsigned long long items = 0, out_total = 0;
-    build_segs(s, phase, 0, &items, &out_total);
-    SPG_TRY(upload_segs(s));
+    // scalar prefix and the active variable's eq line l(t), left to the host by the kernels
+    const hfq &tau = phase == 0 ? s->tau_x[j] : s->tau_q[j];
+    hfq line[3];
+    hfq_eq_line_023(tau, line);  // l(0), l(2), l(3); l(1) = tau
+    hfq c = hfq_mul(phase == 0 ? s->cx : hfq_mul(s->cx, s->cq), s->scale);
     size_t n_phase = phase == 0 ? s->nx : s->nq;
     const fq *S = s_table(s, phase, n_phase - j - 1);
     const fq *RW = phase == 0 ? s->RWx : s->Ap;
-    int grid = grid_for(ctx, items, RB, 4);
-    SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
-    ctx->next_units = 192.0 * (double)items;  // 2 scalars x 3 tables read per pair
-    SPG_LAUNCH(ctx, k_pair_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
-               s->tab[s->cur][2], s->d_segs, (int)s->P, items, RW, S, ctx->d_partials);
-    SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
-    spg_fq tmp[3];
-    SPG_TRY(fetch_result(ctx, 3, tmp));
-    for (int t = 0; t < 3; t++) raw[t] = hfq_from(tmp[t]);
+    bool done = false;
+    if (s->cached_kind == 2) {
+      // G(0), G(2) from the fused kernel; G(1) from the running claim, G(3) by extrapolation
+      hfq denom = hfq_mul(c, tau);
+      if (!hfq_is_zero(denom)) {
+        hfq e0 = hfq_mul(hfq_mul(c, line[0]), s->cached[0]);
+        hfq G1 = hfq_mul(hfq_sub(s->claim, e0), hfq_invert(denom));
+        hfq d = hfq_sub(s->cached[1], G1);
+        hfq G3 = hfq_add(s->cached[0], hfq_add(hfq_add(d, d), d));
+        ev[0] = e0;
+        ev[1] = hfq_mul(hfq_mul(c, line[1]), s->cached[1]);
+        ev[2] = hfq_mul(hfq_mul(c, line[2]), G3);
+        done = true;
+      }
+      s->cached_kind = 0;  // denom == 0 (probability ~2^-252): recompute from the bound tables below
+    } else if (s->cached_kind == 3) {
+      for (int t = 0; t < 3; t++) ev[t] = hfq_mul(hfq_mul(c, line[t]), s->cached[t]);
+      s->cached_kind = 0;
+      done = true;
+    }
+    if (!done && rows_eligible(s, 0)) {
+      unsigned long long tiles = 0, out_total = 0;
+      build_tile_segs(s, phase, 0, &tiles, &out_total);
+      SPG_TRY(upload_segs(s));
+      SPG_TRY(ensure_partials(ctx, (size_t)tiles * 3));
+      fq zero = fq{};
+      double pairs = 0;
+      for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
+      ctx->next_units = 192.0 * pairs;  // 2 scalars x 3 tables read per pair
+      SPG_LAUNCH(ctx, k_rows<0>, (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, zero, RW, S, ctx->d_partials);
+      SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 3, ctx->d_result));
+      spg_fq tmp[3];
+      SPG_TRY(fetch_result(ctx, 3, tmp));
+      hfq G0 = hfq_from(tmp[0]), G1 = hfq_from(tmp[1]), G2 = hfq_from(tmp[2]);
+      hfq d = hfq_sub(G2, G1);
+      hfq G3 = hfq_add(G0, hfq_add(hfq_add(d, d), d));
+      ev[0] = hfq_mul(hfq_mul(c, line[0]), G0);
+      ev[1] = hfq_mul(hfq_mul(c, line[1]), G2);
+      ev[2] = hfq_mul(hfq_mul(c, line[2]), G3);
+      s->claim = hfq_add(ev[0], hfq_mul(hfq_mul(c, tau), G1));  // e(0) + e(1): the true claim
+      s->claim_known = true;
+      done = true;
+    }
+    if (!done) {
+      unsigned long long items = 0, out_total = 0;
+      build_segs(s, phase, 0, &items, &out_total);
+      SPG_TRY(upload_segs(s));
+      int grid = grid_for(ctx, items, RB, 4);
+      SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+      ctx->next_units = 192.0 * (double)items;
+      SPG_LAUNCH(ctx, k_pair_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
+                 s->tab[s->cur][2], s->d_segs, (int)s->P, items, RW, S, ctx->d_partials);
+      SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
+      spg_fq tmp[3];
+      SPG_TRY(fetch_result(ctx, 3, tmp));
+      for (int t = 0; t < 3; t++) ev[t] = hfq_mul(hfq_mul(c, line[t]), hfq_from(tmp[t]));
+    }
   }
-  // scalar prefix and the active variable's eq line, left to the host by the kernels
-  hfq line[3];
-  const hfq &tau = phase == 0 ? s->tau_x[j] : s->tau_q[j];
-  hfq_eq_line_023(tau, line);
-  hfq c = hfq_mul(phase == 0 ? s->cx : hfq_mul(s->cx, s->cq), s->scale);
-  for (int t = 0; t < 3; t++) e[t] = hfq_to(hfq_mul(hfq_mul(c, line[t]), raw[t]));
+  for (int t = 0; t < 3; t++) {
+    s->last_e[t] = ev[t];
+    e[t] = hfq_to(ev[t]);
+  }
   s->evaluated = true;
   return SPG_OK;
 }
@@ -534,6 +715,9 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
   fq rr;
   memcpy(&rr, r, sizeof rr);
   hfq rh = hfq_from(*r);
+  // claim_{j+1} = s_j(r_j)
+  if (s->claim_known)
+    s->claim = cubic_at(s->last_e[0], hfq_sub(s->claim, s->last_e[0]), s->last_e[1], s->last_e[2], rh);
   if (phase == 2) {
     size_t half = s->p_len / 2;
     SPG_LAUNCH(ctx, k_p_bind, 1, 128, 0, s->Ap, s->tab[s->cur][0], s->tab[s->cur][1],
@@ -546,12 +730,28 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
     for (size_t p = 0; p < s->P; p++) minlen = s->loglen[p] < minlen ? s->loglen[p] : minlen;
     int nxt = s->cur ^ 1;
     unsigned long long items = 0, out_total = 0;
-    if (s->fuse && next_same && minlen >= 2) {
+    const fq *RW = phase == 0 ? s->RWx : s->Ap;
+    if (s->fuse && next_same && s->claim_known && rows_eligible(s, 1)) {
+      unsigned long long tiles = 0;
+      build_tile_segs(s, phase, 1, &tiles, &out_total);
+      SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
+      SPG_TRY(upload_segs(s));
+      const fq *Snext = s_table(s, phase, n_phase - j - 2);
+      SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
+      ctx->next_units = 288.0 * (double)out_total;  // per bound pair: 4 read + 2 written scalars x 3 tables
+      SPG_LAUNCH(ctx, k_rows<1>, (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                 s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, rr, RW, Snext, ctx->d_partials);
+      SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
+      spg_fq tmp[2];
+      SPG_TRY(fetch_result(ctx, 2, tmp));
+      s->cached[0] = hfq_from(tmp[0]);
+      s->cached[1] = hfq_from(tmp[1]);
+      s->cached_kind = 2;
+    } else if (s->fuse && next_same && minlen >= 2) {
       build_segs(s, phase, 1, &items, &out_total);
       SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
       SPG_TRY(upload_segs(s));
       const fq *Snext = s_table(s, phase, n_phase - j - 2);
-      const fq *RW = phase == 0 ? s->RWx : s->Ap;
       int grid = grid_for(ctx, items, RB, 4);
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
       ctx->next_units = 576.0 * (double)items;  // 4 read + 2 written scalars x 3 tables per item
@@ -562,7 +762,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       spg_fq tmp[3];
       SPG_TRY(fetch_result(ctx, 3, tmp));
       for (int t = 0; t < 3; t++) s->cached[t] = hfq_from(tmp[t]);
-      s->have_cached = true;
+      s->cached_kind = 3;
     } else {
       build_segs(s, phase, 0, &items, &out_total);
       SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");

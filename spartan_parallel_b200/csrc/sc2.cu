@@ -21,13 +21,27 @@ constexpr int RB2 = 128;
 // Z_rq[p][w][y] = sum_q E[q] * Z[p][q][w][y]; E = LSB-first eq table of rq_rev, whose
 // entries q < Q_p already carry the (1 - r) factors of the rounds after instance p ran
 // out of proofs (bound_poly_q, custom_dense_mlpoly.rs:222-244).
-__global__ void k_z_bind_rq(const fq *__restrict__ Z, const fq *__restrict__ E, size_t Q, size_t WY,
-                            fq *__restrict__ out) {
+__global__ void k_z_bind_rq(const SecView *__restrict__ secs, const fq *__restrict__ E, size_t Q, size_t W,
+                            unsigned int log_y, fq *__restrict__ out) {
+  size_t WY = W << log_y;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < WY;
        t += (size_t)gridDim.x * blockDim.x) {
+    size_t w = t >> log_y, y = t & (((size_t)1 << log_y) - 1);
+    SecView v = secs[w];
     fq acc = fq_zero();
-    for (size_t q = 0; q < Q; q++) acc = fq_add(acc, fq_mul(fq_load(E + q), fq_load_stream(Z + q * WY + t)));
-    fq_store(out + t, acc);
+    if (y < v.copy) {
+      const fq *src = v.ptr + y;
+      if (v.q_stride == 0) {
+        // a short section holds one row for every proof: sum_q E[q] * z = (sum_q E[q]) * z
+        fq es = fq_zero();
+        for (size_t q = 0; q < Q; q++) es = fq_add_lazy(es, fq_load(E + q));
+        acc = fq_mul_lazy(es, fq_load(src));
+      } else {
+        for (size_t q = 0; q < Q; q++)
+          acc = fq_add_lazy(acc, fq_mul_lazy(fq_load(E + q), fq_load_stream(src + q * v.q_stride)));
+      }
+    }
+    fq_store(out + t, fq_canon(acc));
   }
 }
 
@@ -223,7 +237,7 @@ void build_segs2(spg_sc2 *s, int phase, int quad, unsigned long long *items_out,
     g.log_len = ll;
     g.n_rows = (unsigned)rows;
     g.rw_off = (unsigned)p;
-    g.pad = 0;
+    g.log_tiles = 0;
     unsigned long long in_sz = rows << ll;
     unsigned long long out_sz = ll >= 1 ? in_sz >> 1 : in_sz;
     in_off += in_sz;
@@ -289,8 +303,8 @@ static int z_bind_rq_all(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, 
       break;
     }
     ctx->next_units = 32.0 * (double)WY * (double)(z->num_proofs[p] + 1);
-    k_z_bind_rq<<<grid_for(ctx, WY, 128), 128, 0, ctx->stream>>>(z->d + z->off[p], E, z->num_proofs[p], WY, dst + off[p]);
-    ctx->launches++;
+    SPG_LAUNCH(ctx, k_z_bind_rq, grid_for(ctx, WY, 128), 128, 0, z->views + p * z->W, E, z->num_proofs[p], z->W,
+               log2u(z->num_inputs[p]), dst + off[p]);
   }
   if (rc == SPG_OK && cudaGetLastError() != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "k_z_bind_rq", __FILE__, __LINE__);
   dev_free(ctx, Sq);
