@@ -267,12 +267,28 @@ def run_gpu(args):
                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms,
                     "launches_per_step": dom["launches"] / args.steps,
                     "share_of_step": dom["total_ms"] / ms_dev}
-        if dom["kernel"].startswith("k_quad_bind_eval"):
-            # 13 Montgomery products per 576 algorithmic bytes (6 bind + 3 products + 1 weight + 3 weighted)
-            mm = dom["units"] / 576.0 * 13.0 / (dom["total_ms"] * 1e-3)
+        if dom["kernel"].startswith("k_rows<1>"):
+            # fused bind + eval item: 576 algorithmic bytes, 10 Montgomery products
+            # (6 binds + 2 products + 2 eq-weighted accumulations)
+            mm = dom["units"] / 576.0 * 10.0 / (dom["total_ms"] * 1e-3)
             roofline["int_pipe"] = {"achieved_modmul_per_s": mm, "peak_modmul_per_s": int_peak,
                                     "frac": (mm / int_peak) if int_peak else None,
                                     "peak_source": "tools/imad_peak.cu in-register fq_mul_lazy rate (profiles/r1_imad_peak.json)"}
+        # DRAM traffic of the largest launch of this kernel from the committed ncu --set full capture
+        try:
+            rd = wr = None
+            for ln in open(os.path.join(ROOT, "profiles", "r1_k_rows_ncu_full.txt")):
+                if ln.startswith("== launch 2"):
+                    break
+                if ln.startswith("dram__bytes_read.sum ="):
+                    rd = float(ln.split("=")[1].split()[0]) * 1e9
+                if ln.startswith("dram__bytes_write.sum ="):
+                    wr = float(ln.split("=")[1].split()[0]) * 1e9
+            if rd and wr and dom["kernel"].startswith("k_rows<1>"):
+                roofline["traffic"] = rd + wr
+                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1_k_rows_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
+        except Exception:
+            pass
     cpu = cpu_baseline_sample(args, threads=1)
     line = {
         "metric": "sumcheck_constraints_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world,
