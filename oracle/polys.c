@@ -286,6 +286,7 @@ void opqx_bound_poly(opqx *s, const ofq *r, int mode) {
             }
         } else {
           s->num_proofs[p] /= 2;
+#pragma omp parallel for schedule(static) if (s->num_proofs[p] * s->num_inputs[p] >= 8192)
           for (size_t q = 0; q < s->num_proofs[p]; q++)
             for (size_t w = 0; w < min_sz(s->num_witness_secs, s->W); w++)
               for (size_t x = 0; x < s->num_inputs[p]; x++)
@@ -314,6 +315,7 @@ void opqx_bound_poly(opqx *s, const ofq *r, int mode) {
             }
         } else {
           s->num_inputs[p] /= 2;
+#pragma omp parallel for collapse(2) schedule(static) if (s->num_proofs[p] * s->num_inputs[p] >= 8192)
           for (size_t q = 0; q < s->num_proofs[p]; q++)
             for (size_t w = 0; w < min_sz(s->num_witness_secs, s->W); w++)
               for (size_t x = 0; x < s->num_inputs[p]; x++)

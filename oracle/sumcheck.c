@@ -68,37 +68,50 @@ void osc1_round_eval(osc1 *s, ofq out[3]) {
   for (size_t p = 0; p < min_sz(s->instance_len, s->P); p++) {
     if (mode == OMODE_X && s->num_cons[p] > 1) s->num_cons[p] /= 2;
     if (mode == OMODE_Q && s->num_proofs[p] > 1) s->num_proofs[p] /= 2;
-    for (size_t q = 0; q < s->num_proofs[p]; q++) {
-      size_t step_q = s->proof_len / s->num_proofs[p];
-      size_t step_x = s->cons_len / s->num_cons[p];
-      for (size_t x = 0; x < s->num_cons[p]; x++) {
-        ofq pq = ofq_mul(&s->Ap[p], &s->Aq[q * step_q]);
-        ofq A_lo = ofq_mul(&pq, &s->Ax[x * step_x]);
-        ofq A_hi;
-        if (mode == OMODE_P) {
-          ofq t = ofq_mul(&s->Ap[p + s->instance_len], &s->Aq[q * step_q]);
-          A_hi = ofq_mul(&t, &s->Ax[x * step_x]);
-        } else if (mode == OMODE_Q) {
-          ofq t = ofq_mul(&s->Ap[p], &s->Aq[q * step_q + s->proof_len]);
-          A_hi = ofq_mul(&t, &s->Ax[x * step_x]);
-        } else {
-          A_hi = ofq_mul(&pq, &s->Ax[x * step_x + s->cons_len]);
+    /* the (q, x) iterations are independent; field sums are exact, so per-thread partial
+     * sums combined at the end equal the reference's sequential accumulation bit for bit */
+    size_t nq = s->num_proofs[p], nxp = s->num_cons[p];
+#pragma omp parallel if (nq * nxp >= 8192)
+    {
+      ofq t0 = ofq_zero(), t2 = ofq_zero(), t3 = ofq_zero();
+#pragma omp for collapse(2) schedule(static)
+      for (size_t q = 0; q < nq; q++) {
+        for (size_t x = 0; x < nxp; x++) {
+          size_t step_q = s->proof_len / nq;
+          size_t step_x = s->cons_len / nxp;
+          ofq pq = ofq_mul(&s->Ap[p], &s->Aq[q * step_q]);
+          ofq A_lo = ofq_mul(&pq, &s->Ax[x * step_x]);
+          ofq A_hi;
+          if (mode == OMODE_P) {
+            ofq t = ofq_mul(&s->Ap[p + s->instance_len], &s->Aq[q * step_q]);
+            A_hi = ofq_mul(&t, &s->Ax[x * step_x]);
+          } else if (mode == OMODE_Q) {
+            ofq t = ofq_mul(&s->Ap[p], &s->Aq[q * step_q + s->proof_len]);
+            A_hi = ofq_mul(&t, &s->Ax[x * step_x]);
+          } else {
+            A_hi = ofq_mul(&pq, &s->Ax[x * step_x + s->cons_len]);
+          }
+          ofq B_lo = opqx_index(s->B, p, q, 0, x), B_hi = opqx_index_high(s->B, p, q, 0, x, mode);
+          ofq C_lo = opqx_index(s->C, p, q, 0, x), C_hi = opqx_index_high(s->C, p, q, 0, x, mode);
+          ofq D_lo = opqx_index(s->D, p, q, 0, x), D_hi = opqx_index_high(s->D, p, q, 0, x, mode);
+          ofq t = comb1(&A_lo, &B_lo, &C_lo, &D_lo);
+          t0 = ofq_add(&t0, &t);
+          ofq A2, A3, B2, B3, C2, C3, D2, D3;
+          extrap(&A_lo, &A_hi, &A2, &A3);
+          extrap(&B_lo, &B_hi, &B2, &B3);
+          extrap(&C_lo, &C_hi, &C2, &C3);
+          extrap(&D_lo, &D_hi, &D2, &D3);
+          t = comb1(&A2, &B2, &C2, &D2);
+          t2 = ofq_add(&t2, &t);
+          t = comb1(&A3, &B3, &C3, &D3);
+          t3 = ofq_add(&t3, &t);
         }
-        ofq B_lo = opqx_index(s->B, p, q, 0, x), B_hi = opqx_index_high(s->B, p, q, 0, x, mode);
-        ofq C_lo = opqx_index(s->C, p, q, 0, x), C_hi = opqx_index_high(s->C, p, q, 0, x, mode);
-        ofq D_lo = opqx_index(s->D, p, q, 0, x), D_hi = opqx_index_high(s->D, p, q, 0, x, mode);
-
-        ofq t = comb1(&A_lo, &B_lo, &C_lo, &D_lo);
-        e0 = ofq_add(&e0, &t);
-        ofq A2, A3, B2, B3, C2, C3, D2, D3;
-        extrap(&A_lo, &A_hi, &A2, &A3);
-        extrap(&B_lo, &B_hi, &B2, &B3);
-        extrap(&C_lo, &C_hi, &C2, &C3);
-        extrap(&D_lo, &D_hi, &D2, &D3);
-        t = comb1(&A2, &B2, &C2, &D2);
-        e2 = ofq_add(&e2, &t);
-        t = comb1(&A3, &B3, &C3, &D3);
-        e3 = ofq_add(&e3, &t);
+      }
+#pragma omp critical
+      {
+        e0 = ofq_add(&e0, &t0);
+        e2 = ofq_add(&e2, &t2);
+        e3 = ofq_add(&e3, &t3);
       }
     }
   }
