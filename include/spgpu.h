@@ -232,6 +232,42 @@ int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const
 /* AddrTimestamps::deref_mem, :255-264: out[i] = mem[addr[i]] */
 int spg_deref(spg_ctx *ctx, const uint64_t *addr, size_t n, const spg_vec *mem, spg_vec **out);
 
+/* hash_func over scalar tables already on the device (the ops/timestamp polynomials of a
+ * spg_sparse): addr == NULL means addr[i] = i, ts == NULL means ts = 0. */
+int spg_hash_layer_fq(spg_ctx *ctx, const spg_vec *addr, const spg_vec *val, const spg_vec *ts,
+                      int ts_plus_one, const spg_fq *gamma, const spg_fq *tau, spg_vec **out);
+
+/* MultiSparseMatPolynomialAsDense, src/sparse_mlpoly.rs:273-280, 368-425: `batch` sparse
+ * matrices (entries concatenated, nnz[i] each) padded to N = max next_pow2(nnz), their
+ * address / read-timestamp / audit-timestamp polynomials and the merged comb_ops / comb_mem. */
+typedef struct spg_sparse spg_sparse;
+int spg_sparse_create(spg_ctx *ctx, size_t batch, size_t num_vars_x, size_t num_vars_y,
+                      const size_t *nnz, const uint32_t *rows, const uint32_t *cols,
+                      const spg_fq *vals, spg_sparse **out);
+void spg_sparse_destroy(spg_sparse *s);
+size_t spg_sparse_num_ops(const spg_sparse *s);       /* N */
+size_t spg_sparse_num_mem_cells(const spg_sparse *s); /* 2^max(num_vars_x, num_vars_y) */
+enum {
+  SPG_SPARSE_ROW_ADDR = 0,
+  SPG_SPARSE_ROW_READ_TS = 1,
+  SPG_SPARSE_COL_ADDR = 2,
+  SPG_SPARSE_COL_READ_TS = 3,
+  SPG_SPARSE_VAL = 4,
+  SPG_SPARSE_ROW_AUDIT_TS = 5,
+  SPG_SPARSE_COL_AUDIT_TS = 6,
+  SPG_SPARSE_COMB_OPS = 7,
+  SPG_SPARSE_COMB_MEM = 8
+};
+/* non-owning view of one polynomial (i = matrix index for kinds 0-4); free with spg_vec_free,
+ * the spg_sparse must outlive it */
+int spg_sparse_view(spg_sparse *s, int kind, size_t i, spg_vec **out);
+/* MultiSparseMatPolynomialAsDense::deref + Derefs::new, :34-62, 588-598: the merged lookup
+ * table [row_ops_val[batch] | col_ops_val[batch] | zero pad], blocks of N */
+int spg_sparse_deref(spg_ctx *ctx, const spg_sparse *s, const spg_vec *mem_rx,
+                     const spg_vec *mem_ry, spg_vec **out);
+/* device copy of v[offset, offset + n) */
+int spg_vec_clone(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_vec **out);
+
 /* ---------------------------------------------------------------- commitments (a16)
  * MultiCommitGens::new is host-side setup (src/commitments.rs:15-33); the caller
  * passes the n+1 generators as compressed ristretto points (G[0..n], h). */

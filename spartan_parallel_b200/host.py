@@ -34,6 +34,10 @@ def lib():
                                      C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+        L.sph_sparse_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 
@@ -86,3 +90,26 @@ def r1cs_prove(ctx, inst, witness_secs, num_proofs, max_num_proofs, num_inputs, 
         outs.append(ch[pos:pos + int(c)].copy())
         pos += int(c)
     return proof, outs
+
+
+def sparse_prove(ctx, polys, num_vars_x: int, num_vars_y: int, rx, ry, evals, transcript_label: bytes, gens_label: bytes,
+                 tape_seed):
+    """SparseMatPolynomial::multi_commit + SparseMatPolyEvalProof::prove (src/sparse_mlpoly.rs:566-586,
+    1509-1564) for a batch of matrices `polys` = [(rows, cols, vals), ...].
+    Returns (SparseMatPolyCommitment bytes, SparseMatPolyEvalProof bytes), both in bincode layout."""
+    nnz = _sz([len(p_[0]) for p_ in polys])
+    rows = np.ascontiguousarray(np.concatenate([np.asarray(p_[0], dtype=np.uint32) for p_ in polys]))
+    cols = np.ascontiguousarray(np.concatenate([np.asarray(p_[1], dtype=np.uint32) for p_ in polys]))
+    vals = np.ascontiguousarray(np.concatenate([np.asarray(p_[2], dtype=np.uint64).reshape(-1, 4) for p_ in polys]))
+    fq = lambda a, n: np.ascontiguousarray(np.asarray(a, dtype=np.uint64).reshape(n, 4)) if n else np.zeros((1, 4), dtype=np.uint64)
+    rx_, ry_, ev = fq(rx, num_vars_x), fq(ry, num_vars_y), fq(evals, len(polys))
+    seed = np.ascontiguousarray(tape_seed, dtype=np.uint64)
+    oc, ocl, op, opl = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib().sph_sparse_prove(ctx.h, transcript_label, gens_label, p(seed), len(polys), num_vars_x, num_vars_y, p(nnz),
+                                  p(rows), p(cols), p(vals), p(rx_), p(ry_), p(ev), C.byref(oc), C.byref(ocl), C.byref(op),
+                                  C.byref(opl)), "sph_sparse_prove")
+    comm, proof = C.string_at(oc, ocl.value), C.string_at(op, opl.value)
+    lib().sph_free(oc)
+    lib().sph_free(op)
+    return comm, proof

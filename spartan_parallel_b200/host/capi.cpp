@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "protocol.hpp"
+#include "sparse.hpp"
 
 using namespace sph;
 
@@ -76,6 +77,50 @@ int sph_r1cs_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_
     }
     return 0;
   } catch (const std::exception &e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+// SparseMatPolynomial::multi_commit + SparseMatPolyEvalProof::prove (src/sparse_mlpoly.rs:566-586, 1509-1564)
+// for `batch` matrices given as concatenated (row, col, val) entries, nnz[i] each.
+//   out_comm: bincode of SparseMatPolyCommitment; out_proof: bincode of SparseMatPolyEvalProof (malloc'ed)
+int sph_sparse_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_label, const uint64_t tape_seed[4],
+                     size_t batch, size_t num_vars_x, size_t num_vars_y, const size_t *nnz, const uint32_t *rows,
+                     const uint32_t *cols, const spg_fq *vals, const spg_fq *rx, const spg_fq *ry, const spg_fq *evals,
+                     uint8_t **out_comm, size_t *out_comm_len, uint8_t **out_proof, size_t *out_proof_len) {
+  spg_sparse *sp = nullptr;
+  try {
+    size_t max_nz = 0;
+    for (size_t i = 0; i < batch; i++) max_nz = nnz[i] > max_nz ? nnz[i] : max_nz;
+    check(spg_sparse_create(ctx, batch, num_vars_x, num_vars_y, nnz, rows, cols, vals, &sp), "spg_sparse_create");
+    SparseGens gens(ctx, gens_label, num_vars_x, num_vars_y, max_nz, batch);
+    SparseCommitment c = sparse_commit(ctx, sp, batch, gens);
+    Writer wc;
+    wc.u64(c.batch_size);
+    wc.u64(c.num_ops);
+    wc.u64(c.num_mem_cells);
+    wc.points(c.comm_comb_ops);
+    wc.points(c.comm_comb_mem);
+    ProofTranscript t(transcript_label);
+    hfq seed{{tape_seed[0], tape_seed[1], tape_seed[2], tape_seed[3]}};
+    RandomTape tape("proof", Scalar(seed));
+    std::vector<Scalar> vrx, vry, vev;
+    for (size_t i = 0; i < num_vars_x; i++) vrx.push_back(Scalar::from_fq(rx[i]));
+    for (size_t i = 0; i < num_vars_y; i++) vry.push_back(Scalar::from_fq(ry[i]));
+    for (size_t i = 0; i < batch; i++) vev.push_back(Scalar::from_fq(evals[i]));
+    std::vector<uint8_t> proof = sparse_prove(ctx, sp, batch, vrx, vry, vev, gens, t, tape);
+    spg_sparse_destroy(sp);
+    sp = nullptr;
+    *out_comm_len = wc.out.size();
+    *out_comm = (uint8_t *)malloc(wc.out.size());
+    memcpy(*out_comm, wc.out.data(), wc.out.size());
+    *out_proof_len = proof.size();
+    *out_proof = (uint8_t *)malloc(proof.size());
+    memcpy(*out_proof, proof.data(), proof.size());
+    return 0;
+  } catch (const std::exception &e) {
+    spg_sparse_destroy(sp);
     g_err = e.what();
     return -1;
   }
