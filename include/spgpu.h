@@ -131,6 +131,12 @@ int spg_r1cs_multi_evaluate(spg_ctx *ctx, const spg_r1cs *inst, const spg_fq *rx
  * num_instances is 1 (single) or P; num_proofs[p] is 1 (short) or Q_p. */
 int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
                        const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out);
+/* same, but the copy runs on the context's copy stream and returns immediately: host_w_mat
+ * must be pinned and stay valid until a consumer (spg_zmat_build, spg_witness_poly) has
+ * been enqueued AND the context is next synchronised. Lets the upload of batch i+1 overlap
+ * the proving of batch i. */
+int spg_witness_upload_async(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                       const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out);
 void spg_witness_destroy(spg_witness *w);
 /* poly_w[p] as a dense vector view (not owned by the caller) */
 int spg_witness_poly(spg_witness *w, size_t p, spg_vec **out);
@@ -160,6 +166,14 @@ int spg_sc1_create_from_tables(spg_ctx *ctx, size_t num_instances, const size_t 
  * axis (multi-GPU) carries the eq factor of the proof bits it does not hold; the tail
  * rounds after a gather carry the eq products already bound on the shards. */
 int spg_sc1_set_scale(spg_sc1 *s, const spg_fq *c);
+/* The claim of the sumcheck, as the reference's prover receives it (`claim`,
+ * src/sumcheck.rs:1069; R1CSProof::prove passes Scalar::zero(), src/r1csproof.rs:330). The
+ * reference never evaluates the round polynomial at 1: it uses e(1) = claim - e(0)
+ * (:1250-1256). With the claim supplied the device does the same from the first round on
+ * (two evaluation points per pair instead of three). Results are identical to the
+ * reference's whenever the claim really is the sum over the tables, i.e. for a satisfying
+ * witness; without this call every round is exact for arbitrary tables. Call before round 0. */
+int spg_sc1_set_claim(spg_sc1 *s, const spg_fq *claim);
 size_t spg_sc1_num_rounds(const spg_sc1 *s);
 /* e = (eval_point_0, eval_point_2, eval_point_3) of the current round, :1166-1245 */
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]);

@@ -76,11 +76,18 @@ def _proto(L):
         "spg_r1cs_create": [P, SZ, SZ, P, SZ, P, P, P, P, PP],
         "spg_r1cs_multi_evaluate": [P, P, P, SZ, P, SZ, P],
         "spg_witness_upload": [P, SZ, P, P, P, PP],
+        "spg_witness_upload_async": [P, SZ, P, P, P, PP],
+        "spg_sparse_create": [P, SZ, SZ, SZ, P, P, P, P, PP],
+        "spg_sparse_view": [P, INT, SZ, PP],
+        "spg_sparse_deref": [P, P, P, P, PP],
+        "spg_hash_layer_fq": [P, P, P, P, INT, P, P, PP],
+        "spg_vec_clone": [P, P, SZ, SZ, PP],
         "spg_witness_poly": [P, SZ, PP],
         "spg_zmat_build": [P, SZ, P, P, SZ, P, PP],
         "spg_sc1_create": [P, P, P, SZ, P, SZ, P, SZ, SZ, P, P, P, PP],
         "spg_sc1_create_from_tables": [P, SZ, P, SZ, P, SZ, P, P, P, P, P, P, PP],
         "spg_sc1_set_scale": [P, P],
+        "spg_sc1_set_claim": [P, P],
         "spg_fq_host_sum": [P, SZ, SZ, P],
         "spg_fq_host_mul": [P, P, P],
         "spg_fq_host_eq_weight": [P, SZ, C.c_uint64, P],
@@ -115,12 +122,13 @@ def _proto(L):
         f.argtypes = args
     for name in ("spg_ctx_destroy", "spg_host_free", "spg_vec_free", "spg_r1cs_destroy", "spg_witness_destroy",
                  "spg_zmat_destroy", "spg_sc1_destroy", "spg_sc2_destroy", "spg_prodtree_destroy",
-                 "spg_cubic_destroy", "spg_gens_destroy"):
+                 "spg_cubic_destroy", "spg_gens_destroy", "spg_sparse_destroy"):
         f = getattr(L, name, None)
         if f is not None:
             f.restype = None
             f.argtypes = [P]
-    for name in ("spg_vec_len", "spg_sc1_num_rounds", "spg_sc2_num_rounds", "spg_prodtree_num_layers"):
+    for name in ("spg_vec_len", "spg_sc1_num_rounds", "spg_sc2_num_rounds", "spg_prodtree_num_layers", "spg_sparse_num_ops",
+                 "spg_sparse_num_mem_cells"):
         f = getattr(L, name, None)
         if f is not None:
             f.restype = SZ

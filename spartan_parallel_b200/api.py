@@ -224,6 +224,11 @@ class SumcheckPhase1:
         """Multiply every evaluation and the eq claim by c (shards of the proof axis)."""
         check(self.ctx.L.spg_sc1_set_scale(self.h, _ptr(_fq(c))), "spg_sc1_set_scale")
 
+    def set_claim(self, claim):
+        """The prover's `claim` argument (src/sumcheck.rs:1069; zero in R1CSProof::prove): lets round 0
+        use e(1) = claim - e(0) like the reference does. Exact iff the claim is the true sum."""
+        check(self.ctx.L.spg_sc1_set_claim(self.h, _ptr(_fq(claim))), "spg_sc1_set_claim")
+
     def round_eval(self) -> np.ndarray:
         out = np.empty((3, 4), dtype=np.uint64)
         check(self.ctx.L.spg_sc1_round_eval(self.h, _ptr(out)), "spg_sc1_round_eval")
@@ -318,14 +323,18 @@ class ProverWitnessSecInfo:
     """One witness section (src/lib.rs ProverWitnessSecInfo): ``w_mat`` flattened
     [p][q][i]; ``num_proofs[p]`` is 1 for a short section; one instance for a single one."""
 
-    def __init__(self, ctx: Context, num_proofs, num_inputs, w_mat):
+    def __init__(self, ctx: Context, num_proofs, num_inputs, w_mat, asynchronous: bool = False):
+        """asynchronous=True: the H2D copy runs on the context's copy stream (w_mat must be
+        pinned host memory and is kept referenced until this object is freed)."""
         self.ctx = ctx
         self.num_proofs, self.num_inputs = list(num_proofs), list(num_inputs)
         w = _fq(w_mat).reshape(-1, 4)
         assert w.shape[0] == sum(a * b for a, b in zip(self.num_proofs, self.num_inputs))
         h = C.c_void_p()
-        check(ctx.L.spg_witness_upload(ctx.h, len(self.num_proofs), _ptr(_sz(num_proofs)), _ptr(_sz(num_inputs)), _ptr(w),
-                                       C.byref(h)), "spg_witness_upload")
+        fn = ctx.L.spg_witness_upload_async if asynchronous else ctx.L.spg_witness_upload
+        check(fn(ctx.h, len(self.num_proofs), _ptr(_sz(num_proofs)), _ptr(_sz(num_inputs)), _ptr(w), C.byref(h)),
+              "spg_witness_upload")
+        self._host = w if asynchronous else None
         self.h = h
 
     def poly_w(self, p: int) -> DensePolynomial:

@@ -60,6 +60,7 @@ struct spg_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D uploads that overlap with kernels on `stream`
   uint64_t launches = 0;
   // per-block partial sums of the round kernels, and the 3-scalar result slot
   spg::fq *d_partials = nullptr;

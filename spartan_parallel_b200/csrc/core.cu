@@ -145,6 +145,7 @@ int spg_ctx_create(int device, spg_ctx **out) {
   SPG_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
   SPG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  SPG_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   {
     cudaMemPool_t pool;
     SPG_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -168,6 +169,10 @@ void spg_ctx_destroy(spg_ctx *ctx) {
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+  }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -196,6 +196,15 @@ int r1cs_abc_table(spg_ctx *ctx, const spg_r1cs *inst, const fq *evals_rx, size_
 
 int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch);
 
+int witness_wait(spg_witness *w) {
+  if (w->ready) {
+    SPG_CUDA(cudaStreamWaitEvent(w->ctx->stream, w->ready, 0));
+    SPG_CUDA(cudaEventDestroy(w->ready));  // released once the recorded work completes
+    w->ready = nullptr;
+  }
+  return SPG_OK;
+}
+
 }  // namespace spg
 
 using namespace spg;
@@ -291,8 +300,8 @@ int spg_r1cs_multi_evaluate(spg_ctx *ctx, const spg_r1cs *inst, const spg_fq *rx
   return rc;
 }
 
-int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
-                       const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out) {
+static int witness_upload_impl(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                               const size_t *num_inputs, const spg_fq *host_w_mat, bool async, spg_witness **out) {
   SPG_CHECK(ctx && out && num_proofs && num_inputs && host_w_mat, "spg_witness_upload: null argument");
   SPG_CHECK(num_instances >= 1, "spg_witness_upload: need at least one instance");
   spg_witness *w = new (std::nothrow) spg_witness();
@@ -314,8 +323,21 @@ int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_pro
   }
   w->total = tot;
   cudaError_t e = dev_alloc(ctx, &w->d, tot * sizeof(fq));
-  if (e == cudaSuccess) e = cudaMemcpyAsync(w->d, host_w_mat, tot * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (async) {
+    // the buffer comes from the compute stream's pool: order the copy stream after the
+    // allocation, copy there, and leave an event for the first consumer
+    cudaEvent_t alloc_done = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&alloc_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(alloc_done, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, alloc_done, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w->d, host_w_mat, tot * sizeof(fq), cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(w->ready, ctx->copy_stream);
+    if (alloc_done) cudaEventDestroy(alloc_done);
+  } else {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w->d, host_w_mat, tot * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
   if (e != cudaSuccess) {
     spg_witness_destroy(w);
     return cuda_fail(e, "witness upload", __FILE__, __LINE__);
@@ -325,8 +347,24 @@ int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_pro
   return SPG_OK;
 }
 
+int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                       const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out) {
+  return witness_upload_impl(ctx, num_instances, num_proofs, num_inputs, host_w_mat, false, out);
+}
+
+int spg_witness_upload_async(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
+                             const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out) {
+  return witness_upload_impl(ctx, num_instances, num_proofs, num_inputs, host_w_mat, true, out);
+}
+
 void spg_witness_destroy(spg_witness *w) {
   if (!w) return;
+  if (w->ready) {
+    // a section freed before anyone consumed it: the free below is stream-ordered on the
+    // compute stream, so the copy must be ordered before it
+    cudaStreamWaitEvent(w->ctx->stream, w->ready, 0);
+    cudaEventDestroy(w->ready);
+  }
   for (spg_vec *v : w->views)
     if (v) spg_vec_free(v);
   if (w->d) dev_free(w->ctx, w->d);
@@ -336,6 +374,7 @@ void spg_witness_destroy(spg_witness *w) {
 int spg_witness_poly(spg_witness *w, size_t p, spg_vec **out) {
   SPG_CHECK(w && out, "spg_witness_poly: null argument");
   SPG_CHECK(p < w->num_instances, "spg_witness_poly: instance %zu out of range", p);
+  SPG_TRY(witness_wait(w));
   if (!w->views[p]) {
     spg_vec *v = nullptr;
     SPG_TRY(spg_vec_wrap(w->ctx, w->d + w->off[p], w->num_proofs[p] * w->num_inputs[p], &v));
@@ -362,6 +401,7 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
                 "spg_zmat_build: section %zu instance %zu has %zu proofs, expected 1 or %zu", w, p,
                 ws->num_proofs[p], num_proofs[p]);
   }
+  for (size_t w = 0; w < num_witness_secs; w++) SPG_TRY(witness_wait(witness_secs[w]));
   spg_zmat *z = new (std::nothrow) spg_zmat();
   if (!z) return SPG_ENOMEM;
   z->ctx = ctx;

@@ -49,6 +49,7 @@ struct spg_witness {
   spg::fq *d = nullptr;
   size_t total = 0;
   std::vector<spg_vec *> views;
+  cudaEvent_t ready = nullptr;  // async upload: recorded on the copy stream, awaited by the first consumer
 };
 
 struct spg_zmat {
@@ -59,6 +60,9 @@ struct spg_zmat {
 };
 
 namespace spg {
+
+// orders the compute stream after a pending asynchronous upload of the section
+int witness_wait(spg_witness *w);
 
 // multiply_vec_block (src/r1csinstance.rs:363-436): Az/Bz/Cz in natural ragged [p][q][x] order
 int r1cs_multiply_vec_block(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t P,

@@ -13,13 +13,14 @@ namespace spg {
 int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch);
 __global__ void k_eq_expand(const fq *__restrict__ prev, fq *__restrict__ out, size_t n, fq r);
 
-// 128-thread blocks: the round kernels need ~160 registers, so three 128-thread blocks
-// (12 warps) fit an SM where a single 256-thread block (8 warps) would (measured +13 %)
+// 128-thread blocks capped at 128 registers: four blocks (16 warps) per SM. Measured on
+// B200 for the 2^20 x 64 batch: 256 threads x 1 block 11.5 ms, 128 x 3 (160 regs) 10.16 ms,
+// 128 x 4 (128 regs, no spills) 9.88 ms, 64 x 6 10.25 ms.
 #ifndef SPG_RB
 #define SPG_RB 128
 #endif
 #ifndef SPG_MINB
-#define SPG_MINB 1
+#define SPG_MINB 4
 #endif
 constexpr int RB = SPG_RB;  // threads per block of the round kernels
 
@@ -144,19 +145,21 @@ k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq 
 // One block = one tile of one row, so the row weight RW[row] is applied once per block
 // (after the block reduction) instead of once per item, and all arithmetic between the
 // loads and the stores runs in the lazy range [0, 2q).
-//   FUSED = 0: evaluation only, points t = 0, 1, 2 (first round: also yields the true claim)
+//   FUSED = 0: evaluation only; NE = 3 points t = 0, 1, 2 (first round: also yields the true
+//              claim) or NE = 2 points t = 0, 2 when the caller supplied the claim
+//              (spg_sc1_set_claim)
 //   FUSED = 1: bind with r, then evaluate the bound pair at t = 0, 2. The round polynomial is
 //              l_j(t) * G(t) with G quadratic, so G(0), G(2) and the running claim determine
 //              it (the host side solves for G(1), G(3); exact field arithmetic, see
 //              spg_sc1_round_eval).
 constexpr int ROWS_LOG_TILE = 10;  // 1024 items per tile = 8 per thread at 128 threads
 
-template <int FUSED>
+template <int FUSED, int NE>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
        fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
        int nseg, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
-  constexpr int NE = FUSED ? 2 : 3;
+  static_assert(NE == 2 || (NE == 3 && !FUSED), "k_rows: 2 points, or 3 for the evaluation-only form");
   __shared__ fq sm[NE * 32];
   unsigned long long tile = blockIdx.x;
   int si = nseg == 1 ? 0 : find_seg(segs, nseg, tile);
@@ -202,7 +205,7 @@ k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restric
     fq w = fq_load(S + it);
     // t = 0
     acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a0, b0), c0)));
-    if (!FUSED)  // t = 1
+    if (NE == 3)  // t = 1
       acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a1, b1), c1)));
     // t = 2: 2*hi - lo
     fq a2 = fq_add_lazy(a1, fq_sub_lazy(a1, a0));
@@ -552,6 +555,17 @@ int spg_sc1_set_scale(spg_sc1 *s, const spg_fq *c) {
   return SPG_OK;
 }
 
+int spg_sc1_set_claim(spg_sc1 *s, const spg_fq *claim) {
+  SPG_CHECK(s && claim, "spg_sc1_set_claim: null argument");
+  if (s->round != 0 || s->evaluated) {
+    set_error("spg_sc1_set_claim: must be called before the first round");
+    return SPG_ESTATE;
+  }
+  s->claim = hfq_from(*claim);
+  s->claim_known = true;
+  return SPG_OK;
+}
+
 size_t spg_sc1_num_rounds(const spg_sc1 *s) { return s ? s->nx + s->nq + s->np : 0; }
 
 namespace {
@@ -637,6 +651,25 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
     const fq *S = s_table(s, phase, n_phase - j - 1);
     const fq *RW = phase == 0 ? s->RWx : s->Ap;
     bool done = false;
+    if (s->cached_kind == 0 && s->claim_known && rows_eligible(s, 0) && !hfq_is_zero(hfq_mul(c, tau))) {
+      // the claim is known (spg_sc1_set_claim, or tracked from earlier rounds): two points suffice
+      unsigned long long tiles = 0, out_total = 0;
+      build_tile_segs(s, phase, 0, &tiles, &out_total);
+      SPG_TRY(upload_segs(s));
+      SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
+      fq zero = fq{};
+      double pairs = 0;
+      for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
+      ctx->next_units = 192.0 * pairs;
+      SPG_LAUNCH(ctx, (k_rows<0, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, zero, RW, S, ctx->d_partials);
+      SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
+      spg_fq tmp[2];
+      SPG_TRY(fetch_result(ctx, 2, tmp));
+      s->cached[0] = hfq_from(tmp[0]);
+      s->cached[1] = hfq_from(tmp[1]);
+      s->cached_kind = 2;
+    }
     if (s->cached_kind == 2) {
       // G(0), G(2) from the fused kernel; G(1) from the running claim, G(3) by extrapolation
       hfq denom = hfq_mul(c, tau);
@@ -665,7 +698,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;  // 2 scalars x 3 tables read per pair
-      SPG_LAUNCH(ctx, k_rows<0>, (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+      SPG_LAUNCH(ctx, (k_rows<0, 3>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
                  (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, zero, RW, S, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 3, ctx->d_result));
       spg_fq tmp[3];
@@ -739,7 +772,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       const fq *Snext = s_table(s, phase, n_phase - j - 2);
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
       ctx->next_units = 288.0 * (double)out_total;  // per bound pair: 4 read + 2 written scalars x 3 tables
-      SPG_LAUNCH(ctx, k_rows<1>, (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+      SPG_LAUNCH(ctx, (k_rows<1, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
                  s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, rr, RW, Snext, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
       spg_fq tmp[2];

@@ -31,7 +31,7 @@ def canonical(rng, n):
     return a
 
 
-def run_shape(ctx, log_x, Q):
+def run_shape(ctx, log_x, Q, supply_claim=False):
     import spartan_parallel_b200 as sp
 
     X, N = 1 << log_x, (1 << log_x) * Q
@@ -55,6 +55,8 @@ def run_shape(ctx, log_x, Q):
 
     sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, e, tau_q, tau_x)
     claim = O.ZERO  # satisfied instance
+    if supply_claim:
+        sc1.set_claim(claim)
     for j in range(sc1.num_rounds):
         e0, e2, e3 = sc1.round_eval()
         if j == 0:
@@ -100,3 +102,8 @@ def test_c3_2_16_x_256(ctx):
 
 def test_c5_2_20_x_64(ctx):
     run_shape(ctx, 20, 64)
+
+
+def test_c5_2_20_x_64_supplied_claim(ctx):
+    """same shape with spg_sc1_set_claim(0): two-point first round (what bench.py times)"""
+    run_shape(ctx, 20, 64, supply_claim=True)

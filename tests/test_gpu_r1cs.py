@@ -19,7 +19,7 @@ def ctx():
     return sp.Context(0)
 
 
-def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2):
+def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2, claim=None):
     import spartan_parallel_b200 as sp
 
     A = [inst.mats[3 * i] for i in range(inst.num_instances)]
@@ -34,6 +34,8 @@ def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p
     z = sp.ZMat(ctx, num_proofs, num_inputs, dsecs)
     block_cons = [inst.num_cons[0]] * P if inst.num_instances == 1 else inst.num_cons
     sc1 = sp.sumcheck_phase1(ctx, dinst, z, num_proofs, max_q, block_cons, inst.max_num_cons, max_y, tau_p, tau_q, tau_x)
+    if claim is not None:
+        sc1.set_claim(claim)
     e1 = []
     for j in range(sc1.num_rounds):
         e1.append(sc1.round_eval())
@@ -52,7 +54,7 @@ def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p
     return e1, c1, e2, c2, dinst, dsecs
 
 
-def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed):
+def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, claim=None):
     max_q = max(num_proofs)
     Pp = 1 if P == 1 else 1 << (P - 1).bit_length()
     W = len(secs)
@@ -64,7 +66,7 @@ def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed):
     ch2 = rand_scalars(max(np_ + nw + ny, 1), seed + 2)
     r_abc = rand_scalars(3, seed + 3)
     want = R.prove_tables(inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
-    e1, c1, e2, c2, dinst, _ = gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
+    e1, c1, e2, c2, dinst, _ = gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2, claim)
     assert len(e1) == len(want.evals1) and len(e2) == len(want.evals2)
     for j, (g, w) in enumerate(zip(e1, want.evals1)):
         assert np.array_equal(g, w), f"phase 1 round {j}"
@@ -83,6 +85,28 @@ def test_c1_synthetic(ctx):
     dinst, want = run_case(ctx, inst, 1, [Q], [X], X, secs, seed=100)
     # a satisfying witness makes the phase-1 claim vanish at every round-0 point
     assert np.array_equal(want.evals1[0][0], O.ZERO)
+
+
+@pytest.mark.parametrize("log_x,Q,P", [(10, 4, 1), (9, 8, 1), (8, 4, 3)])
+def test_supplied_claim_two_point_first_round(ctx, log_x, Q, P):
+    """spg_sc1_set_claim(0), what R1CSProof::prove passes (src/r1csproof.rs:330): the first round
+    then evaluates two points per pair and takes e(1) from the claim like the reference
+    (src/sumcheck.rs:1250-1256); bit-exact for a satisfying witness."""
+    X = 1 << log_x
+    inst = R.synthetic_instance(X, num_instances=P, unit=(P == 1), seed=7)
+    secs = R.synthetic_witness(X, [Q] * P, seed=15)
+    run_case(ctx, inst, P, [Q] * P, [X] * P, X, secs, seed=105, claim=O.ZERO)
+
+
+def test_set_claim_after_first_round_is_refused(ctx):
+    import spartan_parallel_b200 as sp
+
+    X, Q = 1 << 9, 2
+    tabs = [rand_scalars(X * Q, s) for s in (1, 2, 3)]
+    sc1 = sp.SumcheckPhase1.from_tables(ctx, [Q], Q, [X], X, *tabs, rand_scalars(0, 1), rand_scalars(1, 4), rand_scalars(9, 5))
+    sc1.round_eval()
+    with pytest.raises(sp.SpgError, match="before the first round"):
+        sc1.set_claim(O.ZERO)
 
 
 def test_synthetic_non_unit_coefficients(ctx):
