@@ -93,6 +93,31 @@ k_msm_partial(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_str
   partial[i * nchunks + k] = acc;
 }
 
+// few rows, many bases (the L / R vectors of a bullet reduction round, Cx of an opening):
+// one thread per base, a block sums its 128 points through shared memory.
+// grid (ceil(R / 128), L); partial[i * gridDim.x + blockIdx.x]
+template <int C>
+__global__ void __launch_bounds__(128)
+k_msm_wide(const fq *__restrict__ scalars, size_t R, size_t row_stride, const ge_cached *__restrict__ table,
+           ge *__restrict__ partial) {
+  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
+  __shared__ ge sm[64];
+  size_t i = blockIdx.y;
+  size_t j = (size_t)blockIdx.x * 128 + threadIdx.x;
+  ge acc = ge_identity();
+  if (j < R) {
+    fq s = fq_load(scalars + i * row_stride + j);
+    if (!fq_is_zero(s)) accumulate_scalar<C>(acc, s, table + j * WINS * ENT);
+  }
+  for (int half = 64; half >= 1; half >>= 1) {
+    if ((int)threadIdx.x >= half && (int)threadIdx.x < 2 * half) sm[threadIdx.x - half] = acc;
+    __syncthreads();
+    if ((int)threadIdx.x < half) acc = ge_add(acc, ge_to_cached(sm[threadIdx.x]));
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[i * gridDim.x + blockIdx.x] = acc;
+}
+
 // out[i] = compress(sum_k partial[i][k] + blind[i] * h); h's table sits in slot `hslot`
 template <int C>
 __global__ void k_msm_finish(const ge *__restrict__ partial, size_t L, size_t nchunks,
@@ -161,6 +186,18 @@ template <int C>
 int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
             uint8_t *d_out) {
   spg_ctx *ctx = g->ctx;
+  if (L <= 16 && R >= 256) {
+    size_t nblk = (R + 127) / 128;
+    ge *partial = nullptr;
+    SPG_CUDA(cudaMalloc(&partial, L * nblk * sizeof(ge)));
+    dim3 grid((unsigned)nblk, (unsigned)L);
+    ctx->next_units = 32.0 * (double)L * (double)R;
+    SPG_LAUNCH(ctx, k_msm_wide<C>, grid, 128, 0, scalars, R, row_stride, g->table, partial);
+    SPG_LAUNCH(ctx, k_msm_finish<C>, 1, 64, 0, partial, L, nblk, d_blinds, g->table, g->tab_R, d_out);
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(partial);
+    return SPG_OK;
+  }
   size_t chunk = 1;
   while (chunk < 64 && (L * R) / (chunk * 2) >= 131072) chunk *= 2;
   size_t nchunks = (R + chunk - 1) / chunk;

@@ -32,8 +32,12 @@ def lib():
         L.sph_transcript_kat.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t, C.c_void_p]
         L.sph_r1cs_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                      C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p),
+                                     C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p]
+        L.sph_r1cs_gens_new.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.sph_r1cs_gens_new.restype = C.c_void_p
+        L.sph_r1cs_gens_free.argtypes = [C.c_void_p]
+        L.sph_r1cs_gens_free.restype = None
         L.sph_sparse_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
@@ -64,8 +68,31 @@ def _sz(v):
     return np.ascontiguousarray(np.asarray(v, dtype=np.uint64).reshape(-1))
 
 
+class R1CSGens:
+    """R1CSGens::new (src/r1csproof.rs:45-80) with the opening-proof generators also resident on the
+    device: the n-sized multiscalar multiplications of DotProductProofLog / BulletReductionProof then
+    run there. Create once, reuse across proofs (like the reference's SNARKGens)."""
+
+    def __init__(self, ctx, label: bytes, num_vars: int):
+        self.ctx = ctx
+        self.h = lib().sph_r1cs_gens_new(ctx.h, label, num_vars)
+        if not self.h:
+            raise SpgError(f"sph_r1cs_gens_new: {lib().sph_last_error().decode('utf-8', 'replace')}")
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().sph_r1cs_gens_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def r1cs_prove(ctx, inst, witness_secs, num_proofs, max_num_proofs, num_inputs, max_num_inputs, transcript_label: bytes,
-               gens_label: bytes, tape_seed, gens_num_vars: int):
+               gens_label: bytes, tape_seed, gens_num_vars: int, gens: "R1CSGens | None" = None):
     """R1CSProof::prove (src/r1csproof.rs:210-685) with a caller-seeded RandomTape.
     Returns (proof bytes in bincode layout, [rp, rq_rev, rx, rw ++ ry])."""
     P = len(num_proofs)
@@ -81,7 +108,7 @@ def r1cs_prove(ctx, inst, witness_secs, num_proofs, max_num_proofs, num_inputs, 
     npf, nin, inc = _sz(num_proofs), _sz(num_inputs), _sz(inst.num_cons)
     _check(lib().sph_r1cs_prove(ctx.h, transcript_label, gens_label, p(seed), P, max_num_proofs, p(npf), max_num_inputs, p(nin),
                                 len(witness_secs), secs, p(sec_ni), p(sec_np), p(sec_nin), inst.h, inst.num_instances,
-                                inst.max_num_cons, p(inc), gens_num_vars, C.byref(out_bytes), C.byref(out_len), p(ch), p(counts)),
+                                inst.max_num_cons, p(inc), gens_num_vars, gens.h if gens else None, C.byref(out_bytes), C.byref(out_len), p(ch), p(counts)),
            "sph_r1cs_prove")
     proof = C.string_at(out_bytes, out_len.value)
     lib().sph_free(out_bytes)

@@ -1,6 +1,7 @@
 // C entry points of libspghost.so: the C++ host mirror of the reference's transcript-side
 // prover (what stays in Rust in production), driving libspgpu.so through its C ABI.
 #include <cstdlib>
+#include <memory>
 
 #include "protocol.hpp"
 #include "sparse.hpp"
@@ -36,7 +37,21 @@ int sph_transcript_kat(const char *label, const char *l, const char *m, const ch
   return 0;
 }
 
+// R1CSGens::new (src/r1csproof.rs:45-80), created once by the caller like the reference's SNARKGens; with a
+// context the opening-proof generators also live on the device (fixed-base tables built on first use)
+void *sph_r1cs_gens_new(spg_ctx *ctx, const char *label, size_t num_vars) {
+  try {
+    return new R1CSGens(label, num_vars, ctx);
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+void sph_r1cs_gens_free(void *g) { delete (R1CSGens *)g; }
+
 // R1CSProof::prove (src/r1csproof.rs:210-685). The caller owns the device handles.
+//   gens_handle: from sph_r1cs_gens_new, or NULL to derive host-only generators for this call
 //   sec_*: per witness section: number of instances, then num_proofs / num_inputs per instance (flattened)
 //   out_bytes / out_len: bincode layout of the proof (malloc'ed; free with sph_free)
 //   out_challenges: rp | rq_rev | rx | rw ++ ry as Montgomery scalars; out_counts[4] their lengths
@@ -45,7 +60,8 @@ int sph_r1cs_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_
                    const size_t *num_inputs, size_t num_witness_secs, spg_witness *const *secs,
                    const size_t *sec_num_instances, const size_t *sec_num_proofs, const size_t *sec_num_inputs,
                    const spg_r1cs *inst, size_t inst_num_instances, size_t inst_max_num_cons, const size_t *inst_num_cons,
-                   size_t gens_num_vars, uint8_t **out_bytes, size_t *out_len, spg_fq *out_challenges, size_t out_counts[4]) {
+                   size_t gens_num_vars, const void *gens_handle, uint8_t **out_bytes, size_t *out_len, spg_fq *out_challenges,
+                   size_t out_counts[4]) {
   try {
     std::vector<WitnessSec> ws;
     size_t k = 0;
@@ -58,7 +74,9 @@ int sph_r1cs_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_
       }
       ws.push_back(w);
     }
-    R1CSGens gens(gens_label, gens_num_vars);  // sized for the largest committed polynomial
+    std::unique_ptr<R1CSGens> own;
+    if (!gens_handle) own.reset(new R1CSGens(gens_label, gens_num_vars));  // sized for the largest committed polynomial
+    const R1CSGens &gens = gens_handle ? *(const R1CSGens *)gens_handle : *own;
     ProofTranscript t(transcript_label);
     hfq seed{{tape_seed[0], tape_seed[1], tape_seed[2], tape_seed[3]}};
     RandomTape tape("proof", Scalar(seed));

@@ -3,6 +3,7 @@
 // source the CUDA commitment kernels compile); scalars reuse csrc/host_fq.h.
 //   reference: src/group.rs, src/commitments.rs, src/transcript.rs, src/random.rs
 #pragma once
+#include <memory>
 #include <stdexcept>
 
 #include "../csrc/ed25519.cuh"
@@ -104,6 +105,35 @@ inline Point multiscalar_mul(const std::vector<Scalar> &s, const std::vector<Poi
   return acc;
 }
 
+// Fixed-base scalar multiplication for the handful of generators every sigma protocol and
+// every ZK-sumcheck round commits with (gens_1, gens_3, gens_4): 8-bit windows,
+//   T[w][d-1] = d * 2^(8w) * P  in cached form, so  s * P = sum_w T[w][digit_w(s)]
+// -- 32 additions, no doublings (the same layout the device MSM uses, csrc/msm.cu).
+struct FixedBaseTable {
+  std::vector<spg::ge_cached> t;  // 32 windows x 255 entries
+  explicit FixedBaseTable(const Point &p) : t(32 * 255) {
+    spg::ge base = p.p;
+    for (int w = 0; w < 32; w++) {
+      spg::ge_cached bc = spg::ge_to_cached(base);
+      spg::ge m = base;
+      t[w * 255] = bc;
+      for (int d = 2; d <= 255; d++) {
+        m = spg::ge_add(m, bc);
+        t[w * 255 + d - 1] = spg::ge_to_cached(m);
+      }
+      for (int k = 0; k < 8; k++) base = spg::ge_double(base);
+    }
+  }
+  Point mul(const Scalar &s) const {
+    uint8_t k[32];
+    s.to_bytes(k);
+    spg::ge acc = spg::ge_identity();
+    for (int w = 0; w < 32; w++)
+      if (k[w]) acc = spg::ge_add(acc, t[w * 255 + k[w] - 1]);
+    return Point(acc);
+  }
+};
+
 // RISTRETTO_BASEPOINT_COMPRESSED (src/group.rs:23-24)
 inline const uint8_t *basepoint_compressed() {
   static const uint8_t B[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9,
@@ -117,6 +147,14 @@ struct MultiCommitGens {
   size_t n = 0;
   std::vector<Point> G;
   Point h;
+  // optional fixed-base tables for G[0..n) and h (slot n); shared by copies
+  std::shared_ptr<std::vector<FixedBaseTable>> tabs;
+  void precompute() {
+    auto v = std::make_shared<std::vector<FixedBaseTable>>();
+    for (auto &g : G) v->emplace_back(g);
+    v->emplace_back(h);
+    tabs = v;
+  }
   MultiCommitGens() {}
   // MultiCommitGens::new (src/commitments.rs:15-33)
   MultiCommitGens(size_t n_, const std::string &label) : n(n_) {
@@ -161,11 +199,16 @@ struct MultiCommitGens {
 // Commitments for Scalar / [Scalar] (src/commitments.rs:69-92)
 inline Point commit(const Scalar &v, const Scalar &blind, const MultiCommitGens &g) {
   if (g.n != 1) throw std::runtime_error("commit(scalar): gens.n != 1");
+  if (g.tabs) return (*g.tabs)[0].mul(v) + (*g.tabs)[1].mul(blind);
   return g.G[0] * v + g.h * blind;
 }
 inline Point commit(const std::vector<Scalar> &v, const Scalar &blind, const MultiCommitGens &g) {
   if (g.n < v.size()) throw std::runtime_error("commit(vec): not enough generators");
   Point acc;
+  if (g.tabs) {
+    for (size_t i = 0; i < v.size(); i++) acc = acc + (*g.tabs)[i].mul(v[i]);
+    return acc + (*g.tabs)[g.n].mul(blind);
+  }
   for (size_t i = 0; i < v.size(); i++)
     if (!(v[i] == Scalar::zero())) acc = acc + g.G[i] * v[i];
   return acc + g.h * blind;

@@ -6,6 +6,9 @@
 //              src/sumcheck.rs:788-1380 (ZK glue), src/dense_mlpoly.rs:861-960,
 //              src/r1csproof.rs:210-685
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 
 #include "../../include/spgpu.h"
@@ -16,6 +19,18 @@ namespace sph {
 inline void check(int rc, const char *what) {
   if (rc != SPG_OK) throw std::runtime_error(std::string(what) + ": " + spg_last_error());
 }
+// SPH_TRACE=1: wall time of the prover's stages on stderr (development aid)
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  Trace() : on(getenv("SPH_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char *what) {
+    if (!on) return;
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[sph] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 inline size_t log2z(size_t n) {
   size_t l = 0;
   while (((size_t)1 << l) < n) l++;
@@ -120,7 +135,7 @@ struct EqualityProof {
     t.append_point("C1", commit(v1, s1, g).compress());
     t.append_point("C2", commit(v2, s2, g).compress());
     EqualityProof p;
-    p.alpha = (g.h * r).compress();
+    p.alpha = (g.tabs ? (*g.tabs)[g.n].mul(r) : g.h * r).compress();
     t.append_point("alpha", p.alpha);
     Scalar c = t.challenge_scalar("c");
     p.z = c * (s1 - s2) + r;
@@ -217,6 +232,41 @@ struct DotProductProof {
   }
 };
 
+// DotProductProofGens (src/nizk/mod.rs:406-418). `dev` (optional, not owned) is the same
+// gens_n resident on the device with its fixed-base window tables: when present the
+// n-sized multiscalar multiplications of the opening proofs run there.
+struct DotProductProofGens {
+  size_t n = 0;
+  MultiCommitGens gens_n, gens_1;
+  spg_ctx *ctx = nullptr;
+  spg_gens *dev = nullptr;
+  DotProductProofGens() {}
+  DotProductProofGens(size_t n_, const std::string &label) : n(n_) {
+    auto pr = MultiCommitGens(n + 1, label).split_at(n);
+    gens_n = pr.first;
+    gens_1 = pr.second;
+  }
+  void attach_device(spg_ctx *c, spg_gens *g) {
+    ctx = c;
+    dev = g;
+  }
+};
+
+// sum_j s[i][j] G_j + blind[i] h for `count` rows of `len` scalars on the device
+inline std::vector<Point> device_msm(const DotProductProofGens &g, const std::vector<Scalar> &rows, size_t len, size_t count,
+                                     const std::vector<Scalar> *blinds) {
+  std::vector<spg_fq> s(rows.size()), b;
+  for (size_t i = 0; i < rows.size(); i++) s[i] = rows[i].to_fq();
+  if (blinds)
+    for (auto &x : *blinds) b.push_back(x.to_fq());
+  std::vector<Compressed> out(count);
+  check(spg_commit_batch(g.ctx, g.dev, s.data(), len, blinds ? b.data() : nullptr, count, (uint8_t *)out.data()),
+        "spg_commit_batch");
+  std::vector<Point> pts;
+  for (auto &c : out) pts.push_back(Point::decompress(c));
+  return pts;
+}
+
 // ---------------------------------------------------------------- bullet reduction (src/nizk/bullet.rs:32-132)
 struct BulletReductionProof {
   std::vector<Compressed> L_vec, R_vec;
@@ -262,21 +312,65 @@ struct BulletReductionProof {
     Out o{a[0], b[0], blind_fin, G[0]};
     return {p, o};
   }
+  // Same protocol with the generators never folded on the host. After k rounds the folded
+  // generator is G_k[i] = sum over original indices m with (m mod n_k) == i of s_k[m] G[m],
+  // s_k[m] = prod_j (bit_j(m) ? u_j : u_j^-1) over the k top bits of m (the fold at :113-118
+  // unrolled), so every L, R (and the final G) is a multiscalar multiplication over the
+  // ORIGINAL bases, which the device serves from fixed-base tables with no doublings:
+  //   L = sum_m [m mod n_k >= n_k/2] a[(m mod n_k) - n_k/2] s[m] G[m] + c_L Q + blind_L H
+  //   R = sum_m [m mod n_k <  n_k/2] a[(m mod n_k) + n_k/2] s[m] G[m] + c_R Q + blind_R H
+  // Group elements are the same, so the compressed encodings are the reference's.
+  static std::pair<BulletReductionProof, Out> prove_device(ProofTranscript &t, const Point &Q, const DotProductProofGens &gens,
+                                                           size_t n, std::vector<Scalar> a, std::vector<Scalar> b,
+                                                           const Scalar &blind,
+                                                           const std::vector<std::pair<Scalar, Scalar>> &blinds) {
+    BulletReductionProof p;
+    Scalar blind_fin = blind;
+    std::vector<Scalar> s(n, Scalar::one()), rows(2 * n);
+    size_t nk = n, round = 0;
+    while (nk != 1) {
+      size_t nh = nk / 2;
+      Scalar c_L, c_R;
+      for (size_t i = 0; i < nh; i++) {
+        c_L += a[i] * b[nh + i];
+        c_R += a[nh + i] * b[i];
+      }
+      const Scalar &blind_L = blinds[round].first, &blind_R = blinds[round].second;
+      round++;
+      for (size_t m = 0; m < n; m++) {
+        size_t j = m & (nk - 1);
+        if (j >= nh) {
+          rows[m] = a[j - nh] * s[m];
+          rows[n + m] = Scalar::zero();
+        } else {
+          rows[m] = Scalar::zero();
+          rows[n + m] = a[nh + j] * s[m];
+        }
+      }
+      std::vector<Scalar> bl = {blind_L, blind_R};
+      std::vector<Point> lr = device_msm(gens, rows, n, 2, &bl);
+      Compressed Lc = (lr[0] + Q * c_L).compress(), Rc = (lr[1] + Q * c_R).compress();
+      t.append_point("L", Lc);
+      t.append_point("R", Rc);
+      Scalar u = t.challenge_scalar("u");
+      Scalar u_inv = u.invert();
+      for (size_t i = 0; i < nh; i++) {
+        a[i] = a[i] * u + u_inv * a[nh + i];
+        b[i] = b[i] * u_inv + u * b[nh + i];
+      }
+      for (size_t m = 0; m < n; m++) s[m] = s[m] * ((m & (nk - 1)) >= nh ? u : u_inv);
+      blind_fin = blind_fin + blind_L * u * u + blind_R * u_inv * u_inv;
+      p.L_vec.push_back(Lc);
+      p.R_vec.push_back(Rc);
+      nk = nh;
+    }
+    Point G_hat = n == 1 ? gens.gens_n.G[0] : device_msm(gens, s, n, 1, nullptr)[0];
+    Out o{a[0], b[0], blind_fin, G_hat};
+    return {p, o};
+  }
   void write(Writer &w) const {
     w.points(L_vec);
     w.points(R_vec);
-  }
-};
-
-// DotProductProofGens (src/nizk/mod.rs:406-418)
-struct DotProductProofGens {
-  size_t n = 0;
-  MultiCommitGens gens_n, gens_1;
-  DotProductProofGens() {}
-  DotProductProofGens(size_t n_, const std::string &label) : n(n_) {
-    auto pr = MultiCommitGens(n + 1, label).split_at(n);
-    gens_n = pr.first;
-    gens_1 = pr.second;
   }
 };
 
@@ -298,15 +392,22 @@ struct DotProductProofLog {
     std::vector<Scalar> v1 = tape.random_vector("blinds_vec_1", 2 * lg), v2 = tape.random_vector("blinds_vec_2", 2 * lg);
     std::vector<std::pair<Scalar, Scalar>> blinds;
     for (size_t i = 0; i < v1.size(); i++) blinds.push_back({v1[i], v2[i]});
-    MultiCommitGens gn = gens.gens_n;
-    t.append_point("Cx", commit(x, blind_x, gn).compress());
+    const MultiCommitGens &gn = gens.gens_n;
+    bool on_device = gens.dev != nullptr && n >= 32;
+    if (on_device) {
+      std::vector<Scalar> bl = {blind_x};
+      t.append_point("Cx", device_msm(gens, x, n, 1, &bl)[0].compress());
+    } else {
+      t.append_point("Cx", commit(x, blind_x, gn).compress());
+    }
     t.append_point("Cy", commit(y, blind_y, gens.gens_1).compress());
     t.append_scalars("a", a);
     Scalar r = t.challenge_scalar("r");
     MultiCommitGens g1s = gens.gens_1.scale(r);
     Scalar blind_Gamma = blind_x + r * blind_y;
-    std::vector<Point> G(gn.G.begin(), gn.G.begin() + n);
-    auto br = BulletReductionProof::prove(t, g1s.G[0], G, gn.h, x, a, blind_Gamma, blinds);
+    auto br = on_device ? BulletReductionProof::prove_device(t, g1s.G[0], gens, n, x, a, blind_Gamma, blinds)
+                        : BulletReductionProof::prove(t, g1s.G[0], std::vector<Point>(gn.G.begin(), gn.G.begin() + n), gn.h,
+                                                      x, a, blind_Gamma, blinds);
     const auto &o = br.second;
     Scalar y_hat = o.a * o.b;
     DotProductProofLog p;
@@ -337,14 +438,28 @@ struct DotProductProofLog {
 struct R1CSGens {
   MultiCommitGens sc_gens_1, sc_gens_3, sc_gens_4;
   DotProductProofGens pc;
-  R1CSGens(const std::string &label, size_t num_vars) {
+  spg_gens *d_pc = nullptr;
+  // with a context the opening-proof generators are also uploaded (tables are built on first use)
+  R1CSGens(const std::string &label, size_t num_vars, spg_ctx *ctx = nullptr) {
     size_t ell = log2z(num_vars);
     size_t right = ell - ell / 2;
     pc = DotProductProofGens((size_t)1 << right, label);
     sc_gens_1 = pc.gens_1;
     sc_gens_3 = MultiCommitGens(3, label);
     sc_gens_4 = MultiCommitGens(4, label);
+    pc.gens_1.precompute();
+    sc_gens_1 = pc.gens_1;
+    sc_gens_3.precompute();
+    sc_gens_4.precompute();
+    if (ctx) {
+      std::vector<uint8_t> c = pc.gens_n.compressed();
+      check(spg_gens_upload(ctx, c.data(), pc.gens_n.n + 1, &d_pc), "spg_gens_upload");
+      pc.attach_device(ctx, d_pc);
+    }
   }
+  ~R1CSGens() { spg_gens_destroy(d_pc); }
+  R1CSGens(const R1CSGens &) = delete;
+  R1CSGens &operator=(const R1CSGens &) = delete;
 };
 
 // ---------------------------------------------------------------- ZK sumcheck glue
@@ -502,6 +617,7 @@ inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_nu
                                const spg_r1cs *inst, size_t inst_num_instances, size_t inst_max_num_cons,
                                const std::vector<size_t> &inst_num_cons, const R1CSGens &gens, ProofTranscript &t,
                                RandomTape &tape) {
+  Trace tr;
   t.append_protocol_name("R1CS proof");
   size_t W = secs.size();
   size_t P = num_instances;
@@ -532,12 +648,14 @@ inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_nu
     spg_fq zero = Scalar::zero().to_fq();  // claim_phase1 (:330)
     check(spg_sc1_set_claim(sc1, &zero), "spg_sc1_set_claim");
   }
+  tr.lap("z_mat + SpMV + sc1 setup");
   std::vector<Scalar> r1;
   Scalar blind_claim_postsc1;
   ZKSumcheckProof sc_proof_phase1 = zk_sumcheck(
       Scalar::zero(), Scalar::zero(), nrx + nrq + nrp, [&](spg_fq *e) { check(spg_sc1_round_eval(sc1, e), "spg_sc1_round_eval"); },
       [&](const spg_fq *r) { check(spg_sc1_round_bind(sc1, r), "spg_sc1_round_bind"); }, gens.sc_gens_1, gens.sc_gens_4, t,
       tape, &r1, &blind_claim_postsc1);
+  tr.lap("phase-1 rounds (zk)");
   spg_fq claims1[4];
   check(spg_sc1_final(sc1, claims1), "spg_sc1_final");
   spg_sc1_destroy(sc1);
@@ -566,17 +684,20 @@ inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_nu
   Scalar r_A = t.challenge_scalar("challenge_Az"), r_B = t.challenge_scalar("challenge_Bz"), r_C = t.challenge_scalar("challenge_Cz");
   Scalar claim_phase2 = r_A * Az_claim + r_B * Bz_claim + r_C * Cz_claim;
   Scalar blind_claim_phase2 = r_A * Az_blind + r_B * Bz_blind + r_C * Cz_blind;
+  tr.lap("sigma protocols");
   spg_sc2 *sc2 = nullptr;
   spg_fq fA = r_A.to_fq(), fB = r_B.to_fq(), fC = r_C.to_fq();
   check(spg_sc2_create(ctx, inst, z, P, num_proofs.data(), max_num_proofs, num_inputs.data(), max_num_inputs, W,
                        fqv(rx).data(), fqv(rq_rev).data(), fqv(rp).data(), &fA, &fB, &fC, &sc2),
         "spg_sc2_create");
+  tr.lap("sc2 setup (ABC, Z bind)");
   std::vector<Scalar> r2;
   Scalar blind_claim_postsc2;
   ZKSumcheckProof sc_proof_phase2 = zk_sumcheck(
       claim_phase2, blind_claim_phase2, nry + nrw + nrp, [&](spg_fq *e) { check(spg_sc2_round_eval(sc2, e), "spg_sc2_round_eval"); },
       [&](const spg_fq *r) { check(spg_sc2_round_bind(sc2, r), "spg_sc2_round_bind"); }, gens.sc_gens_1, gens.sc_gens_4, t,
       tape, &r2, &blind_claim_postsc2);
+  tr.lap("phase-2 rounds (zk)");
   spg_fq claims2[3];
   check(spg_sc2_final(sc2, claims2), "spg_sc2_final");
   spg_sc2_destroy(sc2);
@@ -613,8 +734,10 @@ inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_nu
       comm_vars_at_ry_list[i].push_back(commit(e, Scalar::zero(), gens.pc.gens_1).compress());
     }
   }
+  tr.lap("witness evaluations");
   std::vector<DotProductProofLog> proof_eval_vars =
       prove_batched_instances_disjoint_rounds(ctx, poly_list, rq, ry, Zr_list, gens.pc, t, tape);
+  tr.lap("opening proofs");
   // combine per instance (:588-638)
   size_t Wp = next_pow2(W);
   if (Wp > 8) throw std::runtime_error("Unsupported num_witness_secs");  // the reference panics (:629-631)
@@ -663,6 +786,7 @@ inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_nu
   w.u64(proof_eval_vars.size());
   for (auto &p : proof_eval_vars) p.write(w);
   proof_eq_sc_phase2.write(w);
+  tr.lap("tail + serialization");
   R1CSProofOut out;
   out.bytes = w.out;
   out.rp = rp2;

@@ -46,6 +46,9 @@ struct SparseGens {
     up(ops, &d_ops);
     up(mem, &d_mem);
     up(derefs, &d_derefs);
+    ops.attach_device(ctx, d_ops);
+    mem.attach_device(ctx, d_mem);
+    derefs.attach_device(ctx, d_derefs);
   }
   ~SparseGens() {
     spg_gens_destroy(d_ops);

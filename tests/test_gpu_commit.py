@@ -84,3 +84,22 @@ def test_hyrax_row_identity_at_scale(ctx):
     lhs = G.multiscalar_mul([O.to_int(x) for x in L], [G.decompress(c) for c in rows]).compress()
     rhs = dg.commit_batch(LZ.reshape(1, 128, 4))[0]
     assert lhs == rhs
+
+
+def test_few_rows_many_bases_kernel(ctx):
+    """the wide MSM path (<= 16 rows, >= 256 bases): zeros, a sparse row, blinds; bytes vs the oracle"""
+    import spartan_parallel_b200 as sp
+
+    n = 300
+    gens = G.MultiCommitGens(n, b"wide-gens")
+    dg = sp.MultiCommitGens(ctx, gens.compressed())
+    s = rand_scalars(3 * n, 7).reshape(3, n, 4)
+    s[1, ::2] = 0
+    s[2] = 0
+    s[2, 299] = O.ONE
+    blinds = rand_scalars(3, 8)
+    blinds[2] = 0
+    got = dg.commit_batch(s, blinds)
+    for i in range(3):
+        want = G.commit_vec([O.to_int(x) for x in s[i]], O.to_int(blinds[i]), gens).compress()
+        assert got[i] == want, i

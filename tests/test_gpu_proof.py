@@ -35,7 +35,7 @@ def device_setup(ctx, inst, secs):
     return dinst, dsecs
 
 
-def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, verify=True):
+def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, verify=True, device_gens=False):
     import spartan_parallel_b200 as sp
     from spartan_parallel_b200 import host
 
@@ -48,8 +48,9 @@ def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, verify=Tru
                              Pr.RandomTape(b"proof", seed_scalar), trace=trace)
     want_bytes = Pr.serialize_r1cs_proof(want)
     dinst, dsecs = device_setup(ctx, inst, secs)
+    dgens = host.R1CSGens(ctx, b"gens_r1cs_sat", gnv) if device_gens else None
     got_bytes, got_ch = host.r1cs_prove(ctx, dinst, dsecs, num_proofs, max_q, num_inputs, max_y, b"spgpu-parity", b"gens_r1cs_sat",
-                                        seed_scalar, gnv)
+                                        seed_scalar, gnv, dgens)
     assert len(got_bytes) == len(want_bytes)
     if got_bytes != want_bytes:
         first = next(i for i in range(len(want_bytes)) if got_bytes[i] != want_bytes[i])
@@ -92,3 +93,28 @@ def test_c1_baseline_config(ctx):
     secs = R.synthetic_witness(X, [Q], seed=8)
     blob = run_case(ctx, inst, 1, [Q], [X], X, secs, seed=9, verify=False)
     assert len(blob) > 8000
+
+
+def test_c1_device_openings(ctx):
+    """same proof with the opening-proof MSMs (Cx, every bullet-reduction L / R, the folded
+    generator) served by the device from unfolded fixed-base tables: identical bytes"""
+    X, Q = 1 << 10, 4
+    inst = R.synthetic_instance(X)
+    secs = R.synthetic_witness(X, [Q], seed=8)
+    run_case(ctx, inst, 1, [Q], [X], X, secs, seed=9, verify=False, device_gens=True)
+
+
+def test_ragged_device_openings(ctx):
+    P, X = 3, 1 << 6
+    inst = R.synthetic_instance(X, num_instances=P, unit=False, seed=5)
+    secs = R.synthetic_witness(X, [8, 4, 1], seed=6)
+    run_case(ctx, inst, P, [8, 4, 1], [X] * P, X, secs, seed=7, device_gens=True)
+
+
+@pytest.mark.slow
+def test_wide_msm_device_openings(ctx):
+    """2^16-entry witness polynomials: openings of size 256, the few-rows / many-bases MSM kernel"""
+    X, Q = 1 << 13, 8
+    inst = R.synthetic_instance(X)
+    secs = R.synthetic_witness(X, [Q], seed=18)
+    run_case(ctx, inst, 1, [Q], [X], X, secs, seed=19, verify=False, device_gens=True)
