@@ -170,7 +170,7 @@ int spg_prodtree_build(spg_ctx *ctx, const spg_vec *leaves, spg_prodtree **out) 
   t->ctx = ctx;
   t->n = n;
   t->num_layers = log2u(n);
-  cudaError_t e = cudaMalloc(&t->buf, 2 * n * sizeof(fq));
+  cudaError_t e = dev_alloc(ctx, &t->buf, 2 * n * sizeof(fq));
   if (e != cudaSuccess) {
     delete t;
     return cuda_fail(e, "cudaMalloc(prodtree)", __FILE__, __LINE__);
@@ -227,7 +227,7 @@ void spg_prodtree_destroy(spg_prodtree *t) {
   if (!t) return;
   for (spg_vec *v : t->left) spg_vec_free(v);
   for (spg_vec *v : t->right) spg_vec_free(v);
-  if (t->buf) cudaFree(t->buf);
+  if (t->buf) dev_free(t->ctx, t->buf);
   delete t;
 }
 
@@ -265,7 +265,7 @@ int spg_cubic_create(spg_ctx *ctx, size_t npar, spg_vec *const *A_par, spg_vec *
   }
   s->len = len;
   for (size_t i = 0; i < npar + nseq; i++) s->coeffs.push_back(hfq_from(coeffs[i]));
-  if (cudaMalloc(&s->d_evals, 24 * 3 * sizeof(fq)) != cudaSuccess) {
+  if (dev_alloc(ctx, &s->d_evals, 24 * 3 * sizeof(fq)) != cudaSuccess) {
     delete s;
     return cuda_fail(cudaGetLastError(), "cudaMalloc(cubic)", __FILE__, __LINE__);
   }
@@ -370,7 +370,7 @@ int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
 
 void spg_cubic_destroy(spg_cubic *s) {
   if (!s) return;
-  if (s->d_evals) cudaFree(s->d_evals);
+  if (s->d_evals) dev_free(s->ctx, s->d_evals);
   delete s;
 }
 
@@ -382,11 +382,11 @@ int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const
   SPG_TRY(vec_new(ctx, n, &o));
   unsigned long long *d_addr = nullptr, *d_ts = nullptr;
   if (addr) {
-    SPG_CUDA(cudaMalloc(&d_addr, n * 8));
+    SPG_CUDA(dev_alloc(ctx, &d_addr, n * 8));
     SPG_CUDA(cudaMemcpyAsync(d_addr, addr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (ts) {
-    SPG_CUDA(cudaMalloc(&d_ts, n * 8));
+    SPG_CUDA(dev_alloc(ctx, &d_ts, n * 8));
     SPG_CUDA(cudaMemcpyAsync(d_ts, ts, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   hfq g = hfq_from(*gamma);
@@ -398,8 +398,8 @@ int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const
   ctx->next_units = (double)n * (32.0 + 32.0 + (addr ? 8 : 0) + (ts ? 8 : 0));
   SPG_LAUNCH(ctx, k_hash_layer, grid_for(ctx, n, 256), 256, 0, d_addr, val->d, d_ts, n, fg, fg2, ft, ts_plus_one, o->d);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (d_addr) cudaFree(d_addr);
-  if (d_ts) cudaFree(d_ts);
+  if (d_addr) dev_free(ctx, d_addr);
+  if (d_ts) dev_free(ctx, d_ts);
   *out = o;
   return SPG_OK;
 }
@@ -412,11 +412,11 @@ int spg_deref(spg_ctx *ctx, const uint64_t *addr, size_t n, const spg_vec *mem, 
   spg_vec *o = nullptr;
   SPG_TRY(vec_new(ctx, n, &o));
   unsigned long long *d_addr = nullptr;
-  SPG_CUDA(cudaMalloc(&d_addr, (n ? n : 1) * 8));
+  SPG_CUDA(dev_alloc(ctx, &d_addr, (n ? n : 1) * 8));
   SPG_CUDA(cudaMemcpyAsync(d_addr, addr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   SPG_LAUNCH(ctx, k_deref, grid_for(ctx, n, 256), 256, 0, d_addr, n, mem->d, o->d);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_addr);
+  dev_free(ctx, d_addr);
   *out = o;
   return SPG_OK;
 }

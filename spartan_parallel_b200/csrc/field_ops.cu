@@ -181,8 +181,8 @@ int dense_evaluate_device(spg_ctx *ctx, const fq *Z, size_t n, const spg_fq *r, 
   size_t left = ell / 2, right = ell - left;
   size_t Ls = (size_t)1 << left, Rs = (size_t)1 << right;
   fq *tabs = nullptr, *d_r = nullptr;
-  SPG_CUDA(cudaMalloc(&tabs, (Ls + Rs + Rs) * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&d_r, (ell ? ell : 1) * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &tabs, (Ls + Rs + Rs) * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &d_r, (ell ? ell : 1) * sizeof(fq)));
   SPG_CUDA(cudaMemcpyAsync(d_r, r, ell * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   fq *dL = tabs, *dR = tabs + Ls, *scratch = tabs + Ls + Rs;
   int rc = eq_evals_device(ctx, d_r, r, left, dL, scratch);
@@ -201,8 +201,8 @@ int dense_evaluate_device(spg_ctx *ctx, const fq *Z, size_t n, const spg_fq *r, 
   }
   (void)n;
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(tabs);
-  cudaFree(d_r);
+  dev_free(ctx, tabs);
+  dev_free(ctx, d_r);
   return rc;
 }
 
@@ -239,11 +239,11 @@ int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec 
   SPG_TRY(vec_new(ctx, n, &v));
   if (n) {
     uint32_t *d_wide = nullptr;
-    SPG_CUDA(cudaMalloc(&d_wide, n * 64));
+    SPG_CUDA(dev_alloc(ctx, &d_wide, n * 64));
     SPG_CUDA(cudaMemcpyAsync(d_wide, host_wide, n * 64, cudaMemcpyHostToDevice, ctx->stream));
     SPG_LAUNCH(ctx, k_from_u512, grid_for(ctx, n, 256), 256, 0, d_wide, v->d, n);
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    SPG_CUDA(cudaFree(d_wide));
+    dev_free(ctx, d_wide);
   }
   *out = v;
   return SPG_OK;
@@ -256,13 +256,13 @@ int spg_eq_evals(spg_ctx *ctx, const spg_fq *r, size_t ell, spg_vec **out) {
   spg_vec *v = nullptr;
   SPG_TRY(vec_new(ctx, n, &v));
   fq *d_r = nullptr, *scratch = nullptr;
-  SPG_CUDA(cudaMalloc(&d_r, (ell ? ell : 1) * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &d_r, (ell ? ell : 1) * sizeof(fq)));
   SPG_CUDA(cudaMemcpyAsync(d_r, r, ell * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
-  if (ell > (size_t)EQ_SMALL_LV) SPG_CUDA(cudaMalloc(&scratch, (n / 2) * sizeof(fq)));
+  if (ell > (size_t)EQ_SMALL_LV) SPG_CUDA(dev_alloc(ctx, &scratch, (n / 2) * sizeof(fq)));
   int rc = eq_evals_device(ctx, d_r, r, ell, v->d, scratch);
   cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_r);
-  if (scratch) cudaFree(scratch);
+  dev_free(ctx, d_r);
+  if (scratch) dev_free(ctx, scratch);
   if (rc != SPG_OK) {
     spg_vec_free(v);
     return rc;
@@ -324,15 +324,15 @@ int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_
   size_t slab = 64;
   size_t nslabs = (L_size + slab - 1) / slab;
   fq *dL = nullptr, *partial = nullptr;
-  SPG_CUDA(cudaMalloc(&dL, L_size * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&partial, nslabs * Rs * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &dL, L_size * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &partial, nslabs * Rs * sizeof(fq)));
   SPG_CUDA(cudaMemcpyAsync(dL, L, L_size * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   dim3 grid((unsigned)((Rs + 127) / 128), (unsigned)nslabs);
   SPG_LAUNCH(ctx, k_bound_L_partial, grid, 128, 0, v->d, dL, L_size, Rs, slab, partial);
   SPG_LAUNCH(ctx, k_sum_slabs, (unsigned)((Rs + 127) / 128), 128, 0, partial, nslabs, Rs, o->d);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(dL);
-  cudaFree(partial);
+  dev_free(ctx, dL);
+  dev_free(ctx, partial);
   *out = o;
   return SPG_OK;
 }

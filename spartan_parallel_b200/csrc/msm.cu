@@ -189,13 +189,13 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
   if (L <= 16 && R >= 256) {
     size_t nblk = (R + 127) / 128;
     ge *partial = nullptr;
-    SPG_CUDA(cudaMalloc(&partial, L * nblk * sizeof(ge)));
+    SPG_CUDA(dev_alloc(ctx, &partial, L * nblk * sizeof(ge)));
     dim3 grid((unsigned)nblk, (unsigned)L);
     ctx->next_units = 32.0 * (double)L * (double)R;
     SPG_LAUNCH(ctx, k_msm_wide<C>, grid, 128, 0, scalars, R, row_stride, g->table, partial);
     SPG_LAUNCH(ctx, k_msm_finish<C>, 1, 64, 0, partial, L, nblk, d_blinds, g->table, g->tab_R, d_out);
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(partial);
+    dev_free(ctx, partial);
     return SPG_OK;
   }
   size_t chunk = 1;
@@ -203,14 +203,14 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
   size_t nchunks = (R + chunk - 1) / chunk;
   if (nchunks == 0) nchunks = 1;
   ge *partial = nullptr;
-  SPG_CUDA(cudaMalloc(&partial, L * nchunks * sizeof(ge)));
+  SPG_CUDA(dev_alloc(ctx, &partial, L * nchunks * sizeof(ge)));
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)nchunks);
   ctx->next_units = 32.0 * (double)L * (double)R;
   SPG_LAUNCH(ctx, k_msm_partial<C>, grid, 128, 0, scalars, L, R, row_stride, g->table, chunk, nchunks, partial);
   SPG_LAUNCH(ctx, k_msm_finish<C>, (unsigned)((L + 63) / 64), 64, 0, partial, L, nchunks, d_blinds, g->table,
              g->tab_R, d_out);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(partial);
+  dev_free(ctx, partial);
   return SPG_OK;
 }
 
@@ -219,14 +219,15 @@ int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stri
   SPG_CHECK(R <= g->n, "commit: %zu scalars per row but only %zu generators", R, g->n);
   SPG_TRY(ensure_table(g, R));
   uint8_t *d_out = nullptr;
-  SPG_CUDA(cudaMalloc(&d_out, L * 32));
+  spg_ctx *ctx = g->ctx;
+  SPG_CUDA(dev_alloc(ctx, &d_out, L * 32));
   int rc = g->tab_C == 8 ? run_msm<8>(g, scalars, L, R, row_stride, d_blinds, d_out)
                          : run_msm<4>(g, scalars, L, R, row_stride, d_blinds, d_out);
   if (rc == SPG_OK) {
     cudaError_t e = cudaMemcpy(host_out, d_out, L * 32, cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = cuda_fail(e, "commit download", __FILE__, __LINE__);
   }
-  cudaFree(d_out);
+  dev_free(ctx, d_out);
   return rc;
 }
 
@@ -245,8 +246,8 @@ int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, sp
   int *d_bad = nullptr;
   int bad = 0;
   cudaError_t e = cudaMalloc(&g->bases, n_plus_1 * sizeof(ge));
-  if (e == cudaSuccess) e = cudaMalloc(&d_in, n_plus_1 * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&d_bad, sizeof(int));
+  if (e == cudaSuccess) e = dev_alloc(ctx, &d_in, n_plus_1 * 32);
+  if (e == cudaSuccess) e = dev_alloc(ctx, &d_bad, sizeof(int));
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, compressed, n_plus_1 * 32, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream);
   if (e == cudaSuccess) {
@@ -255,8 +256,8 @@ int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, sp
     e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (d_in) cudaFree(d_in);
-  if (d_bad) cudaFree(d_bad);
+  if (d_in) dev_free(ctx, d_in);
+  if (d_bad) dev_free(ctx, d_bad);
   if (e != cudaSuccess) {
     spg_gens_destroy(g);
     return cuda_fail(e, "spg_gens_upload", __FILE__, __LINE__);
@@ -290,15 +291,15 @@ int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, 
   SPG_CHECK(ctx && gens && scalars && out_compressed, "spg_commit_batch: null argument");
   SPG_CHECK(len >= 1 && count >= 1, "spg_commit_batch: empty batch");
   fq *d_s = nullptr, *d_b = nullptr;
-  SPG_CUDA(cudaMalloc(&d_s, len * count * sizeof(fq)));
+  SPG_CUDA(dev_alloc(ctx, &d_s, len * count * sizeof(fq)));
   SPG_CUDA(cudaMemcpyAsync(d_s, scalars, len * count * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   if (blinds) {
-    SPG_CUDA(cudaMalloc(&d_b, count * sizeof(fq)));
+    SPG_CUDA(dev_alloc(ctx, &d_b, count * sizeof(fq)));
     SPG_CUDA(cudaMemcpyAsync(d_b, blinds, count * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   }
   int rc = msm_rows(const_cast<spg_gens *>(gens), d_s, count, len, len, d_b, out_compressed);
-  cudaFree(d_s);
-  if (d_b) cudaFree(d_b);
+  dev_free(ctx, d_s);
+  if (d_b) dev_free(ctx, d_b);
   return rc;
 }
 
