@@ -2,6 +2,8 @@
 driving the CUDA kernels through the C ABI must emit, byte for byte, the proof the oracle's
 restatement of R1CSProof::prove emits for the same inputs, transcript label and tape seed
 -- and the oracle's restatement of R1CSProof::verify must accept it."""
+import os
+
 import numpy as np
 import pytest
 
@@ -76,7 +78,9 @@ def test_small_single_instance(ctx):
     X, Q = 1 << 5, 2
     inst = R.synthetic_instance(X, unit=False, seed=1)
     secs = R.synthetic_witness(X, [Q], seed=2)
-    run_case(ctx, inst, 1, [Q], [X], X, secs, seed=3)
+    blob = run_case(ctx, inst, 1, [Q], [X], X, secs, seed=3)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "r1cs_proof_x32_q2.bin")
+    assert blob == open(golden, "rb").read(), "device proof differs from the committed golden fixture"
 
 
 def test_three_instances_ragged(ctx):

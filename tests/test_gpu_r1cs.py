@@ -181,3 +181,20 @@ def test_bad_shapes_rejected(ctx):
     bad = (inst.mats[0][0], (inst.mats[0][1] + 100).astype(np.uint32), inst.mats[0][2])
     with pytest.raises(sp.SpgError):
         sp.R1CSInstance(ctx, 1, 8, [8], 16, [bad], [inst.mats[1]], [inst.mats[2]])  # column out of range
+
+
+def test_golden_round_tables(ctx):
+    """device rounds against the committed fixture tests/golden/tables_p3_ragged.npz"""
+    import os
+
+    P, X = 3, 1 << 4
+    num_proofs = [4, 2, 1]
+    inst = R.synthetic_instance(X, num_instances=P, unit=False, seed=5)
+    secs = R.synthetic_witness(X, num_proofs, seed=6)
+    big = rand_scalars(64, 40)
+    tau_p, tau_q, tau_x = big[:2], big[8:10], big[16:20]
+    ch1, ch2, r_abc = rand_scalars(8, 41), rand_scalars(2 + 1 + 4, 42), rand_scalars(3, 43)
+    e1, c1, e2, c2, _, _ = gpu_pipeline(ctx, inst, P, 4, num_proofs, X, [X] * P, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tables_p3_ragged.npz"))
+    assert np.array_equal(np.stack(e1), g["evals1"]) and np.array_equal(np.asarray(c1), g["claims1"])
+    assert np.array_equal(np.stack(e2), g["evals2"]) and np.array_equal(np.asarray(c2), g["claims2"])

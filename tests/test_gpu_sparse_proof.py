@@ -2,6 +2,8 @@
 C++ host mirror must emit, byte for byte, the commitment and proof the oracle's restatement
 of SparseMatPolynomial::multi_commit / SparseMatPolyEvalProof::prove emits, and the oracle's
 restatement of ::verify must accept the device bytes."""
+import os
+
 import numpy as np
 import pytest
 
@@ -54,6 +56,9 @@ def test_sparse_proof_bytes(ctx, nvx, nvy, nnz_list):
         first = next(i for i in range(len(want)) if got[i] != want[i])
         raise AssertionError(f"proof bytes differ from offset {first} of {len(want)}")
     assert SP.sparse_verify(SP.deserialize_sparse_proof(got), want_comm, rx, ry, evals, gens, Transcript(b"spark-parity"))
+    if (nvx, nvy, nnz_list) == (3, 3, [8, 8, 8]):
+        golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sparse_proof_3x8.bin")
+        assert got == open(golden, "rb").read(), "device proof differs from the committed golden fixture"
 
 
 def test_wrong_evaluation_is_refused(ctx):
