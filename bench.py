@@ -156,9 +156,7 @@ def run_gpu(args):
         if world == 1:
             sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
             sc1.set_claim(ZERO)  # claim_phase1 = 0 (src/r1csproof.rs:330); the synthetic witness satisfies the instance
-            for j in range(sc1.num_rounds):
-                sc1.round_eval()
-                sc1.round_bind(ch1[j])
+            sc1.run_rounds(ch1[:sc1.num_rounds])  # C loop: eval -> host -> bind per round, no Python in between
             c1 = sc1.final()
             sc1.free()
             sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[nx:nx + nq], ch1[:0], r_abc[0], r_abc[1], r_abc[2])
@@ -173,9 +171,7 @@ def run_gpu(args):
             sc1.engine.free()
             zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q)
             sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
-        for j in range(sc2.num_rounds):
-            sc2.round_eval()
-            sc2.round_bind(ch2[j])
+        sc2.run_rounds(ch2[:sc2.num_rounds])
         c2 = sc2.final()
         sc2.free()
         z.free()
@@ -329,7 +325,7 @@ def run_gpu(args):
                    "constraints_per_step": total_units, "sharding": ("single GPU" if world == 1 else f"one batch of {Q * world} proofs sharded by proof index over {world} ranks: per-round exchange of 3 scalars per rank through host shared memory (the values already live in pinned host memory) + one NCCL all-gather of the rq-bound Z table"),
                    "e2e_pipeline": "double-buffered: the H2D copy of batch i+1 overlaps the proving of batch i; all copies are inside the timed region",
                    "l2": "inputs (>= 4 GiB/step) exceed the 126 MB L2; no flush needed",
-                   "challenges": "precomputed per-round challenges; one host round trip (96 B out, 32 B in) per round is inside the timed region",
+                   "challenges": "precomputed per-round challenges replayed by a C loop (spg_sc1_run_rounds / spg_sc2_run_rounds); every round still returns its 3 evaluations to the host (96 B) before the bind with that round's challenge (32 B) is issued",
                    "phases": "z_mat + SpMV + phase-1 rounds + ABC/Z tables + phase-2 rounds"},
         "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * N * 32), "d2h_bytes_per_step": int(96 * (2 * nx + nq + ng + 1) + 7 * 32)},

@@ -179,6 +179,10 @@ size_t spg_sc1_num_rounds(const spg_sc1 *s);
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]);
 /* bind the round's variable to r_j, :1265-1275 */
 int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r);
+/* num_rounds x (round_eval, round_bind) with challenges known in advance (replaying a
+ * transcript, benchmarking): evals_out[3 * j ..] = (e0, e2, e3) of round j. Every round still
+ * returns its evaluations to the host before the bind is issued. */
+int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out);
 /* (tau_claim, Az, Bz, Cz) after the last bind, :1372-1377 */
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]);
 /* copy the current Az/Bz/Cz tables back in natural ragged order (tests) */
@@ -209,6 +213,7 @@ int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size
 size_t spg_sc2_num_rounds(const spg_sc2 *s);
 int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]);
 int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r);
+int spg_sc2_run_rounds(spg_sc2 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out);
 /* (eq claim, ABC claim, Z claim), :1058-1062 */
 int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]);
 void spg_sc2_destroy(spg_sc2 *s);

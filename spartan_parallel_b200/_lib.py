@@ -93,6 +93,8 @@ def _proto(L):
         "spg_fq_host_eq_weight": [P, SZ, C.c_uint64, P],
         "spg_sc1_round_eval": [P, P],
         "spg_sc1_round_bind": [P, P],
+        "spg_sc1_run_rounds": [P, SZ, P, P],
+        "spg_sc2_run_rounds": [P, SZ, P, P],
         "spg_sc1_final": [P, P],
         "spg_sc1_debug_tables": [P, P, P, P, SZ, P],
         "spg_sc2_create": [P, P, P, SZ, P, SZ, P, SZ, SZ, P, P, P, P, P, P, PP],

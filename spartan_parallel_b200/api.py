@@ -224,6 +224,13 @@ class SumcheckPhase1:
         """Multiply every evaluation and the eq claim by c (shards of the proof axis)."""
         check(self.ctx.L.spg_sc1_set_scale(self.h, _ptr(_fq(c))), "spg_sc1_set_scale")
 
+    def run_rounds(self, challenges) -> np.ndarray:
+        """eval + bind for len(challenges) rounds with challenges known in advance; returns (n, 3, 4)."""
+        ch = _fq(challenges).reshape(-1, 4)
+        out = np.empty((ch.shape[0], 3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc1_run_rounds(self.h, ch.shape[0], _ptr(ch), _ptr(out)), "spg_sc1_run_rounds")
+        return out
+
     def set_claim(self, claim):
         """The prover's `claim` argument (src/sumcheck.rs:1069; zero in R1CSProof::prove): lets round 0
         use e(1) = claim - e(0) like the reference does. Exact iff the claim is the true sum."""
@@ -458,6 +465,12 @@ class SumcheckPhase2:
     @property
     def num_rounds(self) -> int:
         return int(self.ctx.L.spg_sc2_num_rounds(self.h))
+
+    def run_rounds(self, challenges) -> np.ndarray:
+        ch = _fq(challenges).reshape(-1, 4)
+        out = np.empty((ch.shape[0], 3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc2_run_rounds(self.h, ch.shape[0], _ptr(ch), _ptr(out)), "spg_sc2_run_rounds")
+        return out
 
     def round_eval(self) -> np.ndarray:
         out = np.empty((3, 4), dtype=np.uint64)

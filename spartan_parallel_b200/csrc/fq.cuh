@@ -296,6 +296,79 @@ __device__ __forceinline__ fq fq_mul_lazy(const fq &a, const fq &b) {
   return r;
 }
 
+// further products of the SAME row: T += a * bi with P0 the position-0 array and P1 the
+// position-1 array (no shift). Used by the dot product below.
+__device__ __forceinline__ void fq_row_acc(uint32_t P0[8], uint32_t P1[8], const fq &a, uint32_t bi) {
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %8,  %12, %0;\n\t"
+      "madc.hi.cc.u32  %1, %8,  %12, %1;\n\t"
+      "madc.lo.cc.u32  %2, %9,  %12, %2;\n\t"
+      "madc.hi.cc.u32  %3, %9,  %12, %3;\n\t"
+      "madc.lo.cc.u32  %4, %10, %12, %4;\n\t"
+      "madc.hi.cc.u32  %5, %10, %12, %5;\n\t"
+      "madc.lo.cc.u32  %6, %11, %12, %6;\n\t"
+      "madc.hi.u32     %7, %11, %12, %7;\n\t"
+      "}"
+      : "+r"(P1[0]), "+r"(P1[1]), "+r"(P1[2]), "+r"(P1[3]), "+r"(P1[4]), "+r"(P1[5]), "+r"(P1[6]),
+        "+r"(P1[7])
+      : "r"(a.v[1]), "r"(a.v[3]), "r"(a.v[5]), "r"(a.v[7]), "r"(bi));
+  asm("{\n\t"
+      "mad.lo.cc.u32   %0, %9,  %13, %0;\n\t"
+      "madc.hi.cc.u32  %1, %9,  %13, %1;\n\t"
+      "madc.lo.cc.u32  %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32  %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32  %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32  %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32  %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32  %7, %12, %13, %7;\n\t"
+      "addc.u32        %8, %8, 0;\n\t"
+      "}"
+      : "+r"(P0[0]), "+r"(P0[1]), "+r"(P0[2]), "+r"(P0[3]), "+r"(P0[4]), "+r"(P0[5]), "+r"(P0[6]),
+        "+r"(P0[7]), "+r"(P1[7])
+      : "r"(a.v[0]), "r"(a.v[2]), "r"(a.v[4]), "r"(a.v[6]), "r"(bi));
+}
+
+// sum_{k<4} a_k * b_k * R^-1 mod q with ONE reduction per row instead of four: 8*(4*8+5) = 296
+// wide multiplies instead of 4*104. Inputs must be CANONICAL (< q < 2^253): then the running
+// value stays below 4*2^253*2^32 + 2^257 + 2^285 < 2^288, and the result is
+// < 4 q^2 / R + q < 1.26 q, i.e. in the lazy range.
+__device__ __forceinline__ fq fq_dot4_lazy(const fq (&a)[4], const fq (&b)[4]) {
+  uint32_t E[8], O[8];
+  fq_row0(E, O, a[0], b[0].v[0]);
+#pragma unroll
+  for (int k = 1; k < 4; k++) fq_row_acc(E, O, a[k], b[k].v[0]);
+  fq_row_red(E, O);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    fq_row_mul(E, O, a[0], b[0].v[i]);  // O is now the position-0 array
+#pragma unroll
+    for (int k = 1; k < 4; k++) fq_row_acc(O, E, a[k], b[k].v[i]);
+    fq_row_red(O, E);
+    if (i + 1 < 8) {
+      fq_row_mul(O, E, a[0], b[0].v[i + 1]);  // and E again
+#pragma unroll
+      for (int k = 1; k < 4; k++) fq_row_acc(E, O, a[k], b[k].v[i + 1]);
+      fq_row_red(E, O);
+    }
+  }
+  fq r;
+  asm("{\n\t"
+      "add.cc.u32  %0, %8,  %16;\n\t"
+      "addc.cc.u32 %1, %9,  %17;\n\t"
+      "addc.cc.u32 %2, %10, %18;\n\t"
+      "addc.cc.u32 %3, %11, %19;\n\t"
+      "addc.cc.u32 %4, %12, %20;\n\t"
+      "addc.cc.u32 %5, %13, %21;\n\t"
+      "addc.cc.u32 %6, %14, %22;\n\t"
+      "addc.u32    %7, %15, 0;\n\t"
+      "}"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+        "=r"(r.v[6]), "=r"(r.v[7])
+      : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
+        "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+  return r;
+}
+
 // canonical in, canonical out: Scalar::mul (ristretto255.rs:690-714)
 __device__ __forceinline__ fq fq_mul(const fq &a, const fq &b) { return fq_canon(fq_mul_lazy(a, b)); }
 __device__ __forceinline__ fq fq_sqr(const fq &a) { return fq_mul(a, a); }

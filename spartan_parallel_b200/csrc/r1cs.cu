@@ -31,18 +31,56 @@ __device__ __forceinline__ fq spmv_row(const CsxView &M, unsigned int x, const S
   return acc;
 }
 
-// thread t = q * X + x computes row x of A, B, C against z[p][q]
+// rest of a row after its first entry (which the caller prefetched)
+__device__ __forceinline__ fq spmv_row_tail(const CsxView &M, uint32_t e0, uint32_t e1, fq acc,
+                                            const SecView *__restrict__ secs, size_t q, unsigned int log_ymax) {
+  for (uint32_t e = e0; e < e1; e++) {
+    uint32_t c = M.idx[e];
+    bool unit = c & UNIT_FLAG;
+    c &= ~UNIT_FLAG;
+    size_t w = c >> log_ymax, y = c & ((1u << log_ymax) - 1);
+    fq zz = z_load(secs[w], q, y);
+    acc = fq_add(acc, unit ? zz : fq_mul(fq_load(M.val + e), zz));
+  }
+  return acc;
+}
+
+// thread t = q * X + x computes row x of A, B, C against z[p][q]. The kernel is bound by
+// the latency of its dependent loads (row pointer -> column index -> z), so the three
+// matrices' first entries are fetched together: three independent chains in flight per
+// thread instead of one after the other (most R1CS rows have one or two entries).
 __global__ void k_spmv3(CsxView A, CsxView B, CsxView C, const SecView *__restrict__ secs, size_t Q,
                         unsigned int log_x, unsigned int log_ymax,
                         fq *__restrict__ outA, fq *__restrict__ outB, fq *__restrict__ outC) {
   size_t total = Q << log_x;
+  const uint32_t ymask = (1u << log_ymax) - 1;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
     size_t q = t >> log_x;
     unsigned int x = (unsigned int)(t & (((size_t)1 << log_x) - 1));
-    fq_store(outA + t, spmv_row(A, x, secs, q, log_ymax));
-    fq_store(outB + t, spmv_row(B, x, secs, q, log_ymax));
-    fq_store(outC + t, spmv_row(C, x, secs, q, log_ymax));
+    const CsxView *M[3] = {&A, &B, &C};
+    uint32_t e0[3], e1[3], c[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      e0[m] = M[m]->ptr[x];
+      e1[m] = M[m]->ptr[x + 1];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) c[m] = e0[m] < e1[m] ? M[m]->idx[e0[m]] : 0u;
+    fq zz[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      uint32_t cc = c[m] & ~UNIT_FLAG;
+      zz[m] = e0[m] < e1[m] ? z_load(secs[cc >> log_ymax], q, cc & ymask) : fq_zero();
+    }
+    fq *out[3] = {outA, outB, outC};
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      fq acc = zz[m];
+      if (e0[m] < e1[m] && !(c[m] & UNIT_FLAG)) acc = fq_mul(fq_load(M[m]->val + e0[m]), acc);
+      if (e0[m] + 1 < e1[m]) acc = spmv_row_tail(*M[m], e0[m] + 1, e1[m], acc, secs, q, log_ymax);
+      fq_store(out[m] + t, acc);
+    }
   }
 }
 

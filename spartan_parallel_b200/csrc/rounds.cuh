@@ -45,6 +45,33 @@ __device__ __forceinline__ int find_seg(const Seg *__restrict__ segs, int nseg, 
   return lo;
 }
 
+// Up to SEG_INLINE segments travel as a kernel argument (constant bank), so the per-round
+// segment table costs no host-to-device copy; larger instance counts use the device array.
+constexpr int SEG_INLINE = 16;
+struct SegPack {
+  Seg s[SEG_INLINE];
+};
+
+__device__ __forceinline__ Seg pick_seg(const SegPack &pk, const Seg *__restrict__ segs, int nseg,
+                                        unsigned long long item) {
+  if (nseg == 1) return pk.s[0];
+  if (nseg > SEG_INLINE) return segs[find_seg(segs, nseg, item)];
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (pk.s[mid].item_start <= item) lo = mid;
+    else hi = mid - 1;
+  }
+  return pk.s[lo];
+}
+
+static inline SegPack make_pack(const std::vector<Seg> &v) {
+  SegPack pk;
+  memset(&pk, 0, sizeof pk);
+  for (size_t i = 0; i < v.size() && i < (size_t)SEG_INLINE; i++) pk.s[i] = v[i];
+  return pk;
+}
+
 // value of the line through (0, lo), (1, hi) at 2 and 3
 __device__ __forceinline__ void line23(const fq &lo, const fq &hi, fq &at2, fq &at3) {
   fq d = fq_sub(hi, lo);

@@ -30,14 +30,13 @@ constexpr int RB = SPG_RB;  // threads per block of the round kernels
 template <int COMB>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_pair_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
-            const Seg *__restrict__ segs, int nseg, unsigned long long total_items,
+            const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk, unsigned long long total_items,
             const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
   __shared__ fq sm[3 * 32];
   fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
   for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
        item += (unsigned long long)gridDim.x * RB) {
-    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
-    Seg sg = segs[s];
+    Seg sg = pick_seg(pk, segs, nseg, item);
     unsigned long long local = item - sg.item_start;
     fq a0, a1, b0, b1, c0, c1, w;
     if (sg.log_len >= 1) {
@@ -68,11 +67,10 @@ k_pair_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__re
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_pair_bind(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
             fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2,
-            const Seg *__restrict__ segs, int nseg, unsigned long long total_items, fq r) {
+            const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk, unsigned long long total_items, fq r) {
   for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
        item += (unsigned long long)gridDim.x * RB) {
-    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
-    Seg sg = segs[s];
+    Seg sg = pick_seg(pk, segs, nseg, item);
     unsigned long long local = item - sg.item_start;
     unsigned long long o = sg.out_off + local;
     if (sg.log_len >= 1) {
@@ -102,14 +100,13 @@ template <int COMB>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
                  fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2,
-                 const Seg *__restrict__ segs, int nseg, unsigned long long total_items, fq r,
+                 const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk, unsigned long long total_items, fq r,
                  const fq *__restrict__ RW, const fq *__restrict__ Snext, fq *__restrict__ partials) {
   __shared__ fq sm[3 * 32];
   fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
   for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
        item += (unsigned long long)gridDim.x * RB) {
-    int s = nseg == 1 ? 0 : find_seg(segs, nseg, item);
-    Seg sg = segs[s];
+    Seg sg = pick_seg(pk, segs, nseg, item);
     unsigned long long local = item - sg.item_start;
     unsigned int ql = sg.log_len - 2;
     unsigned long long row = local >> ql, i = local & ((1ull << ql) - 1);
@@ -158,12 +155,11 @@ template <int FUSED, int NE>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
        fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
-       int nseg, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
+       int nseg, const __grid_constant__ SegPack pk, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
   static_assert(NE == 2 || (NE == 3 && !FUSED), "k_rows: 2 points, or 3 for the evaluation-only form");
   __shared__ fq sm[NE * 32];
   unsigned long long tile = blockIdx.x;
-  int si = nseg == 1 ? 0 : find_seg(segs, nseg, tile);
-  Seg sg = segs[si];
+  Seg sg = pick_seg(pk, segs, nseg, tile);
   unsigned long long tl = tile - sg.item_start;
   unsigned long long row = tl >> sg.log_tiles, tr = tl & ((1ull << sg.log_tiles) - 1);
   unsigned int li = sg.log_len - (FUSED ? 2 : 1);
@@ -325,6 +321,13 @@ struct spg_sc1 {
   bool claim_known = false;
   hfq claim;
   hfq last_e[3];
+  // the same claim divided by the scalar prefix c of the current round: with
+  // s_j(t) = c_j l_j(t) G_j(t) and c_{j+1} = c_j l_j(r_j) it is simply G_j(r_j), so the
+  // two-point rounds need no field inversion (tau^-1 is precomputed)
+  bool g_known = false, lastG_valid = false;
+  hfq gclaim;
+  hfq lastG[3];  // G(0), G(1), G(2) of the round just evaluated
+  std::vector<hfq> tau_x_inv, tau_q_inv;  // zero where tau is zero
   hfq cx, cq;    // prod eq(tau_k, r_k) over the bound x / q variables
   hfq scale;     // external factor on every evaluation (spg_sc1_set_scale); one by default
   size_t p_len = 1;  // current instance_len during the p rounds
@@ -369,6 +372,7 @@ void build_segs(spg_sc1 *s, int phase, int quad, unsigned long long *total_items
 }
 
 int upload_segs(spg_sc1 *s) {
+  if (s->P <= (size_t)SEG_INLINE) return SPG_OK;  // the segments ride in the kernel arguments
   SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice,
                            s->ctx->stream));
   return SPG_OK;
@@ -415,6 +419,22 @@ int sc1_alloc_common(spg_ctx *ctx, size_t P, const size_t *num_proofs, size_t ma
   for (size_t i = 0; i < s->np; i++) s->tau_p.push_back(hfq_from(tau_p[i]));
   for (size_t i = 0; i < s->nq; i++) s->tau_q.push_back(hfq_from(tau_q[i]));
   for (size_t i = 0; i < s->nx; i++) s->tau_x.push_back(hfq_from(tau_x[i]));
+  {
+    // Montgomery batch inversion of all taus (one field inversion)
+    std::vector<hfq> all(s->tau_x);
+    all.insert(all.end(), s->tau_q.begin(), s->tau_q.end());
+    std::vector<hfq> pre(all.size() + 1, hfq_one());
+    for (size_t i = 0; i < all.size(); i++) pre[i + 1] = hfq_is_zero(all[i]) ? pre[i] : hfq_mul(pre[i], all[i]);
+    hfq inv = hfq_invert(pre[all.size()]);
+    std::vector<hfq> out(all.size(), hfq_zero());
+    for (size_t i = all.size(); i-- > 0;) {
+      if (hfq_is_zero(all[i])) continue;
+      out[i] = hfq_mul(inv, pre[i]);
+      inv = hfq_mul(inv, all[i]);
+    }
+    s->tau_x_inv.assign(out.begin(), out.begin() + s->nx);
+    s->tau_q_inv.assign(out.begin() + s->nx, out.end());
+  }
   size_t N = 0, rows = 0;
   for (size_t p = 0; p < P; p++) {
     N += s->Q[p] * s->X[p];
@@ -662,7 +682,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;
       SPG_LAUNCH(ctx, (k_rows<0, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, zero, RW, S, ctx->d_partials);
+                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
       spg_fq tmp[2];
       SPG_TRY(fetch_result(ctx, 2, tmp));
@@ -671,19 +691,27 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       s->cached_kind = 2;
     }
     if (s->cached_kind == 2) {
-      // G(0), G(2) from the fused kernel; G(1) from the running claim, G(3) by extrapolation
-      hfq denom = hfq_mul(c, tau);
-      if (!hfq_is_zero(denom)) {
-        hfq e0 = hfq_mul(hfq_mul(c, line[0]), s->cached[0]);
-        hfq G1 = hfq_mul(hfq_sub(s->claim, e0), hfq_invert(denom));
-        hfq d = hfq_sub(s->cached[1], G1);
-        hfq G3 = hfq_add(s->cached[0], hfq_add(hfq_add(d, d), d));
-        ev[0] = e0;
-        ev[1] = hfq_mul(hfq_mul(c, line[1]), s->cached[1]);
+      // G(0), G(2) from the kernel; G(1) from the running claim, G(3) by extrapolation
+      const hfq &tau_inv = phase == 0 ? s->tau_x_inv[j] : s->tau_q_inv[j];
+      if (!hfq_is_zero(tau_inv) && !hfq_is_zero(c)) {
+        if (!s->g_known) {
+          s->gclaim = hfq_mul(s->claim, hfq_invert(c));
+          s->g_known = true;
+        }
+        const hfq &G0 = s->cached[0], &G2 = s->cached[1];
+        hfq G1 = hfq_mul(hfq_sub(s->gclaim, hfq_mul(line[0], G0)), tau_inv);  // l(1) = tau
+        hfq d = hfq_sub(G2, G1);
+        hfq G3 = hfq_add(G0, hfq_add(hfq_add(d, d), d));
+        ev[0] = hfq_mul(hfq_mul(c, line[0]), G0);
+        ev[1] = hfq_mul(hfq_mul(c, line[1]), G2);
         ev[2] = hfq_mul(hfq_mul(c, line[2]), G3);
+        s->lastG[0] = G0;
+        s->lastG[1] = G1;
+        s->lastG[2] = G2;
+        s->lastG_valid = true;
         done = true;
       }
-      s->cached_kind = 0;  // denom == 0 (probability ~2^-252): recompute from the bound tables below
+      s->cached_kind = 0;  // tau == 0 or c == 0 (probability ~2^-252): recompute from the bound tables below
     } else if (s->cached_kind == 3) {
       for (int t = 0; t < 3; t++) ev[t] = hfq_mul(hfq_mul(c, line[t]), s->cached[t]);
       s->cached_kind = 0;
@@ -699,7 +727,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;  // 2 scalars x 3 tables read per pair
       SPG_LAUNCH(ctx, (k_rows<0, 3>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, zero, RW, S, ctx->d_partials);
+                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 3, ctx->d_result));
       spg_fq tmp[3];
       SPG_TRY(fetch_result(ctx, 3, tmp));
@@ -711,6 +739,10 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       ev[2] = hfq_mul(hfq_mul(c, line[2]), G3);
       s->claim = hfq_add(ev[0], hfq_mul(hfq_mul(c, tau), G1));  // e(0) + e(1): the true claim
       s->claim_known = true;
+      s->lastG[0] = G0;
+      s->lastG[1] = G1;
+      s->lastG[2] = G2;
+      s->lastG_valid = true;
       done = true;
     }
     if (!done) {
@@ -721,7 +753,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
       ctx->next_units = 192.0 * (double)items;
       SPG_LAUNCH(ctx, k_pair_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
-                 s->tab[s->cur][2], s->d_segs, (int)s->P, items, RW, S, ctx->d_partials);
+                 s->tab[s->cur][2], s->d_segs, (int)s->P, make_pack(s->segs), items, RW, S, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
       spg_fq tmp[3];
       SPG_TRY(fetch_result(ctx, 3, tmp));
@@ -751,6 +783,19 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
   // claim_{j+1} = s_j(r_j)
   if (s->claim_known)
     s->claim = cubic_at(s->last_e[0], hfq_sub(s->claim, s->last_e[0]), s->last_e[1], s->last_e[2], rh);
+  if (s->lastG_valid) {
+    // G(r) for the quadratic through (0, G0), (1, G1), (2, G2)
+    static const hfq two_inv = hfq_invert(hfq_from_u64(2));
+    const hfq &G0 = s->lastG[0], &G1 = s->lastG[1], &G2 = s->lastG[2];
+    hfq d1 = hfq_sub(G1, G0);
+    hfq d2 = hfq_mul(two_inv, hfq_add(hfq_sub(hfq_sub(G2, G1), G1), G0));
+    hfq rr1 = hfq_mul(rh, hfq_sub(rh, hfq_one()));
+    s->gclaim = hfq_add(G0, hfq_add(hfq_mul(rh, d1), hfq_mul(rr1, d2)));
+    s->g_known = true;
+  } else {
+    s->g_known = false;
+  }
+  s->lastG_valid = false;
   if (phase == 2) {
     size_t half = s->p_len / 2;
     SPG_LAUNCH(ctx, k_p_bind, 1, 128, 0, s->Ap, s->tab[s->cur][0], s->tab[s->cur][1],
@@ -773,7 +818,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
       ctx->next_units = 288.0 * (double)out_total;  // per bound pair: 4 read + 2 written scalars x 3 tables
       SPG_LAUNCH(ctx, (k_rows<1, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, rr, RW, Snext, ctx->d_partials);
+                 s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, make_pack(s->segs), rr, RW, Snext, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
       spg_fq tmp[2];
       SPG_TRY(fetch_result(ctx, 2, tmp));
@@ -790,7 +835,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       ctx->next_units = 576.0 * (double)items;  // 4 read + 2 written scalars x 3 tables per item
       SPG_LAUNCH(ctx, k_quad_bind_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
                  s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs,
-                 (int)s->P, items, rr, RW, Snext, ctx->d_partials);
+                 (int)s->P, make_pack(s->segs), items, rr, RW, Snext, ctx->d_partials);
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
       spg_fq tmp[3];
       SPG_TRY(fetch_result(ctx, 3, tmp));
@@ -803,7 +848,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       ctx->next_units = 288.0 * (double)items;
       SPG_LAUNCH(ctx, k_pair_bind, grid_for(ctx, items, RB, 8), RB, 0, s->tab[s->cur][0],
                  s->tab[s->cur][1], s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1],
-                 s->tab[nxt][2], s->d_segs, (int)s->P, items, rr);
+                 s->tab[nxt][2], s->d_segs, (int)s->P, make_pack(s->segs), items, rr);
     }
     s->cur = nxt;
     for (size_t p = 0; p < s->P; p++)
@@ -817,6 +862,15 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
   }
   s->round++;
   s->evaluated = false;
+  return SPG_OK;
+}
+
+int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out) {
+  SPG_CHECK(s && challenges && evals_out, "spg_sc1_run_rounds: null argument");
+  for (size_t j = 0; j < num_rounds; j++) {
+    SPG_TRY(spg_sc1_round_eval(s, evals_out + 3 * j));
+    SPG_TRY(spg_sc1_round_bind(s, challenges + j));
+  }
   return SPG_OK;
 }
 

@@ -71,3 +71,22 @@ def test_sc1_state_errors(ctx):
         sc.final()  # not all rounds bound
     with pytest.raises(sp.SpgError):
         sp.SumcheckPhase1.from_tables(ctx, [3], 4, [8], 8, Az, Az, Az, tau[:0], tau[:2], tau)  # non power of two
+
+
+def test_run_rounds_equals_round_by_round(ctx):
+    """spg_sc1_run_rounds (C loop with known challenges) == eval/bind driven round by round"""
+    import spartan_parallel_b200 as sp
+
+    X, Q = 1 << 10, 4
+    tabs = [rand_scalars(X * Q, s) for s in (21, 22, 23)]
+    tau_q, tau_x, ch = rand_scalars(2, 24), rand_scalars(10, 25), rand_scalars(12, 26)
+    none = rand_scalars(0, 1)
+    a = sp.SumcheckPhase1.from_tables(ctx, [Q], Q, [X], X, *tabs, none, tau_q, tau_x)
+    want = []
+    for j in range(a.num_rounds):
+        want.append(a.round_eval())
+        a.round_bind(ch[j])
+    b = sp.SumcheckPhase1.from_tables(ctx, [Q], Q, [X], X, *tabs, none, tau_q, tau_x)
+    got = b.run_rounds(ch)
+    assert np.array_equal(got, np.stack(want))
+    assert np.array_equal(a.final(), b.final())
