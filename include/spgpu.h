@@ -291,6 +291,10 @@ int spg_vec_clone(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_v
  * MultiCommitGens::new is host-side setup (src/commitments.rs:15-33); the caller
  * passes the n+1 generators as compressed ristretto points (G[0..n], h). */
 int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, spg_gens **out);
+/* MultiCommitGens::new on the device (src/commitments.rs:15-33): the caller supplies the
+ * SHAKE256 output, 64 bytes per point (n generators, then h); each point is
+ * RistrettoPoint::from_uniform_bytes of its 64 bytes. */
+int spg_gens_from_uniform(spg_ctx *ctx, const uint8_t *uniform, size_t n_plus_1, spg_gens **out);
 void spg_gens_destroy(spg_gens *g);
 /* DensePolynomial::commit with zero blinds, src/dense_mlpoly.rs:199-239:
  * out = L_size compressed row commitments (32 bytes each). */

@@ -113,6 +113,7 @@ def _proto(L):
         "spg_hash_layer": [P, P, P, P, SZ, P, P, INT, PP],
         "spg_deref": [P, P, SZ, P, PP],
         "spg_gens_upload": [P, P, SZ, PP],
+        "spg_gens_from_uniform": [P, P, SZ, PP],
         "spg_poly_commit": [P, P, P, SZ, P],
         "spg_commit_batch": [P, P, P, SZ, P, SZ, P],
     }

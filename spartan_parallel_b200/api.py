@@ -611,6 +611,19 @@ class MultiCommitGens:
         check(ctx.L.spg_gens_upload(ctx.h, _ptr(buf), self.n + 1, C.byref(h)), "spg_gens_upload")
         self.h = h
 
+    @classmethod
+    def from_uniform(cls, ctx: Context, uniform: bytes):
+        """MultiCommitGens::new on the device from its SHAKE256 output (64 bytes per point, h last)."""
+        assert len(uniform) % 64 == 0 and len(uniform) >= 128
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.n = len(uniform) // 64 - 1
+        buf = np.frombuffer(bytes(uniform), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        check(ctx.L.spg_gens_from_uniform(ctx.h, _ptr(buf), self.n + 1, C.byref(h)), "spg_gens_from_uniform")
+        self.h = h
+        return self
+
     def commit_poly(self, poly: DensePolynomial, L_size: int | None = None) -> list:
         """DensePolynomial::commit with zero blinds (src/dense_mlpoly.rs:214-239): L_size
         compressed row commitments."""

@@ -39,6 +39,16 @@ __global__ void k_decompress(const uint8_t *__restrict__ in, size_t n, ge *__res
   out[i] = p;
 }
 
+// MultiCommitGens::new's per-point step (src/commitments.rs:23-31): 64 uniform bytes ->
+// RistrettoPoint::from_uniform_bytes (two Elligator maps and an addition)
+__global__ void k_from_uniform(const uint8_t *__restrict__ in, size_t n, ge *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t b[64];
+  for (int k = 0; k < 64; k++) b[k] = in[64 * i + k];
+  out[i] = ristretto_from_uniform_bytes(b);
+}
+
 // thread (j, w): entries d = 1 .. 2^C - 1 of window w of base j
 template <int C>
 __global__ void k_build_table(const ge *__restrict__ bases, size_t nbases, ge_cached *__restrict__ table) {
@@ -266,6 +276,31 @@ int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, sp
     spg_gens_destroy(g);
     set_error("spg_gens_upload: generator %d is not a valid ristretto255 encoding", bad - 1);
     return SPG_EINVAL;
+  }
+  *out = g;
+  return SPG_OK;
+}
+
+int spg_gens_from_uniform(spg_ctx *ctx, const uint8_t *uniform, size_t n_plus_1, spg_gens **out) {
+  SPG_CHECK(ctx && uniform && out, "spg_gens_from_uniform: null argument");
+  SPG_CHECK(n_plus_1 >= 2, "spg_gens_from_uniform: need at least one generator and h");
+  spg_gens *g = new (std::nothrow) spg_gens();
+  if (!g) return SPG_ENOMEM;
+  g->ctx = ctx;
+  g->n = n_plus_1 - 1;
+  uint8_t *d_in = nullptr;
+  cudaError_t e = cudaMalloc(&g->bases, n_plus_1 * sizeof(ge));
+  if (e == cudaSuccess) e = dev_alloc(ctx, &d_in, n_plus_1 * 64);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, uniform, n_plus_1 * 64, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    k_from_uniform<<<(unsigned)((n_plus_1 + 63) / 64), 64, 0, ctx->stream>>>(d_in, n_plus_1, g->bases);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  if (d_in) dev_free(ctx, d_in);
+  if (e != cudaSuccess) {
+    spg_gens_destroy(g);
+    return cuda_fail(e, "spg_gens_from_uniform", __FILE__, __LINE__);
   }
   *out = g;
   return SPG_OK;

@@ -111,9 +111,13 @@ int sph_sparse_prove(spg_ctx *ctx, const char *transcript_label, const char *gen
   try {
     size_t max_nz = 0;
     for (size_t i = 0; i < batch; i++) max_nz = nnz[i] > max_nz ? nnz[i] : max_nz;
+    Trace tr;
     check(spg_sparse_create(ctx, batch, num_vars_x, num_vars_y, nnz, rows, cols, vals, &sp), "spg_sparse_create");
+    tr.lap("sparse: dense representation");
     SparseGens gens(ctx, gens_label, num_vars_x, num_vars_y, max_nz, batch);
+    tr.lap("sparse: generators");
     SparseCommitment c = sparse_commit(ctx, sp, batch, gens);
+    tr.lap("sparse: multi_commit");
     Writer wc;
     wc.u64(c.batch_size);
     wc.u64(c.num_ops);

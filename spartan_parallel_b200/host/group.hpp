@@ -156,11 +156,15 @@ struct MultiCommitGens {
     tabs = v;
   }
   MultiCommitGens() {}
-  // MultiCommitGens::new (src/commitments.rs:15-33)
-  MultiCommitGens(size_t n_, const std::string &label) : n(n_) {
+  // the SHAKE256 stream MultiCommitGens::new reads its points from (src/commitments.rs:16-26)
+  static std::vector<uint8_t> uniform_bytes(size_t n_, const std::string &label) {
     std::vector<uint8_t> in(label.begin(), label.end());
     in.insert(in.end(), basepoint_compressed(), basepoint_compressed() + 32);
-    std::vector<uint8_t> xof = shake256(in, 64 * (n + 1));
+    return shake256(in, 64 * (n_ + 1));
+  }
+  // MultiCommitGens::new (src/commitments.rs:15-33)
+  MultiCommitGens(size_t n_, const std::string &label) : n(n_) {
+    std::vector<uint8_t> xof = uniform_bytes(n, label);
     for (size_t i = 0; i < n + 1; i++) {
       Point pt(spg::ristretto_from_uniform_bytes(xof.data() + 64 * i));
       if (i < n) G.push_back(pt);

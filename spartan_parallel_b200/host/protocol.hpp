@@ -250,6 +250,26 @@ struct DotProductProofGens {
     ctx = c;
     dev = g;
   }
+  // Same generators with the n-sized part derived ON the device (the hash-to-group of
+  // thousands of points is the expensive part of MultiCommitGens::new): the host keeps only
+  // gens_1 (point n) and h (point n + 1); gens_n.G stays empty. *owned receives the handle.
+  static DotProductProofGens on_device(spg_ctx *c, size_t n_, const std::string &label, spg_gens **owned) {
+    DotProductProofGens g;
+    g.n = n_;
+    std::vector<uint8_t> xof = MultiCommitGens::uniform_bytes(n_ + 1, label);  // n + 2 points
+    Point gn(spg::ristretto_from_uniform_bytes(xof.data() + 64 * n_));
+    Point h(spg::ristretto_from_uniform_bytes(xof.data() + 64 * (n_ + 1)));
+    g.gens_n.n = n_;
+    g.gens_n.h = h;
+    g.gens_1.n = 1;
+    g.gens_1.G = {gn};
+    g.gens_1.h = h;
+    std::vector<uint8_t> dev_bytes(xof.begin(), xof.begin() + 64 * n_);
+    dev_bytes.insert(dev_bytes.end(), xof.begin() + 64 * (n_ + 1), xof.end());
+    check(spg_gens_from_uniform(c, dev_bytes.data(), n_ + 1, owned), "spg_gens_from_uniform");
+    g.attach_device(c, *owned);
+    return g;
+  }
 };
 
 // sum_j s[i][j] G_j + blind[i] h for `count` rows of `len` scalars on the device
@@ -364,7 +384,7 @@ struct BulletReductionProof {
       p.R_vec.push_back(Rc);
       nk = nh;
     }
-    Point G_hat = n == 1 ? gens.gens_n.G[0] : device_msm(gens, s, n, 1, nullptr)[0];
+    Point G_hat = device_msm(gens, s, n, 1, nullptr)[0];
     Out o{a[0], b[0], blind_fin, G_hat};
     return {p, o};
   }
@@ -393,7 +413,7 @@ struct DotProductProofLog {
     std::vector<std::pair<Scalar, Scalar>> blinds;
     for (size_t i = 0; i < v1.size(); i++) blinds.push_back({v1[i], v2[i]});
     const MultiCommitGens &gn = gens.gens_n;
-    bool on_device = gens.dev != nullptr && n >= 32;
+    bool on_device = gens.dev != nullptr && (n >= 32 || gens.gens_n.G.empty());
     if (on_device) {
       std::vector<Scalar> bl = {blind_x};
       t.append_point("Cx", device_msm(gens, x, n, 1, &bl)[0].compress());
@@ -443,19 +463,23 @@ struct R1CSGens {
   R1CSGens(const std::string &label, size_t num_vars, spg_ctx *ctx = nullptr) {
     size_t ell = log2z(num_vars);
     size_t right = ell - ell / 2;
-    pc = DotProductProofGens((size_t)1 << right, label);
-    sc_gens_1 = pc.gens_1;
+    size_t n = (size_t)1 << right;
+    if (ctx && n >= 256) {
+      pc = DotProductProofGens::on_device(ctx, n, label, &d_pc);
+    } else {
+      pc = DotProductProofGens(n, label);
+      if (ctx) {
+        std::vector<uint8_t> c = pc.gens_n.compressed();
+        check(spg_gens_upload(ctx, c.data(), pc.gens_n.n + 1, &d_pc), "spg_gens_upload");
+        pc.attach_device(ctx, d_pc);
+      }
+    }
     sc_gens_3 = MultiCommitGens(3, label);
     sc_gens_4 = MultiCommitGens(4, label);
     pc.gens_1.precompute();
     sc_gens_1 = pc.gens_1;
     sc_gens_3.precompute();
     sc_gens_4.precompute();
-    if (ctx) {
-      std::vector<uint8_t> c = pc.gens_n.compressed();
-      check(spg_gens_upload(ctx, c.data(), pc.gens_n.n + 1, &d_pc), "spg_gens_upload");
-      pc.attach_device(ctx, d_pc);
-    }
   }
   ~R1CSGens() { spg_gens_destroy(d_pc); }
   R1CSGens(const R1CSGens &) = delete;

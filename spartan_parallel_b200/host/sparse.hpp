@@ -34,21 +34,22 @@ struct SparseGens {
   DotProductProofGens ops, mem, derefs;
   spg_gens *d_ops = nullptr, *d_mem = nullptr, *d_derefs = nullptr;
   SparseGens(spg_ctx *ctx, const std::string &label, size_t nvx, size_t nvy, size_t num_nz, size_t batch) {
-    auto pcg = [&](size_t nv) { return DotProductProofGens((size_t)1 << (nv - nv / 2), label); };
-    size_t lg = log2z(next_pow2(num_nz));
-    ops = pcg(lg + log2z(next_pow2(batch * 5)));
-    mem = pcg((nvx > nvy ? nvx : nvy) + 1);
-    derefs = pcg(lg + log2z(next_pow2(batch * 2)));
-    auto up = [&](const DotProductProofGens &g, spg_gens **out) {
+    auto pcg = [&](size_t nv, spg_gens **d) {
+      size_t n = (size_t)1 << (nv - nv / 2);
+      if (n >= 256) return DotProductProofGens::on_device(ctx, n, label, d);
+      DotProductProofGens g(n, label);
       std::vector<uint8_t> c = g.gens_n.compressed();
-      check(spg_gens_upload(ctx, c.data(), g.gens_n.n + 1, out), "spg_gens_upload");
+      check(spg_gens_upload(ctx, c.data(), g.gens_n.n + 1, d), "spg_gens_upload");
+      g.attach_device(ctx, *d);
+      return g;
     };
-    up(ops, &d_ops);
-    up(mem, &d_mem);
-    up(derefs, &d_derefs);
-    ops.attach_device(ctx, d_ops);
-    mem.attach_device(ctx, d_mem);
-    derefs.attach_device(ctx, d_derefs);
+    size_t lg = log2z(next_pow2(num_nz));
+    ops = pcg(lg + log2z(next_pow2(batch * 5)), &d_ops);
+    mem = pcg((nvx > nvy ? nvx : nvy) + 1, &d_mem);
+    derefs = pcg(lg + log2z(next_pow2(batch * 2)), &d_derefs);
+    ops.gens_1.precompute();
+    mem.gens_1.precompute();
+    derefs.gens_1.precompute();
   }
   ~SparseGens() {
     spg_gens_destroy(d_ops);
@@ -269,6 +270,7 @@ struct TreeSet {
 inline std::vector<uint8_t> sparse_prove(spg_ctx *ctx, spg_sparse *sp, size_t batch, const std::vector<Scalar> &rx,
                                          const std::vector<Scalar> &ry, const std::vector<Scalar> &evals,
                                          const SparseGens &gens, ProofTranscript &t, RandomTape &tape) {
+  Trace tr;
   t.append_protocol_name("Sparse polynomial evaluation proof");
   if (evals.size() != batch) throw std::runtime_error("sparse_prove: one evaluation per matrix expected");
   size_t N = spg_sparse_num_ops(sp), M = spg_sparse_num_mem_cells(sp);
@@ -302,7 +304,9 @@ inline std::vector<uint8_t> sparse_prove(spg_ctx *ctx, spg_sparse *sp, size_t ba
     col_ops_val.push_back(slice(comb, (batch + i) * N, N));
     val.push_back(view(SPG_SPARSE_VAL, i));
   }
+  tr.lap("sparse: eq tables + derefs");
   std::vector<Compressed> comm_derefs = poly_commit_dev(ctx, gens.d_derefs, comb);
+  tr.lap("sparse: derefs commitment");
   t.append_message("derefs_commitment", "begin_derefs_commitment");
   append_poly_commitment(t, "comm_poly_row_col_ops_val", comm_derefs);
   t.append_message("derefs_commitment", "end_derefs_commitment");
@@ -339,6 +343,7 @@ inline std::vector<uint8_t> sparse_prove(spg_ctx *ctx, spg_sparse *sp, size_t ba
       side[s].write.push_back(trees.build(ctx, hash(addr, ov, rts, 1)));
     }
   }
+  tr.lap("sparse: hash layers + trees");
   // PolyEvalNetworkProof::prove -> ProductLayerProof::prove (:1118-1263)
   t.append_protocol_name("Sparse polynomial evaluation proof");
   t.append_protocol_name("Sparse polynomial product layer proof");
@@ -396,11 +401,13 @@ inline std::vector<uint8_t> sparse_prove(spg_ctx *ctx, spg_sparse *sp, size_t ba
     for (size_t i = 0; i < batch; i++) ops_trees.push_back(side[s].read[i]), ops_evals.push_back(side[s].e_read[i]);
     for (size_t i = 0; i < batch; i++) ops_trees.push_back(side[s].write[i]), ops_evals.push_back(side[s].e_write[i]);
   }
+  tr.lap("sparse: tree evals + dotp");
   std::vector<Scalar> rand_ops, rand_mem;
   ProductCircuitEvalProofBatched proof_ops = pcepb_prove(ctx, ops_trees, ops_evals, dotp, t, &rand_ops);
   ProductCircuitEvalProofBatched proof_mem =
       pcepb_prove(ctx, {side[0].init, side[0].audit, side[1].init, side[1].audit},
                   {side[0].e_init, side[0].e_audit, side[1].e_init, side[1].e_audit}, {}, t, &rand_mem);
+  tr.lap("sparse: product-circuit sumchecks");
   // HashLayerProof::prove (:805-918)
   t.append_protocol_name("Sparse polynomial hash layer proof");
   auto evaluate = [&](spg_vec *v, const std::vector<Scalar> &r) {
@@ -461,6 +468,7 @@ inline std::vector<uint8_t> sparse_prove(spg_ctx *ctx, spg_sparse *sp, size_t ba
   r_joint_mem.insert(r_joint_mem.end(), rand_mem.begin(), rand_mem.end());
   t.append_scalar("joint_claim_eval_mem", joint_mem);
   DotProductProofLog proof_mem_eval = polyeval_prove(ctx, view(SPG_SPARSE_COMB_MEM, 0), r_joint_mem, joint_mem, gens.mem, t, tape);
+  tr.lap("sparse: hash-layer evals + 3 openings");
   // bincode layout: SparseMatPolyEvalProof { comm_derefs, PolyEvalNetworkProof { ProductLayerProof, HashLayerProof } }
   Writer w;
   w.points(comm_derefs);
