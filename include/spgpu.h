@@ -151,7 +151,10 @@ void spg_zmat_destroy(spg_zmat *z);
  * ZKSumcheckInstanceProof::prove_cubic_with_additive_term_disjoint_rounds,
  * src/sumcheck.rs:1067-1380, with comb = A*(B*C - D) (src/r1csproof.rs:100-104).
  * create = multiply_vec_block (src/r1csinstance.rs:363-436) + the three eq tables
- * (src/r1csproof.rs:305-322). num_cons is per proving instance (block_num_cons). */
+ * (src/r1csproof.rs:305-322). num_cons is per proving instance (block_num_cons).
+ * The matrix-vector products are validated here but computed inside the first round kernel
+ * (one pass: read z, write Az/Bz/Cz, evaluate round 0), so `inst` and `z` must stay alive
+ * until the first spg_sc1_round_eval (or spg_sc1_final / _debug_tables) has returned. */
 int spg_sc1_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t num_instances,
                    const size_t *num_proofs, size_t max_num_proofs, const size_t *num_cons,
                    size_t max_num_cons, size_t max_num_inputs, const spg_fq *tau_p,

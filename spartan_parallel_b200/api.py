@@ -396,7 +396,9 @@ def sumcheck_phase1(ctx: Context, inst: R1CSInstance, z: ZMat, num_proofs, max_n
     h = C.c_void_p()
     check(ctx.L.spg_sc1_create(ctx.h, inst.h, z.h, len(npf), _ptr(npf), max_num_proofs, _ptr(nc), max_num_cons,
                                max_num_inputs, _ptr(tp), _ptr(tq), _ptr(tx), C.byref(h)), "spg_sc1_create")
-    return SumcheckPhase1(ctx, h)
+    sc = SumcheckPhase1(ctx, h)
+    sc._keep = (inst, z)  # multiply_vec_block is fused into the first round: both must outlive it
+    return sc
 
 
 def host_sum(vals) -> np.ndarray:

@@ -12,75 +12,27 @@
 namespace spg {
 
 // ---------------------------------------------------------------- kernels
-struct CsxView {
-  const uint32_t *ptr, *idx;
-  const fq *val;
-};
-
-__device__ __forceinline__ fq spmv_row(const CsxView &M, unsigned int x, const SecView *__restrict__ secs,
-                                       size_t q, unsigned int log_ymax) {
-  fq acc = fq_zero();
-  for (uint32_t e = M.ptr[x]; e < M.ptr[x + 1]; e++) {
-    uint32_t c = M.idx[e];
-    bool unit = c & UNIT_FLAG;
-    c &= ~UNIT_FLAG;
-    size_t w = c >> log_ymax, y = c & ((1u << log_ymax) - 1);
-    fq zz = z_load(secs[w], q, y);
-    acc = fq_add(acc, unit ? zz : fq_mul(fq_load(M.val + e), zz));
-  }
-  return acc;
-}
-
-// rest of a row after its first entry (which the caller prefetched)
-__device__ __forceinline__ fq spmv_row_tail(const CsxView &M, uint32_t e0, uint32_t e1, fq acc,
-                                            const SecView *__restrict__ secs, size_t q, unsigned int log_ymax) {
-  for (uint32_t e = e0; e < e1; e++) {
-    uint32_t c = M.idx[e];
-    bool unit = c & UNIT_FLAG;
-    c &= ~UNIT_FLAG;
-    size_t w = c >> log_ymax, y = c & ((1u << log_ymax) - 1);
-    fq zz = z_load(secs[w], q, y);
-    acc = fq_add(acc, unit ? zz : fq_mul(fq_load(M.val + e), zz));
-  }
-  return acc;
-}
-
 // thread t = q * X + x computes row x of A, B, C against z[p][q]. The kernel is bound by
 // the latency of its dependent loads (row pointer -> column index -> z), so the three
-// matrices' first entries are fetched together: three independent chains in flight per
-// thread instead of one after the other (most R1CS rows have one or two entries).
+// matrices' first entries are fetched together (spmv_rows3): three independent chains in
+// flight per thread instead of one after the other (most R1CS rows have one or two entries).
 __global__ void k_spmv3(CsxView A, CsxView B, CsxView C, const SecView *__restrict__ secs, size_t Q,
                         unsigned int log_x, unsigned int log_ymax,
                         fq *__restrict__ outA, fq *__restrict__ outB, fq *__restrict__ outC) {
   size_t total = Q << log_x;
-  const uint32_t ymask = (1u << log_ymax) - 1;
+  CsxView3 V;
+  V.M[0] = A;
+  V.M[1] = B;
+  V.M[2] = C;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
     size_t q = t >> log_x;
     unsigned int x = (unsigned int)(t & (((size_t)1 << log_x) - 1));
-    const CsxView *M[3] = {&A, &B, &C};
-    uint32_t e0[3], e1[3], c[3];
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-      e0[m] = M[m]->ptr[x];
-      e1[m] = M[m]->ptr[x + 1];
-    }
-#pragma unroll
-    for (int m = 0; m < 3; m++) c[m] = e0[m] < e1[m] ? M[m]->idx[e0[m]] : 0u;
-    fq zz[3];
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-      uint32_t cc = c[m] & ~UNIT_FLAG;
-      zz[m] = e0[m] < e1[m] ? z_load(secs[cc >> log_ymax], q, cc & ymask) : fq_zero();
-    }
-    fq *out[3] = {outA, outB, outC};
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-      fq acc = zz[m];
-      if (e0[m] < e1[m] && !(c[m] & UNIT_FLAG)) acc = fq_mul(fq_load(M[m]->val + e0[m]), acc);
-      if (e0[m] + 1 < e1[m]) acc = spmv_row_tail(*M[m], e0[m] + 1, e1[m], acc, secs, q, log_ymax);
-      fq_store(out[m] + t, acc);
-    }
+    fq r[3];
+    spmv_rows3(V, x, secs, q, log_ymax, r);
+    fq_store(outA + t, r[0]);
+    fq_store(outB + t, r[1]);
+    fq_store(outC + t, r[2]);
   }
 }
 
@@ -168,17 +120,16 @@ static void free_csx(Csx &c) {
   c = Csx();
 }
 
-static CsxView view(const Csx &c) { return CsxView{c.ptr, c.idx, c.val}; }
+CsxView csx_view(const Csx &c) { return CsxView{c.ptr, c.idx, c.val}; }
+static CsxView view(const Csx &c) { return csx_view(c); }
 
-int r1cs_multiply_vec_block(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t P,
-                            const size_t *num_proofs, const size_t *num_cons, size_t max_num_inputs,
-                            fq *Az, fq *Bz, fq *Cz) {
+int r1cs_spmv_validate(const spg_r1cs *inst, const spg_zmat *z, size_t P, const size_t *num_proofs,
+                       const size_t *num_cons, size_t max_num_inputs) {
   SPG_CHECK(inst->num_instances == 1 || inst->num_instances == P,
             "multiply_vec_block: instance has %zu blocks, proving %zu", inst->num_instances, P);
   SPG_CHECK(z->P == P, "multiply_vec_block: z_mat has %zu instances, expected %zu", z->P, P);
   SPG_CHECK(is_pow2(max_num_inputs), "multiply_vec_block: max_num_inputs must be a power of two");
   unsigned log_ymax = log2u(max_num_inputs);
-  size_t off = 0;
   for (size_t p = 0; p < P; p++) {
     size_t pi = inst->num_instances == 1 ? 0 : p;
     SPG_CHECK(num_cons[p] == inst->num_cons[pi], "multiply_vec_block: num_cons[%zu] = %zu, instance has %zu",
@@ -196,6 +147,18 @@ int r1cs_multiply_vec_block(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *
           SPG_CHECK((c & (max_num_inputs - 1)) < Yp,
                     "multiply_vec_block: column %u exceeds num_inputs[%zu] = %zu", c, p, Yp);
     }
+  }
+  return SPG_OK;
+}
+
+int r1cs_multiply_vec_block(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t P,
+                            const size_t *num_proofs, const size_t *num_cons, size_t max_num_inputs,
+                            fq *Az, fq *Bz, fq *Cz) {
+  SPG_TRY(r1cs_spmv_validate(inst, z, P, num_proofs, num_cons, max_num_inputs));
+  unsigned log_ymax = log2u(max_num_inputs);
+  size_t off = 0;
+  for (size_t p = 0; p < P; p++) {
+    size_t pi = inst->num_instances == 1 ? 0 : p;
     size_t items = num_proofs[p] * num_cons[p];
     ctx->next_units = 32.0 * (double)items * 3.0 * 2.0;  // >= one z read + one write per (row, q, matrix)
     SPG_LAUNCH(ctx, k_spmv3, grid_for(ctx, items, 256), 256, 0, view(inst->by_row[3 * pi]),

@@ -31,6 +31,79 @@ __device__ __forceinline__ fq z_load(const SecView &v, size_t q, size_t y) {
   return y < v.copy ? fq_load(v.ptr + q * v.q_stride + y) : fq_zero();
 }
 
+struct CsxView {
+  const uint32_t *ptr, *idx;
+  const fq *val;
+};
+
+__device__ __forceinline__ fq spmv_row(const CsxView &M, unsigned int x, const SecView *__restrict__ secs,
+                                       size_t q, unsigned int log_ymax) {
+  fq acc = fq_zero();
+  for (uint32_t e = M.ptr[x]; e < M.ptr[x + 1]; e++) {
+    uint32_t c = M.idx[e];
+    bool unit = c & UNIT_FLAG;
+    c &= ~UNIT_FLAG;
+    size_t w = c >> log_ymax, y = c & ((1u << log_ymax) - 1);
+    fq zz = z_load(secs[w], q, y);
+    acc = fq_add(acc, unit ? zz : fq_mul(fq_load(M.val + e), zz));
+  }
+  return acc;
+}
+
+// rest of a row after its first entry (which the caller prefetched)
+__device__ __forceinline__ fq spmv_row_tail(const CsxView &M, uint32_t e0, uint32_t e1, fq acc,
+                                            const SecView *__restrict__ secs, size_t q, unsigned int log_ymax) {
+  for (uint32_t e = e0; e < e1; e++) {
+    uint32_t c = M.idx[e];
+    bool unit = c & UNIT_FLAG;
+    c &= ~UNIT_FLAG;
+    size_t w = c >> log_ymax, y = c & ((1u << log_ymax) - 1);
+    fq zz = z_load(secs[w], q, y);
+    acc = fq_add(acc, unit ? zz : fq_mul(fq_load(M.val + e), zz));
+  }
+  return acc;
+}
+
+// the first entries of the three matrices' rows x are fetched together (three independent
+// ptr -> idx -> z chains in flight), then each row is finished: Az[x], Bz[x], Cz[x] for proof q
+struct CsxView3 {
+  CsxView M[3];
+};
+// row heads: entry range and first column index of row x in each of the three matrices
+struct RowHead3 {
+  uint32_t e0[3], e1[3], c[3];
+};
+__device__ __forceinline__ RowHead3 spmv_head3(const CsxView3 &V, unsigned int x) {
+  RowHead3 h;
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    h.e0[m] = V.M[m].ptr[x];
+    h.e1[m] = V.M[m].ptr[x + 1];
+  }
+#pragma unroll
+  for (int m = 0; m < 3; m++) h.c[m] = h.e0[m] < h.e1[m] ? V.M[m].idx[h.e0[m]] : 0u;
+  return h;
+}
+__device__ __forceinline__ void spmv_finish3(const CsxView3 &V, const RowHead3 &h, const SecView *__restrict__ secs,
+                                             size_t q, unsigned int log_ymax, fq (&out)[3]) {
+  const uint32_t ymask = (1u << log_ymax) - 1;
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    uint32_t cc = h.c[m] & ~UNIT_FLAG;
+    out[m] = h.e0[m] < h.e1[m] ? z_load(secs[cc >> log_ymax], q, cc & ymask) : fq_zero();
+  }
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    if (h.e0[m] < h.e1[m] && !(h.c[m] & UNIT_FLAG)) out[m] = fq_mul(fq_load(V.M[m].val + h.e0[m]), out[m]);
+    if (h.e0[m] + 1 < h.e1[m]) out[m] = spmv_row_tail(V.M[m], h.e0[m] + 1, h.e1[m], out[m], secs, q, log_ymax);
+  }
+}
+__device__ __forceinline__ void spmv_rows3(const CsxView3 &V, unsigned int x, const SecView *__restrict__ secs,
+                                           size_t q, unsigned int log_ymax, fq (&out)[3]) {
+  RowHead3 h = spmv_head3(V, x);
+  spmv_finish3(V, h, secs, q, log_ymax, out);
+}
+
 }  // namespace spg
 
 struct spg_r1cs {
@@ -64,6 +137,10 @@ namespace spg {
 // orders the compute stream after a pending asynchronous upload of the section
 int witness_wait(spg_witness *w);
 
+CsxView csx_view(const Csx &c);
+// the shape / range checks of multiply_vec_block without the launch
+int r1cs_spmv_validate(const spg_r1cs *inst, const spg_zmat *z, size_t P, const size_t *num_proofs,
+                       const size_t *num_cons, size_t max_num_inputs);
 // multiply_vec_block (src/r1csinstance.rs:363-436): Az/Bz/Cz in natural ragged [p][q][x] order
 int r1cs_multiply_vec_block(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t P,
                             const size_t *num_proofs, const size_t *num_cons, size_t max_num_inputs,

@@ -219,6 +219,83 @@ k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restric
   }
 }
 
+// First round with the SpMV fused in (multiply_vec_block + round 0 in one pass): the block
+// computes Az, Bz, Cz of its tile straight from the witness sections, writes them for the
+// next round and evaluates the round polynomial on the fly, so the three tables are written
+// once and not read back (k_spmv3 + k_rows<0> wrote 96 N bytes and read them again).
+struct SpmvSegs {
+  CsxView3 mats[SEG_INLINE];
+  const SecView *secs[SEG_INLINE];
+};
+
+template <int NE>
+__global__ void __launch_bounds__(RB, SPG_MINB)
+k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__restrict__ O0, fq *__restrict__ O1,
+            fq *__restrict__ O2, int nseg, const __grid_constant__ SegPack pk, const fq *__restrict__ RW,
+            const fq *__restrict__ S, fq *__restrict__ partials) {
+  __shared__ fq sm[NE * 32];
+  unsigned long long tile = blockIdx.x;
+  int si = 0;
+  if (nseg > 1) {
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (pk.s[mid].item_start <= tile) lo = mid;
+      else hi = mid - 1;
+    }
+    si = lo;
+  }
+  const Seg sg = pk.s[si];
+  const SecView *__restrict__ secs = SP.secs[si];
+  unsigned long long tl = tile - sg.item_start;
+  unsigned long long row = tl >> sg.log_tiles, tr = tl & ((1ull << sg.log_tiles) - 1);
+  unsigned int li = sg.log_len - 1;
+  unsigned long long items_row = 1ull << li, tile_items = items_row >> sg.log_tiles;
+  unsigned long long base = tr * tile_items;
+  fq acc[NE];
+#pragma unroll
+  for (int k = 0; k < NE; k++) acc[k] = fq_zero();
+  // software pipeline: the row heads (pointer + first column index, two dependent L2 hits) of
+  // the next item are in flight while the current item's products run, so an iteration waits
+  // for one DRAM latency (z) instead of three dependent ones. (Measured: 4.05 ms unpipelined,
+  // 3.41 ms with this; a second stage that also L2-prefetches the next z operands spills at
+  // 128 registers and is slower, 3.96 ms.)
+  unsigned long long it = base + threadIdx.x;
+  RowHead3 h_lo, h_hi;
+  if (it < base + tile_items) {
+    h_lo = spmv_head3(SP.mats[si], (unsigned int)(2 * it));
+    h_hi = spmv_head3(SP.mats[si], (unsigned int)(2 * it + 1));
+  }
+  for (; it < base + tile_items; it += RB) {
+    unsigned long long idx = sg.in_off + 2 * (row * items_row + it);
+    fq lo3[3], hi3[3];
+    spmv_finish3(SP.mats[si], h_lo, secs, row, log_ymax, lo3);
+    spmv_finish3(SP.mats[si], h_hi, secs, row, log_ymax, hi3);
+    if (it + RB < base + tile_items) {
+      h_lo = spmv_head3(SP.mats[si], (unsigned int)(2 * (it + RB)));
+      h_hi = spmv_head3(SP.mats[si], (unsigned int)(2 * (it + RB) + 1));
+    }
+    fq_store(O0 + idx, lo3[0]); fq_store(O0 + idx + 1, hi3[0]);
+    fq_store(O1 + idx, lo3[1]); fq_store(O1 + idx + 1, hi3[1]);
+    fq_store(O2 + idx, lo3[2]); fq_store(O2 + idx + 1, hi3[2]);
+    fq w = fq_load(S + it);
+    acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(lo3[0], lo3[1]), lo3[2])));
+    if (NE == 3) acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(hi3[0], hi3[1]), hi3[2])));
+    fq a2 = fq_add_lazy(hi3[0], fq_sub_lazy(hi3[0], lo3[0]));
+    fq b2 = fq_add_lazy(hi3[1], fq_sub_lazy(hi3[1], lo3[1]));
+    fq c2 = fq_add_lazy(hi3[2], fq_sub_lazy(hi3[2], lo3[2]));
+    acc[NE - 1] = fq_add_lazy(acc[NE - 1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a2, b2), c2)));
+  }
+#pragma unroll
+  for (int k = 0; k < NE; k++) acc[k] = fq_canon(acc[k]);
+  block_sum<NE>(acc, sm);
+  if (threadIdx.x == 0) {
+    fq rw = RW[sg.rw_off + row];
+#pragma unroll
+    for (int k = 0; k < NE; k++) partials[(unsigned long long)blockIdx.x * NE + k] = fq_mul(rw, acc[k]);
+  }
+}
+
 // ---------------------------------------------------------------- p rounds (tiny)
 // tables hold one scalar per instance, zero padded to P'. MODE_P binds the TOP bit
 // of p (no reversal): pairs (p, p + half). sumcheck.rs:1186-1245 with mode P.
@@ -330,12 +407,20 @@ struct spg_sc1 {
   std::vector<hfq> tau_x_inv, tau_q_inv;  // zero where tau is zero
   hfq cx, cq;    // prod eq(tau_k, r_k) over the bound x / q variables
   hfq scale;     // external factor on every evaluation (spg_sc1_set_scale); one by default
+  // multiply_vec_block deferred into the first round (see k_rows_spmv); the instance and
+  // the z_mat must stay alive until the first spg_sc1_round_eval has returned
+  const spg_r1cs *pend_inst = nullptr;
+  const spg_zmat *pend_z = nullptr;
+  size_t pend_max_num_inputs = 0;
   size_t p_len = 1;  // current instance_len during the p rounds
   bool fuse = true;
   bool p_ready = false;
 };
 
 namespace {
+
+int sc1_materialize(spg_sc1 *s);
+bool sc1_rows_eligible0(const spg_sc1 *s);
 
 int phase_of(const spg_sc1 *s, size_t round) {
   if (round < s->nx) return 0;
@@ -506,6 +591,23 @@ int sc1_build_weights(spg_sc1 *s) {
   return SPG_OK;
 }
 
+// runs the deferred multiply_vec_block (anything but the fused first round needs the tables)
+int sc1_materialize(spg_sc1 *s) {
+  if (!s->pend_inst) return SPG_OK;
+  const spg_r1cs *inst = s->pend_inst;
+  const spg_zmat *z = s->pend_z;
+  s->pend_inst = nullptr;
+  s->pend_z = nullptr;
+  return r1cs_multiply_vec_block(s->ctx, inst, z, s->P, s->Q.data(), s->X.data(), s->pend_max_num_inputs, s->tab[0][0],
+                                 s->tab[0][1], s->tab[0][2]);
+}
+
+bool sc1_rows_eligible0(const spg_sc1 *s) {
+  for (size_t p = 0; p < s->P; p++)
+    if (s->loglen[p] < 8) return false;
+  return true;
+}
+
 // after the last q round every table holds one scalar per instance: pad to P' with zeros
 int sc1_enter_p_phase(spg_sc1 *s) {
   if (s->p_ready) return SPG_OK;
@@ -558,8 +660,14 @@ int spg_sc1_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
   spg_sc1 *s = nullptr;
   SPG_TRY(sc1_alloc_common(ctx, num_instances, num_proofs, max_num_proofs, num_cons, max_num_cons,
                            tau_p, tau_q, tau_x, &s));
-  int rc = r1cs_multiply_vec_block(ctx, inst, z, num_instances, num_proofs, num_cons, max_num_inputs,
-                                   s->tab[0][0], s->tab[0][1], s->tab[0][2]);
+  int rc = r1cs_spmv_validate(inst, z, num_instances, num_proofs, num_cons, max_num_inputs);
+  if (rc == SPG_OK) {
+    s->pend_inst = inst;
+    s->pend_z = z;
+    s->pend_max_num_inputs = max_num_inputs;
+    // the fused first round needs tile-able rows and an inline segment table; otherwise multiply now
+    if (!(s->nx >= 1 && s->P <= (size_t)SEG_INLINE && sc1_rows_eligible0(s))) rc = sc1_materialize(s);
+  }
   if (rc == SPG_OK) rc = sc1_build_weights(s);
   if (rc != SPG_OK) {
     spg_sc1_destroy(s);
@@ -624,6 +732,19 @@ bool rows_eligible(const spg_sc1 *s, int fused) {
   return true;
 }
 
+// per-segment matrices and witness views for the fused first round
+SpmvSegs make_spmv_segs(const spg_sc1 *s) {
+  SpmvSegs sp;
+  memset(&sp, 0, sizeof sp);
+  const spg_r1cs *inst = s->pend_inst;
+  for (size_t p = 0; p < s->P && p < (size_t)SEG_INLINE; p++) {
+    size_t pi = inst->num_instances == 1 ? 0 : p;
+    for (int m = 0; m < 3; m++) sp.mats[p].M[m] = csx_view(inst->by_row[3 * pi + m]);
+    sp.secs[p] = s->pend_z->views + p * s->pend_z->W;
+  }
+  return sp;
+}
+
 // value at r of the cubic through (0, e0), (1, e1), (2, e2), (3, e3)  (UniPoly::from_evals + evaluate)
 hfq cubic_at(const hfq &e0, const hfq &e1, const hfq &e2, const hfq &e3, const hfq &r) {
   static const hfq two_inv = hfq_invert(hfq_from_u64(2)), six_inv = hfq_invert(hfq_from_u64(6));
@@ -652,6 +773,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
   size_t j = phase_round(s, s->round);
   hfq ev[3];  // e(0), e(2), e(3)
   if (phase == 2) {
+    SPG_TRY(sc1_materialize(s));
     SPG_TRY(sc1_enter_p_phase(s));
     size_t half = s->p_len / 2;
     size_t limit = half < s->P ? half : s->P;
@@ -681,8 +803,17 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;
-      SPG_LAUNCH(ctx, (k_rows<0, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
+      if (s->pend_inst) {
+        // tables do not exist yet: compute them in the same pass (read z once, write 96 N bytes once)
+        ctx->next_units = 288.0 * pairs;
+        SPG_LAUNCH(ctx, (k_rows_spmv<2>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
+                   s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+        s->pend_inst = nullptr;
+        s->pend_z = nullptr;
+      } else {
+        SPG_LAUNCH(ctx, (k_rows<0, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
+      }
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
       spg_fq tmp[2];
       SPG_TRY(fetch_result(ctx, 2, tmp));
@@ -726,8 +857,16 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;  // 2 scalars x 3 tables read per pair
-      SPG_LAUNCH(ctx, (k_rows<0, 3>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
+      if (s->pend_inst) {
+        ctx->next_units = 288.0 * pairs;
+        SPG_LAUNCH(ctx, (k_rows_spmv<3>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
+                   s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+        s->pend_inst = nullptr;
+        s->pend_z = nullptr;
+      } else {
+        SPG_LAUNCH(ctx, (k_rows<0, 3>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
+      }
       SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 3, ctx->d_result));
       spg_fq tmp[3];
       SPG_TRY(fetch_result(ctx, 3, tmp));
@@ -746,6 +885,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       done = true;
     }
     if (!done) {
+      SPG_TRY(sc1_materialize(s));
       unsigned long long items = 0, out_total = 0;
       build_segs(s, phase, 0, &items, &out_total);
       SPG_TRY(upload_segs(s));
@@ -881,6 +1021,7 @@ int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
     return SPG_ESTATE;
   }
   spg_ctx *ctx = s->ctx;
+  SPG_TRY(sc1_materialize(s));
   // with zero q rounds the x phase never re-keys the segments; everything is length one anyway
   fq h[4];
   SPG_CUDA(cudaMemcpyAsync(&h[0], s->Ap, sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
@@ -896,6 +1037,7 @@ int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
 
 int spg_sc1_debug_tables(spg_sc1 *s, spg_fq *Az, spg_fq *Bz, spg_fq *Cz, size_t cap, size_t *n) {
   SPG_CHECK(s && n, "spg_sc1_debug_tables: null argument");
+  SPG_TRY(sc1_materialize(s));
   size_t total = 0;
   int phase = s->round < spg_sc1_num_rounds(s) ? phase_of(s, s->round) : 2;
   if (phase == 2) total = s->p_len < s->P ? s->p_len : s->P;
