@@ -163,10 +163,8 @@ def run_gpu(args):
         else:
             # one proof over Q * world proofs: shards exchange 3 scalars per round, then one
             # all-gather of the rq-bound Z table; phase 2 (independent of Q) runs replicated
-            sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, tau_q, tau_x)
-            for j in range(sc1.num_rounds):
-                sc1.round_eval()
-                sc1.round_bind(ch1[j])
+            sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, tau_q, tau_x, satisfied=True)
+            sc1.run_rounds(ch1[:sc1.num_rounds])
             c1 = sc1.final()
             sc1.engine.free()
             zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q)

@@ -186,6 +186,14 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r);
  * transcript, benchmarking): evals_out[3 * j ..] = (e0, e2, e3) of round j. Every round still
  * returns its evaluations to the host before the bind is issued. */
 int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out);
+/* the same loop for one shard of a proof whose proofs are spread over `world` processes of
+ * one host: after each round_eval the 3 partial evaluations are exchanged through a POSIX
+ * shared-memory mailbox (slot (b, r) at mailbox + (b * world + r) * slot_stride; word 0 =
+ * sequence number, payload at +64; double-buffered by the parity of *calls) and summed with
+ * Scalar::add; evals_out receives the sums. See spartan_parallel_b200/parallel.py. */
+int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges,
+                               spg_fq *evals_out, void *mailbox, size_t slot_stride, int rank,
+                               int world, uint64_t *calls);
 /* (tau_claim, Az, Bz, Cz) after the last bind, :1372-1377 */
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]);
 /* copy the current Az/Bz/Cz tables back in natural ragged order (tests) */

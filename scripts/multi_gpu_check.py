@@ -22,7 +22,18 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = sp.Context(local)
     comm = parallel.TorchComm(device=torch.device("cuda", local))
-    X, Ql = 1 << 7, 4
+    shm = parallel.ShmComm(device=torch.device("cuda", local))
+    for log_x in (7, 9):
+        check(ctx, comm, shm, rank, world, log_x)
+    dist.barrier()
+    if rank == 0:
+        print(f"multi-GPU parity ok: world={world}, every round bit-exact on every rank (per-round driver and C round loop)")
+    shm.close()
+    dist.destroy_process_group()
+
+
+def check(ctx, comm, shm, rank, world, log_x):
+    X, Ql = 1 << log_x, 4
     Q = Ql * world
     nx, nq = log2(X), log2(Q)
     inst = R.synthetic_instance(X, unit=False, seed=9)
@@ -53,10 +64,11 @@ def main():
         assert np.array_equal(got, want.evals2[j]), f"rank {rank}: phase-2 round {j} differs"
         sc2.round_bind(ch2[j])
     assert np.array_equal(sc2.final(), want.claims2), f"rank {rank}: phase-2 claims differ"
-    dist.barrier()
-    if rank == 0:
-        print(f"multi-GPU parity ok: world={world}, {sc1.num_rounds}+{sc2.num_rounds} rounds bit-exact on every rank")
-    dist.destroy_process_group()
+    # the same phase 1 through the shared-memory mailbox and the C round loop
+    sc1 = parallel.gpu_phase1(ctx, shm, dinst, z, Ql, X, X, tau_q, tau_x, satisfied=True)
+    got = sc1.run_rounds(ch1)
+    assert np.array_equal(got, np.stack(want.evals1)), f"rank {rank}: C round loop differs"
+    assert np.array_equal(sc1.final(), want.claims1), f"rank {rank}: C round loop claims differ"
 
 
 if __name__ == "__main__":

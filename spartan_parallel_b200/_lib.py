@@ -94,6 +94,7 @@ def _proto(L):
         "spg_sc1_round_eval": [P, P],
         "spg_sc1_round_bind": [P, P],
         "spg_sc1_run_rounds": [P, SZ, P, P],
+        "spg_sc1_run_rounds_sharded": [P, SZ, P, P, P, SZ, INT, INT, P],
         "spg_sc2_run_rounds": [P, SZ, P, P],
         "spg_sc1_final": [P, P],
         "spg_sc1_debug_tables": [P, P, P, P, SZ, P],

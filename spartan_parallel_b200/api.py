@@ -231,6 +231,15 @@ class SumcheckPhase1:
         check(self.ctx.L.spg_sc1_run_rounds(self.h, ch.shape[0], _ptr(ch), _ptr(out)), "spg_sc1_run_rounds")
         return out
 
+    def run_rounds_sharded(self, challenges, mailbox_addr: int, slot_stride: int, rank: int, world: int, calls: np.ndarray):
+        """run_rounds for one shard: per-round exchange of the partial evaluations through the shared-memory
+        mailbox at `mailbox_addr` (see parallel.ShmComm); `calls` is the shared call counter (1 uint64)."""
+        ch = _fq(challenges).reshape(-1, 4)
+        out = np.empty((ch.shape[0], 3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc1_run_rounds_sharded(self.h, ch.shape[0], _ptr(ch), _ptr(out), C.c_void_p(mailbox_addr),
+                                                    slot_stride, rank, world, _ptr(calls)), "spg_sc1_run_rounds_sharded")
+        return out
+
     def set_claim(self, claim):
         """The prover's `claim` argument (src/sumcheck.rs:1069; zero in R1CSProof::prove): lets round 0
         use e(1) = claim - e(0) like the reference does. Exact iff the claim is the true sum."""

@@ -1014,6 +1014,41 @@ int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, 
   return SPG_OK;
 }
 
+// Rounds of a proof whose proofs are sharded over `world` processes of one host (one GPU
+// each): every rank evaluates its shard, the 3 partial evaluations are exchanged through a
+// shared-memory mailbox and summed with Scalar::add, and every rank binds with the same
+// challenge. The mailbox is the one spartan_parallel_b200.parallel.ShmComm maps:
+//   slot(b, r) = mailbox + (b * world + r) * slot_stride; word 0 = sequence number, data at +64
+// double-buffered by the parity of the call counter *calls (shared with the Python side).
+int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out,
+                               void *mailbox, size_t slot_stride, int rank, int world, uint64_t *calls) {
+  SPG_CHECK(s && challenges && evals_out && mailbox && calls, "spg_sc1_run_rounds_sharded: null argument");
+  SPG_CHECK(world >= 1 && rank >= 0 && rank < world && slot_stride >= 64 + 3 * sizeof(spg_fq),
+            "spg_sc1_run_rounds_sharded: bad mailbox geometry");
+  char *base = (char *)mailbox;
+  for (size_t j = 0; j < num_rounds; j++) {
+    spg_fq part[3];
+    SPG_TRY(spg_sc1_round_eval(s, part));
+    uint64_t c = ++*calls;
+    size_t b = c & 1;
+    char *mine = base + (b * world + rank) * slot_stride;
+    memcpy(mine + 64, part, sizeof part);
+    __atomic_store_n((uint64_t *)mine, c, __ATOMIC_RELEASE);
+    hfq acc[3] = {hfq_zero(), hfq_zero(), hfq_zero()};
+    for (int r = 0; r < world; r++) {
+      char *slot = base + (b * world + r) * slot_stride;
+      while (__atomic_load_n((uint64_t *)slot, __ATOMIC_ACQUIRE) != c) {
+      }
+      spg_fq v[3];
+      memcpy(v, slot + 64, sizeof v);
+      for (int t = 0; t < 3; t++) acc[t] = hfq_add(acc[t], hfq_from(v[t]));
+    }
+    for (int t = 0; t < 3; t++) evals_out[3 * j + t] = hfq_to(acc[t]);
+    SPG_TRY(spg_sc1_round_bind(s, challenges + j));
+  }
+  return SPG_OK;
+}
+
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
   SPG_CHECK(s && claims, "spg_sc1_final: null argument");
   if (s->round != spg_sc1_num_rounds(s)) {

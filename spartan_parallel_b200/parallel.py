@@ -91,10 +91,18 @@ class ShmComm(TorchComm):
         self.dist.barrier()
         if self.rank != 0:
             self.shm = shared_memory.SharedMemory(name=name)
+            try:  # rank 0 owns the segment; keep this process's resource tracker from unlinking it again
+                from multiprocessing import resource_tracker
+
+                resource_tracker.unregister(self.shm._name, "shared_memory")
+            except Exception:
+                pass
         self.dist.barrier()
         words = np.ndarray((2, self.world, (self.SLOT + 64) // 8), dtype=np.uint64, buffer=self.shm.buf)
         self.seq = words[:, :, 0]
         self.data = words[:, :, 8:]
+        self.addr = words.ctypes.data  # for the C round loop (spg_sc1_run_rounds_sharded)
+        self.slot_stride = self.SLOT + 64
 
     def all_gather(self, arr: np.ndarray) -> np.ndarray:
         a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1)
@@ -165,6 +173,25 @@ class ShardedPhase1:
             self._tail().round_bind(r)
         self.round += 1
 
+    def run_rounds(self, challenges) -> np.ndarray:
+        """All rounds with challenges known in advance. On a GPU engine with the shared-memory
+        mailbox the local rounds run in one C loop (no Python between rounds)."""
+        ch = np.asarray(challenges, dtype=np.uint64).reshape(-1, 4)
+        out = []
+        n_local = self.nx + self.nql
+        if self.round == 0 and hasattr(self.engine, "run_rounds_sharded") and isinstance(self.comm, ShmComm):
+            calls = np.array([self.comm.calls], dtype=np.uint64)
+            ev = self.engine.run_rounds_sharded(ch[:n_local], self.comm.addr, self.comm.slot_stride, self.comm.rank,
+                                                self.comm.world, calls)
+            self.comm.calls = int(calls[0])
+            out.extend(ev)
+            self.round = n_local
+        while self.round < self.num_rounds:
+            j = self.round
+            out.append(self.round_eval())
+            self.round_bind(ch[j])
+        return np.stack(out)
+
     def _tail(self):
         if self.tail is None:
             # one scalar per table per rank; the bound eq products are identical on all ranks
@@ -179,12 +206,17 @@ class ShardedPhase1:
         return self._tail().final()
 
 
-def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x) -> ShardedPhase1:
-    """ShardedPhase1 on this rank's GPU."""
+def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, satisfied: bool = False) -> ShardedPhase1:
+    """ShardedPhase1 on this rank's GPU. satisfied=True asserts that the witness satisfies the
+    instance: Az*Bz - Cz then vanishes entry by entry, so every shard's own sum is zero and the
+    shard may take e(1) from that claim (spg_sc1_set_claim) exactly like the unsharded prover."""
     empty = np.zeros((0, 4), dtype=np.uint64)
 
     def make_engine(tau_q_local):
-        return api.sumcheck_phase1(ctx, inst, z, [Q_local], Q_local, [X], X, max_num_inputs, empty, tau_q_local, tau_x)
+        sc = api.sumcheck_phase1(ctx, inst, z, [Q_local], Q_local, [X], X, max_num_inputs, empty, tau_q_local, tau_x)
+        if satisfied:
+            sc.set_claim(np.zeros(4, dtype=np.uint64))
+        return sc
 
     def make_tail(Az, Bz, Cz, tau_high):
         G = Az.shape[0]

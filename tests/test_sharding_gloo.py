@@ -89,6 +89,10 @@ def _worker(rank, world, port, Q_local, X, use_shm=False):
             assert np.array_equal(got, want[j]), f"rank {rank} round {j}"
             sh.round_bind(ch[j])
         assert np.array_equal(sh.final(), want_final), f"rank {rank} final claims"
+        # the all-rounds driver (the GPU engine runs its local rounds in one C loop; here the python path)
+        sh2 = parallel.ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)
+        assert np.array_equal(sh2.run_rounds(ch), np.stack(want)), f"rank {rank} run_rounds"
+        assert np.array_equal(sh2.final(), want_final)
 
         # sharded Z-bind: partial tables scaled by the rank weight sum to the full bind
         import spartan_parallel_b200 as sp
