@@ -292,7 +292,7 @@ def run_gpu(args):
                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms,
                     "launches_per_step": dom["launches"] / args.steps,
                     "share_of_step": dom["total_ms"] / ms_dev}
-        if dom["kernel"].startswith("k_rows<1>"):
+        if "k_rows<1, 2>" in dom["kernel"]:
             # fused bind + eval item: 576 algorithmic bytes, 10 Montgomery products
             # (6 binds + 2 products + 2 eq-weighted accumulations)
             mm = dom["units"] / 576.0 * 10.0 / (dom["total_ms"] * 1e-3)
@@ -302,16 +302,19 @@ def run_gpu(args):
         # DRAM traffic of the largest launch of this kernel from the committed ncu --set full capture
         try:
             rd = wr = None
-            for ln in open(os.path.join(ROOT, "profiles", "r1_k_rows_ncu_full.txt")):
-                if ln.startswith("== launch 2"):
-                    break
-                if ln.startswith("dram__bytes_read.sum ="):
+            seen = False
+            for ln in open(os.path.join(ROOT, "profiles", "r1c_ncu_full.txt")):
+                if ln.startswith("== launch"):
+                    if seen:
+                        break
+                    seen = "k_rows<1, 2>" in ln
+                elif seen and ln.startswith("dram__bytes_read.sum ="):
                     rd = float(ln.split("=")[1].split()[0]) * 1e9
-                if ln.startswith("dram__bytes_write.sum ="):
+                elif seen and ln.startswith("dram__bytes_write.sum ="):
                     wr = float(ln.split("=")[1].split()[0]) * 1e9
-            if rd and wr and dom["kernel"].startswith("k_rows<1>"):
+            if rd and wr and "k_rows<1, 2>" in dom["kernel"]:
                 roofline["traffic"] = rd + wr
-                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1_k_rows_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
+                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1c_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
         except Exception:
             pass
     cpu = cpu_baseline_sample(args, threads=1)

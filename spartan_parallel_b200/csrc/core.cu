@@ -231,10 +231,13 @@ int spg_ctx_profile_end(spg_ctx *ctx, char *out, size_t cap) {
   std::string js = "[";
   char buf[512];
   for (size_t i = 0; i < aggs.size(); i++) {
+    // template instantiations are passed to SPG_LAUNCH in parentheses: drop them from the name
+    std::string nm = aggs[i].name;
+    if (nm.size() >= 2 && nm.front() == '(' && nm.back() == ')') nm = nm.substr(1, nm.size() - 2);
     snprintf(buf, sizeof buf,
              "%s{\"kernel\": \"%s\", \"launches\": %zu, \"total_ms\": %.6f, \"units\": %.6g, "
              "\"max_ms\": %.6f, \"max_units\": %.6g}",
-             i ? ", " : "", aggs[i].name, aggs[i].n, aggs[i].ms, aggs[i].units, aggs[i].max_ms, aggs[i].max_units);
+             i ? ", " : "", nm.c_str(), aggs[i].n, aggs[i].ms, aggs[i].units, aggs[i].max_ms, aggs[i].max_units);
     js += buf;
   }
   js += "]";

@@ -406,6 +406,15 @@ __device__ __forceinline__ void fq_store(fq *p, const fq &a) {
                : "memory");
 }
 
+// streaming store (evict-first): tables written once and read back only after far more than
+// an L2's worth of other traffic, so they should not displace data that is re-read (CSR arrays)
+__device__ __forceinline__ void fq_store_stream(fq *p, const fq &a) {
+  asm volatile("st.global.cs.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]),
+               "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+               "r"(a.v[7])
+               : "memory");
+}
+
 // warp-wide modular sum of canonical values; result valid in lane 0
 __device__ __forceinline__ fq fq_warp_sum(fq x) {
 #pragma unroll

@@ -275,9 +275,9 @@ k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__re
       h_lo = spmv_head3(SP.mats[si], (unsigned int)(2 * (it + RB)));
       h_hi = spmv_head3(SP.mats[si], (unsigned int)(2 * (it + RB) + 1));
     }
-    fq_store(O0 + idx, lo3[0]); fq_store(O0 + idx + 1, hi3[0]);
-    fq_store(O1 + idx, lo3[1]); fq_store(O1 + idx + 1, hi3[1]);
-    fq_store(O2 + idx, lo3[2]); fq_store(O2 + idx + 1, hi3[2]);
+    fq_store_stream(O0 + idx, lo3[0]); fq_store_stream(O0 + idx + 1, hi3[0]);
+    fq_store_stream(O1 + idx, lo3[1]); fq_store_stream(O1 + idx + 1, hi3[1]);
+    fq_store_stream(O2 + idx, lo3[2]); fq_store_stream(O2 + idx + 1, hi3[2]);
     fq w = fq_load(S + it);
     acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(lo3[0], lo3[1]), lo3[2])));
     if (NE == 3) acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(hi3[0], hi3[1]), hi3[2])));
