@@ -67,6 +67,11 @@ struct spg_ctx {
   size_t partial_cap = 0;  // in fq
   spg::fq *h_result = nullptr;  // pinned + mapped
   spg::fq *d_result = nullptr;  // device alias of h_result
+  // in-kernel final reduction of small grids: ticket counter (zero between launches) and the
+  // sequence flag the last block publishes in mapped host memory after the result
+  unsigned int *d_counter = nullptr;
+  unsigned long long *h_flag = nullptr, *d_flag = nullptr;
+  unsigned long long seq = 0;
   // small staging for scalar arguments
   spg::fq *d_scalars = nullptr;  // device scratch, 64 fq
   spg::fq *d_stage = nullptr;    // first-stage output of large reductions
@@ -132,6 +137,22 @@ int reduce_partials(spg_ctx *ctx, const fq *partials, size_t nblocks, int width,
 // fetch `width` scalars from the mapped result slot after a stream sync
 int fetch_result(spg_ctx *ctx, int width, spg_fq *out);
 
+// Final reduction inside the round kernel: every block stores its partial sums; the block
+// that draws the last ticket adds all of them, writes the result to mapped host memory and then
+// publishes `seq` in the flag word, which the host polls (spg::wait_flag) -- one launch and no
+// stream synchronisation per round. seq == 0: a separate reduce kernel follows instead.
+struct FinishArgs {
+  fq *partials;  // [gridDim.x][W]
+  unsigned int *counter;
+  fq *result;
+  unsigned long long *flag;
+  unsigned long long seq;
+};
+FinishArgs finish_args(spg_ctx *ctx, size_t nblocks);  // seq != 0 iff the grid is small enough
+int wait_flag(spg_ctx *ctx, unsigned long long seq, int width, spg_fq *out);
+// the launch's result: polled when the kernel finished the reduction itself, else reduce + sync
+int finish_result(spg_ctx *ctx, const FinishArgs &fa, size_t nblocks, int width, spg_fq *out);
+
 // block-level modular sum of `W` accumulators; thread 0 of the block gets the result
 template <int W>
 __device__ __forceinline__ void block_sum(fq (&acc)[W], fq *smem /* [W * 32] */) {
@@ -150,6 +171,40 @@ __device__ __forceinline__ void block_sum(fq (&acc)[W], fq *smem /* [W * 32] */)
       fq v = lane < nwarps ? smem[k * 32 + lane] : fq_zero();
       acc[k] = fq_warp_sum(v);
     }
+  }
+}
+
+// `mine` (valid in thread 0) = this block's W sums; see FinishArgs
+template <int W>
+__device__ __forceinline__ void finish_block(const FinishArgs &fa, const fq (&mine)[W], fq *smem /* [W * 32] */) {
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < W; k++) fq_store(fa.partials + (size_t)blockIdx.x * W + k, mine[k]);
+    int last = 0;
+    if (fa.seq) {
+      __threadfence();
+      last = atomicAdd(fa.counter, 1u) == gridDim.x - 1;
+    }
+    is_last = last;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  fq acc[W];
+#pragma unroll
+  for (int k = 0; k < W; k++) acc[k] = fq_zero();
+  for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < W; k++) acc[k] = fq_add(acc[k], fq_load_cg(fa.partials + (size_t)b * W + k));
+  __syncthreads();  // smem may still hold the caller's own block_sum
+  block_sum<W>(acc, smem);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < W; k++) fq_store(fa.result + k, acc[k]);
+    *fa.counter = 0;
+    __threadfence_system();
+    *(volatile unsigned long long *)fa.flag = fa.seq;
   }
 }
 

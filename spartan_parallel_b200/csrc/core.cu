@@ -1,4 +1,7 @@
 // Context, device vectors, error reporting and the shared reduction kernels.
+#include <atomic>
+#include <chrono>
+
 #include "common.cuh"
 
 namespace spg {
@@ -111,6 +114,48 @@ int reduce_partials(spg_ctx *ctx, const fq *partials, size_t nblocks, int width,
   return SPG_OK;
 }
 
+FinishArgs finish_args(spg_ctx *ctx, size_t nblocks) {
+  FinishArgs fa;
+  fa.partials = ctx->d_partials;
+  fa.counter = ctx->d_counter;
+  fa.result = ctx->d_result;
+  fa.flag = ctx->d_flag;
+  // one block adding up to 4096 partial rows costs a few microseconds; beyond that the
+  // two-stage reduce kernels are faster and the extra launch is noise next to the main kernel
+  fa.seq = nblocks <= 4096 ? ++ctx->seq : 0;
+  return fa;
+}
+
+int wait_flag(spg_ctx *ctx, unsigned long long seq, int width, spg_fq *out) {
+  volatile unsigned long long *f = ctx->h_flag;
+  unsigned int spins = 0;
+  auto t0 = std::chrono::steady_clock::now();
+  while (*f != seq) {
+    if ((++spins & 0x3fff) == 0) {
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "round kernel", __FILE__, __LINE__);
+      if (e == cudaSuccess && *f != seq) {
+        set_error("round kernel finished without publishing its result (flag %llu, expected %llu)", (unsigned long long)*f,
+                  seq);
+        return SPG_ECUDA;
+      }
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0) {
+        set_error("timed out waiting for a round kernel");
+        return SPG_ECUDA;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  memcpy(out, ctx->h_result, sizeof(spg_fq) * width);
+  return SPG_OK;
+}
+
+int finish_result(spg_ctx *ctx, const FinishArgs &fa, size_t nblocks, int width, spg_fq *out) {
+  if (fa.seq) return wait_flag(ctx, fa.seq, width, out);
+  SPG_TRY(reduce_partials(ctx, ctx->d_partials, nblocks, width, ctx->d_result));
+  return fetch_result(ctx, width, out);
+}
+
 int fetch_result(spg_ctx *ctx, int width, spg_fq *out) {
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   memcpy(out, ctx->h_result, sizeof(spg_fq) * width);
@@ -155,6 +200,11 @@ int spg_ctx_create(int device, spg_ctx **out) {
   SPG_CUDA(cudaHostAlloc(&ctx->h_result, 64 * sizeof(fq), cudaHostAllocMapped));
   SPG_CUDA(cudaHostGetDevicePointer(&ctx->d_result, ctx->h_result, 0));
   SPG_CUDA(cudaMalloc(&ctx->d_scalars, 64 * sizeof(fq)));
+  SPG_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  SPG_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  ctx->h_flag = (unsigned long long *)(ctx->h_result + 56);  // tail of the mapped result page
+  ctx->d_flag = (unsigned long long *)(ctx->d_result + 56);
+  *ctx->h_flag = 0;
   int rc = ensure_partials(ctx, (size_t)ctx->sm_count * 16 * 8);
   if (rc != SPG_OK) return rc;
   *out = ctx;
@@ -167,6 +217,7 @@ void spg_ctx_destroy(spg_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);
+  if (ctx->d_counter) cudaFree(ctx->d_counter);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   if (ctx->copy_stream) {

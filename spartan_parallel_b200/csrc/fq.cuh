@@ -399,6 +399,16 @@ __device__ __forceinline__ fq fq_load_stream(const fq *p) {
                : "l"(p));
   return r;
 }
+// L1-bypassing load for data written by other blocks of the same kernel
+__device__ __forceinline__ fq fq_load_cg(const fq *p) {
+  fq r;
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]),
+                 "=r"(r.v[6]), "=r"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ void fq_store(fq *p, const fq &a) {
   asm volatile("st.global.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.v[0]),
                "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),

@@ -5,6 +5,9 @@
 // The transcript / ZK glue of that function stays on the host; this file owns the
 // two hot loops: round evaluation (:1166-1245) and binding (:1265-1275).
 // See rounds.cuh for the device layout and the eq factorisation.
+#include <chrono>
+#include <cstdlib>
+
 #include "rounds.cuh"
 #include "r1cs.cuh"
 
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(RB, SPG_MINB)
 k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
                  fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2,
                  const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk, unsigned long long total_items, fq r,
-                 const fq *__restrict__ RW, const fq *__restrict__ Snext, fq *__restrict__ partials) {
+                 const fq *__restrict__ RW, const fq *__restrict__ Snext, FinishArgs fa) {
   __shared__ fq sm[3 * 32];
   fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
   for (unsigned long long item = (unsigned long long)blockIdx.x * RB + threadIdx.x; item < total_items;
@@ -131,11 +134,7 @@ k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq 
     comb_accumulate<COMB>(acc, w, a0, a1, b0, b1, c0, c1);
   }
   block_sum<3>(acc, sm);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x * 3 + 0] = acc[0];
-    partials[blockIdx.x * 3 + 1] = acc[1];
-    partials[blockIdx.x * 3 + 2] = acc[2];
-  }
+  finish_block<3>(fa, acc, sm);
 }
 
 // ---------------------------------------------------------------- row-tiled fast path
@@ -155,7 +154,7 @@ template <int FUSED, int NE>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
        fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
-       int nseg, const __grid_constant__ SegPack pk, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, fq *__restrict__ partials) {
+       int nseg, const __grid_constant__ SegPack pk, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, FinishArgs fa) {
   static_assert(NE == 2 || (NE == 3 && !FUSED), "k_rows: 2 points, or 3 for the evaluation-only form");
   __shared__ fq sm[NE * 32];
   unsigned long long tile = blockIdx.x;
@@ -215,8 +214,9 @@ k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restric
   if (threadIdx.x == 0) {
     fq rw = RW[sg.rw_off + row];
 #pragma unroll
-    for (int k = 0; k < NE; k++) partials[(unsigned long long)blockIdx.x * NE + k] = fq_mul(rw, acc[k]);
+    for (int k = 0; k < NE; k++) acc[k] = fq_mul(rw, acc[k]);
   }
+  finish_block<NE>(fa, acc, sm);
 }
 
 // First round with the SpMV fused in (multiply_vec_block + round 0 in one pass): the block
@@ -803,6 +803,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;
+      FinishArgs fa = {};  // seq == 0: separate reduce
       if (s->pend_inst) {
         // tables do not exist yet: compute them in the same pass (read z once, write 96 N bytes once)
         ctx->next_units = 288.0 * pairs;
@@ -811,12 +812,12 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
         s->pend_inst = nullptr;
         s->pend_z = nullptr;
       } else {
+        fa = finish_args(ctx, tiles);
         SPG_LAUNCH(ctx, (k_rows<0, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
+                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, fa);
       }
-      SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
       spg_fq tmp[2];
-      SPG_TRY(fetch_result(ctx, 2, tmp));
+      SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));
       s->cached[0] = hfq_from(tmp[0]);
       s->cached[1] = hfq_from(tmp[1]);
       s->cached_kind = 2;
@@ -857,6 +858,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;  // 2 scalars x 3 tables read per pair
+      FinishArgs fa = {};
       if (s->pend_inst) {
         ctx->next_units = 288.0 * pairs;
         SPG_LAUNCH(ctx, (k_rows_spmv<3>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
@@ -864,12 +866,12 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
         s->pend_inst = nullptr;
         s->pend_z = nullptr;
       } else {
+        fa = finish_args(ctx, tiles);
         SPG_LAUNCH(ctx, (k_rows<0, 3>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, ctx->d_partials);
+                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, fa);
       }
-      SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 3, ctx->d_result));
       spg_fq tmp[3];
-      SPG_TRY(fetch_result(ctx, 3, tmp));
+      SPG_TRY(finish_result(ctx, fa, tiles, 3, tmp));
       hfq G0 = hfq_from(tmp[0]), G1 = hfq_from(tmp[1]), G2 = hfq_from(tmp[2]);
       hfq d = hfq_sub(G2, G1);
       hfq G3 = hfq_add(G0, hfq_add(hfq_add(d, d), d));
@@ -957,11 +959,11 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       const fq *Snext = s_table(s, phase, n_phase - j - 2);
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
       ctx->next_units = 288.0 * (double)out_total;  // per bound pair: 4 read + 2 written scalars x 3 tables
+      FinishArgs fa = finish_args(ctx, tiles);
       SPG_LAUNCH(ctx, (k_rows<1, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, make_pack(s->segs), rr, RW, Snext, ctx->d_partials);
-      SPG_TRY(reduce_partials(ctx, ctx->d_partials, tiles, 2, ctx->d_result));
+                 s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, make_pack(s->segs), rr, RW, Snext, fa);
       spg_fq tmp[2];
-      SPG_TRY(fetch_result(ctx, 2, tmp));
+      SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));
       s->cached[0] = hfq_from(tmp[0]);
       s->cached[1] = hfq_from(tmp[1]);
       s->cached_kind = 2;
@@ -972,13 +974,13 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       const fq *Snext = s_table(s, phase, n_phase - j - 2);
       int grid = grid_for(ctx, items, RB, 4);
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+      FinishArgs fa = finish_args(ctx, grid);
       ctx->next_units = 576.0 * (double)items;  // 4 read + 2 written scalars x 3 tables per item
       SPG_LAUNCH(ctx, k_quad_bind_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
                  s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs,
-                 (int)s->P, make_pack(s->segs), items, rr, RW, Snext, ctx->d_partials);
-      SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
+                 (int)s->P, make_pack(s->segs), items, rr, RW, Snext, fa);
       spg_fq tmp[3];
-      SPG_TRY(fetch_result(ctx, 3, tmp));
+      SPG_TRY(finish_result(ctx, fa, grid, 3, tmp));
       for (int t = 0; t < 3; t++) s->cached[t] = hfq_from(tmp[t]);
       s->cached_kind = 3;
     } else {
@@ -1007,9 +1009,17 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
 
 int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out) {
   SPG_CHECK(s && challenges && evals_out, "spg_sc1_run_rounds: null argument");
+  static const bool trace = getenv("SPG_TRACE_ROUNDS") != nullptr;
   for (size_t j = 0; j < num_rounds; j++) {
+    auto t0 = std::chrono::steady_clock::now();
     SPG_TRY(spg_sc1_round_eval(s, evals_out + 3 * j));
+    auto t1 = std::chrono::steady_clock::now();
     SPG_TRY(spg_sc1_round_bind(s, challenges + j));
+    auto t2 = std::chrono::steady_clock::now();
+    if (trace)
+      fprintf(stderr, "[spg] round %zu: eval %.1f us, bind %.1f us\n", j,
+              std::chrono::duration<double, std::micro>(t1 - t0).count(),
+              std::chrono::duration<double, std::micro>(t2 - t1).count());
   }
   return SPG_OK;
 }

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(RB2)
 k2_quad_bind_eval(const fq *__restrict__ B, const fq *__restrict__ C, fq *__restrict__ OB,
                   fq *__restrict__ OC, const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk,
                   unsigned long long total_items, fq r, const fq *__restrict__ A,
-                  fq *__restrict__ partials) {
+                  FinishArgs fa) {
   __shared__ fq sm[3 * 32];
   fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
   for (unsigned long long item = (unsigned long long)blockIdx.x * RB2 + threadIdx.x; item < total_items;
@@ -149,11 +149,7 @@ k2_quad_bind_eval(const fq *__restrict__ B, const fq *__restrict__ C, fq *__rest
     comb_accumulate<2>(acc, fq_load(A + sg.rw_off), b0, b1, c0, c1, c0, c1);
   }
   block_sum<3>(acc, sm);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x * 3 + 0] = acc[0];
-    partials[blockIdx.x * 3 + 1] = acc[1];
-    partials[blockIdx.x * 3 + 2] = acc[2];
-  }
+  finish_block<3>(fa, acc, sm);
 }
 
 // [p][w] (W per instance) -> [p][bitrev(w)] with W' slots, zero padded
@@ -533,10 +529,10 @@ int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r) {
       if (s->P > (size_t)SEG_INLINE) SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
       int grid = grid_for(ctx, items, RB2, 4);
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
+      FinishArgs fa = finish_args(ctx, grid);
       SPG_LAUNCH(ctx, k2_quad_bind_eval, grid, RB2, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[nxt][0],
-                 s->tab[nxt][1], s->d_segs, (int)s->P, make_pack(s->segs), items, rr, s->A, ctx->d_partials);
-      SPG_TRY(reduce_partials(ctx, ctx->d_partials, grid, 3, ctx->d_result));
-      SPG_TRY(fetch_result(ctx, 3, s->cached));
+                 s->tab[nxt][1], s->d_segs, (int)s->P, make_pack(s->segs), items, rr, s->A, fa);
+      SPG_TRY(finish_result(ctx, fa, grid, 3, s->cached));
       s->have_cached = true;
     } else {
       build_segs2(s, phase, 0, &items, &out_total);
