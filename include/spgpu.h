@@ -298,6 +298,20 @@ int spg_sparse_deref(spg_ctx *ctx, const spg_sparse *s, const spg_vec *mem_rx,
 /* device copy of v[offset, offset + n) */
 int spg_vec_clone(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_vec **out);
 
+/* ---------------------------------------------------------------- peer-memory all-reduce (e)
+ * Modular sum of one table held at the same offset on `world` GPUs of a node (the rq-bound Z
+ * table of a sharded proof, src/r1csproof.rs:478). Each process allocates the table with
+ * spg_peer_alloc, passes the 64-byte IPC handle to its peers (any host channel), opens theirs
+ * with spg_peer_open, and after every rank has finished writing its partial table (stream
+ * sync + host barrier) calls spg_peer_sum: rank r sums chunk r over all peers with P2P loads
+ * and writes the result into every peer's table with P2P stores. After a second stream sync +
+ * host barrier every table holds the full sum. peer_ptrs[rank] is the rank's own table. */
+int spg_peer_alloc(spg_ctx *ctx, size_t n, spg_vec **out, uint8_t handle[64]);
+int spg_peer_free(spg_vec *v);
+int spg_peer_open(spg_ctx *ctx, const uint8_t handle[64], void **ptr);
+int spg_peer_close(void *ptr);
+int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n);
+
 /* ---------------------------------------------------------------- commitments (a16)
  * MultiCommitGens::new is host-side setup (src/commitments.rs:15-33); the caller
  * passes the n+1 generators as compressed ristretto points (G[0..n], h). */

@@ -69,6 +69,15 @@ def check(ctx, comm, shm, rank, world, log_x):
     got = sc1.run_rounds(ch1)
     assert np.array_equal(got, np.stack(want.evals1)), f"rank {rank}: C round loop differs"
     assert np.array_equal(sc1.final(), want.claims1), f"rank {rank}: C round loop claims differ"
+    # the Z table reduced over peer memory instead of NCCL + additions
+    peer = parallel.PeerTable(ctx, shm, 2 * X)
+    for _ in range(2):  # twice: the table is reused across proofs
+        zrq2 = parallel.gpu_bind_rq_sharded(ctx, shm, z, ch1[nx:nx + nq], Ql, peer)
+        assert np.array_equal(zrq2.to_host(), zrq.to_host()), f"rank {rank}: peer-memory reduction differs"
+    sc2 = sp.SumcheckPhase2.from_zrq(ctx, dinst, zrq2, [X], X, 2, rx, ch1[:0], *r_abc)
+    assert np.array_equal(sc2.run_rounds(ch2), np.stack(want.evals2)), f"rank {rank}: phase 2 on the peer table differs"
+    sc2.free()
+    peer.close()
 
 
 if __name__ == "__main__":

@@ -113,6 +113,11 @@ def _proto(L):
         "spg_cubic_final": [P, P],
         "spg_hash_layer": [P, P, P, P, SZ, P, P, INT, PP],
         "spg_deref": [P, P, SZ, P, PP],
+        "spg_peer_alloc": [P, SZ, PP, P],
+        "spg_peer_free": [P],
+        "spg_peer_open": [P, P, PP],
+        "spg_peer_close": [P],
+        "spg_peer_sum": [P, P, INT, INT, SZ],
         "spg_gens_upload": [P, P, SZ, PP],
         "spg_gens_from_uniform": [P, P, SZ, PP],
         "spg_poly_commit": [P, P, P, SZ, P],

@@ -176,6 +176,24 @@ __global__ void k_sum_slabs(const fq *__restrict__ partial, size_t nslabs, size_
   fq_store(out + i, acc);
 }
 
+// Modular all-reduce of one table replicated-by-address on `world` GPUs of one node, over
+// peer memory: rank r owns chunk r. A thread loads element i of that chunk from every peer
+// (P2P loads over NVLink), adds them, and stores the sum back into every peer's table (P2P
+// stores), so each rank moves 2 (G-1)/G of the table instead of receiving G-1 whole copies
+// and adding them in separate passes. The same thread reads and writes element i everywhere,
+// so the update is in place; visibility is by kernel boundaries + a host barrier.
+struct PeerPtrs {
+  fq *p[16];
+};
+__global__ void k_peer_sum(const __grid_constant__ PeerPtrs P, int world, size_t begin, size_t count) {
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) {
+    size_t i = begin + t;
+    fq acc = fq_load_cg(P.p[0] + i);
+    for (int r = 1; r < world; r++) acc = fq_add(acc, fq_load_cg(P.p[r] + i));
+    for (int r = 0; r < world; r++) fq_store(P.p[r] + i, acc);
+  }
+}
+
 int dense_evaluate_device(spg_ctx *ctx, const fq *Z, size_t n, const spg_fq *r, size_t ell, fq *d_out) {
   // split r = (r_hi | r_lo) like compute_factored_lens (dense_mlpoly.rs:118-120)
   size_t left = ell / 2, right = ell - left;
@@ -334,6 +352,69 @@ int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_
   dev_free(ctx, dL);
   dev_free(ctx, partial);
   *out = o;
+  return SPG_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int spg_peer_alloc(spg_ctx *ctx, size_t n, spg_vec **out, uint8_t handle[64]) {
+  SPG_CHECK(ctx && out && handle && n, "spg_peer_alloc: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  fq *d = nullptr;
+  SPG_CUDA(cudaMalloc(&d, n * sizeof(fq)));  // IPC needs a plain allocation, not pool memory
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, d);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return cuda_fail(e, "cudaIpcGetMemHandle", __FILE__, __LINE__);
+  }
+  memcpy(handle, &h, 64);
+  spg_vec *v = nullptr;
+  int rc = spg_vec_wrap(ctx, d, n, &v);
+  if (rc != SPG_OK) {
+    cudaFree(d);
+    return rc;
+  }
+  *out = v;
+  return SPG_OK;
+}
+
+int spg_peer_free(spg_vec *v) {
+  if (!v) return SPG_OK;
+  void *d = v->d;
+  spg_vec_free(v);
+  SPG_CUDA(cudaFree(d));
+  return SPG_OK;
+}
+
+int spg_peer_open(spg_ctx *ctx, const uint8_t handle[64], void **ptr) {
+  SPG_CHECK(ctx && handle && ptr, "spg_peer_open: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  SPG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SPG_OK;
+}
+
+int spg_peer_close(void *ptr) {
+  if (ptr) SPG_CUDA(cudaIpcCloseMemHandle(ptr));
+  return SPG_OK;
+}
+
+int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n) {
+  SPG_CHECK(ctx && peer_ptrs, "spg_peer_sum: null argument");
+  SPG_CHECK(world >= 1 && world <= 16 && rank >= 0 && rank < world, "spg_peer_sum: bad rank %d of %d", rank, world);
+  SPG_CHECK(n % (size_t)world == 0, "spg_peer_sum: %zu scalars do not split over %d ranks", n, world);
+  PeerPtrs P;
+  memset(&P, 0, sizeof P);
+  // own table first so that at least one operand is a local load
+  P.p[0] = (fq *)peer_ptrs[rank];
+  for (int r = 0, k = 1; r < world; r++)
+    if (r != rank) P.p[k++] = (fq *)peer_ptrs[r];
+  size_t chunk = n / world;
+  ctx->next_units = 64.0 * (double)chunk * (double)(world - 1);
+  SPG_LAUNCH(ctx, k_peer_sum, grid_for(ctx, chunk, 256), 256, 0, P, world, (size_t)rank * chunk, chunk);
   return SPG_OK;
 }
 

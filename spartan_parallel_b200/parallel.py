@@ -59,6 +59,9 @@ class TorchComm:
         self.dist.all_gather(outs, tensor)
         return outs
 
+    def barrier(self):
+        self.all_gather(np.zeros(1, dtype=np.uint64))
+
 
 class ShmComm(TorchComm):
     """Per-round exchange through a POSIX shared-memory mailbox.
@@ -135,6 +138,66 @@ class LocalComm:
 
     def all_gather(self, arr):
         return np.stack([arr])
+
+    def barrier(self):
+        pass
+
+
+class PeerTable:
+    """One table of n scalars per rank, all mapped into every rank's address space through
+    CUDA IPC (spg_peer_alloc / spg_peer_open): the modular all-reduce between the two phases
+    of a sharded proof runs as one kernel per rank over NVLink peer memory (spg_peer_sum)
+    instead of an NCCL all-gather of whole tables followed by separate additions.
+    Create once, reuse for every proof."""
+
+    def __init__(self, ctx, comm, n: int):
+        import ctypes as C
+
+        from ._lib import check
+
+        self.ctx, self.comm, self.n = ctx, comm, n
+        handle = np.zeros(64, dtype=np.uint8)
+        h = C.c_void_p()
+        check(ctx.L.spg_peer_alloc(ctx.h, n, C.byref(h), handle.ctypes.data_as(C.c_void_p)), "spg_peer_alloc")
+        self._vec = h
+        self.device_ptr = int(ctx.L.spg_vec_device_ptr(h))
+        self.poly = api.DensePolynomial.wrap(ctx, self.device_ptr, n, owner=self)
+        handles = comm.all_gather(handle.view(np.uint64))  # (world, 8)
+        self._opened = []
+        ptrs = []
+        for r in range(comm.world):
+            if r == comm.rank:
+                ptrs.append(self.device_ptr)
+                continue
+            hr = np.ascontiguousarray(handles[r]).view(np.uint8)
+            pp = C.c_void_p()
+            check(ctx.L.spg_peer_open(ctx.h, hr.ctypes.data_as(C.c_void_p), C.byref(pp)), "spg_peer_open")
+            self._opened.append(pp)
+            ptrs.append(pp.value)
+        self._ptrs = (C.c_void_p * comm.world)(*ptrs)
+        comm.barrier()
+
+    def all_reduce(self):
+        """Every rank has written its partial table into self.poly (on the context's stream)."""
+        from ._lib import check
+
+        self.ctx.sync()
+        self.comm.barrier()  # all partial tables are complete and visible
+        check(self.ctx.L.spg_peer_sum(self.ctx.h, self._ptrs, self.comm.world, self.comm.rank, self.n), "spg_peer_sum")
+        self.ctx.sync()
+        self.comm.barrier()  # every chunk has been written everywhere
+        return self.poly
+
+    def close(self):
+        if getattr(self, "_vec", None) is None:
+            return
+        self.comm.barrier()  # nobody is still reading a peer's table
+        for pp in self._opened:
+            self.ctx.L.spg_peer_close(pp)
+        self._opened = []
+        self.comm.barrier()
+        self.ctx.L.spg_peer_free(self._vec)
+        self._vec = None
 
 
 class ShardedPhase1:
@@ -225,14 +288,19 @@ def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, sat
     return ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)
 
 
-def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local):
-    """Z bound to rq over all shards: local bind scaled by the rank's eq weight, one
-    all-gather of the partial tables (device tensors over NCCL), modular sum on the device."""
+def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local, peer: "PeerTable | None" = None):
+    """Z bound to rq over all shards: local bind scaled by the rank's eq weight, then the modular
+    sum over ranks -- over peer memory when a PeerTable is given (one kernel per rank, 2 (G-1)/G
+    of a table over NVLink), else one NCCL all-gather of the partial tables + device additions."""
     import torch
 
     rq_rev = np.asarray(rq_rev, dtype=np.uint64).reshape(-1, 4)
     nql = log2(Q_local)
     total = sum(len(z.witness_secs) * y for y in z.num_inputs)
+    if peer is not None and comm.world > 1:
+        assert peer.n == total
+        api.zmat_bind_rq(ctx, z, rq_rev[:nql], api.host_eq_weight(rq_rev[nql:], comm.rank), peer.poly)
+        return peer.all_reduce()
     dev = torch.device("cuda", ctx.device)
     mine = torch.empty((total, 4), dtype=torch.int64, device=dev)
     out = api.DensePolynomial.wrap(ctx, mine.data_ptr(), total, owner=mine)
