@@ -148,6 +148,8 @@ def _proto(L):
     L.ocubic_batched_eval.argtypes = [_SZ, _SZ, _P, _P, _P, _SZ, _P, _P, _P, _P, _P]
     L.ospmv.restype = None
     L.ospmv.argtypes = [_SZ, _P, _P, _P, _SZ, _SZ, _P, _SZ, _P]
+    L.ospmv_batch.restype = None
+    L.ospmv_batch.argtypes = [_SZ, _P, _P, _P, _SZ, _SZ, _P, _SZ, _SZ, _SZ, _P]
     L.oeval_table_sparse.restype = None
     L.oeval_table_sparse.argtypes = [_SZ, _P, _P, _P, _P, _SZ, _SZ, _SZ, _P]
     L.osparse_evaluate_with_tables.restype = Fq
@@ -488,6 +490,18 @@ def spmv(row, col, val, num_rows, max_num_cols, z, seg_stride):
     val, z = fq_array(val), fq_array(z)
     out = np.empty((num_rows, 4), dtype=np.uint64)
     lib().ospmv(len(row), _ptr(row), _ptr(col), _ptr(val), num_rows, max_num_cols, _ptr(z), seg_stride, _ptr(out))
+    return out
+
+
+def spmv_batch(row, col, val, num_rows, max_num_cols, z_batch, seg_stride):
+    """spmv for every proof of one instance: z_batch is (Q, W * Y, 4); returns (Q * num_rows, 4)."""
+    row = np.ascontiguousarray(row, dtype=np.uint32)
+    col = np.ascontiguousarray(col, dtype=np.uint32)
+    val, zb = fq_array(val), fq_array(z_batch)
+    nq = zb.shape[0]
+    out = np.empty((nq * num_rows, 4), dtype=np.uint64)
+    lib().ospmv_batch(len(row), _ptr(row), _ptr(col), _ptr(val), num_rows, max_num_cols, _ptr(zb), seg_stride, nq,
+                      zb.shape[1], _ptr(out))
     return out
 
 

@@ -199,9 +199,10 @@ opqx *opqx_new_rev(const ofq *z, size_t P, size_t W, const size_t *num_proofs,
   for (size_t p = 0; p < P; p++) {
     size_t step_q = max_num_proofs / num_proofs[p];
     size_t step_x = max_num_inputs / num_inputs[p];
+#pragma omp parallel for collapse(2) schedule(static) if (num_proofs[p] * num_inputs[p] >= 8192)
     for (size_t q = 0; q < num_proofs[p]; q++) {
-      size_t q_rev = orev_bits(q, max_num_proofs) / step_q;
       for (size_t x = 0; x < num_inputs[p]; x++) {
+        size_t q_rev = orev_bits(q, max_num_proofs) / step_q;
         size_t x_rev = orev_bits(x, max_num_inputs) / step_x;
         for (size_t w = 0; w < W; w++)
           *at(s, p, q_rev, w, x_rev) = z[s->off[p] + (q * W + w) * num_inputs[p] + x];

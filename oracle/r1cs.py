@@ -72,11 +72,11 @@ def multiply_vec_block(inst: Instance, num_instances, num_proofs, max_num_inputs
     outs = [[], [], []]
     for p in range(num_instances):
         pi = 0 if inst.num_instances == 1 else p
-        for q in range(num_proofs[p]):
-            z = np.ascontiguousarray(z_mat[p][q])  # (W, Y_p, 4)
-            for m in range(3):
-                rows, cols, vals = inst.mats[3 * pi + m]
-                outs[m].append(O.spmv(rows, cols, vals, num_cons[pi], max_num_inputs, z.reshape(-1, 4), z.shape[1]))
+        zp = np.ascontiguousarray(z_mat[p])  # (Q_p, W, Y_p, 4): the proofs are independent
+        Qp, Wn, Yp = zp.shape[0], zp.shape[1], zp.shape[2]
+        for m in range(3):
+            rows, cols, vals = inst.mats[3 * pi + m]
+            outs[m].append(O.spmv_batch(rows, cols, vals, num_cons[pi], max_num_inputs, zp.reshape(Qp, Wn * Yp, 4), Yp))
     return [np.concatenate(o) for o in outs]
 
 

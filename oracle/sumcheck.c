@@ -260,6 +260,15 @@ void ospmv(size_t nnz, const uint32_t *row, const uint32_t *col, const ofq *val,
   }
 }
 
+/* the same product for `nq` proofs of one instance (z and out advance by z_stride / num_rows
+ * scalars per proof): the proofs are independent, which is the reference's data-parallel axis */
+void ospmv_batch(size_t nnz, const uint32_t *row, const uint32_t *col, const ofq *val, size_t num_rows,
+                 size_t max_num_cols, const ofq *z, size_t seg_stride, size_t nq, size_t z_stride, ofq *out) {
+#pragma omp parallel for schedule(static) if (nq > 1 && nq * nnz >= 8192)
+  for (size_t q = 0; q < nq; q++)
+    ospmv(nnz, row, col, val, num_rows, max_num_cols, z + q * z_stride, seg_stride, out + q * num_rows);
+}
+
 void oeval_table_sparse(size_t nnz, const uint32_t *row, const uint32_t *col, const ofq *val,
                         const ofq *rx, size_t num_segs, size_t max_num_cols, size_t num_cols,
                         ofq *out) {

@@ -69,6 +69,8 @@ void ocubic_batched_eval(size_t len, size_t npar, ofq *const *A_par, ofq *const 
  * z[col / max_num_cols][col % max_num_cols] with segment stride seg_stride */
 void ospmv(size_t nnz, const uint32_t *row, const uint32_t *col, const ofq *val, size_t num_rows,
            size_t max_num_cols, const ofq *z, size_t seg_stride, ofq *out);
+void ospmv_batch(size_t nnz, const uint32_t *row, const uint32_t *col, const ofq *val, size_t num_rows,
+                 size_t max_num_cols, const ofq *z, size_t seg_stride, size_t nq, size_t z_stride, ofq *out);
 /* sparse_mlpoly.rs:524-541 : out[num_segs][num_cols] (zeroed here) */
 void oeval_table_sparse(size_t nnz, const uint32_t *row, const uint32_t *col, const ofq *val,
                         const ofq *rx, size_t num_segs, size_t max_num_cols, size_t num_cols,
