@@ -85,7 +85,8 @@ void spg_vec_free(spg_vec *v);
 
 /* ---------------------------------------------------------------- field (a1)
  * Scalar::{mul,add,sub,neg} elementwise, src/scalar/ristretto255.rs:690-763.
- * op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 square(a), 5 to canonical integer (to_bytes) */
+ * op: 0 mul, 1 add, 2 sub, 3 neg(a), 4 square(a), 5 to canonical integer (to_bytes),
+ *     6 invert(a) (Scalar::invert, :541-595; 0 -> 0) */
 int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_vec *out);
 /* Scalar::from_u512 / from_bytes_wide on n wide values (8 u64 each), :435-466 */
 int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec **out);

@@ -159,7 +159,7 @@ class DensePolynomial:
 
 def vec_op(ctx: Context, op: str, a: DensePolynomial, b: DensePolynomial | None = None) -> DensePolynomial:
     """Scalar::{mul,add,sub,neg,square,to_bytes} elementwise on the device."""
-    code = {"mul": 0, "add": 1, "sub": 2, "neg": 3, "square": 4, "to_canonical": 5}[op]
+    code = {"mul": 0, "add": 1, "sub": 2, "neg": 3, "square": 4, "to_canonical": 5, "invert": 6}[op]
     out = DensePolynomial.empty(ctx, len(a))
     check(ctx.L.spg_fq_vec_op(ctx.h, code, a.h, b.h if b is not None else None, out.h), "spg_fq_vec_op")
     return out

@@ -19,7 +19,8 @@ __global__ void k_vec_op(const fq *__restrict__ a, const fq *__restrict__ b, fq 
     else if (OP == 2) r = fq_sub(x, fq_load(b + i));
     else if (OP == 3) r = fq_neg(x);
     else if (OP == 4) r = fq_sqr(x);
-    else r = fq_from_mont(x);
+    else if (OP == 5) r = fq_from_mont(x);
+    else r = fq_invert(x);
     fq_store(out + i, r);
   }
 }
@@ -232,7 +233,7 @@ extern "C" {
 
 int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_vec *out) {
   SPG_CHECK(ctx && a && out, "spg_fq_vec_op: null argument");
-  SPG_CHECK(op >= 0 && op <= 5, "spg_fq_vec_op: unknown op %d", op);
+  SPG_CHECK(op >= 0 && op <= 6, "spg_fq_vec_op: unknown op %d", op);
   bool binary = op <= 2;
   SPG_CHECK(!binary || (b && b->n == a->n), "spg_fq_vec_op: operand length mismatch");
   SPG_CHECK(out->n == a->n, "spg_fq_vec_op: output length mismatch");
@@ -246,7 +247,8 @@ int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_
     case 2: SPG_LAUNCH(ctx, k_vec_op<2>, grid, 256, 0, a->d, pb, out->d, n); break;
     case 3: SPG_LAUNCH(ctx, k_vec_op<3>, grid, 256, 0, a->d, pb, out->d, n); break;
     case 4: SPG_LAUNCH(ctx, k_vec_op<4>, grid, 256, 0, a->d, pb, out->d, n); break;
-    default: SPG_LAUNCH(ctx, k_vec_op<5>, grid, 256, 0, a->d, pb, out->d, n); break;
+    case 5: SPG_LAUNCH(ctx, k_vec_op<5>, grid, 256, 0, a->d, pb, out->d, n); break;
+    default: SPG_LAUNCH(ctx, k_vec_op<6>, grid, 256, 0, a->d, pb, out->d, n); break;
   }
   return SPG_OK;
 }

@@ -373,6 +373,21 @@ __device__ __forceinline__ fq fq_dot4_lazy(const fq (&a)[4], const fq (&b)[4]) {
 __device__ __forceinline__ fq fq_mul(const fq &a, const fq &b) { return fq_canon(fq_mul_lazy(a, b)); }
 __device__ __forceinline__ fq fq_sqr(const fq &a) { return fq_mul(a, a); }
 
+// Scalar::invert (ristretto255.rs:541-595) as a^(q-2) by square-and-multiply over the bits of
+// q - 2 (any exponentiation schedule gives the same canonical value); 0 maps to 0
+// (the reference returns CtOption::none there).
+__device__ __forceinline__ fq fq_invert(const fq &a) {
+  // q - 2, little-endian 32-bit words
+  const uint32_t e[8] = {SPG_Q0 - 2u, SPG_Q1, SPG_Q2, SPG_Q3, 0u, 0u, 0u, SPG_Q7};
+  fq acc = fq_one();
+#pragma unroll 1
+  for (int i = 252; i >= 0; i--) {
+    acc = fq_mul_lazy(acc, acc);
+    if ((e[i >> 5] >> (i & 31)) & 1u) acc = fq_mul_lazy(acc, a);
+  }
+  return fq_canon(acc);
+}
+
 // to_bytes(): leave Montgomery form (ristretto255.rs:419-431)
 __device__ __forceinline__ fq fq_from_mont(const fq &a) {
   fq one = fq_zero();
