@@ -25,11 +25,73 @@ def main():
     shm = parallel.ShmComm(device=torch.device("cuda", local))
     for log_x in (7, 9):
         check(ctx, comm, shm, rank, world, log_x)
+    if "--full" in sys.argv:
+        full_size(ctx, shm, rank, world)
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU parity ok: world={world}, every round bit-exact on every rank (per-round driver and C round loop)")
     shm.close()
     dist.destroy_process_group()
+
+
+def full_size(ctx, shm, rank, world):
+    """BASELINE config C3 (X = 2^16, Q = 256) sharded over all ranks against the SAME batch proven
+    unsharded on every rank's own GPU: every round and both claim vectors must be bit-identical."""
+    log_x, Q = 16, 256
+    X, Ql = 1 << log_x, 256 // world
+    nq = log2(Q)
+    rng = np.random.default_rng(77)  # same stream on every rank
+
+    def canon(n):
+        a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        return a
+
+    u = canon(X * Q)
+    du = sp.DensePolynomial.new(ctx, u)
+    dun = sp.DensePolynomial.new(ctx, np.ascontiguousarray(np.roll(u.reshape(Q, X, 4), -1, axis=1).reshape(X * Q, 4)))
+    v = sp.vec_op(ctx, "mul", du, dun).to_host()
+    del du, dun
+    rows = np.arange(X, dtype=np.uint32)
+    ones = np.tile(O.ONE, (X, 1))
+    inst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [(rows, rows, ones)], [(rows, ((rows + 1) % X).astype(np.uint32), ones)],
+                           [(rows, (rows + X).astype(np.uint32), ones)])
+    tau_q, tau_x = canon(nq), canon(log_x)
+    ch1, ch2, r_abc = canon(log_x + nq), canon(1 + log_x), canon(3)
+    none = canon(1)[:0]
+    rx = ch1[:log_x][::-1].copy()
+    # unsharded
+    secs = [sp.ProverWitnessSecInfo(ctx, [Q], [X], u), sp.ProverWitnessSecInfo(ctx, [Q], [X], v)]
+    z = sp.ZMat(ctx, [Q], [X], secs)
+    sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, none, tau_q, tau_x)
+    want1 = sc1.run_rounds(ch1)
+    wantc1 = sc1.final()
+    sc1.free()
+    sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[log_x:], none, *r_abc)
+    want2 = sc2.run_rounds(ch2)
+    wantc2 = sc2.final()
+    sc2.free()
+    z.free()
+    for s_ in secs:
+        s_.free()
+    # sharded: this rank's slice of the proofs
+    lo, hi = rank * Ql * X, (rank + 1) * Ql * X
+    secs = [sp.ProverWitnessSecInfo(ctx, [Ql], [X], u[lo:hi]), sp.ProverWitnessSecInfo(ctx, [Ql], [X], v[lo:hi])]
+    z = sp.ZMat(ctx, [Ql], [X], secs)
+    peer = parallel.PeerTable(ctx, shm, 2 * X)
+    for satisfied in (False, True):
+        sh = parallel.gpu_phase1(ctx, shm, inst, z, Ql, X, X, tau_q, tau_x, satisfied=satisfied)
+        got1 = sh.run_rounds(ch1)
+        assert np.array_equal(got1, want1), f"rank {rank}: sharded C3 phase 1 differs (satisfied={satisfied})"
+        assert np.array_equal(sh.final(), wantc1), f"rank {rank}: sharded C3 claims differ"
+        zrq = parallel.gpu_bind_rq_sharded(ctx, shm, z, ch1[log_x:], Ql, peer)
+        sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, none, *r_abc)
+        assert np.array_equal(sc2.run_rounds(ch2), want2), f"rank {rank}: sharded C3 phase 2 differs"
+        assert np.array_equal(sc2.final(), wantc2)
+        sc2.free()
+    peer.close()
+    if rank == 0:
+        print(f"C3 (2^16 x 256) sharded over {world} GPUs == unsharded: every round and claim bit-identical")
 
 
 def check(ctx, comm, shm, rank, world, log_x):
