@@ -422,8 +422,8 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
       v.copy = ni < num_inputs[p] ? ni : num_inputs[p];
     }
   cudaError_t e = dev_alloc(ctx, &z->views, hv.size() * sizeof(SecView));
+  // (pageable source: staged before the call returns, so hv may go out of scope)
   if (e == cudaSuccess) e = cudaMemcpyAsync(z->views, hv.data(), hv.size() * sizeof(SecView), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) {
     spg_zmat_destroy(z);
     return cuda_fail(e, "z_mat views", __FILE__, __LINE__);

@@ -352,14 +352,36 @@ __global__ void k_row_weights(const fq *__restrict__ Ap, const fq *__restrict__ 
 // suffix eq tables for LSB-first binding: level m (2^m entries) lives at buf + 2^m,
 //   level_m[2i + b] = level_{m-1}[i] * eq(tau[n - m], b),  level_0 = [1]
 // so level m is the eq table of tau[n-m .. n-1] with index bit k <-> tau[n-m+k].
+// The first SUFFIX_SMALL levels are built by one block in one launch (no host round trip for
+// the leading one either); the larger levels take one streaming launch each.
+constexpr int SUFFIX_SMALL = 9;
+struct SmallTaus {
+  fq t[SUFFIX_SMALL];
+};
+__global__ void k_suffix_small(fq *__restrict__ buf, const __grid_constant__ SmallTaus taus, int levels) {
+  if (threadIdx.x == 0) buf[1] = fq_one();
+  __syncthreads();
+  for (int m = 1; m <= levels; m++) {
+    size_t cnt = (size_t)1 << (m - 1);
+    fq r = taus.t[m - 1];
+    for (size_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      fq s = buf[cnt + i];
+      fq hi = fq_mul(s, r);
+      buf[2 * cnt + 2 * i + 1] = hi;
+      buf[2 * cnt + 2 * i] = fq_sub(s, hi);
+    }
+    __syncthreads();
+  }
+}
+
 int build_suffix_tables(spg_ctx *ctx, const std::vector<hfq> &tau, size_t max_level, fq *buf) {
-  fq one_h;
-  hfq one = hfq_one();
-  memcpy(&one_h, &one, sizeof one_h);
-  SPG_CUDA(cudaMemcpyAsync(buf + 1, &one_h, sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   size_t n = tau.size();
-  for (size_t m = 1; m <= max_level; m++) {
+  SmallTaus st;
+  memset(&st, 0, sizeof st);
+  int small = (int)(max_level < (size_t)SUFFIX_SMALL ? max_level : SUFFIX_SMALL);
+  for (int m = 1; m <= small; m++) memcpy(&st.t[m - 1], &tau[n - m], sizeof(fq));
+  SPG_LAUNCH(ctx, k_suffix_small, 1, 256, 0, buf, st, small);
+  for (size_t m = small + 1; m <= max_level; m++) {
     fq r;
     memcpy(&r, &tau[n - m], sizeof r);
     size_t cnt = (size_t)1 << (m - 1);
@@ -562,8 +584,8 @@ int sc1_build_weights(spg_sc1 *s) {
     SPG_CUDA(dev_alloc(ctx, &d_r, hr.size() * sizeof(fq)));
     SPG_CUDA(dev_alloc(ctx, &scratch, s->Pp * sizeof(fq)));
     SPG_CUDA(cudaMemcpyAsync(d_r, hr.data(), s->np * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+    // (the pageable upload above is staged before cudaMemcpyAsync returns, so hr may go out of scope)
     int rc = eq_evals_device(ctx, d_r, hr.data(), s->np, s->Ap, scratch);
-    cudaStreamSynchronize(ctx->stream);  // hr (host) is read by the upload above
     dev_free(ctx, d_r);
     dev_free(ctx, scratch);
     SPG_TRY(rc);
@@ -587,7 +609,6 @@ int sc1_build_weights(spg_sc1 *s) {
   dim3 grid((maxQ + 127) / 128, (unsigned)s->P);
   SPG_LAUNCH(ctx, k_row_weights, grid, 128, 0, s->Ap, s->Sq + ((size_t)1 << s->nq), s->d_rw_off,
              s->d_Qp, (int)s->P, s->RWx);
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
 }
 

@@ -420,8 +420,7 @@ static int sc2_build(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, cons
     if (s->np && cudaMemcpyAsync(d_r, rp, s->np * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = cuda_fail(cudaGetLastError(), "rp upload", __FILE__, __LINE__); break; }
     if ((rc = eq_evals_device(ctx, d_r, rp, s->np, s->A, eq_scratch)) != SPG_OK) break;
   } while (0);
-  cudaStreamSynchronize(ctx->stream);
-  dev_free(ctx, scr);
+  dev_free(ctx, scr);  // stream-ordered: no host synchronisation needed before the first round is queued
   if (rc != SPG_OK) return fail(rc);
   s->loglen.resize(P);
   for (size_t p = 0; p < P; p++) s->loglen[p] = log2u(s->Y[p]);
