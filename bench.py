@@ -11,8 +11,9 @@ round trips included. One JSON line on stdout (rank 0).
 
 Workload (BASELINE.json configs[4], "2^20 x 64"): P = 1 instance, X = 2^20 constraints,
 Q = 64 proofs per GPU, sections (u, v), constraint x: u_x * u_{x+1} = v_x. Under
-torchrun every rank holds its own 64-proof shard (weak scaling over the independent
-proof axis; each rank proves its shard, no data-path collective).
+torchrun the N ranks prove ONE batch of 64 * N proofs sharded over the proof axis (weak
+scaling: per-GPU work is fixed): per round 3 scalars per rank cross a host mailbox, and
+the rq-bound Z table is summed once over NVLink peer memory (parallel.py).
 """
 from __future__ import annotations
 
@@ -70,6 +71,25 @@ class ClockSampler:
         self.thread = None
 
     def _run(self):
+        """NVML in-process when the bindings load (one cheap query per sample); the nvidia-smi
+        subprocess otherwise. A fresh nvidia-smi per sample re-initialises NVML over every GPU of
+        the box and contends with the ranks' kernel launches, so it is the fallback only."""
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+                time.sleep(0.05)
+            return
+        except Exception:
+            pass
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
@@ -114,6 +134,9 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    from spartan_parallel_b200 import parallel
+
+    numa = parallel.bind_host_to_gpu(local)  # before any pinned allocation (first-touch pages)
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -145,13 +168,24 @@ def run_gpu(args):
     ch1, ch2 = challenges(crng, nx + nq + ng), challenges(crng, 1 + nx)
     r_abc = challenges(crng, 3)
     setup_s = time.time() - t_setup
-    from spartan_parallel_b200 import parallel
 
     comm = parallel.ShmComm(device=torch.device("cuda", local)) if world > 1 else parallel.LocalComm()
     peer = parallel.PeerTable(ctx, comm, 2 * X) if world > 1 else None  # the rq-bound Z table: W * Y scalars
 
+    trace, tracing = [], [False]
+
+    nosync_trace = bool(os.environ.get("SPG_BENCH_TRACE_NOSYNC"))  # development: host timestamps in the timed loop
+
+    def mark(name):
+        if tracing[0]:
+            ctx.sync()
+            trace.append((name, time.perf_counter()))
+        elif nosync_trace:
+            trace.append((name, time.perf_counter()))
+
     def one_pass(secs):
         """The hot path for one batch: everything R1CSProof::prove does on tables."""
+        mark("start")
         z = sp.ZMat(ctx, [Q], [X], secs)
         rx = ch1[:nx][::-1].copy()
         if world == 1:
@@ -165,15 +199,22 @@ def run_gpu(args):
             # one proof over Q * world proofs: shards exchange 3 scalars per round, then one
             # all-gather of the rq-bound Z table; phase 2 (independent of Q) runs replicated
             sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, tau_q, tau_x, satisfied=True)
+            mark("phase1 create")
             sc1.run_rounds(ch1[:sc1.num_rounds])
+            mark("phase1 rounds (local C loop + tail)")
             c1 = sc1.final()
             sc1.engine.free()
+            mark("phase1 final")
             zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q, peer)
+            mark("Z bind + peer all-reduce")
             sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
+        mark("phase2 create")
         sc2.run_rounds(ch2[:sc2.num_rounds])
         c2 = sc2.final()
+        mark("phase2 rounds")
         sc2.free()
         z.free()
+        mark("free")
         return c1, c2
 
     def upload(asynchronous=False):
@@ -210,12 +251,19 @@ def run_gpu(args):
     for _ in range(args.warmup):
         first = one_pass(secs)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("SPG_NO_CLOCKS"):
         sampler.start()
     launches0 = ctx.launches
-    ctx.profile_begin()
+    no_prof = bool(os.environ.get("SPG_BENCH_NO_PROFILE"))  # development: without per-launch events
+    if not no_prof:
+        ctx.profile_begin()
+    del trace[:]
     ms_dev, wall_dev = timed(lambda: one_pass(secs), args.steps)
-    prof = ctx.profile_end()
+    prof = [] if no_prof else ctx.profile_end()
+    if nosync_trace and rank in (0, world - 1):
+        print(f"[rank {rank}] timed loop, host clock, no syncs: " + ", ".join(f"{n}: {(t - trace[i][1]) * 1e3:.2f}" for i, (n, t) in enumerate(trace[1:])),
+              file=sys.stderr, flush=True)
+        print(f"[rank {rank}] cpus {len(os.sched_getaffinity(0))} loadavg {os.getloadavg()}", file=sys.stderr, flush=True)
     launches = (ctx.launches - launches0) // max(args.steps, 1)
     for s in secs:
         s.free()
@@ -233,11 +281,24 @@ def run_gpu(args):
             for s in cur:
                 s.free()
 
-    e2e_run(min(args.warmup, 2))
-    ms_e2e, wall_e2e = timed(lambda: e2e_run(args.steps), 1)
-    last = e2e_out[-1]
+    if args.no_e2e:  # development runs only: the reported line then carries no end-to-end number
+        ms_e2e, last = float("nan"), first
+    else:
+        e2e_run(min(args.warmup, 2))
+        ms_e2e, wall_e2e = timed(lambda: e2e_run(args.steps), 1)
+        last = e2e_out[-1]
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(first[0], last[0]) and np.array_equal(first[1], last[1])
+    if args.trace_phases:  # wall clock per phase of one more pass, every rank, to stderr (syncs between phases)
+        secs = upload()
+        barrier()
+        del trace[:]
+        tracing[0] = True
+        one_pass(secs)
+        tracing[0] = False
+        print(f"[rank {rank}] " + ", ".join(f"{n}: {(t - trace[i][1]) * 1e3:.2f} ms" for i, (n, t) in enumerate(trace[1:])), file=sys.stderr, flush=True)
+        for s_ in secs:
+            s_.free()
 
     # ---- whole R1CSProof::prove (transcript, sigma protocols, openings) through the C++ host mirror
     full_proof = None
@@ -340,9 +401,9 @@ def run_gpu(args):
                 "h2d_bytes_per_step": int(2 * N * 32), "d2h_bytes_per_step": int(96 * (2 * nx + nq + ng + 1) + 7 * 32)},
         "gpu_launches": int(launches), "full_proof": full_proof, "wall_ms_per_step": wall_dev / args.steps,
         "prove_time_s": step_ms * 1e-3, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s,
+        "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s, "host_affinity": numa,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -418,7 +479,28 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "constraints/s", "cores": cores, "kind": "port", "sample": sample, "host_cores": host_cores},
         "e2e": {"value": val, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on
+    stdout. Point fd 1 at stderr for the duration of the run and keep the real stdout for the line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -432,7 +514,10 @@ def main():
     ap.add_argument("--cpu-log-x", type=int, default=18)
     ap.add_argument("--cpu-proofs", type=int, default=16)
     ap.add_argument("--no-full-proof", action="store_true", help="skip the extra whole-proof timing")
+    ap.add_argument("--no-e2e", action="store_true", help="development: skip the end-to-end leg")
+    ap.add_argument("--trace-phases", action="store_true", help="development: per-phase wall clock of one extra pass on stderr")
     args = ap.parse_args()
+    protect_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

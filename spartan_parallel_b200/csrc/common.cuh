@@ -148,6 +148,12 @@ struct FinishArgs {
   unsigned long long *flag;
   unsigned long long seq;
 };
+// polite busy-wait: the spinning hardware thread yields its pipeline to the sibling hyperthread
+static inline void spin_pause() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#endif
+}
 FinishArgs finish_args(spg_ctx *ctx, size_t nblocks);  // seq != 0 iff the grid is small enough
 int wait_flag(spg_ctx *ctx, unsigned long long seq, int width, spg_fq *out);
 // the launch's result: polled when the kernel finished the reduction itself, else reduce + sync

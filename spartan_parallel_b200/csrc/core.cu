@@ -131,6 +131,7 @@ int wait_flag(spg_ctx *ctx, unsigned long long seq, int width, spg_fq *out) {
   unsigned int spins = 0;
   auto t0 = std::chrono::steady_clock::now();
   while (*f != seq) {
+    spin_pause();
     if ((++spins & 0x3fff) == 0) {
       cudaError_t e = cudaStreamQuery(ctx->stream);
       if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "round kernel", __FILE__, __LINE__);

@@ -1057,9 +1057,12 @@ int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *chal
   SPG_CHECK(world >= 1 && rank >= 0 && rank < world && slot_stride >= 64 + 3 * sizeof(spg_fq),
             "spg_sc1_run_rounds_sharded: bad mailbox geometry");
   char *base = (char *)mailbox;
+  static const bool trace = getenv("SPG_TRACE_ROUNDS") != nullptr;
   for (size_t j = 0; j < num_rounds; j++) {
     spg_fq part[3];
+    auto t0 = std::chrono::steady_clock::now();
     SPG_TRY(spg_sc1_round_eval(s, part));
+    auto t1 = std::chrono::steady_clock::now();
     uint64_t c = ++*calls;
     size_t b = c & 1;
     char *mine = base + (b * world + rank) * slot_stride;
@@ -1068,14 +1071,21 @@ int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *chal
     hfq acc[3] = {hfq_zero(), hfq_zero(), hfq_zero()};
     for (int r = 0; r < world; r++) {
       char *slot = base + (b * world + r) * slot_stride;
-      while (__atomic_load_n((uint64_t *)slot, __ATOMIC_ACQUIRE) != c) {
-      }
+      while (__atomic_load_n((uint64_t *)slot, __ATOMIC_ACQUIRE) != c) spin_pause();
       spg_fq v[3];
       memcpy(v, slot + 64, sizeof v);
       for (int t = 0; t < 3; t++) acc[t] = hfq_add(acc[t], hfq_from(v[t]));
     }
     for (int t = 0; t < 3; t++) evals_out[3 * j + t] = hfq_to(acc[t]);
+    auto t2 = std::chrono::steady_clock::now();
     SPG_TRY(spg_sc1_round_bind(s, challenges + j));
+    if (trace && rank == 0) {
+      auto t3 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[spg] sharded round %zu: eval %.1f us, mailbox %.1f us, bind %.1f us\n", j,
+              std::chrono::duration<double, std::micro>(t1 - t0).count(),
+              std::chrono::duration<double, std::micro>(t2 - t1).count(),
+              std::chrono::duration<double, std::micro>(t3 - t2).count());
+    }
   }
   return SPG_OK;
 }
