@@ -203,7 +203,7 @@ def run_gpu(args):
             sc1.run_rounds(ch1[:sc1.num_rounds])
             mark("phase1 rounds (local C loop + tail)")
             c1 = sc1.final()
-            sc1.engine.free()
+            sc1.free()
             mark("phase1 final")
             zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q, peer)
             mark("Z bind + peer all-reduce")

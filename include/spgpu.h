@@ -299,6 +299,24 @@ int spg_sparse_deref(spg_ctx *ctx, const spg_sparse *s, const spg_vec *mem_rx,
 /* device copy of v[offset, offset + n) */
 int spg_vec_clone(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_vec **out);
 
+/* ---------------------------------------------------------------- witness sections (f2)
+ * The permutation-product recurrence behind every (pi, D) pair of the w3 witness sections
+ * SNARK::prove builds before committing them (src/lib.rs:1378-1400 perm_exec_w3, :862-880
+ * mem_gen, :1533-1570 block_w3 and its PHY / VIR pairs). Per segment (one proving
+ * instance), from its last proof q down to its first:
+ *     D[q]  = x[q] * (pi[q+1] + 1 - v[q+1])     (D[last] = x[last])
+ *     pi[q] = v[q] * D[q]
+ * The reference loops sequentially; here it is a parallel suffix scan of affine maps (exact
+ * field arithmetic, so bit-identical). v, x, D, pi are strided views: entry q of a view is
+ * vec[off + q * stride], which lets the caller point them at the columns of a row-major
+ * w3 table (stride 8: v = col 0, x = col 1, pi = col 2, D = col 3, ...). seg_len[n_seg] sums
+ * to n. */
+int spg_perm_scan(spg_ctx *ctx, size_t n, const size_t *seg_len, size_t n_seg,
+                  const spg_vec *v, size_t v_off, size_t v_stride,
+                  const spg_vec *x, size_t x_off, size_t x_stride,
+                  spg_vec *D, size_t D_off, size_t D_stride,
+                  spg_vec *pi, size_t pi_off, size_t pi_stride);
+
 /* ---------------------------------------------------------------- peer-memory all-reduce (e)
  * Modular sum of one table held at the same offset on `world` GPUs of a node (the rq-bound Z
  * table of a sharded proof, src/r1csproof.rs:478). Each process allocates the table with

@@ -18,7 +18,7 @@ MODE_P, MODE_Q, MODE_W, MODE_X = 1, 2, 3, 4
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("fq.c", "polys.c", "sumcheck.c", "fq.h", "polys.h", "sumcheck.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("fq.c", "polys.c", "sumcheck.c", "witness.c", "fq.h", "polys.h", "sumcheck.h", "witness.h")]
     stale = not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
@@ -90,6 +90,8 @@ def _proto(L):
     L.odense_evaluate.argtypes = [_P, _SZ, _P, _SZ]
     L.odense_bound_L.restype = None
     L.odense_bound_L.argtypes = [_P, _SZ, _P, _P]
+    L.owit_perm_fill.restype = None
+    L.owit_perm_fill.argtypes = [_P, _SZ, _P, _SZ, _SZ, _SZ, _SZ, _SZ]
     L.odot.restype = Fq
     L.odot.argtypes = [_P, _P, _SZ]
     L.ounipoly_from_evals.restype = None
@@ -328,6 +330,15 @@ def dense_bound_L(Z, L):
     out = np.empty((1 << (ell - ell // 2), 4), dtype=np.uint64)
     lib().odense_bound_L(_ptr(Z), ell, _ptr(L), _ptr(out))
     return out
+
+
+def perm_fill(w3, seg_len, width=8, v_col=0, x_col=1, pi_col=2, d_col=3):
+    """(pi, D) columns of a row-major w3 table, src/lib.rs:1378-1400 (sequential, last proof first)."""
+    w3 = np.ascontiguousarray(fq_array(w3).copy())
+    seg = np.ascontiguousarray(seg_len, dtype=np.uint64)
+    assert w3.shape[0] == int(seg.sum()) * width
+    lib().owit_perm_fill(_ptr(w3), width, _ptr(seg), seg.size, v_col, x_col, pi_col, d_col)
+    return w3
 
 
 def dot(a, b):

@@ -113,6 +113,7 @@ def _proto(L):
         "spg_cubic_final": [P, P],
         "spg_hash_layer": [P, P, P, P, SZ, P, P, INT, PP],
         "spg_deref": [P, P, SZ, P, PP],
+        "spg_perm_scan": [P, SZ, P, SZ, P, SZ, SZ, P, SZ, SZ, P, SZ, SZ, P, SZ, SZ],
         "spg_peer_alloc": [P, SZ, PP, P],
         "spg_peer_free": [P],
         "spg_peer_open": [P, P, PP],

@@ -165,6 +165,19 @@ def vec_op(ctx: Context, op: str, a: DensePolynomial, b: DensePolynomial | None 
     return out
 
 
+def perm_scan(ctx: Context, w3: DensePolynomial, seg_len, width: int = 8, v_col: int = 0, x_col: int = 1,
+              pi_col: int = 2, d_col: int = 3) -> DensePolynomial:
+    """Fills the (pi, D) columns of a row-major w3 table in place (src/lib.rs:1378-1400, 862-880,
+    1533-1570): D[q] = x[q] * (pi[q+1] + 1 - v[q+1]), pi[q] = v[q] * D[q], from the last row of
+    every segment (proving instance) upwards. ``seg_len`` lists the rows per segment."""
+    seg = np.ascontiguousarray(seg_len, dtype=np.uint64)
+    n = int(seg.sum())
+    assert len(w3) >= n * width
+    check(ctx.L.spg_perm_scan(ctx.h, n, _ptr(seg), seg.size, w3.h, v_col, width, w3.h, x_col, width, w3.h, d_col, width,
+                              w3.h, pi_col, width), "spg_perm_scan")
+    return w3
+
+
 def from_u512(ctx: Context, wide) -> DensePolynomial:
     wide = np.ascontiguousarray(wide, dtype=np.uint64)
     assert wide.shape[-1] == 8

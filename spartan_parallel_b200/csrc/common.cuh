@@ -85,6 +85,13 @@ struct spg_ctx {
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   double next_units = 0;  // set by the launcher just before SPG_LAUNCH
+  // large per-proof buffers (tables, witness sections) recycled by the context itself, see dev_alloc
+  struct BigBlock {
+    void *p;
+    size_t bytes;
+    bool busy;
+  };
+  std::vector<BigBlock> big;
 };
 
 struct spg_vec {
@@ -111,14 +118,21 @@ namespace spg {
 
 void prof_begin(spg_ctx *ctx, const char *name, cudaEvent_t *a, cudaEvent_t *b);
 
-// stream-ordered allocation from the device's default pool (kept warm: the release
-// threshold is raised in spg_ctx_create), so per-proof tables cost no cudaMalloc/cudaFree
+// Stream-ordered allocation. Small buffers come from the device's default pool (kept warm: the
+// release threshold is raised in spg_ctx_create). Buffers of SPG_BIG_BYTES and more -- the
+// per-proof tables and witness sections, GiBs each -- are recycled by the context itself: a
+// freed block stays with the context and serves the next request it fits (same stream, so the
+// stream order that made cudaFreeAsync -> cudaMallocAsync reuse legal still holds). The pool
+// alone is not enough: one small live allocation carved out of a freed 2 GiB block (the tail
+// prover of a sharded proof, say) forces the pool to map fresh physical memory for the next
+// 2 GiB request, and with eight processes doing that at once the mapping calls serialise in
+// the driver -- 12-15 ms per proof at 8 GPUs, as measured.
+constexpr size_t SPG_BIG_BYTES = (size_t)16 << 20;
+cudaError_t dev_alloc_bytes(spg_ctx *ctx, void **p, size_t bytes);
+void dev_free(spg_ctx *ctx, void *p);
 template <typename T>
 static inline cudaError_t dev_alloc(spg_ctx *ctx, T **p, size_t bytes) {
-  return cudaMallocAsync((void **)p, bytes ? bytes : 32, ctx->stream);
-}
-static inline void dev_free(spg_ctx *ctx, void *p) {
-  if (p) cudaFreeAsync(p, ctx->stream);
+  return dev_alloc_bytes(ctx, (void **)p, bytes);
 }
 int ensure_partials(spg_ctx *ctx, size_t n_fq);
 int vec_new(spg_ctx *ctx, size_t n, spg_vec **out);

@@ -20,6 +20,42 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
   return e == cudaErrorMemoryAllocation ? SPG_ENOMEM : SPG_ECUDA;
 }
 
+cudaError_t dev_alloc_bytes(spg_ctx *ctx, void **p, size_t bytes) {
+  if (bytes < SPG_BIG_BYTES) return cudaMallocAsync(p, bytes ? bytes : 32, ctx->stream);
+  // best fit among the context's free blocks, wasting at most half of a block
+  spg_ctx::BigBlock *best = nullptr;
+  for (auto &b : ctx->big)
+    if (!b.busy && b.bytes >= bytes && b.bytes / 2 <= bytes && (!best || b.bytes < best->bytes)) best = &b;
+  if (best) {
+    best->busy = true;
+    *p = best->p;
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e == cudaErrorMemoryAllocation) {
+    // give the idle blocks back and try once more
+    cudaGetLastError();
+    for (size_t i = ctx->big.size(); i-- > 0;)
+      if (!ctx->big[i].busy) {
+        cudaFreeAsync(ctx->big[i].p, ctx->stream);
+        ctx->big.erase(ctx->big.begin() + i);
+      }
+    e = cudaMallocAsync(p, bytes, ctx->stream);
+  }
+  if (e == cudaSuccess) ctx->big.push_back(spg_ctx::BigBlock{*p, bytes, true});
+  return e;
+}
+
+void dev_free(spg_ctx *ctx, void *p) {
+  if (!p) return;
+  for (auto &b : ctx->big)
+    if (b.p == p) {
+      b.busy = false;
+      return;
+    }
+  cudaFreeAsync(p, ctx->stream);
+}
+
 void prof_begin(spg_ctx *ctx, const char *name, cudaEvent_t *a, cudaEvent_t *b) {
   auto get = [&]() {
     cudaEvent_t e = nullptr;
@@ -215,6 +251,9 @@ int spg_ctx_create(int device, spg_ctx **out) {
 void spg_ctx_destroy(spg_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &b : ctx->big) cudaFreeAsync(b.p, ctx->stream);
+  ctx->big.clear();
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_partials) cudaFree(ctx->d_partials);
   if (ctx->d_scalars) cudaFree(ctx->d_scalars);

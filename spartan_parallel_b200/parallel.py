@@ -301,6 +301,15 @@ class ShardedPhase1:
     def final(self) -> np.ndarray:
         return self._tail().final()
 
+    def free(self):
+        """Releases the shard prover and the tail prover now (not when the object is collected):
+        a lingering tail pins small pieces of the freed table memory until the NEXT proof has
+        already allocated its tables."""
+        for eng in (self.engine, self.tail):
+            if eng is not None and hasattr(eng, "free"):
+                eng.free()
+        self.engine = self.tail = None
+
 
 def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, satisfied: bool = False) -> ShardedPhase1:
     """ShardedPhase1 on this rank's GPU. satisfied=True asserts that the witness satisfies the

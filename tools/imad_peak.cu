@@ -14,13 +14,14 @@ __global__ void k_imad_wide(unsigned long long *out, unsigned int a, unsigned in
 #pragma unroll
   for (int i = 0; i < ILP; i++) acc[i] = threadIdx.x + i;
   unsigned int y = b + threadIdx.x;
-  // the multiplicand of chain i is the low word of chain i+1: every product is distinct, so
+  // the multiplicand of chain i is the low word of its own accumulator: every product is distinct
+  // (ILP independent chains per thread, so the pipe and not the latency is measured), so
   // ptxas cannot hoist one common x*y out of the loop and leave only 64-bit additions behind
   // (which is what the first version of this kernel measured).
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int i = 0; i < ILP; i++)
-      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((unsigned int)acc[(i + 1) % ILP] | a), "r"(y));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((unsigned int)acc[i] | a), "r"(y));
   }
   unsigned long long s = 0;
 #pragma unroll
