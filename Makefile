@@ -15,7 +15,7 @@ all: $(LIB) $(HOSTLIB)
 
 # C++ mirror of the reference's transcript-side host code, above the C ABI
 $(HOSTLIB): $(HOSTSRC) $(PKG)/csrc/ed25519.cuh $(PKG)/csrc/host_fq.h include/spgpu.h $(LIB)
-	g++ -O2 -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o $@ $(PKG)/host/capi.cpp -L$(PKG) -lspgpu -Wl,-rpath,'$$ORIGIN'
+	g++ -O3 -std=c++17 -fPIC -shared -Wall -Wno-unknown-pragmas -o $@ $(PKG)/host/capi.cpp -L$(PKG) -lspgpu -Wl,-rpath,'$$ORIGIN'
 
 build/%.o: $(PKG)/csrc/%.cu $(HDR)
 	@mkdir -p build

@@ -42,6 +42,7 @@ typedef struct spg_sc1 spg_sc1;       /* phase-1 sumcheck state */
 typedef struct spg_sc2 spg_sc2;       /* phase-2 sumcheck state */
 typedef struct spg_cubic spg_cubic;   /* prove_cubic_batched state */
 typedef struct spg_gens spg_gens;     /* MultiCommitGens on the device */
+typedef struct spg_bullet spg_bullet; /* BulletReductionProof::prove state (unfolded generators) */
 
 enum {
   SPG_OK = 0,
@@ -348,6 +349,21 @@ int spg_poly_commit(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, siz
  * round polynomials etc.): out[i] = sum_j s[i*len+j] G[j] + blind[i] h */
 int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, size_t len,
                      const spg_fq *blinds, size_t count, uint8_t *out_compressed);
+
+/* ---------------------------------------------------------------- bullet reduction (f1)
+ * BulletReductionProof::prove, src/nizk/bullet.rs:72-119, without folding the generators: the
+ * library keeps s[m] = prod_j (u_j or u_j^-1 by the top bits of m) on the device, and a round's
+ * L and R are multiscalar multiplications over the ORIGINAL n bases (fixed-base tables, no
+ * doublings). The host keeps the transcript and the O(nk) folds of a and b. Per round:
+ *   spg_bullet_lr(nk, a[0..nk), {blind_L, blind_R}) -> sum_m scalar(m) G[m] + blind h for L and R
+ *     (the caller adds c_L Q / c_R Q and compresses: src/nizk/bullet.rs:86-110);
+ *   spg_bullet_fold(nk, u, u^-1) after the challenge (bullet.rs:113-118).
+ * spg_bullet_final returns the fully folded generator G_hat (compressed). n: power of two. */
+int spg_bullet_create(spg_ctx *ctx, const spg_gens *gens, size_t n, spg_bullet **out);
+int spg_bullet_lr(spg_bullet *b, size_t nk, const spg_fq *a, const spg_fq blinds[2], uint8_t out_LR[64]);
+int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_inv);
+int spg_bullet_final(spg_bullet *b, uint8_t out_G[32]);
+void spg_bullet_destroy(spg_bullet *b);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ for rows, cols, vals in polys:
     a = sp.DensePolynomial.new(ctx, hrx[rows]); b = sp.DensePolynomial.new(ctx, hry[cols]); v = sp.DensePolynomial.new(ctx, vals)
     evals.append(sp.dot(ctx, sp.vec_op(ctx, "mul", a, b), v))
 seed = np.array([1, 2, 3, 4], dtype=np.uint64)
-for it in range(2):
+for it in range(3):
     t0 = time.perf_counter()
     comm, proof = host.sparse_prove(ctx, polys, nvx, nvy, rx, ry, np.stack(evals), b"bench", b"gens_sparse_poly", seed)
     print(f"sparse commit+prove nnz=2^{lg} x {batch}: {time.perf_counter() - t0:.3f} s, proof {len(proof)} B, commitment {len(comm)} B", flush=True)

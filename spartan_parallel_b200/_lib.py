@@ -119,6 +119,10 @@ def _proto(L):
         "spg_peer_open": [P, P, PP],
         "spg_peer_close": [P],
         "spg_peer_sum": [P, P, INT, INT, SZ],
+        "spg_bullet_create": [P, P, SZ, PP],
+        "spg_bullet_lr": [P, SZ, P, P, P],
+        "spg_bullet_fold": [P, SZ, P, P],
+        "spg_bullet_final": [P, P],
         "spg_gens_upload": [P, P, SZ, PP],
         "spg_gens_from_uniform": [P, P, SZ, PP],
         "spg_poly_commit": [P, P, P, SZ, P],
@@ -132,7 +136,7 @@ def _proto(L):
         f.argtypes = args
     for name in ("spg_ctx_destroy", "spg_host_free", "spg_vec_free", "spg_r1cs_destroy", "spg_witness_destroy",
                  "spg_zmat_destroy", "spg_sc1_destroy", "spg_sc2_destroy", "spg_prodtree_destroy",
-                 "spg_cubic_destroy", "spg_gens_destroy", "spg_sparse_destroy"):
+                 "spg_cubic_destroy", "spg_gens_destroy", "spg_sparse_destroy", "spg_bullet_destroy"):
         f = getattr(L, name, None)
         if f is not None:
             f.restype = None

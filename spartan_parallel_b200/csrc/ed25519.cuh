@@ -4,9 +4,8 @@
 // and CompressedRistretto encode/decode (RFC 9496 4.3.1 / 4.3.2).
 //
 // Field elements are ten unsigned limbs in radix 2^25.5 (26/25/26/... bits): every
-// limb product fits a 64-bit accumulator without carries, i.e. one full-rate
-// IMAD.WIDE.U32 per product (the carry-chained .X form used for F_q runs at half rate
-// on B200, see profiles/r1_imad_peak.json), and the reduction by 19 is folded into the
+// limb product fits a 64-bit accumulator without carries (ptxas emits IMAD.WIDE.U32 products
+// summed by three-input IADD3 pairs), and the reduction by 19 is folded into the
 // operands. All functions take and return "reduced" elements (limbs <= 2^26 / 2^25 plus
 // a few units) so no bound bookkeeping leaks to the callers.
 //
@@ -86,6 +85,41 @@ __host__ __device__ __forceinline__ fe fe_sub(const fe &a, const fe &b) {
 __host__ __device__ __forceinline__ fe fe_neg(const fe &a) { return fe_sub(fe_zero(), a); }
 
 __host__ __device__ __forceinline__ fe fe_mul(const fe &f, const fe &g) {
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__)
+  // Host build (the transcript-side mirror, host/group.hpp): pair the limbs into five of
+  // radix 2^51 and use 64 x 64 -> 128 products: 25 multiplications instead of 100. The result
+  // is unpacked into the same reduced ten-limb form, so callers cannot tell the difference
+  // (equal modulo p; fe_tobytes canonicalises).
+  typedef unsigned __int128 u128;
+  uint64_t a[5], b[5], b19[5];
+  for (int i = 0; i < 5; i++) {
+    a[i] = (uint64_t)f.v[2 * i] + ((uint64_t)f.v[2 * i + 1] << 26);
+    b[i] = (uint64_t)g.v[2 * i] + ((uint64_t)g.v[2 * i + 1] << 26);
+    b19[i] = 19 * b[i];
+  }
+  u128 r0 = (u128)a[0] * b[0] + (u128)a[1] * b19[4] + (u128)a[2] * b19[3] + (u128)a[3] * b19[2] + (u128)a[4] * b19[1];
+  u128 r1 = (u128)a[0] * b[1] + (u128)a[1] * b[0] + (u128)a[2] * b19[4] + (u128)a[3] * b19[3] + (u128)a[4] * b19[2];
+  u128 r2 = (u128)a[0] * b[2] + (u128)a[1] * b[1] + (u128)a[2] * b[0] + (u128)a[3] * b19[4] + (u128)a[4] * b19[3];
+  u128 r3 = (u128)a[0] * b[3] + (u128)a[1] * b[2] + (u128)a[2] * b[1] + (u128)a[3] * b[0] + (u128)a[4] * b19[4];
+  u128 r4 = (u128)a[0] * b[4] + (u128)a[1] * b[3] + (u128)a[2] * b[2] + (u128)a[3] * b[1] + (u128)a[4] * b[0];
+  const uint64_t M51 = ((uint64_t)1 << 51) - 1;
+  r1 += (uint64_t)(r0 >> 51);
+  r2 += (uint64_t)(r1 >> 51);
+  r3 += (uint64_t)(r2 >> 51);
+  r4 += (uint64_t)(r3 >> 51);
+  uint64_t t0 = (uint64_t)r0 & M51, t1 = (uint64_t)r1 & M51, t2 = (uint64_t)r2 & M51, t3 = (uint64_t)r3 & M51,
+           t4 = (uint64_t)r4 & M51;
+  t0 += 19 * (uint64_t)(r4 >> 51);
+  t1 += t0 >> 51;
+  t0 &= M51;
+  const uint64_t t[5] = {t0, t1, t2, t3, t4};
+  fe r;
+  for (int i = 0; i < 5; i++) {
+    r.v[2 * i] = (uint32_t)(t[i] & SPG_FE_M26);
+    r.v[2 * i + 1] = (uint32_t)(t[i] >> 26);
+  }
+  return r;
+#else
   uint32_t g19[10], f2[10];
 #pragma unroll
   for (int i = 0; i < 10; i++) {
@@ -107,6 +141,7 @@ __host__ __device__ __forceinline__ fe fe_mul(const fe &f, const fe &g) {
     }
   }
   return fe_carry64(h);
+#endif
 }
 
 __host__ __device__ __forceinline__ fe fe_sq(const fe &f) { return fe_mul(f, f); }

@@ -241,9 +241,102 @@ int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stri
   return rc;
 }
 
+// ---------------------------------------------------------------- bullet reduction on unfolded bases
+// BulletReductionProof::prove (src/nizk/bullet.rs:72-119) with the generator fold unrolled
+// (DESIGN.md section 4): s[m] = prod over the rounds so far of (u_j or u_j^-1) by the top bits
+// of m stays on the device; a round's L and R are MSMs over the ORIGINAL bases with scalars
+//   L: [m mod nk >= nk/2] a[(m mod nk) - nk/2] s[m],   R: [m mod nk < nk/2] a[(m mod nk) + nk/2] s[m].
+__global__ void k_bullet_rows(const fq *__restrict__ a, const fq *__restrict__ s, size_t n, size_t nk,
+                              fq *__restrict__ rows) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  size_t nh = nk >> 1, j = m & (nk - 1);
+  fq sm = fq_load(s + m);
+  if (j >= nh) {
+    fq_store(rows + m, fq_mul(fq_load(a + j - nh), sm));
+    fq_store(rows + n + m, fq_zero());
+  } else {
+    fq_store(rows + m, fq_zero());
+    fq_store(rows + n + m, fq_mul(fq_load(a + nh + j), sm));
+  }
+}
+// the fold of one round applied to the scalars instead of the generators (bullet.rs:113-118)
+__global__ void k_bullet_fold(fq *__restrict__ s, size_t n, size_t nk, fq u, fq u_inv) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  fq_store(s + m, fq_mul(fq_load(s + m), (m & (nk - 1)) >= (nk >> 1) ? u : u_inv));
+}
+__global__ void k_fill_one(fq *__restrict__ s, size_t n) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < n) fq_store(s + m, fq_one());
+}
+
 }  // namespace
 
+struct spg_bullet {
+  spg_ctx *ctx = nullptr;
+  spg_gens *gens = nullptr;
+  size_t n = 0;
+  fq *s = nullptr, *rows = nullptr, *a = nullptr, *blinds = nullptr;
+};
+
 extern "C" {
+
+int spg_bullet_create(spg_ctx *ctx, const spg_gens *gens, size_t n, spg_bullet **out) {
+  SPG_CHECK(ctx && gens && out, "spg_bullet_create: null argument");
+  SPG_CHECK(n >= 2 && (n & (n - 1)) == 0 && n <= gens->n, "spg_bullet_create: n = %zu must be a power of two <= %zu generators", n,
+            gens->n);
+  spg_bullet *b = new (std::nothrow) spg_bullet();
+  if (!b) return SPG_ENOMEM;
+  b->ctx = ctx;
+  b->gens = const_cast<spg_gens *>(gens);
+  b->n = n;
+  cudaError_t e = dev_alloc(ctx, &b->s, n * sizeof(fq));
+  if (e == cudaSuccess) e = dev_alloc(ctx, &b->rows, 2 * n * sizeof(fq));
+  if (e == cudaSuccess) e = dev_alloc(ctx, &b->a, n * sizeof(fq));
+  if (e == cudaSuccess) e = dev_alloc(ctx, &b->blinds, 2 * sizeof(fq));
+  if (e != cudaSuccess) {
+    spg_bullet_destroy(b);
+    return cuda_fail(e, "spg_bullet_create", __FILE__, __LINE__);
+  }
+  SPG_LAUNCH(ctx, k_fill_one, (unsigned)((n + 255) / 256), 256, 0, b->s, n);
+  *out = b;
+  return SPG_OK;
+}
+
+int spg_bullet_lr(spg_bullet *b, size_t nk, const spg_fq *a, const spg_fq blinds[2], uint8_t out_LR[64]) {
+  SPG_CHECK(b && a && blinds && out_LR, "spg_bullet_lr: null argument");
+  SPG_CHECK(nk >= 2 && nk <= b->n && (nk & (nk - 1)) == 0, "spg_bullet_lr: bad round size %zu", nk);
+  spg_ctx *ctx = b->ctx;
+  SPG_CUDA(cudaMemcpyAsync(b->a, a, nk * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaMemcpyAsync(b->blinds, blinds, 2 * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_LAUNCH(ctx, k_bullet_rows, (unsigned)((b->n + 255) / 256), 256, 0, b->a, b->s, b->n, nk, b->rows);
+  return msm_rows(b->gens, b->rows, 2, b->n, b->n, b->blinds, out_LR);
+}
+
+int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_inv) {
+  SPG_CHECK(b && u && u_inv, "spg_bullet_fold: null argument");
+  SPG_CHECK(nk >= 2 && nk <= b->n && (nk & (nk - 1)) == 0, "spg_bullet_fold: bad round size %zu", nk);
+  fq fu, fi;
+  memcpy(&fu, u, sizeof(fq));
+  memcpy(&fi, u_inv, sizeof(fq));
+  SPG_LAUNCH(b->ctx, k_bullet_fold, (unsigned)((b->n + 255) / 256), 256, 0, b->s, b->n, nk, fu, fi);
+  return SPG_OK;
+}
+
+int spg_bullet_final(spg_bullet *b, uint8_t out_G[32]) {
+  SPG_CHECK(b && out_G, "spg_bullet_final: null argument");
+  return msm_rows(b->gens, b->s, 1, b->n, b->n, nullptr, out_G);
+}
+
+void spg_bullet_destroy(spg_bullet *b) {
+  if (!b) return;
+  dev_free(b->ctx, b->s);
+  dev_free(b->ctx, b->rows);
+  dev_free(b->ctx, b->a);
+  dev_free(b->ctx, b->blinds);
+  delete b;
+}
 
 int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, spg_gens **out) {
   SPG_CHECK(ctx && compressed && out, "spg_gens_upload: null argument");

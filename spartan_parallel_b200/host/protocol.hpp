@@ -69,7 +69,7 @@ struct UniPoly {
   std::vector<Scalar> coeffs;  // lowest degree first
   static UniPoly from_evals(const std::vector<Scalar> &e) {
     // (2_usize).to_scalar() sums ones (src/scalar/mod.rs:10-15): same value as from_u64
-    Scalar two_inv = Scalar::from_u64(2).invert();
+    static const Scalar two_inv = Scalar::from_u64(2).invert();
     UniPoly p;
     if (e.size() == 3) {
       Scalar c = e[0];
@@ -77,7 +77,7 @@ struct UniPoly {
       Scalar b = e[1] - c - a;
       p.coeffs = {c, b, a};
     } else if (e.size() == 4) {
-      Scalar six_inv = Scalar::from_u64(6).invert();
+      static const Scalar six_inv = Scalar::from_u64(6).invert();
       Scalar d = e[0];
       Scalar a = six_inv * (e[3] - e[2] - e[2] - e[2] + e[1] + e[1] + e[1] - e[0]);
       Scalar b = two_inv * (e[0] + e[0] - e[1] - e[1] - e[1] - e[1] - e[1] + e[2] + e[2] + e[2] + e[2] - e[3]);
@@ -204,12 +204,14 @@ struct DotProductProof {
   }
   static DotProductProof prove(const MultiCommitGens &g1, const MultiCommitGens &gn, ProofTranscript &t, RandomTape &tape,
                                const std::vector<Scalar> &x, const Scalar &blind_x, const std::vector<Scalar> &a,
-                               const Scalar &y, const Scalar &blind_y) {
+                               const Scalar &y, const Scalar &blind_y, const Compressed *Cx_known = nullptr) {
     t.append_protocol_name("dot product proof");
     size_t n = x.size();
     std::vector<Scalar> d = tape.random_vector("d_vec", n);
     Scalar r_delta = tape.random_scalar("r_delta"), r_beta = tape.random_scalar("r_beta");
-    t.append_point("Cx", commit(x, blind_x, gn).compress());
+    // Cx = commit(x, blind_x): the ZK sumcheck has just computed exactly this point as comm_poly
+    // (src/sumcheck.rs:1247-1253 and :1336-1347 commit the same coefficients with the same blind)
+    t.append_point("Cx", Cx_known ? *Cx_known : commit(x, blind_x, gn).compress());
     t.append_point("Cy", commit(y, blind_y, g1).compress());
     t.append_scalars("a", a);
     DotProductProof p;
@@ -340,13 +342,23 @@ struct BulletReductionProof {
   //   L = sum_m [m mod n_k >= n_k/2] a[(m mod n_k) - n_k/2] s[m] G[m] + c_L Q + blind_L H
   //   R = sum_m [m mod n_k <  n_k/2] a[(m mod n_k) + n_k/2] s[m] G[m] + c_R Q + blind_R H
   // Group elements are the same, so the compressed encodings are the reference's.
-  static std::pair<BulletReductionProof, Out> prove_device(ProofTranscript &t, const Point &Q, const DotProductProofGens &gens,
+  // `q_mul(c)` returns c * Q (the caller knows Q = r * G_1 and has a fixed-base table for G_1).
+  template <typename QMul>
+  static std::pair<BulletReductionProof, Out> prove_device(ProofTranscript &t, QMul q_mul, const DotProductProofGens &gens,
                                                            size_t n, std::vector<Scalar> a, std::vector<Scalar> b,
                                                            const Scalar &blind,
                                                            const std::vector<std::pair<Scalar, Scalar>> &blinds) {
     BulletReductionProof p;
     Scalar blind_fin = blind;
-    std::vector<Scalar> s(n, Scalar::one()), rows(2 * n);
+    // the per-base scalars s[m] and the L / R scalar rows (O(n) per round) live on the device
+    // (spg_bullet_*); the host keeps a, b (O(nk) per round) and the transcript
+    spg_bullet *st = nullptr;
+    check(spg_bullet_create(gens.ctx, gens.dev, n, &st), "spg_bullet_create");
+    struct Guard {
+      spg_bullet *s;
+      ~Guard() { spg_bullet_destroy(s); }
+    } guard{st};
+    std::vector<spg_fq> a_fq(n);
     size_t nk = n, round = 0;
     while (nk != 1) {
       size_t nh = nk / 2;
@@ -357,35 +369,29 @@ struct BulletReductionProof {
       }
       const Scalar &blind_L = blinds[round].first, &blind_R = blinds[round].second;
       round++;
-      for (size_t m = 0; m < n; m++) {
-        size_t j = m & (nk - 1);
-        if (j >= nh) {
-          rows[m] = a[j - nh] * s[m];
-          rows[n + m] = Scalar::zero();
-        } else {
-          rows[m] = Scalar::zero();
-          rows[n + m] = a[nh + j] * s[m];
-        }
-      }
-      std::vector<Scalar> bl = {blind_L, blind_R};
-      std::vector<Point> lr = device_msm(gens, rows, n, 2, &bl);
-      Compressed Lc = (lr[0] + Q * c_L).compress(), Rc = (lr[1] + Q * c_R).compress();
+      for (size_t i = 0; i < nk; i++) a_fq[i] = a[i].to_fq();
+      spg_fq bl[2] = {blind_L.to_fq(), blind_R.to_fq()};
+      Compressed lr[2];
+      check(spg_bullet_lr(st, nk, a_fq.data(), bl, (uint8_t *)lr), "spg_bullet_lr");
+      Compressed Lc = (Point::decompress(lr[0]) + q_mul(c_L)).compress(), Rc = (Point::decompress(lr[1]) + q_mul(c_R)).compress();
       t.append_point("L", Lc);
       t.append_point("R", Rc);
       Scalar u = t.challenge_scalar("u");
       Scalar u_inv = u.invert();
+      spg_fq fu = u.to_fq(), fi = u_inv.to_fq();
+      check(spg_bullet_fold(st, nk, &fu, &fi), "spg_bullet_fold");
       for (size_t i = 0; i < nh; i++) {
         a[i] = a[i] * u + u_inv * a[nh + i];
         b[i] = b[i] * u_inv + u * b[nh + i];
       }
-      for (size_t m = 0; m < n; m++) s[m] = s[m] * ((m & (nk - 1)) >= nh ? u : u_inv);
       blind_fin = blind_fin + blind_L * u * u + blind_R * u_inv * u_inv;
       p.L_vec.push_back(Lc);
       p.R_vec.push_back(Rc);
       nk = nh;
     }
-    Point G_hat = device_msm(gens, s, n, 1, nullptr)[0];
-    Out o{a[0], b[0], blind_fin, G_hat};
+    Compressed gh;
+    check(spg_bullet_final(st, gh.b), "spg_bullet_final");
+    Out o{a[0], b[0], blind_fin, Point::decompress(gh)};
     return {p, o};
   }
   void write(Writer &w) const {
@@ -425,7 +431,10 @@ struct DotProductProofLog {
     Scalar r = t.challenge_scalar("r");
     MultiCommitGens g1s = gens.gens_1.scale(r);
     Scalar blind_Gamma = blind_x + r * blind_y;
-    auto br = on_device ? BulletReductionProof::prove_device(t, g1s.G[0], gens, n, x, a, blind_Gamma, blinds)
+    // Q = r * G_1: with a fixed-base table for G_1, c * Q is the table product (c r) * G_1
+    const MultiCommitGens &g1 = gens.gens_1;
+    auto q_mul = [&](const Scalar &c) { return g1.tabs ? (*g1.tabs)[0].mul(c * r) : g1s.G[0] * c; };
+    auto br = on_device ? BulletReductionProof::prove_device(t, q_mul, gens, n, x, a, blind_Gamma, blinds)
                         : BulletReductionProof::prove(t, g1s.G[0], std::vector<Point>(gn.G.begin(), gn.G.begin() + n), gn.h,
                                                       x, a, blind_Gamma, blinds);
     const auto &o = br.second;
@@ -534,7 +543,7 @@ ZKSumcheckProof zk_sumcheck(const Scalar &claim, const Scalar &blind_claim, size
     a_sc[0] += Scalar::one();
     for (size_t k = 1; k <= deg; k++) a_ev[k] = a_ev[k - 1] * r_j;
     for (size_t k = 0; k <= deg; k++) a.push_back(w[0] * a_sc[k] + w[1] * a_ev[k]);
-    pr.proofs.push_back(DotProductProof::prove(g1, gn, t, tape, poly.coeffs, blinds_poly[j], a, target, blind));
+    pr.proofs.push_back(DotProductProof::prove(g1, gn, t, tape, poly.coeffs, blinds_poly[j], a, target, blind, &comm_poly));
     claim_per_round = ev;
     comm_claim_per_round = comm_eval;
     r_out->push_back(r_j);

@@ -1,6 +1,9 @@
 // Integer-pipe roofline microbenchmark for B200:
-//   (a) IMAD.WIDE.U32 issue rate with independent accumulators,
-//   (b) carry-chained IMAD.WIDE.U32.X (mad.lo.cc / madc.hi.cc pairs),
+//   (a) mad.wide.u32 into a 64-bit accumulator, 8 independent chains per thread. ptxas does NOT
+//       keep this fused on sm_100a: it emits IMAD.WIDE.U32 (zero addend) + IADD3 + IADD3.X
+//       (cuobjdump -sass build/imad_peak), so this is the rate of that three-instruction form,
+//   (b) carry-chained IMAD.WIDE.U32.X (mad.lo.cc / madc.hi.cc pairs), which ptxas does fuse:
+//       the form fq_mul_lazy is made of, and the multiply rate the roofline is built on,
 //   (c) in-register 256-bit Montgomery products/s with the library's fq_mul_lazy / fq_mul.
 // Prints one JSON object. Build: make tools ; run on the GPU box.
 #include <cstdio>
@@ -115,14 +118,15 @@ int main() {
     int blocks = sms * 8, threads = 256;
     float ms = time_ms([&] { k_imad_wide<8><<<blocks, threads>>>((unsigned long long *)buf, 3, 5, iters); });
     double ops = (double)blocks * threads * iters * 8;
-    printf(", \"imad_wide_per_s\": %.4g, \"imad_wide_per_clk_per_sm_at_1965\": %.2f", ops / (ms * 1e-3),
+    printf(", \"mad_wide_acc64_split_per_s\": %.4g, \"mad_wide_acc64_split_per_clk_per_sm_at_1965\": %.2f", ops / (ms * 1e-3),
            ops / (ms * 1e-3) / sms / 1.965e9);
   }
   {
     int blocks = sms * 8, threads = 256;
     float ms = time_ms([&] { k_imad_carry<<<blocks, threads>>>((unsigned int *)buf, 3, 5, iters); });
     double ops = (double)blocks * threads * iters * 4 * 4;  // wide mads (pairs)
-    printf(", \"imad_wide_carry_per_s\": %.4g", ops / (ms * 1e-3));
+    printf(", \"imad_wide_carry_per_s\": %.4g, \"imad_wide_carry_per_clk_per_sm_at_1965\": %.2f", ops / (ms * 1e-3),
+           ops / (ms * 1e-3) / sms / 1.965e9);
   }
   for (int threads : {128, 256, 512}) {
     int blocks = sms * (2048 / threads);
