@@ -372,7 +372,7 @@ def run_gpu(args):
         try:
             rd = wr = None
             seen = False
-            for ln in open(os.path.join(ROOT, "profiles", "r1c_ncu_full.txt")):
+            for ln in open(os.path.join(ROOT, "profiles", "r1d_ncu_full.txt")):
                 if ln.startswith("== launch"):
                     if seen:
                         break
@@ -383,7 +383,7 @@ def run_gpu(args):
                     wr = float(ln.split("=")[1].split()[0]) * 1e9
             if rd and wr and "k_rows<1, 2>" in dom["kernel"]:
                 roofline["traffic"] = rd + wr
-                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1c_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
+                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1d_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
         except Exception:
             pass
     cpu = cpu_baseline_sample(args, threads=1)

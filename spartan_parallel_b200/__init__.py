@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     MODE_Q,
     MODE_W,
     MODE_X,
+    BulletReduction,
     Context,
     CubicBatched,
     DensePolynomial,

@@ -621,6 +621,46 @@ def deref(ctx: Context, addr, mem: DensePolynomial) -> DensePolynomial:
     return DensePolynomial(ctx, h)
 
 
+class BulletReduction:
+    """Device side of BulletReductionProof::prove (src/nizk/bullet.rs:72-119) with the generator
+    fold unrolled onto the scalars (spg_bullet_*): ``lr`` returns the group parts of a round's L
+    and R over the original generators, ``fold`` applies the round's challenge, ``final`` returns
+    the folded generator G_hat. The caller keeps a, b, c_L * Q / c_R * Q and the transcript."""
+
+    def __init__(self, ctx: Context, gens: "MultiCommitGens", n: int):
+        self.ctx, self.n, self.gens = ctx, n, gens
+        h = C.c_void_p()
+        check(ctx.L.spg_bullet_create(ctx.h, gens.h, n, C.byref(h)), "spg_bullet_create")
+        self.h = h
+
+    def lr(self, a, blind_L, blind_R):
+        a = _fq(a)
+        bl = np.stack([_fq(blind_L).reshape(4), _fq(blind_R).reshape(4)])
+        out = np.empty(64, dtype=np.uint8)
+        check(self.ctx.L.spg_bullet_lr(self.h, a.shape[0], _ptr(a), _ptr(bl), _ptr(out)), "spg_bullet_lr")
+        return out[:32].tobytes(), out[32:].tobytes()
+
+    def fold(self, nk: int, u, u_inv):
+        u, ui = _fq(u).reshape(4), _fq(u_inv).reshape(4)
+        check(self.ctx.L.spg_bullet_fold(self.h, nk, _ptr(u), _ptr(ui)), "spg_bullet_fold")
+
+    def final(self) -> bytes:
+        out = np.empty(32, dtype=np.uint8)
+        check(self.ctx.L.spg_bullet_final(self.h, _ptr(out)), "spg_bullet_final")
+        return out.tobytes()
+
+    def free(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.ctx.L.spg_bullet_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class MultiCommitGens:
     """Device copy of MultiCommitGens (src/commitments.rs:8-67). Generator derivation
     (SHAKE256 -> from_uniform_bytes) is one-off host setup; the caller passes the n + 1

@@ -1,0 +1,40 @@
+"""CPU checks of bench.py's contract: the reference arm prints exactly ONE JSON line on stdout
+with the keys the driver reads, and the host-affinity helper degrades gracefully without NVML."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-log-x", "10", "--cpu-proofs", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sumcheck_constraints_per_sec" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["unit"] == "constraints/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_do_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                         capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bind_host_to_gpu_never_raises():
+    sys.path.insert(0, ROOT)
+    from spartan_parallel_b200 import parallel
+
+    before = os.sched_getaffinity(0)
+    info = parallel.bind_host_to_gpu(0)
+    assert info["device"] == 0
+    # no NVML / no GPU in the CPU container: nothing may have changed
+    if info.get("cpus") is None:
+        assert os.sched_getaffinity(0) == before
