@@ -24,15 +24,26 @@ struct CubicPtrs {
   const fq *C[24];
 };
 
-// blockIdx.y = triple k; partials[(k * gridDim.x + blockIdx.x) * 3 + t]
+// One round's evaluations of all triples (sumcheck.rs:297-371) with the random linear combination
+// of the triples (:369-371) and the final reduction done on the device: a 1-D grid of ntriples * gx blocks, block b works on
+// triple b / gx, scales its three sums by that triple's coefficient, and the block that draws
+// the last ticket adds everything up and publishes the three combined evaluations through the
+// mapped result slot (finish_block, common.cuh) -- one launch and no stream synchronisation per
+// round instead of eval + reduce + copy + sync. Field arithmetic is exact, so
+// sum_k c_k (sum_b partial) and sum_{k,b} c_k partial are the same canonical scalar.
+struct CubicCoeffs {
+  fq c[24];
+};
 __global__ void __launch_bounds__(CB)
-k_cubic_eval(CubicPtrs P, size_t half, fq *__restrict__ partials) {
+k_cubic_eval_rlc(const __grid_constant__ CubicPtrs P, const __grid_constant__ CubicCoeffs K, int gx, size_t half,
+                 FinishArgs fa) {
   __shared__ fq sm[3 * 32];
-  const fq *__restrict__ A = P.A[blockIdx.y];
-  const fq *__restrict__ B = P.B[blockIdx.y];
-  const fq *__restrict__ C = P.C[blockIdx.y];
+  const int k = blockIdx.x / gx, bx = blockIdx.x % gx;
+  const fq *__restrict__ A = P.A[k];
+  const fq *__restrict__ B = P.B[k];
+  const fq *__restrict__ C = P.C[k];
   fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
-  for (size_t i = (size_t)blockIdx.x * CB + threadIdx.x; i < half; i += (size_t)gridDim.x * CB) {
+  for (size_t i = (size_t)bx * CB + threadIdx.x; i < half; i += (size_t)gx * CB) {
     fq a0 = fq_load(A + i), a1 = fq_load(A + i + half);
     fq b0 = fq_load(B + i), b1 = fq_load(B + i + half);
     fq c0 = fq_load(C + i), c1 = fq_load(C + i + half);
@@ -46,23 +57,11 @@ k_cubic_eval(CubicPtrs P, size_t half, fq *__restrict__ partials) {
   }
   block_sum<3>(acc, sm);
   if (threadIdx.x == 0) {
-    size_t o = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 3;
-    partials[o] = acc[0];
-    partials[o + 1] = acc[1];
-    partials[o + 2] = acc[2];
+    fq ck = K.c[k];
+#pragma unroll
+    for (int t = 0; t < 3; t++) acc[t] = fq_mul(ck, acc[t]);
   }
-}
-
-// out[k*3 + t] = sum over blocks
-__global__ void k_cubic_reduce(const fq *__restrict__ partials, int nblocks, fq *__restrict__ out) {
-  int k = blockIdx.x;
-  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
-  for (int b = threadIdx.x; b < nblocks; b += 32)
-    for (int t = 0; t < 3; t++) acc[t] = fq_add(acc[t], partials[((size_t)k * nblocks + b) * 3 + t]);
-  for (int t = 0; t < 3; t++) {
-    acc[t] = fq_warp_sum(acc[t]);
-    if (threadIdx.x == 0) out[k * 3 + t] = acc[t];
-  }
+  finish_block<3>(fa, acc, sm);
 }
 
 struct BindPtrs {
@@ -156,7 +155,6 @@ struct spg_cubic {
   std::vector<hfq> coeffs;
   size_t len = 0;
   bool evaluated = false;
-  fq *d_evals = nullptr;  // [ntriples][3]
 };
 
 extern "C" {
@@ -265,10 +263,6 @@ int spg_cubic_create(spg_ctx *ctx, size_t npar, spg_vec *const *A_par, spg_vec *
   }
   s->len = len;
   for (size_t i = 0; i < npar + nseq; i++) s->coeffs.push_back(hfq_from(coeffs[i]));
-  if (dev_alloc(ctx, &s->d_evals, 24 * 3 * sizeof(fq)) != cudaSuccess) {
-    delete s;
-    return cuda_fail(cudaGetLastError(), "cudaMalloc(cubic)", __FILE__, __LINE__);
-  }
   *out = s;
   return SPG_OK;
 }
@@ -294,24 +288,18 @@ int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]) {
   }
   int gx = grid_for(ctx, half, CB, 2);
   if (gx > 1024) gx = 1024;
-  SPG_TRY(ensure_partials(ctx, (size_t)gx * nt * 3));
-  dim3 grid(gx, (unsigned)nt);
-  ctx->next_units = 192.0 * (double)half * (double)nt;
-  SPG_LAUNCH(ctx, k_cubic_eval, grid, CB, 0, P, half, ctx->d_partials);
-  SPG_LAUNCH(ctx, k_cubic_reduce, (unsigned)nt, 32, 0, ctx->d_partials, gx, s->d_evals);
-  std::vector<fq> h(nt * 3);
-  SPG_CUDA(cudaMemcpyAsync(h.data(), s->d_evals, nt * 3 * sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  // evals_combined_t = sum_k evals[k].t * coeffs[k]  (sumcheck.rs:369-371)
-  for (int t = 0; t < 3; t++) {
-    hfq acc = hfq_zero();
-    for (size_t k = 0; k < nt; k++) {
-      hfq v;
-      memcpy(&v, &h[k * 3 + t], 32);
-      acc = hfq_add(acc, hfq_mul(v, s->coeffs[k]));
-    }
-    e[t] = hfq_to(acc);
+  if ((size_t)gx * nt > 4096) gx = (int)(4096 / nt);  // keep the in-kernel final reduction (finish_args)
+  size_t nblocks = (size_t)gx * nt;
+  SPG_TRY(ensure_partials(ctx, nblocks * 3));
+  CubicCoeffs K;
+  for (size_t k = 0; k < nt; k++) {
+    spg_fq c = hfq_to(s->coeffs[k]);
+    memcpy(&K.c[k], &c, sizeof(fq));
   }
+  ctx->next_units = 192.0 * (double)half * (double)nt;
+  FinishArgs fa = finish_args(ctx, nblocks);
+  SPG_LAUNCH(ctx, k_cubic_eval_rlc, (unsigned)nblocks, CB, 0, P, K, gx, half, fa);
+  SPG_TRY(finish_result(ctx, fa, nblocks, 3, e));
   s->evaluated = true;
   return SPG_OK;
 }
@@ -370,7 +358,6 @@ int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
 
 void spg_cubic_destroy(spg_cubic *s) {
   if (!s) return;
-  if (s->d_evals) dev_free(s->ctx, s->d_evals);
   delete s;
 }
 

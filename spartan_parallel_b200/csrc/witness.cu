@@ -194,6 +194,15 @@ int spg_perm_scan(spg_ctx *ctx, size_t n, const size_t *seg_len, size_t n_seg, c
   auto fits = [&](const spg_vec *w, size_t off, size_t stride) { return off + (n - 1) * stride < w->n; };
   SPG_CHECK(fits(v, v_off, v_stride) && fits(x, x_off, x_stride) && fits(D, D_off, D_stride) && fits(pi, pi_off, pi_stride),
             "spg_perm_scan: a strided view runs past its vector");
+  // an output column must not coincide with an input column (the apply pass reads v[q+1] and
+  // x[q] of rows it has not written yet, but only from columns it never writes)
+  auto same = [](const spg_vec *a, size_t ao, size_t as, const spg_vec *b, size_t bo, size_t bs) {
+    return a->d == b->d && as == bs && ao % as == bo % bs;
+  };
+  SPG_CHECK(!same(D, D_off, D_stride, v, v_off, v_stride) && !same(D, D_off, D_stride, x, x_off, x_stride) &&
+                !same(pi, pi_off, pi_stride, v, v_off, v_stride) && !same(pi, pi_off, pi_stride, x, x_off, x_stride) &&
+                !same(D, D_off, D_stride, pi, pi_off, pi_stride),
+            "spg_perm_scan: output columns must differ from the input columns and from each other");
   size_t nchunks = (n + PS_CHUNK - 1) / PS_CHUNK;
   unsigned char *flags = nullptr;
   unsigned long long *d_ends = nullptr;

@@ -82,3 +82,5 @@ def test_bad_segments_rejected(ctx):
     d = sp.DensePolynomial.new(ctx, make_table(8, 1))
     with pytest.raises(sp.SpgError):
         api.perm_scan(ctx, d, [4, 0, 4])
+    with pytest.raises(sp.SpgError):  # D would overwrite the x column it is computed from
+        api.perm_scan(ctx, d, [8], x_col=1, d_col=1)
