@@ -360,8 +360,15 @@ struct BulletReductionProof {
     } guard{st};
     std::vector<spg_fq> a_fq(n);
     size_t nk = n, round = 0;
+    static const bool trace = getenv("SPH_TRACE") != nullptr;
+    double t_dev = 0, t_grp = 0, t_fold = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count();
+    };
     while (nk != 1) {
       size_t nh = nk / 2;
+      auto t0 = now();
       Scalar c_L, c_R;
       for (size_t i = 0; i < nh; i++) {
         c_L += a[i] * b[nh + i];
@@ -372,12 +379,15 @@ struct BulletReductionProof {
       for (size_t i = 0; i < nk; i++) a_fq[i] = a[i].to_fq();
       spg_fq bl[2] = {blind_L.to_fq(), blind_R.to_fq()};
       Compressed lr[2];
+      auto t1 = now();
       check(spg_bullet_lr(st, nk, a_fq.data(), bl, (uint8_t *)lr), "spg_bullet_lr");
+      auto t2 = now();
       Compressed Lc = (Point::decompress(lr[0]) + q_mul(c_L)).compress(), Rc = (Point::decompress(lr[1]) + q_mul(c_R)).compress();
       t.append_point("L", Lc);
       t.append_point("R", Rc);
       Scalar u = t.challenge_scalar("u");
       Scalar u_inv = u.invert();
+      auto t3 = now();
       spg_fq fu = u.to_fq(), fi = u_inv.to_fq();
       check(spg_bullet_fold(st, nk, &fu, &fi), "spg_bullet_fold");
       for (size_t i = 0; i < nh; i++) {
@@ -388,9 +398,17 @@ struct BulletReductionProof {
       p.L_vec.push_back(Lc);
       p.R_vec.push_back(Rc);
       nk = nh;
+      auto t4 = now();
+      t_fold += ms(t0, t1) + ms(t3, t4);
+      t_dev += ms(t1, t2);
+      t_grp += ms(t2, t3);
     }
     Compressed gh;
+    auto t5 = now();
     check(spg_bullet_final(st, gh.b), "spg_bullet_final");
+    if (trace)
+      fprintf(stderr, "[sph]   bullet n=%zu: device L/R %.3f ms, host group+transcript %.3f ms, host scalar folds %.3f ms, G_hat %.3f ms\n",
+              n, t_dev, t_grp, t_fold, ms(t5, now()));
     Out o{a[0], b[0], blind_fin, Point::decompress(gh)};
     return {p, o};
   }
@@ -584,6 +602,7 @@ inline std::vector<Scalar> eq_evals_host(const std::vector<Scalar> &r) {  // EqP
 inline std::vector<DotProductProofLog> prove_batched_instances_disjoint_rounds(
     spg_ctx *ctx, const std::vector<PolyRef> &polys, const std::vector<Scalar> &rq, const std::vector<Scalar> &ry,
     const std::vector<Scalar> &Zr, const DotProductProofGens &gens, ProofTranscript &t, RandomTape &tape) {
+  Trace tr;
   t.append_protocol_name("polynomial evaluation proof");
   std::map<std::pair<size_t, size_t>, size_t> index_map;
   std::vector<std::vector<Scalar>> LZ_list, L_list, R_list;
@@ -632,9 +651,11 @@ inline std::vector<DotProductProofLog> prove_batched_instances_disjoint_rounds(
       R_list.push_back(R);
     }
   }
+  tr.lap("  openings: bound(L) + eq tables");
   std::vector<DotProductProofLog> proofs;
   for (size_t i = 0; i < LZ_list.size(); i++)
     proofs.push_back(DotProductProofLog::prove(gens, t, tape, LZ_list[i], Scalar::zero(), R_list[i], Zc_list[i], Scalar::zero()));
+  tr.lap("  openings: dot-product proofs");
   return proofs;
 }
 
