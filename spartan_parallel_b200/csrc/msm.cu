@@ -104,20 +104,36 @@ k_msm_partial(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_str
 }
 
 // few rows, many bases (the L / R vectors of a bullet reduction round, Cx of an opening):
-// one thread per base, a block sums its 128 points through shared memory.
-// grid (ceil(R / 128), L); partial[i * gridDim.x + blockIdx.x]
+// WIDE_SPLIT threads per base, each adding a quarter of the base's windows (the additions of one
+// scalar are a dependent chain: 8 instead of 32 in a row), a block sums its 128 points through
+// shared memory. grid (ceil(R / WIDE_BASES), L); partial[i * gridDim.x + blockIdx.x]
+constexpr int WIDE_SPLIT = 4, WIDE_BASES = 128 / WIDE_SPLIT;
 template <int C>
 __global__ void __launch_bounds__(128)
 k_msm_wide(const fq *__restrict__ scalars, size_t R, size_t row_stride, const ge_cached *__restrict__ table,
            ge *__restrict__ partial) {
   constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
+  constexpr int PER = (WINS + WIDE_SPLIT - 1) / WIDE_SPLIT;
   __shared__ ge sm[64];
   size_t i = blockIdx.y;
-  size_t j = (size_t)blockIdx.x * 128 + threadIdx.x;
+  size_t j = (size_t)blockIdx.x * WIDE_BASES + threadIdx.x / WIDE_SPLIT;
+  const int part = threadIdx.x % WIDE_SPLIT;
   ge acc = ge_identity();
   if (j < R) {
-    fq s = fq_load(scalars + i * row_stride + j);
-    if (!fq_is_zero(s)) accumulate_scalar<C>(acc, s, table + j * WINS * ENT);
+    fq sm_ = fq_load(scalars + i * row_stride + j);
+    if (!fq_is_zero(sm_)) {
+      // leave Montgomery form: the group multiplies by the integer value (src/scalar/mod.rs:32-36)
+      fq s = fq_from_mont(sm_);
+      const ge_cached *__restrict__ tj = table + j * WINS * ENT;
+#pragma unroll 1
+      for (int w = part * PER; w < (part + 1) * PER && w < WINS; w++) {
+        int bit = C * w;
+        uint32_t d = (s.v[bit >> 5] >> (bit & 31));
+        if ((bit & 31) + C > 32 && (bit >> 5) < 7) d |= s.v[(bit >> 5) + 1] << (32 - (bit & 31));
+        d &= (1u << C) - 1;
+        if (d) acc = ge_add(acc, tj[(size_t)w * ENT + (d - 1)]);
+      }
+    }
   }
   for (int half = 64; half >= 1; half >>= 1) {
     if ((int)threadIdx.x >= half && (int)threadIdx.x < 2 * half) sm[threadIdx.x - half] = acc;
@@ -232,7 +248,7 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
             uint8_t *d_out) {
   spg_ctx *ctx = g->ctx;
   if (L <= 16 && R >= 256) {
-    size_t nblk = (R + 127) / 128;
+    size_t nblk = (R + WIDE_BASES - 1) / WIDE_BASES;
     ge *partial = nullptr;
     SPG_CUDA(dev_alloc(ctx, &partial, L * nblk * sizeof(ge)));
     dim3 grid((unsigned)nblk, (unsigned)L);
@@ -266,14 +282,22 @@ int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stri
   SPG_TRY(ensure_table(g, R));
   uint8_t *d_out = nullptr;
   spg_ctx *ctx = g->ctx;
-  SPG_CUDA(dev_alloc(ctx, &d_out, L * 32));
+  // a handful of points: the finish kernel writes them straight into the context's mapped result
+  // page (run_msm ends with a stream synchronise), no device buffer and no copy call
+  const bool mapped = L * 32 <= 48 * sizeof(fq);
+  if (mapped) d_out = reinterpret_cast<uint8_t *>(ctx->d_result);
+  else SPG_CUDA(dev_alloc(ctx, &d_out, L * 32));
   int rc = g->tab_C == 8 ? run_msm<8>(g, scalars, L, R, row_stride, d_blinds, d_out)
                          : run_msm<4>(g, scalars, L, R, row_stride, d_blinds, d_out);
   if (rc == SPG_OK) {
-    cudaError_t e = cudaMemcpy(host_out, d_out, L * 32, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = cuda_fail(e, "commit download", __FILE__, __LINE__);
+    if (mapped) {
+      memcpy(host_out, ctx->h_result, L * 32);
+    } else {
+      cudaError_t e = cudaMemcpy(host_out, d_out, L * 32, cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) rc = cuda_fail(e, "commit download", __FILE__, __LINE__);
+    }
   }
-  dev_free(ctx, d_out);
+  if (!mapped) dev_free(ctx, d_out);
   return rc;
 }
 
@@ -313,7 +337,9 @@ struct spg_bullet {
   spg_ctx *ctx = nullptr;
   spg_gens *gens = nullptr;
   size_t n = 0;
-  fq *s = nullptr, *rows = nullptr, *a = nullptr, *blinds = nullptr;
+  fq *s = nullptr, *rows = nullptr;
+  fq *in = nullptr;       // device: [blind_L, blind_R, a_0 .. a_{nk-1}]
+  fq *h_in = nullptr;     // pinned staging of the same layout: one copy per round
 };
 
 extern "C" {
@@ -329,8 +355,8 @@ int spg_bullet_create(spg_ctx *ctx, const spg_gens *gens, size_t n, spg_bullet *
   b->n = n;
   cudaError_t e = dev_alloc(ctx, &b->s, n * sizeof(fq));
   if (e == cudaSuccess) e = dev_alloc(ctx, &b->rows, 2 * n * sizeof(fq));
-  if (e == cudaSuccess) e = dev_alloc(ctx, &b->a, n * sizeof(fq));
-  if (e == cudaSuccess) e = dev_alloc(ctx, &b->blinds, 2 * sizeof(fq));
+  if (e == cudaSuccess) e = dev_alloc(ctx, &b->in, (n + 2) * sizeof(fq));
+  if (e == cudaSuccess) e = cudaHostAlloc(&b->h_in, (n + 2) * sizeof(fq), cudaHostAllocDefault);
   if (e != cudaSuccess) {
     spg_bullet_destroy(b);
     return cuda_fail(e, "spg_bullet_create", __FILE__, __LINE__);
@@ -344,10 +370,12 @@ int spg_bullet_lr(spg_bullet *b, size_t nk, const spg_fq *a, const spg_fq blinds
   SPG_CHECK(b && a && blinds && out_LR, "spg_bullet_lr: null argument");
   SPG_CHECK(nk >= 2 && nk <= b->n && (nk & (nk - 1)) == 0, "spg_bullet_lr: bad round size %zu", nk);
   spg_ctx *ctx = b->ctx;
-  SPG_CUDA(cudaMemcpyAsync(b->a, a, nk * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
-  SPG_CUDA(cudaMemcpyAsync(b->blinds, blinds, 2 * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
-  SPG_LAUNCH(ctx, k_bullet_rows, (unsigned)((b->n + 255) / 256), 256, 0, b->a, b->s, b->n, nk, b->rows);
-  return msm_rows(b->gens, b->rows, 2, b->n, b->n, b->blinds, out_LR);
+  // (the previous round ended with a stream synchronise, so the staging buffer is free again)
+  memcpy(b->h_in, blinds, 2 * sizeof(fq));
+  memcpy(b->h_in + 2, a, nk * sizeof(fq));
+  SPG_CUDA(cudaMemcpyAsync(b->in, b->h_in, (nk + 2) * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_LAUNCH(ctx, k_bullet_rows, (unsigned)((b->n + 255) / 256), 256, 0, b->in + 2, b->s, b->n, nk, b->rows);
+  return msm_rows(b->gens, b->rows, 2, b->n, b->n, b->in, out_LR);
 }
 
 int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_inv) {
@@ -369,8 +397,8 @@ void spg_bullet_destroy(spg_bullet *b) {
   if (!b) return;
   dev_free(b->ctx, b->s);
   dev_free(b->ctx, b->rows);
-  dev_free(b->ctx, b->a);
-  dev_free(b->ctx, b->blinds);
+  dev_free(b->ctx, b->in);
+  if (b->h_in) cudaFreeHost(b->h_in);
   delete b;
 }
 
