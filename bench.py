@@ -361,7 +361,7 @@ def run_gpu(args):
                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms,
                     "launches_per_step": dom["launches"] / args.steps,
                     "share_of_step": dom["total_ms"] / ms_dev}
-        if "k_rows<1, 2>" in dom["kernel"]:
+        if "k_rows_rolled" in dom["kernel"]:
             # fused bind + eval item: 576 algorithmic bytes, 10 Montgomery products
             # (6 binds + 2 products + 2 eq-weighted accumulations)
             mm = dom["units"] / 576.0 * 10.0 / (dom["total_ms"] * 1e-3)
@@ -372,18 +372,18 @@ def run_gpu(args):
         try:
             rd = wr = None
             seen = False
-            for ln in open(os.path.join(ROOT, "profiles", "r1d_ncu_full.txt")):
+            for ln in open(os.path.join(ROOT, "profiles", "r1e_ncu_full.txt")):
                 if ln.startswith("== launch"):
                     if seen:
                         break
-                    seen = "k_rows<1, 2>" in ln
+                    seen = "k_rows_rolled" in ln
                 elif seen and ln.startswith("dram__bytes_read.sum ="):
                     rd = float(ln.split("=")[1].split()[0]) * 1e9
                 elif seen and ln.startswith("dram__bytes_write.sum ="):
                     wr = float(ln.split("=")[1].split()[0]) * 1e9
-            if rd and wr and "k_rows<1, 2>" in dom["kernel"]:
+            if rd and wr and "k_rows_rolled" in dom["kernel"]:
                 roofline["traffic"] = rd + wr
-                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1d_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
+                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1e_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
         except Exception:
             pass
     cpu = cpu_baseline_sample(args, threads=1)

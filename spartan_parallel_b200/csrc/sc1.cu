@@ -141,62 +141,36 @@ k_quad_bind_eval(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq 
 // One block = one tile of one row, so the row weight RW[row] is applied once per block
 // (after the block reduction) instead of once per item, and all arithmetic between the
 // loads and the stores runs in the lazy range [0, 2q).
-//   FUSED = 0: evaluation only; NE = 3 points t = 0, 1, 2 (first round: also yields the true
-//              claim) or NE = 2 points t = 0, 2 when the caller supplied the claim
-//              (spg_sc1_set_claim)
-//   FUSED = 1: bind with r, then evaluate the bound pair at t = 0, 2. The round polynomial is
-//              l_j(t) * G(t) with G quadratic, so G(0), G(2) and the running claim determine
-//              it (the host side solves for G(1), G(3); exact field arithmetic, see
-//              spg_sc1_round_eval).
+//   k_rows<NE>:    evaluation only; NE = 3 points t = 0, 1, 2 (first round: also yields the true
+//                  claim) or NE = 2 points t = 0, 2 when the caller supplied the claim
+//                  (spg_sc1_set_claim)
+//   k_rows_rolled: bind with r, then evaluate the bound pair at t = 0, 2. The round polynomial is
+//                  l_j(t) * G(t) with G quadratic, so G(0), G(2) and the running claim determine
+//                  it (the host side solves for G(1), G(3); exact field arithmetic, see
+//                  spg_sc1_round_eval).
 constexpr int ROWS_LOG_TILE = 10;  // 1024 items per tile = 8 per thread at 128 threads
 
-template <int FUSED, int NE>
+template <int NE>
 __global__ void __launch_bounds__(RB, SPG_MINB)
-k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
-       fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
-       int nseg, const __grid_constant__ SegPack pk, fq r, const fq *__restrict__ RW, const fq *__restrict__ S, FinishArgs fa) {
-  static_assert(NE == 2 || (NE == 3 && !FUSED), "k_rows: 2 points, or 3 for the evaluation-only form");
+k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2, const Seg *__restrict__ segs,
+       int nseg, const __grid_constant__ SegPack pk, const fq *__restrict__ RW, const fq *__restrict__ S, FinishArgs fa) {
+  static_assert(NE == 2 || NE == 3, "k_rows: 2 or 3 evaluation points");
   __shared__ fq sm[NE * 32];
   unsigned long long tile = blockIdx.x;
   Seg sg = pick_seg(pk, segs, nseg, tile);
   unsigned long long tl = tile - sg.item_start;
   unsigned long long row = tl >> sg.log_tiles, tr = tl & ((1ull << sg.log_tiles) - 1);
-  unsigned int li = sg.log_len - (FUSED ? 2 : 1);
+  unsigned int li = sg.log_len - 1;
   unsigned long long items_row = 1ull << li, tile_items = items_row >> sg.log_tiles;
   unsigned long long base = tr * tile_items;
   fq acc[NE];
 #pragma unroll
   for (int k = 0; k < NE; k++) acc[k] = fq_zero();
   for (unsigned long long it = base + threadIdx.x; it < base + tile_items; it += RB) {
-    unsigned long long local = row * items_row + it;
-    fq a0, a1, b0, b1, c0, c1;
-    if (FUSED) {
-      unsigned long long idx = sg.in_off + 4 * local, o = sg.out_off + 2 * local;
-      fq lo, hi;
-      lo = fq_load_stream(T0 + idx); hi = fq_load_stream(T0 + idx + 1);
-      a0 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
-      lo = fq_load_stream(T0 + idx + 2); hi = fq_load_stream(T0 + idx + 3);
-      a1 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
-      a0 = fq_canon(a0); a1 = fq_canon(a1);
-      fq_store(O0 + o, a0); fq_store(O0 + o + 1, a1);
-      lo = fq_load_stream(T1 + idx); hi = fq_load_stream(T1 + idx + 1);
-      b0 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
-      lo = fq_load_stream(T1 + idx + 2); hi = fq_load_stream(T1 + idx + 3);
-      b1 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
-      b0 = fq_canon(b0); b1 = fq_canon(b1);
-      fq_store(O1 + o, b0); fq_store(O1 + o + 1, b1);
-      lo = fq_load_stream(T2 + idx); hi = fq_load_stream(T2 + idx + 1);
-      c0 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
-      lo = fq_load_stream(T2 + idx + 2); hi = fq_load_stream(T2 + idx + 3);
-      c1 = fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo)));
-      c0 = fq_canon(c0); c1 = fq_canon(c1);
-      fq_store(O2 + o, c0); fq_store(O2 + o + 1, c1);
-    } else {
-      unsigned long long idx = sg.in_off + 2 * local;
-      a0 = fq_load_stream(T0 + idx); a1 = fq_load_stream(T0 + idx + 1);
-      b0 = fq_load_stream(T1 + idx); b1 = fq_load_stream(T1 + idx + 1);
-      c0 = fq_load_stream(T2 + idx); c1 = fq_load_stream(T2 + idx + 1);
-    }
+    unsigned long long idx = sg.in_off + 2 * (row * items_row + it);
+    fq a0 = fq_load_stream(T0 + idx), a1 = fq_load_stream(T0 + idx + 1);
+    fq b0 = fq_load_stream(T1 + idx), b1 = fq_load_stream(T1 + idx + 1);
+    fq c0 = fq_load_stream(T2 + idx), c1 = fq_load_stream(T2 + idx + 1);
     fq w = fq_load(S + it);
     // t = 0
     acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a0, b0), c0)));
@@ -219,10 +193,88 @@ k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restric
   finish_block<NE>(fa, acc, sm);
 }
 
+// Fused bind_j + eval_{j+1} with ONE copy of the bind code: the six binds of an item (three
+// tables x two pairs) run as a rolled loop whose body -- one Montgomery product, the lazy add /
+// sub, the canonicalisation and the store -- is about 5 KB of SASS, and the bound scalars are
+// handed to the evaluation part through thread-private shared-memory slots. Fully unrolled (the
+// first form of this kernel) the item loop is ~45 KB, more than the 32 KB instruction cache (ncu:
+// 22 % of its stall samples were no_instructions) and measured 5.99 ms per pass at 2^20 x 64; this
+// loop is 21 KB and takes 5.69 ms. The loads of the next (table, pair) are issued
+// before the current product, across items too, so the rolled loop does not expose one DRAM
+// latency per bind.
+__global__ void __launch_bounds__(RB, SPG_MINB)
+k_rows_rolled(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
+              fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
+              int nseg, const __grid_constant__ SegPack pk, fq r, const fq *__restrict__ RW, const fq *__restrict__ S,
+              FinishArgs fa) {
+  extern __shared__ __align__(32) unsigned char stash_raw[];
+  fq *stash = reinterpret_cast<fq *>(stash_raw) + threadIdx.x;  // slot k at stash[k * RB]
+  __shared__ fq sm[2 * 32];
+  unsigned long long tile = blockIdx.x;
+  Seg sg = pick_seg(pk, segs, nseg, tile);
+  unsigned long long tl = tile - sg.item_start;
+  unsigned long long row = tl >> sg.log_tiles, tr = tl & ((1ull << sg.log_tiles) - 1);
+  unsigned int li = sg.log_len - 2;
+  unsigned long long items_row = 1ull << li, tile_items = items_row >> sg.log_tiles;
+  unsigned long long base = tr * tile_items, end = base + tile_items;
+  fq acc[2] = {fq_zero(), fq_zero()};
+  unsigned long long it = base + threadIdx.x;
+  fq lo, hi;
+  if (it < end) {
+    unsigned long long idx = sg.in_off + 4 * (row * items_row + it);
+    lo = fq_load_stream(T0 + idx);
+    hi = fq_load_stream(T0 + idx + 1);
+  }
+  for (; it < end; it += RB) {
+    unsigned long long local = row * items_row + it;
+    unsigned long long idx = sg.in_off + 4 * local, o = sg.out_off + 2 * local;
+    const bool more = it + RB < end;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+      // prefetch the operands of bind k + 1 (or of the next item's first bind)
+      fq nlo, nhi;
+      {
+        int kn = k == 5 ? 0 : k + 1;
+        unsigned long long nidx = (k == 5 ? idx + 4 * (unsigned long long)RB : idx) + 2 * (kn & 1);
+        const fq *Tn = (kn >> 1) == 0 ? T0 : ((kn >> 1) == 1 ? T1 : T2);
+        if (k < 5 || more) {
+          nlo = fq_load_stream(Tn + nidx);
+          nhi = fq_load_stream(Tn + nidx + 1);
+        }
+      }
+      fq v = fq_canon(fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo))));
+      fq *To = (k >> 1) == 0 ? O0 : ((k >> 1) == 1 ? O1 : O2);
+      fq_store(To + o + (k & 1), v);
+      stash[k * RB] = v;
+      lo = nlo;
+      hi = nhi;
+    }
+    fq w = fq_load(S + it);
+    {
+      fq a0 = stash[0], b0 = stash[2 * RB], c0 = stash[4 * RB];
+      acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a0, b0), c0)));
+      fq a1 = stash[RB], b1 = stash[3 * RB], c1 = stash[5 * RB];
+      fq a2 = fq_add_lazy(a1, fq_sub_lazy(a1, a0));
+      fq b2 = fq_add_lazy(b1, fq_sub_lazy(b1, b0));
+      fq c2 = fq_add_lazy(c1, fq_sub_lazy(c1, c0));
+      acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a2, b2), c2)));
+    }
+  }
+  acc[0] = fq_canon(acc[0]);
+  acc[1] = fq_canon(acc[1]);
+  block_sum<2>(acc, sm);
+  if (threadIdx.x == 0) {
+    fq rw = RW[sg.rw_off + row];
+    acc[0] = fq_mul(rw, acc[0]);
+    acc[1] = fq_mul(rw, acc[1]);
+  }
+  finish_block<2>(fa, acc, sm);
+}
+
 // First round with the SpMV fused in (multiply_vec_block + round 0 in one pass): the block
 // computes Az, Bz, Cz of its tile straight from the witness sections, writes them for the
 // next round and evaluates the round polynomial on the fly, so the three tables are written
-// once and not read back (k_spmv3 + k_rows<0> wrote 96 N bytes and read them again).
+// once and not read back (k_spmv3 + k_rows<2> wrote 96 N bytes and read them again).
 struct SpmvSegs {
   CsxView3 mats[SEG_INLINE];
   const SecView *secs[SEG_INLINE];
@@ -495,6 +547,8 @@ size_t phase_round(const spg_sc1 *s, size_t round) {
   int ph = phase_of(s, round);
   return ph == 0 ? round : (ph == 1 ? round - s->nx : round - s->nx - s->nq);
 }
+
+constexpr size_t ROWS_STASH_BYTES = 6 * RB * sizeof(fq);  // k_rows_rolled: six bound scalars per thread
 
 int sc1_alloc_common(spg_ctx *ctx, size_t P, const size_t *num_proofs, size_t max_num_proofs,
                      const size_t *num_cons, size_t max_num_cons, const spg_fq *tau_p,
@@ -820,7 +874,6 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       build_tile_segs(s, phase, 0, &tiles, &out_total);
       SPG_TRY(upload_segs(s));
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
-      fq zero = fq{};
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;
@@ -834,8 +887,8 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
         s->pend_z = nullptr;
       } else {
         fa = finish_args(ctx, tiles);
-        SPG_LAUNCH(ctx, (k_rows<0, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, fa);
+        SPG_LAUNCH(ctx, k_rows<2>, (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                   s->d_segs, (int)s->P, make_pack(s->segs), RW, S, fa);
       }
       spg_fq tmp[2];
       SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));
@@ -875,7 +928,6 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       build_tile_segs(s, phase, 0, &tiles, &out_total);
       SPG_TRY(upload_segs(s));
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 3));
-      fq zero = fq{};
       double pairs = 0;
       for (size_t p = 0; p < s->P; p++) pairs += (double)((phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - 1));
       ctx->next_units = 192.0 * pairs;  // 2 scalars x 3 tables read per pair
@@ -888,8 +940,8 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
         s->pend_z = nullptr;
       } else {
         fa = finish_args(ctx, tiles);
-        SPG_LAUNCH(ctx, (k_rows<0, 3>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                   (fq *)nullptr, (fq *)nullptr, (fq *)nullptr, s->d_segs, (int)s->P, make_pack(s->segs), zero, RW, S, fa);
+        SPG_LAUNCH(ctx, k_rows<3>, (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+                   s->d_segs, (int)s->P, make_pack(s->segs), RW, S, fa);
       }
       spg_fq tmp[3];
       SPG_TRY(finish_result(ctx, fa, tiles, 3, tmp));
@@ -981,8 +1033,9 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
       ctx->next_units = 288.0 * (double)out_total;  // per bound pair: 4 read + 2 written scalars x 3 tables
       FinishArgs fa = finish_args(ctx, tiles);
-      SPG_LAUNCH(ctx, (k_rows<1, 2>), (unsigned)tiles, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
-                 s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P, make_pack(s->segs), rr, RW, Snext, fa);
+      SPG_LAUNCH(ctx, k_rows_rolled, (unsigned)tiles, RB, ROWS_STASH_BYTES, s->tab[s->cur][0], s->tab[s->cur][1],
+                 s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P,
+                 make_pack(s->segs), rr, RW, Snext, fa);
       spg_fq tmp[2];
       SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));
       s->cached[0] = hfq_from(tmp[0]);
