@@ -84,6 +84,18 @@ __device__ __forceinline__ RowHead3 spmv_head3(const CsxView3 &V, unsigned int x
   for (int m = 0; m < 3; m++) h.c[m] = h.e0[m] < h.e1[m] ? V.M[m].idx[h.e0[m]] : 0u;
   return h;
 }
+// Everything a row needs beyond "one entry with a unit coefficient": the product with the first
+// coefficient and the remaining entries. Out of line on purpose (COLD = true): inlined six times
+// into the fused first-round kernel these loops, each with its own Montgomery product, are
+// ~40 KB of SASS threaded through the hot path of a kernel whose common case (R1CS rows are
+// mostly single unit entries per matrix) never executes them.
+static __device__ __noinline__ fq spmv_row_rest(const CsxView M, uint32_t e0, uint32_t e1, uint32_t c0, fq first,
+                                         const SecView *__restrict__ secs, size_t q, unsigned int log_ymax) {
+  if (!(c0 & UNIT_FLAG)) first = fq_mul(fq_load(M.val + e0), first);
+  return spmv_row_tail(M, e0 + 1, e1, first, secs, q, log_ymax);
+}
+
+template <bool COLD = false>
 __device__ __forceinline__ void spmv_finish3(const CsxView3 &V, const RowHead3 &h, const SecView *__restrict__ secs,
                                              size_t q, unsigned int log_ymax, fq (&out)[3]) {
   const uint32_t ymask = (1u << log_ymax) - 1;
@@ -94,8 +106,13 @@ __device__ __forceinline__ void spmv_finish3(const CsxView3 &V, const RowHead3 &
   }
 #pragma unroll
   for (int m = 0; m < 3; m++) {
-    if (h.e0[m] < h.e1[m] && !(h.c[m] & UNIT_FLAG)) out[m] = fq_mul(fq_load(V.M[m].val + h.e0[m]), out[m]);
-    if (h.e0[m] + 1 < h.e1[m]) out[m] = spmv_row_tail(V.M[m], h.e0[m] + 1, h.e1[m], out[m], secs, q, log_ymax);
+    if (COLD) {
+      if (h.e0[m] < h.e1[m] && (!(h.c[m] & UNIT_FLAG) || h.e0[m] + 1 < h.e1[m]))
+        out[m] = spmv_row_rest(V.M[m], h.e0[m], h.e1[m], h.c[m], out[m], secs, q, log_ymax);
+    } else {
+      if (h.e0[m] < h.e1[m] && !(h.c[m] & UNIT_FLAG)) out[m] = fq_mul(fq_load(V.M[m].val + h.e0[m]), out[m]);
+      if (h.e0[m] + 1 < h.e1[m]) out[m] = spmv_row_tail(V.M[m], h.e0[m] + 1, h.e1[m], out[m], secs, q, log_ymax);
+    }
   }
 }
 __device__ __forceinline__ void spmv_rows3(const CsxView3 &V, unsigned int x, const SecView *__restrict__ secs,

@@ -280,7 +280,7 @@ struct SpmvSegs {
   const SecView *secs[SEG_INLINE];
 };
 
-template <int NE>
+template <int NE, bool COLD = false>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__restrict__ O0, fq *__restrict__ O1,
             fq *__restrict__ O2, int nseg, const __grid_constant__ SegPack pk, const fq *__restrict__ RW,
@@ -321,8 +321,8 @@ k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__re
   for (; it < base + tile_items; it += RB) {
     unsigned long long idx = sg.in_off + 2 * (row * items_row + it);
     fq lo3[3], hi3[3];
-    spmv_finish3(SP.mats[si], h_lo, secs, row, log_ymax, lo3);
-    spmv_finish3(SP.mats[si], h_hi, secs, row, log_ymax, hi3);
+    spmv_finish3<COLD>(SP.mats[si], h_lo, secs, row, log_ymax, lo3);
+    spmv_finish3<COLD>(SP.mats[si], h_hi, secs, row, log_ymax, hi3);
     if (it + RB < base + tile_items) {
       h_lo = spmv_head3(SP.mats[si], (unsigned int)(2 * (it + RB)));
       h_hi = spmv_head3(SP.mats[si], (unsigned int)(2 * (it + RB) + 1));
@@ -549,6 +549,13 @@ size_t phase_round(const spg_sc1 *s, size_t round) {
 }
 
 constexpr size_t ROWS_STASH_BYTES = 6 * RB * sizeof(fq);  // k_rows_rolled: six bound scalars per thread
+// The fused first round keeps the multi-entry / non-unit row handling out of line
+// (spmv_row_rest, r1cs.cuh): 3.42 -> 3.14 ms per pass at 2^20 x 64. SPG_SPMV_COLD=0 selects the
+// fully inlined form again (A/B switch).
+bool spmv_cold_enabled() {
+  const char *e = getenv("SPG_SPMV_COLD");
+  return !(e && *e == '0');
+}
 
 int sc1_alloc_common(spg_ctx *ctx, size_t P, const size_t *num_proofs, size_t max_num_proofs,
                      const size_t *num_cons, size_t max_num_cons, const spg_fq *tau_p,
@@ -881,8 +888,13 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       if (s->pend_inst) {
         // tables do not exist yet: compute them in the same pass (read z once, write 96 N bytes once)
         ctx->next_units = 288.0 * pairs;
-        SPG_LAUNCH(ctx, (k_rows_spmv<2>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
-                   s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+        static const bool cold = spmv_cold_enabled();
+        if (cold)
+          SPG_LAUNCH(ctx, (k_rows_spmv<2, true>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
+                     s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+        else
+          SPG_LAUNCH(ctx, (k_rows_spmv<2>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
+                     s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
         s->pend_inst = nullptr;
         s->pend_z = nullptr;
       } else {
