@@ -61,3 +61,18 @@ def test_general_field_valued_v():
     out = O.perm_fill(table(v, x), [4, 2]).reshape(n, 8, 4)
     pi, D = model(v, x, [4, 2])
     assert [O.to_int(s) for s in out[:, 2]] == pi and [O.to_int(s) for s in out[:, 3]] == D
+
+
+def test_affine_composition_equals_the_recurrence():
+    """the algebra spg_perm_scan relies on: D[q] = A_q D[q+1] + B_q with A_q = x[q] v[q+1],
+    B_q = x[q] - A_q, composed right to left, reproduces the sequential loop"""
+    n = 13
+    v = [O.to_int(s) for s in rand_scalars(n, 21)]
+    x = [O.to_int(s) for s in rand_scalars(n, 22)]
+    pi, D = model(v, x, [n])
+    A, B = 1, 0  # composition of the maps of rows q..n-1, applied to an arbitrary start value
+    for q in reversed(range(n)):
+        a_q = 0 if q == n - 1 else x[q] * v[q + 1] % Q
+        b_q = (x[q] - a_q) % Q
+        A, B = a_q * A % Q, (a_q * B + b_q) % Q
+        assert A == 0 and B == D[q]  # the last row has A = 0, so every suffix map is constant
