@@ -60,6 +60,23 @@ def sparse_case():
     return SP.serialize_sparse_proof(pr)
 
 
+def witness_case():
+    """w3 table (rows of 8 scalars) for three proving instances of 37, 5 and 1 proofs: v in {0, 1}
+    (one instance ends in invalid rows), x random; the oracle fills the (pi, D) columns
+    (src/lib.rs:1378-1400)."""
+    seg_len = [37, 5, 1]
+    n = sum(seg_len)
+    rng = np.random.default_rng(77)
+    w3 = np.zeros((n, 8, 4), dtype=np.uint64)
+    valid = rng.integers(0, 2, size=n).astype(bool)
+    valid[30:37] = False  # trailing dummy executions of the first instance
+    w3[:, 0] = np.where(valid[:, None], O.ONE, np.zeros(4, dtype=np.uint64))
+    w3[:, 1] = rand_scalars(n, 78)
+    w3[:, 4] = rand_scalars(n, 79)  # untouched columns must survive
+    w3 = w3.reshape(n * 8, 4)
+    return seg_len, w3, O.perm_fill(w3, seg_len)
+
+
 def main():
     blob, ch = r1cs_case()
     open(os.path.join(HERE, "r1cs_proof_x32_q2.bin"), "wb").write(blob)
@@ -68,6 +85,8 @@ def main():
              evals2=np.stack(t.evals2), claims2=np.stack(t.claims2))
     sblob = sparse_case()
     open(os.path.join(HERE, "sparse_proof_3x8.bin"), "wb").write(sblob)
+    seg_len, w3_in, w3_out = witness_case()
+    np.savez(os.path.join(HERE, "w3_perm_ragged.npz"), seg_len=np.array(seg_len), w3_in=w3_in, w3_out=w3_out)
     meta = {"r1cs_proof_x32_q2.bin": hashlib.sha256(blob).hexdigest(), "sparse_proof_3x8.bin": hashlib.sha256(sblob).hexdigest(),
             "challenge_counts": [len(c) for c in ch]}
     json.dump(meta, open(os.path.join(HERE, "MANIFEST.json"), "w"), indent=1)
