@@ -345,6 +345,21 @@ void spg_gens_destroy(spg_gens *g);
  * out = L_size compressed row commitments (32 bytes each). */
 int spg_poly_commit(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size,
                     uint8_t *out_compressed);
+/* The same for rows [row0, row0 + nrows) only: the rows of a commitment are independent
+ * (src/dense_mlpoly.rs:199-212 maps over them), which is how a commitment is sharded over
+ * GPUs (each rank commits a slice, 32 bytes per row are gathered). out = nrows * 32 bytes. */
+int spg_poly_commit_rows(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size, size_t row0,
+                         size_t nrows, uint8_t *out_compressed);
+/* Builds the fixed-base window tables for the first R generators (and h) now instead of inside
+ * the first commitment that needs them -- setup cost, like MultiCommitGens::new itself. */
+int spg_gens_prepare(spg_ctx *ctx, spg_gens *gens, size_t R);
+/* out = {window bits c, windows per scalar (= point additions per non-zero scalar), table
+ * bytes, bases covered}; zeros before the first table is built. */
+int spg_gens_info(const spg_gens *gens, size_t out[4]);
+/* Development aid: n pseudo-random and edge-case operand pairs through the eight-limb
+ * GF(2^255-19) arithmetic of the commitment kernels, compared on the device with the ten-limb
+ * code; *out_bad = OR of the failing checks' bits (0 = all agree). */
+int spg_debug_fe8_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_bad);
 /* Commitments::commit for a batch of short vectors sharing the bases (sumcheck
  * round polynomials etc.): out[i] = sum_j s[i*len+j] G[j] + blind[i] h */
 int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, size_t len,

@@ -127,6 +127,10 @@ def _proto(L):
         "spg_gens_from_uniform": [P, P, SZ, PP],
         "spg_poly_commit": [P, P, P, SZ, P],
         "spg_commit_batch": [P, P, P, SZ, P, SZ, P],
+        "spg_poly_commit_rows": [P, P, P, SZ, SZ, SZ, P],
+        "spg_gens_prepare": [P, P, SZ],
+        "spg_gens_info": [P, P],
+        "spg_debug_fe8_selftest": [P, SZ, C.c_uint64, P],
     }
     for name, args in sigs.items():
         f = getattr(L, name, None)

@@ -697,6 +697,22 @@ class MultiCommitGens:
         check(self.ctx.L.spg_poly_commit(self.ctx.h, self.h, poly.h, L_size, _ptr(out)), "spg_poly_commit")
         return [out[32 * i: 32 * (i + 1)].tobytes() for i in range(L_size)]
 
+    def commit_poly_rows(self, poly: DensePolynomial, L_size: int, row0: int, nrows: int) -> bytes:
+        """Rows [row0, row0 + nrows) of DensePolynomial::commit (the rows are independent:
+        src/dense_mlpoly.rs:199-212); nrows * 32 bytes."""
+        out = np.empty(32 * max(nrows, 1), dtype=np.uint8)
+        check(self.ctx.L.spg_poly_commit_rows(self.ctx.h, self.h, poly.h, L_size, row0, nrows, _ptr(out)), "spg_poly_commit_rows")
+        return out[:32 * nrows].tobytes()
+
+    def prepare(self, R: int):
+        """Build the fixed-base tables for the first R generators now (setup, not prove time)."""
+        check(self.ctx.L.spg_gens_prepare(self.ctx.h, self.h, R), "spg_gens_prepare")
+
+    def info(self) -> dict:
+        o = np.zeros(4, dtype=np.uint64)
+        check(self.ctx.L.spg_gens_info(self.h, _ptr(o)), "spg_gens_info")
+        return {"window_bits": int(o[0]), "adds_per_scalar": int(o[1]), "table_bytes": int(o[2]), "table_bases": int(o[3])}
+
     def commit_batch(self, scalars, blinds=None) -> list:
         """Commitments::commit for `count` vectors of equal length sharing these generators."""
         s = _fq(scalars)

@@ -7,23 +7,38 @@
 // encoding of the sum is canonical (RFC 9496).
 //
 // Algorithm. All rows of a polynomial commitment use the same R bases, and there are
-// thousands of rows, so the bases get fixed-base window tables once:
-//   T[j][w][d-1] = d * 2^(C*w) * G_j      d in 1..2^C-1, w in 0..ceil(253/C)-1
-// stored in "cached" form (Y+X, Y-X, Z, 2dT). A row commitment is then a pure sum of
-// table entries -- no doublings, no buckets, no atomics, zero digits are skipped:
-//   C_i = sum_j sum_w T[j][w][digit_w(s_ij)]
-// One thread owns (row i, chunk of bases); a warp is 32 consecutive rows of the same
-// chunk, so all its table reads fall in the same few (j, w) slices (L1/L2 resident).
+// thousands of rows, so the bases get fixed-base window tables once (signed digits):
+//   T[j][w][d-1] = d * 2^(c*w) * G_j      d in 1..2^(c-1), w in 0..ceil(254/c)-1
+// stored as AFFINE precomputed points (y+x, y-x, 2dxy) on eight saturated 32-bit limbs
+// (96 bytes, csrc/fe8.cuh). A row commitment is then a pure sum of table entries -- no
+// doublings, no buckets, no atomics, zero digits are skipped:
+//   C_i = sum_j sum_w sign(d) T[j][w][|d|-1],   d = digit_w(s_ij) in [-(2^(c-1)-1), 2^(c-1)]
+// at 7 field multiplications per entry (mixed addition). The window width c (8..13) is the
+// largest whose table fits the memory budget: 8192 bases take 3.2 GB at c = 8 (32 additions
+// per scalar) and 35 GB at c = 12 (22 additions); see pick_window.
+// One thread owns (row i, chunk of bases); a block is 128 consecutive rows of the same chunk and
+// concurrently resident blocks share a handful of chunks, so table reads are L2 hits. The next
+// table entry is fetched before the current addition is computed (its address depends only on
+// the scalar's digits).
 #include "common.cuh"
 #include "ed25519.cuh"
+#include "fe8.cuh"
 
 namespace spg {
 
-template <int C>
-struct WinCfg {
-  static constexpr int WINS = (253 + C - 1) / C;
-  static constexpr int ENTRIES = (1 << C) - 1;
+// window geometry of a table
+struct Win {
+  int c;         // digit width in bits
+  int wins;      // ceil(254 / c): the top digit absorbs the last carry of the signed recoding
+  uint32_t ent;  // entries per window = 2^(c-1) = the largest digit magnitude
 };
+static inline Win make_win(int c) {
+  Win w;
+  w.c = c;
+  w.wins = (254 + c - 1) / c;
+  w.ent = 1u << (c - 1);
+  return w;
+}
 
 __global__ void k_decompress(const uint8_t *__restrict__ in, size_t n, ge *__restrict__ out,
                              int *__restrict__ bad) {
@@ -49,153 +64,352 @@ __global__ void k_from_uniform(const uint8_t *__restrict__ in, size_t n, ge *__r
   out[i] = ristretto_from_uniform_bytes(b);
 }
 
-// thread (j, w): entries d = 1 .. 2^C - 1 of window w of base j
-template <int C>
-__global__ void k_build_table(const ge *__restrict__ bases, size_t nbases, ge_cached *__restrict__ table) {
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbases * WINS) return;
-  size_t j = t / WINS;
-  int w = (int)(t % WINS);
-  ge p = bases[j];
-  for (int k = 0; k < C * w; k++) p = ge_double(p);
-  ge_cached pc = ge_to_cached(p);
-  ge_cached *dst = table + (j * WINS + w) * ENT;
-  dst[0] = pc;
-  ge m = p;
-  for (int d = 2; d <= ENT; d++) {
-    m = ge_add(m, pc);
-    dst[d - 1] = ge_to_cached(m);
+// ---------------------------------------------------------------- table construction (fe8)
+__device__ __forceinline__ ge8 ge8_double(const ge8 &p) {
+  fe8 A = fe8_mul(p.X, p.X), B = fe8_mul(p.Y, p.Y);
+  fe8 ZZ = fe8_mul(p.Z, p.Z);
+  fe8 C = fe8_add(ZZ, ZZ);
+  fe8 H = fe8_add(A, B);
+  fe8 XY = fe8_add(p.X, p.Y);
+  fe8 E = fe8_sub(H, fe8_mul(XY, XY));
+  fe8 G = fe8_sub(A, B);
+  fe8 F = fe8_add(C, G);
+  ge8 r;
+  r.X = fe8_mul(E, F);
+  r.Y = fe8_mul(G, H);
+  r.Z = fe8_mul(F, G);
+  r.T = fe8_mul(E, H);
+  return r;
+}
+__device__ __noinline__ fe8 fe8_sqn(fe8 f, int n) {
+#pragma unroll 1
+  for (int i = 0; i < n; i++) f = fe8_mul(f, f);
+  return f;
+}
+__device__ __noinline__ fe8 fe8_mul_call(const fe8 &a, const fe8 &b) { return fe8_mul(a, b); }
+// z^(p-2) = z^(2^255 - 21) = (z^(2^252 - 3))^8 * z^3
+__device__ __noinline__ fe8 fe8_invert(const fe8 &z) {
+  fe8 t0 = fe8_sqn(z, 1);
+  fe8 t1 = fe8_sqn(t0, 2);
+  t1 = fe8_mul_call(z, t1);
+  t0 = fe8_mul_call(t0, t1);
+  t0 = fe8_sqn(t0, 1);
+  t0 = fe8_mul_call(t1, t0);
+  t1 = fe8_sqn(t0, 5);
+  t0 = fe8_mul_call(t1, t0);
+  t1 = fe8_sqn(t0, 10);
+  t1 = fe8_mul_call(t1, t0);
+  fe8 t2 = fe8_sqn(t1, 20);
+  t1 = fe8_mul_call(t2, t1);
+  t1 = fe8_sqn(t1, 10);
+  t0 = fe8_mul_call(t1, t0);
+  t1 = fe8_sqn(t0, 50);
+  t1 = fe8_mul_call(t1, t0);
+  t2 = fe8_sqn(t1, 100);
+  t1 = fe8_mul_call(t2, t1);
+  t1 = fe8_sqn(t1, 50);
+  t0 = fe8_mul_call(t1, t0);
+  t0 = fe8_sqn(t0, 2);
+  fe8 p22523 = fe8_mul_call(t0, z);
+  fe8 z3 = fe8_mul_call(fe8_sqn(z, 1), z);
+  return fe8_mul_call(fe8_sqn(p22523, 3), z3);
+}
+
+__device__ inline ge8 ge8_from_ge(const ge &p) {
+  ge8 r;
+  r.X = fe8_from_fe(p.X);
+  r.Y = fe8_from_fe(p.Y);
+  r.Z = fe8_from_fe(p.Z);
+  r.T = fe8_from_fe(p.T);
+  return r;
+}
+
+// wb[j * wins + w] = 2^(c w) G_j
+__global__ void k_window_bases(const ge *__restrict__ bases, size_t nbases, Win win, ge8 *__restrict__ wb) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nbases) return;
+  ge8 p = ge8_from_ge(bases[j]);
+#pragma unroll 1
+  for (int w = 0; w < win.wins; w++) {
+    wb[j * win.wins + w] = p;
+#pragma unroll 1
+    for (int k = 0; k < win.c; k++) p = ge8_double(p);
   }
 }
 
-template <int C>
-__device__ __forceinline__ void accumulate_scalar(ge &acc, const fq &s_mont, const ge_cached *__restrict__ tj) {
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
-  // leave Montgomery form: the group multiplies by the integer value (src/scalar/mod.rs:32-36)
-  fq s = fq_from_mont(s_mont);
+// thread (j, w, blk): entries d = blk * TB + 1 .. blk * TB + TB of window w of base j, made affine
+// with one shared inversion
+constexpr int TB = 16;
+__global__ void __launch_bounds__(64)
+k_build_table(const ge8 *__restrict__ wb, size_t nwb, Win win, niels8 *__restrict__ table) {
+  const uint32_t nblk = win.ent / TB;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nwb * nblk) return;
+  size_t jw = t / nblk;
+  uint32_t blk = (uint32_t)(t % nblk);
+  const ge8 P = wb[jw];
+  // (blk * TB + 1) P, most significant bit first
+  uint32_t d0 = blk * TB + 1;
+  ge8 m = P;
+  int top = 31 - __clz(d0);
 #pragma unroll 1
-  for (int w = 0; w < WINS; w++) {
-    int bit = C * w;
-    uint32_t d = (s.v[bit >> 5] >> (bit & 31));
-    if ((bit & 31) + C > 32 && (bit >> 5) < 7) d |= s.v[(bit >> 5) + 1] << (32 - (bit & 31));
-    d &= (1u << C) - 1;
-    if (d) acc = ge_add(acc, tj[(size_t)w * ENT + (d - 1)]);
+  for (int b = top - 1; b >= 0; b--) {
+    m = ge8_double(m);
+    if ((d0 >> b) & 1u) m = ge8_add(m, P);
+  }
+  ge8 pts[TB];
+  fe8 pref[TB];
+  pts[0] = m;
+  pref[0] = m.Z;
+#pragma unroll 1
+  for (int k = 1; k < TB; k++) {
+    m = ge8_add(m, P);
+    pts[k] = m;
+    pref[k] = fe8_mul_call(pref[k - 1], m.Z);
+  }
+  fe8 inv = fe8_invert(pref[TB - 1]);
+  niels8 *dst = table + jw * win.ent + (size_t)blk * TB;
+#pragma unroll 1
+  for (int k = TB - 1; k >= 0; k--) {
+    fe8 zinv = k ? fe8_mul_call(inv, pref[k - 1]) : inv;
+    inv = fe8_mul_call(inv, pts[k].Z);
+    fe8 x = fe8_mul_call(pts[k].X, zinv), y = fe8_mul_call(pts[k].Y, zinv);
+    niels8 e;
+    e.ypx = fe8_add(y, x);
+    e.ymx = fe8_sub(y, x);
+    e.t2d = fe8_mul_call(fe8_mul_call(x, y), fe8_2d());
+    dst[k] = e;
   }
 }
+
+// ---------------------------------------------------------------- signed digits
+// the scalar as an integer (leave Montgomery form: the group multiplies by the integer value,
+// src/scalar/mod.rs:32-36), consumed c bits at a time from the bottom
+struct Recoder {
+  fq s;
+  uint32_t carry;
+  __device__ __forceinline__ explicit Recoder(const fq &mont) : s(fq_from_mont(mont)), carry(0) {}
+  // next digit: magnitude (0 = skip) and sign
+  __device__ __forceinline__ uint32_t next(const Win &win, bool &neg) {
+    uint32_t raw = (s.v[0] & ((1u << win.c) - 1u)) + carry;
+#pragma unroll
+    for (int i = 0; i < 7; i++) s.v[i] = __funnelshift_r(s.v[i], s.v[i + 1], win.c);
+    s.v[7] >>= win.c;
+    carry = raw > win.ent ? 1u : 0u;
+    neg = carry;
+    return carry ? (1u << win.c) - raw : raw;
+  }
+};
 
 // partial[(i * nchunks + k)] = sum over bases j in chunk k of s[i][j] * G_j
-template <int C>
-__global__ void __launch_bounds__(128)
-k_msm_partial(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_stride,
-              const ge_cached *__restrict__ table, size_t chunk, size_t nchunks, ge *__restrict__ partial) {
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
+__global__ void __launch_bounds__(128, 3)
+k_msm_rows(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_stride, const niels8 *__restrict__ table,
+           Win win, size_t chunk, size_t nchunks, ge8 *__restrict__ partial) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t k = blockIdx.y;
   if (i >= L) return;
-  ge acc = ge_identity();
+  ge8 acc = ge8_identity();
+  niels8 cur;
+  bool have = false, cur_neg = false;
   size_t j0 = k * chunk, j1 = j0 + chunk < R ? j0 + chunk : R;
+  const fq *row = scalars + i * row_stride;
+  fq s_next = j0 < j1 ? fq_load(row + j0) : fq_zero();
+#pragma unroll 1
   for (size_t j = j0; j < j1; j++) {
-    fq s = fq_load(scalars + i * row_stride + j);
-    if (fq_is_zero(s)) continue;
-    accumulate_scalar<C>(acc, s, table + j * WINS * ENT);
+    fq sm = s_next;
+    if (j + 1 < j1) s_next = fq_load(row + j + 1);
+    if (fq_is_zero(sm)) continue;
+    Recoder rc(sm);
+    const niels8 *__restrict__ tj = table + j * (size_t)win.wins * win.ent;
+#pragma unroll 1
+    for (int w = 0; w < win.wins; w++) {
+      bool neg;
+      uint32_t mag = rc.next(win, neg);
+      if (mag) {
+        // fetch this entry now, add the previous one while the load is in flight
+        niels8 nxt = niels8_load(tj + (size_t)w * win.ent + (mag - 1));
+        if (have) acc = ge8_madd(acc, cur, cur_neg);
+        cur = nxt;
+        cur_neg = neg;
+        have = true;
+      }
+    }
   }
+  if (have) acc = ge8_madd(acc, cur, cur_neg);
   partial[i * nchunks + k] = acc;
 }
 
 // few rows, many bases (the L / R vectors of a bullet reduction round, Cx of an opening):
 // WIDE_SPLIT threads per base, each adding a quarter of the base's windows (the additions of one
-// scalar are a dependent chain: 8 instead of 32 in a row), a block sums its 128 points through
-// shared memory. grid (ceil(R / WIDE_BASES), L); partial[i * gridDim.x + blockIdx.x]
+// scalar are a dependent chain), a block sums its 128 points through shared memory.
+// grid (ceil(R / WIDE_BASES), L); partial[i * gridDim.x + blockIdx.x]
 constexpr int WIDE_SPLIT = 4, WIDE_BASES = 128 / WIDE_SPLIT;
-template <int C>
 __global__ void __launch_bounds__(128)
-k_msm_wide(const fq *__restrict__ scalars, size_t R, size_t row_stride, const ge_cached *__restrict__ table,
-           ge *__restrict__ partial) {
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
-  constexpr int PER = (WINS + WIDE_SPLIT - 1) / WIDE_SPLIT;
-  __shared__ ge sm[64];
+k_msm_wide(const fq *__restrict__ scalars, size_t R, size_t row_stride, const niels8 *__restrict__ table, Win win,
+           ge8 *__restrict__ partial) {
+  const int per = (win.wins + WIDE_SPLIT - 1) / WIDE_SPLIT;
+  __shared__ ge8 sm[64];
   size_t i = blockIdx.y;
   size_t j = (size_t)blockIdx.x * WIDE_BASES + threadIdx.x / WIDE_SPLIT;
   const int part = threadIdx.x % WIDE_SPLIT;
-  ge acc = ge_identity();
+  ge8 acc = ge8_identity();
   if (j < R) {
     fq sm_ = fq_load(scalars + i * row_stride + j);
     if (!fq_is_zero(sm_)) {
-      // leave Montgomery form: the group multiplies by the integer value (src/scalar/mod.rs:32-36)
-      fq s = fq_from_mont(sm_);
-      const ge_cached *__restrict__ tj = table + j * WINS * ENT;
+      Recoder rc(sm_);
+      const niels8 *__restrict__ tj = table + j * (size_t)win.wins * win.ent;
+      const int w0 = part * per, w1 = min(w0 + per, win.wins);
 #pragma unroll 1
-      for (int w = part * PER; w < (part + 1) * PER && w < WINS; w++) {
-        int bit = C * w;
-        uint32_t d = (s.v[bit >> 5] >> (bit & 31));
-        if ((bit & 31) + C > 32 && (bit >> 5) < 7) d |= s.v[(bit >> 5) + 1] << (32 - (bit & 31));
-        d &= (1u << C) - 1;
-        if (d) acc = ge_add(acc, tj[(size_t)w * ENT + (d - 1)]);
+      for (int w = 0; w < w1; w++) {  // the recoding is sequential (carries); only [w0, w1) is added here
+        bool neg;
+        uint32_t mag = rc.next(win, neg);
+        if (mag && w >= w0) acc = ge8_madd(acc, niels8_load(tj + (size_t)w * win.ent + (mag - 1)), neg);
       }
     }
   }
   for (int half = 64; half >= 1; half >>= 1) {
     if ((int)threadIdx.x >= half && (int)threadIdx.x < 2 * half) sm[threadIdx.x - half] = acc;
     __syncthreads();
-    if ((int)threadIdx.x < half) acc = ge_add(acc, ge_to_cached(sm[threadIdx.x]));
+    if ((int)threadIdx.x < half) acc = ge8_add(acc, sm[threadIdx.x]);
     __syncthreads();
   }
   if (threadIdx.x == 0) partial[i * gridDim.x + blockIdx.x] = acc;
 }
 
-// out[i] = compress(sum_k partial[i][k] + blind[i] * h); h's table sits in slot `hslot`
-template <int C>
-__global__ void k_msm_finish(const ge *__restrict__ partial, size_t L, size_t nchunks,
-                             const fq *__restrict__ blinds, const ge_cached *__restrict__ table,
-                             size_t hslot, uint8_t *__restrict__ out) {
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
+// acc += blind * h, h's table in slot `hslot`
+__device__ __forceinline__ void add_blind(ge8 &acc, const fq &blind, const niels8 *__restrict__ table, size_t hslot,
+                                          const Win &win) {
+  if (fq_is_zero(blind)) return;
+  Recoder rc(blind);
+  const niels8 *__restrict__ th = table + hslot * (size_t)win.wins * win.ent;
+#pragma unroll 1
+  for (int w = 0; w < win.wins; w++) {
+    bool neg;
+    uint32_t mag = rc.next(win, neg);
+    if (mag) acc = ge8_madd(acc, niels8_load(th + (size_t)w * win.ent + (mag - 1)), neg);
+  }
+}
+
+__device__ __forceinline__ void store_compressed(const ge8 &acc, uint8_t *__restrict__ out) {
+  uint8_t enc[32];
+  ristretto_compress(ge8_to_ge(acc), enc);
+  for (int k = 0; k < 32; k++) out[k] = enc[k];
+}
+
+// out[i] = compress(sum_k partial[i][k] + blind[i] * h)
+__global__ void k_msm_finish(const ge8 *__restrict__ partial, size_t L, size_t nchunks,
+                             const fq *__restrict__ blinds, const niels8 *__restrict__ table, size_t hslot, Win win,
+                             uint8_t *__restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L) return;
-  ge acc = partial[i * nchunks];
-  for (size_t k = 1; k < nchunks; k++) acc = ge_add(acc, ge_to_cached(partial[i * nchunks + k]));
-  if (blinds) {
-    fq b = blinds[i];
-    if (!fq_is_zero(b)) accumulate_scalar<C>(acc, b, table + hslot * WINS * ENT);
-  }
-  uint8_t enc[32];
-  ristretto_compress(acc, enc);
-  for (int k = 0; k < 32; k++) out[32 * i + k] = enc[k];
+  ge8 acc = partial[i * nchunks];
+#pragma unroll 1
+  for (size_t k = 1; k < nchunks; k++) acc = ge8_add(acc, partial[i * nchunks + k]);
+  if (blinds) add_blind(acc, blinds[i], table, hslot, win);
+  store_compressed(acc, out + 32 * i);
 }
 
 // Few rows (the L / R of a bullet-reduction round, Cx, the folded generator): one block per row
 // adds the row's per-block partial sums AND the blind's window points as a tree through shared
-// memory -- ~8 dependent additions instead of the (nblk + 32) sequential ones a single thread of
-// k_msm_finish would do, which is what a round of the opening proof used to wait for.
-template <int C>
+// memory -- ~8 dependent additions instead of the (nblk + wins) sequential ones a single thread of
+// k_msm_finish would do, which is what a round of the opening proof waits for.
 __global__ void __launch_bounds__(128)
-k_msm_finish_tree(const ge *__restrict__ partial, size_t nblk, const fq *__restrict__ blinds,
-                  const ge_cached *__restrict__ table, size_t hslot, uint8_t *__restrict__ out) {
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
-  __shared__ ge sm[64];
+k_msm_finish_tree(const ge8 *__restrict__ partial, size_t nblk, const fq *__restrict__ blinds,
+                  const niels8 *__restrict__ table, size_t hslot, Win win, uint8_t *__restrict__ out) {
+  __shared__ ge8 sm[64];
   const size_t i = blockIdx.x;
-  ge acc = ge_identity();
-  for (size_t k = threadIdx.x; k < nblk; k += 128) acc = ge_add(acc, ge_to_cached(partial[i * nblk + k]));
-  if (blinds && (int)threadIdx.x < WINS) {
-    // window w = threadIdx.x of blind * h
-    fq b = fq_from_mont(blinds[i]);
-    int bit = C * (int)threadIdx.x;
-    uint32_t d = (b.v[bit >> 5] >> (bit & 31));
-    if ((bit & 31) + C > 32 && (bit >> 5) < 7) d |= b.v[(bit >> 5) + 1] << (32 - (bit & 31));
-    d &= (1u << C) - 1;
-    if (d) acc = ge_add(acc, table[(hslot * WINS + threadIdx.x) * ENT + (d - 1)]);
+  ge8 acc = ge8_identity();
+  for (size_t k = threadIdx.x; k < nblk; k += 128) acc = ge8_add(acc, partial[i * nblk + k]);
+  if (blinds && (int)threadIdx.x < win.wins && !fq_is_zero(blinds[i])) {
+    // window w = threadIdx.x of blind * h (the recoding up to that window is a few shifts)
+    Recoder rc(blinds[i]);
+    bool neg = false;
+    uint32_t mag = 0;
+    for (int w = 0; w <= (int)threadIdx.x; w++) mag = rc.next(win, neg);
+    if (mag) acc = ge8_madd(acc, niels8_load(table + (hslot * win.wins + threadIdx.x) * (size_t)win.ent + (mag - 1)), neg);
   }
   for (int half = 64; half >= 1; half >>= 1) {
     if ((int)threadIdx.x >= half && (int)threadIdx.x < 2 * half) sm[threadIdx.x - half] = acc;
     __syncthreads();
-    if ((int)threadIdx.x < half) acc = ge_add(acc, ge_to_cached(sm[threadIdx.x]));
+    if ((int)threadIdx.x < half) acc = ge8_add(acc, sm[threadIdx.x]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    uint8_t enc[32];
-    ristretto_compress(acc, enc);
-    for (int k = 0; k < 32; k++) out[32 * i + k] = enc[k];
+  if (threadIdx.x == 0) store_compressed(acc, out + 32 * i);
+}
+
+// ---------------------------------------------------------------- fe8 self-test
+// random and edge operands through fe8_{mul,add,sub} and the mixed / full point additions,
+// compared with the ten-limb code of ed25519.cuh (which the CPU tests pin to the oracle)
+__device__ inline bool fe8_matches(const fe8 &a, const fe &b) { return fe_equal(fe8_to_fe(a), b); }
+__global__ void k_fe8_selftest(size_t n, uint64_t seed, unsigned int *__restrict__ bad) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint64_t st = seed + 0x9E3779B97F4A7C15ull * (t + 1);
+  auto rnd = [&]() {
+    st += 0x9E3779B97F4A7C15ull;
+    uint64_t z = st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  fe8 a, b;
+  for (int i = 0; i < 8; i += 2) {
+    uint64_t x = rnd(), y = rnd();
+    a.v[i] = (uint32_t)x; a.v[i + 1] = (uint32_t)(x >> 32);
+    b.v[i] = (uint32_t)y; b.v[i + 1] = (uint32_t)(y >> 32);
   }
+  // edge patterns: all ones (2^256 - 1), values around p and 2p, zero, small
+  switch (t % 11) {
+    case 1: for (int i = 0; i < 8; i++) a.v[i] = 0xffffffffu; break;
+    case 2: for (int i = 0; i < 8; i++) a.v[i] = b.v[i] = 0xffffffffu; break;
+    case 3: a = fe8_zero(); break;
+    case 4: for (int i = 0; i < 8; i++) b.v[i] = 0xffffffffu; b.v[0] = 0xffffffdau + (uint32_t)(t % 64); break;  // ~2p
+    case 5: for (int i = 0; i < 8; i++) a.v[i] = 0xffffffffu; a.v[7] = 0x7fffffffu; a.v[0] = 0xffffffedu + (uint32_t)(t % 32); break;  // ~p
+    case 6: b = fe8_zero(); b.v[0] = (uint32_t)(t % 40); break;
+    case 7: a = fe8_zero(); a.v[0] = (uint32_t)(t % 40); for (int i = 0; i < 8; i++) b.v[i] = 0xffffffffu; break;
+    default: break;
+  }
+  fe fa = fe8_to_fe(a), fb = fe8_to_fe(b);
+  unsigned int err = 0;
+  if (!fe8_matches(fe8_mul(a, b), fe_mul(fa, fb))) err |= 1;
+  if (!fe8_matches(fe8_add(a, b), fe_add(fa, fb))) err |= 2;
+  if (!fe8_matches(fe8_sub(a, b), fe_sub(fa, fb))) err |= 4;
+  if (!fe8_matches(fe8_from_fe(fa), fa)) err |= 8;
+  // points: P = a-derived multiple of the base point is overkill; use Elligator images of a, b
+  uint8_t ub[64];
+  for (int i = 0; i < 8; i++)
+    for (int k = 0; k < 4; k++) {
+      ub[4 * i + k] = (uint8_t)(a.v[i] >> (8 * k));
+      ub[32 + 4 * i + k] = (uint8_t)(b.v[i] >> (8 * k));
+    }
+  ge p = ristretto_map(fe_frombytes(ub)), q = ristretto_map(fe_frombytes(ub + 32));
+  ge want = ge_add(p, ge_to_cached(q));
+  ge8 p8 = ge8_from_ge(p), q8 = ge8_from_ge(q);
+  ge8 got = ge8_add(p8, q8);
+  uint8_t e1[32], e2[32];
+  ristretto_compress(want, e1);
+  ristretto_compress(ge8_to_ge(got), e2);
+  for (int i = 0; i < 32; i++) if (e1[i] != e2[i]) err |= 16;
+  // mixed addition with the affine form of q, both signs
+  fe8 zinv = fe8_invert(q8.Z);
+  if (!fe8_matches(fe8_mul(zinv, q8.Z), fe_one())) err |= 32;
+  fe8 x = fe8_mul(q8.X, zinv), y = fe8_mul(q8.Y, zinv);
+  niels8 nq;
+  nq.ypx = fe8_add(y, x);
+  nq.ymx = fe8_sub(y, x);
+  nq.t2d = fe8_mul(fe8_mul(x, y), fe8_2d());
+  ristretto_compress(ge8_to_ge(ge8_madd(p8, nq, false)), e2);
+  for (int i = 0; i < 32; i++) if (e1[i] != e2[i]) err |= 64;
+  ge qn = q;
+  qn.X = fe_neg(q.X);
+  qn.T = fe_neg(q.T);
+  ristretto_compress(ge_add(p, ge_to_cached(qn)), e1);
+  ristretto_compress(ge8_to_ge(ge8_madd(p8, nq, true)), e2);
+  for (int i = 0; i < 32; i++) if (e1[i] != e2[i]) err |= 128;
+  ristretto_compress(ge_double(p), e1);
+  ristretto_compress(ge8_to_ge(ge8_double(p8)), e2);
+  for (int i = 0; i < 32; i++) if (e1[i] != e2[i]) err |= 256;
+  if (err) atomicOr(bad, err);
 }
 
 }  // namespace spg
@@ -207,73 +421,119 @@ struct spg_gens {
   size_t n = 0;          // number of G's; h is bases[n]
   ge *bases = nullptr;   // n + 1 points
   // window tables for bases [0, tab_R) and h (slot tab_R)
-  ge_cached *table = nullptr;
+  niels8 *table = nullptr;
   size_t tab_R = 0;
-  int tab_C = 0;
+  Win win = make_win(8);
+  size_t table_bytes = 0;
 };
 
 namespace {
 
-template <int C>
+size_t table_bytes_for(size_t slots, const Win &w) { return slots * (size_t)w.wins * w.ent * sizeof(niels8); }
+
+// Largest window width in [8, 13] whose table fits the budget: SPG_MSM_TABLE_GIB (default 40)
+// and at most 30 % of the device's memory. Wider windows mean fewer additions per scalar
+// (32 at c = 8, 26 at 10, 24 at 11, 22 at 12, 20 at 13) and a table that doubles with each bit.
+Win pick_window(size_t slots) {
+  double gib = 40.0;
+  if (const char *e = getenv("SPG_MSM_TABLE_GIB")) gib = atof(e);
+  size_t budget = (size_t)(gib * 1073741824.0);
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+    if (budget > total_b * 3 / 10) budget = total_b * 3 / 10;
+    if (budget > free_b * 6 / 10) budget = free_b * 6 / 10;
+  }
+  int lo = 8, hi = 13;
+  if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
+    int c = atoi(e);
+    if (c >= 5 && c <= 16) return make_win(c);
+  }
+  Win best = make_win(lo);
+  for (int c = lo + 1; c <= hi; c++) {
+    Win w = make_win(c);
+    if (table_bytes_for(slots, w) <= budget && w.wins < best.wins) best = w;
+  }
+  return best;
+}
+
 int build_table(spg_gens *g, size_t R) {
   spg_ctx *ctx = g->ctx;
-  constexpr int WINS = WinCfg<C>::WINS, ENT = WinCfg<C>::ENTRIES;
   size_t slots = R + 1;
-  ge_cached *t = nullptr;
-  SPG_CUDA(cudaMalloc(&t, slots * WINS * ENT * sizeof(ge_cached)));
-  size_t threads = R * WINS;
-  SPG_LAUNCH(ctx, k_build_table<C>, (unsigned)((threads + 63) / 64), 64, 0, g->bases, R, t);
-  // h goes into slot R
-  SPG_LAUNCH(ctx, k_build_table<C>, (unsigned)((WINS + 63) / 64), 64, 0, g->bases + g->n, (size_t)1,
-             t + R * WINS * ENT);
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  Win win = pick_window(slots);
+  niels8 *t = nullptr;
+  ge8 *wb = nullptr;
+  size_t bytes = table_bytes_for(slots, win);
+  SPG_CUDA(cudaMalloc(&t, bytes));
+  cudaError_t e = cudaMalloc(&wb, slots * win.wins * sizeof(ge8));
+  if (e != cudaSuccess) {
+    cudaFree(t);
+    return cuda_fail(e, "window bases", __FILE__, __LINE__);
+  }
+  int rc = [&]() -> int {
+    SPG_LAUNCH(ctx, k_window_bases, (unsigned)((R + 63) / 64), 64, 0, g->bases, R, win, wb);
+    // h goes into slot R
+    SPG_LAUNCH(ctx, k_window_bases, 1, 64, 0, g->bases + g->n, (size_t)1, win, wb + R * win.wins);
+    size_t threads = slots * win.wins * (win.ent / TB);
+    SPG_LAUNCH(ctx, k_build_table, (unsigned)((threads + 63) / 64), 64, 0, wb, slots * win.wins, win, t);
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SPG_OK;
+  }();
+  cudaFree(wb);
+  if (rc != SPG_OK) {
+    cudaFree(t);
+    return rc;
+  }
   if (g->table) cudaFree(g->table);
   g->table = t;
   g->tab_R = R;
-  g->tab_C = C;
+  g->win = win;
+  g->table_bytes = bytes;
   return SPG_OK;
 }
 
 int ensure_table(spg_gens *g, size_t R) {
   if (g->table && g->tab_R >= R) return SPG_OK;
-  // 8-bit windows cost (R+1) * 32 * 255 * 160 B = 1.3 MB per base; fall back to 4-bit
-  // windows (154 KB per base) when that would exceed 24 GiB
-  size_t bytes8 = (R + 1) * (size_t)WinCfg<8>::WINS * WinCfg<8>::ENTRIES * sizeof(ge_cached);
-  if (bytes8 <= ((size_t)24 << 30)) return build_table<8>(g, R);
-  return build_table<4>(g, R);
+  return build_table(g, R);
 }
 
-template <int C>
 int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
             uint8_t *d_out) {
   spg_ctx *ctx = g->ctx;
+  const Win win = g->win;
+  const double adds = (double)win.wins;
   if (L <= 16 && R >= 256) {
     size_t nblk = (R + WIDE_BASES - 1) / WIDE_BASES;
-    ge *partial = nullptr;
-    SPG_CUDA(dev_alloc(ctx, &partial, L * nblk * sizeof(ge)));
+    ge8 *partial = nullptr;
+    SPG_CUDA(dev_alloc(ctx, &partial, L * nblk * sizeof(ge8)));
     dim3 grid((unsigned)nblk, (unsigned)L);
-    ctx->next_units = 32.0 * (double)L * (double)R;
-    SPG_LAUNCH(ctx, k_msm_wide<C>, grid, 128, 0, scalars, R, row_stride, g->table, partial);
-    static_assert(WinCfg<C>::WINS <= 128, "one thread per window of the blind");
-    SPG_LAUNCH(ctx, k_msm_finish_tree<C>, (unsigned)L, 128, 0, partial, nblk, d_blinds, g->table, g->tab_R, d_out);
-    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->next_units = adds * (double)L * (double)R;
+    int rc = [&]() -> int {
+      SPG_LAUNCH(ctx, k_msm_wide, grid, 128, 0, scalars, R, row_stride, g->table, win, partial);
+      SPG_CHECK(win.wins <= 128, "one thread per window of the blind");
+      SPG_LAUNCH(ctx, k_msm_finish_tree, (unsigned)L, 128, 0, partial, nblk, d_blinds, g->table, g->tab_R, win, d_out);
+      SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+      return SPG_OK;
+    }();
     dev_free(ctx, partial);
-    return SPG_OK;
+    return rc;
   }
   size_t chunk = 1;
   while (chunk < 64 && (L * R) / (chunk * 2) >= 131072) chunk *= 2;
   size_t nchunks = (R + chunk - 1) / chunk;
   if (nchunks == 0) nchunks = 1;
-  ge *partial = nullptr;
-  SPG_CUDA(dev_alloc(ctx, &partial, L * nchunks * sizeof(ge)));
+  ge8 *partial = nullptr;
+  SPG_CUDA(dev_alloc(ctx, &partial, L * nchunks * sizeof(ge8)));
   dim3 grid((unsigned)((L + 127) / 128), (unsigned)nchunks);
-  ctx->next_units = 32.0 * (double)L * (double)R;
-  SPG_LAUNCH(ctx, k_msm_partial<C>, grid, 128, 0, scalars, L, R, row_stride, g->table, chunk, nchunks, partial);
-  SPG_LAUNCH(ctx, k_msm_finish<C>, (unsigned)((L + 63) / 64), 64, 0, partial, L, nchunks, d_blinds, g->table,
-             g->tab_R, d_out);
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->next_units = adds * (double)L * (double)R;
+  int rc = [&]() -> int {
+    SPG_LAUNCH(ctx, k_msm_rows, grid, 128, 0, scalars, L, R, row_stride, g->table, win, chunk, nchunks, partial);
+    SPG_LAUNCH(ctx, k_msm_finish, (unsigned)((L + 63) / 64), 64, 0, partial, L, nchunks, d_blinds, g->table, g->tab_R, win,
+               d_out);
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SPG_OK;
+  }();
   dev_free(ctx, partial);
-  return SPG_OK;
+  return rc;
 }
 
 int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
@@ -287,8 +547,7 @@ int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stri
   const bool mapped = L * 32 <= 48 * sizeof(fq);
   if (mapped) d_out = reinterpret_cast<uint8_t *>(ctx->d_result);
   else SPG_CUDA(dev_alloc(ctx, &d_out, L * 32));
-  int rc = g->tab_C == 8 ? run_msm<8>(g, scalars, L, R, row_stride, d_blinds, d_out)
-                         : run_msm<4>(g, scalars, L, R, row_stride, d_blinds, d_out);
+  int rc = run_msm(g, scalars, L, R, row_stride, d_blinds, d_out);
   if (rc == SPG_OK) {
     if (mapped) {
       memcpy(host_out, ctx->h_result, L * 32);
@@ -472,10 +731,47 @@ void spg_gens_destroy(spg_gens *g) {
 
 int spg_poly_commit(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size,
                     uint8_t *out_compressed) {
+  return spg_poly_commit_rows(ctx, gens, poly, L_size, 0, L_size, out_compressed);
+}
+
+int spg_poly_commit_rows(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size, size_t row0,
+                         size_t nrows, uint8_t *out_compressed) {
   SPG_CHECK(ctx && gens && poly && out_compressed, "spg_poly_commit: null argument");
   SPG_CHECK(L_size >= 1 && poly->n % L_size == 0, "spg_poly_commit: L_size %zu does not divide len %zu", L_size, poly->n);
+  SPG_CHECK(row0 <= L_size && nrows <= L_size - row0, "spg_poly_commit_rows: rows [%zu, %zu) of %zu", row0, row0 + nrows, L_size);
+  if (nrows == 0) return SPG_OK;
   size_t R = poly->n / L_size;
-  return msm_rows(const_cast<spg_gens *>(gens), poly->d, L_size, R, R, nullptr, out_compressed);
+  return msm_rows(const_cast<spg_gens *>(gens), poly->d + row0 * R, nrows, R, R, nullptr, out_compressed);
+}
+
+int spg_gens_prepare(spg_ctx *ctx, spg_gens *gens, size_t R) {
+  SPG_CHECK(ctx && gens, "spg_gens_prepare: null argument");
+  SPG_CHECK(R >= 1 && R <= gens->n, "spg_gens_prepare: %zu bases requested, %zu generators", R, gens->n);
+  return ensure_table(gens, R);
+}
+
+int spg_gens_info(const spg_gens *gens, size_t out[4]) {
+  SPG_CHECK(gens && out, "spg_gens_info: null argument");
+  out[0] = gens->table ? (size_t)gens->win.c : 0;
+  out[1] = gens->table ? (size_t)gens->win.wins : 0;
+  out[2] = gens->table_bytes;
+  out[3] = gens->tab_R;
+  return SPG_OK;
+}
+
+int spg_debug_fe8_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_bad) {
+  SPG_CHECK(ctx && out_bad && n >= 1, "spg_debug_fe8_selftest: bad argument");
+  unsigned int *d_bad = nullptr;
+  SPG_CUDA(dev_alloc(ctx, &d_bad, sizeof(unsigned int)));
+  int rc = [&]() -> int {
+    SPG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), ctx->stream));
+    SPG_LAUNCH(ctx, k_fe8_selftest, (unsigned)((n + 63) / 64), 64, 0, n, seed, d_bad);
+    SPG_CUDA(cudaMemcpyAsync(out_bad, d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SPG_OK;
+  }();
+  dev_free(ctx, d_bad);
+  return rc;
 }
 
 int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, size_t len,

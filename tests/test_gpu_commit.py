@@ -103,3 +103,99 @@ def test_few_rows_many_bases_kernel(ctx):
     for i in range(3):
         want = G.commit_vec([O.to_int(x) for x in s[i]], O.to_int(blinds[i]), gens).compress()
         assert got[i] == want, i
+
+
+def test_fe8_selftest(ctx):
+    """the eight-limb GF(2^255-19) arithmetic of the MSM kernels (csrc/fe8.cuh) against the
+    ten-limb code on random and edge operands: products, sums, differences, point additions"""
+    import ctypes as C
+
+    bad = C.c_uint32(0xFFFFFFFF)
+    from spartan_parallel_b200._lib import check
+
+    check(ctx.L.spg_debug_fe8_selftest(ctx.h, 1 << 16, 12345, C.byref(bad)), "spg_debug_fe8_selftest")
+    assert bad.value == 0, f"failing checks: {bad.value:#x}"
+
+
+@pytest.mark.parametrize("c", [5, 8, 11, 13, 16])
+def test_window_widths(ctx, c, monkeypatch):
+    """every table geometry (signed c-bit digits, ceil(254/c) windows) gives the oracle's bytes;
+    scalars include q-1, 2^252, digit patterns that carry through every window, and blinds"""
+    import spartan_parallel_b200 as sp
+
+    monkeypatch.setenv("SPG_MSM_WINDOW", str(c))
+    n = 6
+    gens = G.MultiCommitGens(n, b"win-gens")
+    dg = sp.MultiCommitGens(ctx, gens.compressed())
+    q = O.Q if hasattr(O, "Q") else (1 << 252) + 27742317777372353535851937790883648493
+    half = 1 << (c - 1)
+    carry_all = sum((half + 1) << (c * w) for w in range(254 // c)) % q   # every digit > half: carries ripple to the top
+    exact_half = sum(half << (c * w) for w in range(254 // c)) % q        # every digit == half: no carry
+    ints = [[q - 1, 1 << 252, carry_all, exact_half, (1 << 253) % q, 0],
+            [1, 2, half, half + 1, (1 << c) - 1, 1 << c]]
+    s = np.stack([np.stack([O.from_int(v) for v in row]) for row in ints])
+    rnd = rand_scalars(n, 40 + c).reshape(1, n, 4)
+    s = np.concatenate([s, rnd])
+    blinds = np.stack([O.from_int(q - 1), O.from_int(0), rand_scalars(1, 41)[0]])
+    got = dg.commit_batch(s, blinds)
+    assert dg.info()["window_bits"] == c
+    for i in range(3):
+        want = G.commit_vec([O.to_int(x) for x in s[i]], O.to_int(blinds[i]), gens).compress()
+        assert got[i] == want, (c, i)
+    dg.free()
+
+
+def test_commit_rows_slices(ctx, gens16):
+    """spg_poly_commit_rows: any slice of rows equals the same rows of the full commitment
+    (the multi-GPU sharding of a commitment relies on it)"""
+    import spartan_parallel_b200 as sp
+
+    dg = sp.MultiCommitGens(ctx, gens16.compressed())
+    poly = sp.DensePolynomial.new(ctx, rand_scalars(256, 9))  # 16 x 16
+    full = b"".join(dg.commit_poly(poly))
+    for row0, nrows in [(0, 16), (0, 5), (5, 11), (15, 1), (7, 0)]:
+        assert dg.commit_poly_rows(poly, 16, row0, nrows) == full[32 * row0: 32 * (row0 + nrows)]
+    with pytest.raises(sp.SpgError):
+        dg.commit_poly_rows(poly, 16, 10, 7)
+
+
+def test_witness_commit_at_config_size(ctx, monkeypatch):
+    """BASELINE config C5's witness geometry: a 2^26-entry section = 8192 row commitments over
+    8192 generators (src/dense_mlpoly.rs:214-239). Checked (a) against the python oracle on rows
+    made sparse enough for it (full-width scalars in chosen columns, incl. the last generator),
+    (b) by the relation PolyEvalProof::verify relies on, sum_i L_i C_i == commit(L * Z)
+    (src/dense_mlpoly.rs:505-513), with the left side computed over the ROW COMMITMENTS as bases."""
+    import hashlib
+
+    import spartan_parallel_b200 as sp
+
+    ell, Lr, R = 26, 8192, 8192
+    base = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
+    uniform = hashlib.shake_256(b"gens_r1cs_sat" + base).digest(64 * (R + 1))
+    dg = sp.MultiCommitGens.from_uniform(ctx, uniform)
+    rng = np.random.default_rng(26)
+    Z = rng.integers(0, 1 << 64, size=(1 << ell, 4), dtype=np.uint64)
+    Z[:, 3] &= np.uint64((1 << 60) - 1)
+    cols = [0, 1, 4095, 8190, 8191]
+    sparse_rows = [0, 4097, 8191]
+    for r in sparse_rows:
+        keep = Z[r * R + np.array(cols)].copy()
+        Z[r * R:(r + 1) * R] = 0
+        Z[r * R + np.array(cols)] = keep
+    poly = sp.DensePolynomial.new(ctx, Z)
+    rows = dg.commit_poly(poly, Lr)
+    assert dg.info()["table_bases"] >= R
+    # (a) oracle on the sparse rows: the same generators derived by the oracle's own hash-to-group
+    og = {c: G.from_uniform_bytes(uniform[64 * c: 64 * (c + 1)]) for c in cols + [R]}
+    for r in sparse_rows:
+        want = G.multiscalar_mul([O.to_int(Z[r * R + c]) for c in cols], [og[c] for c in cols]).compress()
+        assert rows[r] == want, r
+    # (b) linearity over all rows
+    r = rand_scalars(ell, 27)
+    Lv = O.eq_evals(r[:13])
+    LZ = poly.bound(Lv).to_host()
+    rhs = dg.commit_batch(LZ.reshape(1, R, 4))[0]
+    monkeypatch.setenv("SPG_MSM_WINDOW", "8")  # a second, small table over the row commitments as bases
+    row_gens = sp.MultiCommitGens(ctx, b"".join(rows) + og[R].compress())
+    lhs = row_gens.commit_batch(Lv.reshape(1, Lr, 4))[0]
+    assert lhs == rhs
