@@ -42,8 +42,27 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_size_t)]
+        L.sph_timings.argtypes = [C.c_char_p, C.c_size_t]
+        L.sph_timings.restype = C.c_size_t
+        L.sph_timings_reset.restype = None
         _lib = L
     return _lib
+
+
+def timings_reset():
+    lib().sph_timings_reset()
+
+
+def timings() -> list:
+    """[(stage label, milliseconds)] recorded by the host mirror since timings_reset()."""
+    n = lib().sph_timings(None, 0)
+    buf = C.create_string_buffer(n)
+    lib().sph_timings(buf, n)
+    out = []
+    for ln in buf.value.decode().splitlines():
+        k, _, v = ln.rpartition("\t")
+        out.append((k.strip(), float(v)))
+    return out
 
 
 def _check(rc, what):

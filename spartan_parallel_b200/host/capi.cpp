@@ -16,6 +16,24 @@ const char *sph_last_error(void) { return g_err.c_str(); }
 
 void sph_free(void *p) { free(p); }
 
+// stage timings recorded since the last sph_timings_reset, one "label\tmilliseconds\n" line each;
+// returns the length needed (writes at most cap - 1 bytes + NUL)
+void sph_timings_reset(void) { timing_log().clear(); }
+size_t sph_timings(char *out, size_t cap) {
+  std::string s;
+  char buf[64];
+  for (auto &kv : timing_log()) {
+    snprintf(buf, sizeof buf, "\t%.6f\n", kv.second);
+    s += kv.first + buf;
+  }
+  if (out && cap) {
+    size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+    memcpy(out, s.data(), n);
+    out[n] = 0;
+  }
+  return s.size() + 1;
+}
+
 // MultiCommitGens::new(n, label).compressed(): n + 1 points (G[0..n], h), 32 bytes each
 int sph_gens_derive(const char *label, size_t n, uint8_t *out) {
   try {

@@ -19,15 +19,21 @@ namespace sph {
 inline void check(int rc, const char *what) {
   if (rc != SPG_OK) throw std::runtime_error(std::string(what) + ": " + spg_last_error());
 }
-// SPH_TRACE=1: wall time of the prover's stages on stderr (development aid)
+// Wall time of the prover's stages: always recorded (sph_timings returns the log of the last
+// proof, which is how bench.py reports the reference's Timer labels); SPH_TRACE=1 also prints it.
+inline std::vector<std::pair<std::string, double>> &timing_log() {
+  static thread_local std::vector<std::pair<std::string, double>> log;
+  return log;
+}
 struct Trace {
   bool on;
   std::chrono::steady_clock::time_point t0;
   Trace() : on(getenv("SPH_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
   void lap(const char *what) {
-    if (!on) return;
     auto t1 = std::chrono::steady_clock::now();
-    fprintf(stderr, "[sph] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    timing_log().emplace_back(what, ms);
+    if (on) fprintf(stderr, "[sph] %-28s %8.3f ms\n", what, ms);
     t0 = t1;
   }
 };

@@ -1,13 +1,17 @@
-"""Full-size runs (BASELINE.json configs C2, C3, C5 shapes on one GPU) checked through
-size-independent properties, since the CPU oracle cannot finish these sizes in seconds:
+"""Full-size runs at the BASELINE.json config sizes on one GPU.
 
-  * sumcheck verifier relation: with claim_0 = sum over the cube, every round polynomial
-    interpolated from (e0, claim - e0, e2, e3) must hand the next round its claim, and the
-    last claim must equal eq_claim * (Az*Bz - Cz) resp. eq * ABC * Z of the final claims;
-  * a satisfying witness makes the phase-1 claim vanish (e0 = e1 = 0 in round 0);
-  * linearity in the witness: phase-2 claims are checked against the phase-1 ones through
-    r_A*Az + r_B*Bz + r_C*Cz = claim_phase2.
-The same code path is bit-exact against the oracle at small sizes (test_gpu_r1cs.py)."""
+Two kinds of check, side by side:
+  * bit-exact comparison of every round polynomial and every final claim with the oracle
+    (OpenMP restatement of the reference loops) at C2 (2^20 x 1), C3 (2^16 x 256), full-size C4
+    (P = 5, Q_p = {64,16,16,4,1}, W = 5 with a single section) and C5 (2^20 x 64, marked slow:
+    ~30 s of oracle time on 16 cores);
+  * size-independent properties of the same runs:
+    - sumcheck verifier relation: with claim_0 = sum over the cube, every round polynomial
+      interpolated from (e0, claim - e0, e2, e3) must hand the next round its claim, and the
+      last claim must equal eq_claim * (Az*Bz - Cz) resp. eq * ABC * Z of the final claims;
+    - a satisfying witness makes the phase-1 claim vanish (e0 = e1 = 0 in round 0);
+    - linearity in the witness: phase-2 claims are checked against the phase-1 ones through
+      r_A*Az + r_B*Bz + r_C*Cz = claim_phase2."""
 import numpy as np
 import pytest
 
@@ -107,3 +111,57 @@ def test_c5_2_20_x_64(ctx):
 def test_c5_2_20_x_64_supplied_claim(ctx):
     """same shape with spg_sc1_set_claim(0): two-point first round (what bench.py times)"""
     run_shape(ctx, 20, 64, supply_claim=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# Bit-exact comparison with the oracle (OpenMP restatement of the reference loops) at the sizes
+# BASELINE.json names: every round polynomial of both sumchecks and all final claims.
+def test_c2_oracle_every_round(ctx):
+    """C2: one instance, X = 2^20 constraints, one proof"""
+    from oracle import r1cs as R
+    from tests.test_gpu_r1cs import run_case
+
+    X = 1 << 20
+    run_case(ctx, R.synthetic_instance(X), 1, [1], [X], X, R.synthetic_witness(X, [1], seed=202), seed=2020, claim=O.ZERO)
+
+
+def test_c3_oracle_every_round(ctx):
+    """C3: X = 2^16 constraints x 256 proofs"""
+    from oracle import r1cs as R
+    from tests.test_gpu_r1cs import run_case
+
+    X, Q = 1 << 16, 256
+    run_case(ctx, R.synthetic_instance(X), 1, [Q], [X], X, R.synthetic_witness(X, [Q], seed=203), seed=2030)
+
+
+def test_c4_full_size_oracle_every_round(ctx):
+    """C4 as SURVEY 8(d) states it: P = 5 instances of 2^12 constraints, Q_p = {64,16,16,4,1},
+    W = 5 sections with section 1 single (perm_w0, src/lib.rs:1703), Y_p in {2^12, 2^11},
+    random sparse matrices with unit, zero and general coefficients"""
+    from tests.helpers import random_instance, random_witness_secs
+    from tests.test_gpu_r1cs import run_case
+
+    P, W, Ymax = 5, 5, 1 << 12
+    num_proofs = [64, 16, 16, 4, 1]
+    num_cons = [1 << 12] * P
+    Y = [1 << 12, 1 << 12, 1 << 11, 1 << 12, 1 << 11]
+    inst = random_instance(P, num_cons, W, Ymax, Y, nnz=3 << 12, seed=204)
+    kinds = ["full", "single", "full", "full", "full"]
+    sec_inputs = [Y, [1 << 10] * P, [1 << 12, 1 << 13, 1 << 11, 1 << 12, 1 << 10], [8] * P, [8] * P]
+    secs = random_witness_secs(P, num_proofs, W, sec_inputs, kinds, seed=205)
+    run_case(ctx, inst, P, num_proofs, Y, Ymax, secs, seed=2040)
+
+
+@pytest.mark.slow
+def test_c5_oracle_every_round(ctx):
+    """C5: X = 2^20 constraints x 64 proofs (2^26 constraints); about a minute of oracle time on
+    16 host cores. SPG_SKIP_SLOW=1 skips it."""
+    import os
+
+    if os.environ.get("SPG_SKIP_SLOW"):
+        pytest.skip("SPG_SKIP_SLOW set")
+    from oracle import r1cs as R
+    from tests.test_gpu_r1cs import run_case
+
+    X, Q = 1 << 20, 64
+    run_case(ctx, R.synthetic_instance(X), 1, [Q], [X], X, R.synthetic_witness(X, [Q], seed=205), seed=2050, claim=O.ZERO)
