@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the accelerated path: the two sumchecks of R1CSProof::prove (with the
-table builders that feed them) on a synthetic data-parallel R1CS batch.
+table builders that feed them) on a synthetic data-parallel R1CS batch, plus the witness
+commitment and the whole proof around them.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference loops
 
 metric: sumcheck constraints/sec = sum_p Q_p * X_p / time(one full pass of
 z_mat -> SpMV -> phase-1 rounds -> ABC/Z tables -> phase-2 rounds), per-round host
-round trips included. One JSON line on stdout (rank 0).
+round trips included. One JSON line on stdout (rank 0). The same line carries BASELINE's other
+metric, prove time: witness commitment (polycommit) + R1CSProof::prove (+ the sparse-polynomial
+evaluation proof) with the reference's Timer labels, and a roofline entry per kernel class.
 
 Workload (BASELINE.json configs[4], "2^20 x 64"): P = 1 instance, X = 2^20 constraints,
-Q = 64 proofs per GPU, sections (u, v), constraint x: u_x * u_{x+1} = v_x. Under
-torchrun the N ranks prove ONE batch of 64 * N proofs sharded over the proof axis (weak
-scaling: per-GPU work is fixed): per round 3 scalars per rank cross a host mailbox, and
-the rq-bound Z table is summed once over NVLink peer memory (parallel.py).
+Q = 64 proofs, sections (u, v), constraint x: u_x * u_{x+1} = v_x. Under torchrun the N ranks
+prove that ONE batch sharded over the proof axis (strong scaling: 64 / N proofs per GPU; the
+default for N > 1) -- per round 3 scalars per rank cross a host mailbox, and the rq-bound Z table
+is summed once over NVLink peer memory (parallel.py); the rows of the witness commitment are
+sharded the same way. --scaling weak keeps 64 proofs PER GPU instead (a batch of 64 N proofs);
+in the default mode that figure is measured too and reported under "weak".
 """
 from __future__ import annotations
 
@@ -125,6 +130,55 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+# kernel -> (algorithmic bytes per item as the launcher counts them in `units`, Montgomery products
+# per item); DESIGN.md section 4 states both per kernel. MSM kernels count point additions instead.
+KERNEL_MODEL = {
+    "k_rows_rolled": (576.0, 10.0),      # fused bind_j + eval_{j+1}: 4 read + 2 written scalars x 3 tables, 6 binds + 4
+    "k_rows_spmv": (288.0, 4.0),         # SpMV + round 0: z read + 3 tables written per pair, 2 products + 2 weighted sums
+    "k_rows": (192.0, 4.0),
+    "k_quad_bind_eval": (576.0, 13.0),
+    "k_pair_eval": (192.0, 7.0),
+    "k_pair_bind": (288.0, 3.0),
+    "k_z_bind_rq": (32.0, 74.0 / 104.0),  # one product per witness scalar read, as four-term dot products: 296 wide multiplies per 4 instead of 4 x 104
+    "k_cubic_eval_rlc": (192.0, 6.0),
+    "k_multi_bind_top": (96.0, 1.0),
+    "k_prod_layer": (96.0, 1.0),
+    "k_hash_layer_fq": (128.0, 2.0),
+    "k_eq_expand": (96.0, 1.0),
+}
+MSM_WIDE_IMAD_PER_ADD = 7 * 72.0  # mixed addition: 7 field products of 64 + 8 IMAD.WIDE.U32 (csrc/fe8.cuh)
+
+
+def kernel_rooflines(prof, hbm_peak, int_peak, imad_peak):
+    """One entry per kernel of a profile: achieved GB/s of algorithmic bytes against the measured HBM
+    peak and, where the model above knows the kernel, modmul/s against the measured integer peak; for
+    the MSM kernels point additions/s against the IMAD.WIDE issue bound. `bound` names the larger
+    of the two fractions."""
+    out = []
+    for r in sorted(prof, key=lambda r: -r["total_ms"]):
+        name, t = r["kernel"], r["total_ms"] * 1e-3
+        if t <= 0 or not r["units"]:
+            continue
+        e = {"kernel": name, "launches": r["launches"], "total_ms": r["total_ms"]}
+        if name.startswith("k_msm") or name.startswith("(k_msm"):
+            adds = r["units"] / t
+            e.update({"point_adds_per_s": adds, "bound": "int_pipe",
+                      "frac": (adds * MSM_WIDE_IMAD_PER_ADD / imad_peak) if imad_peak else None,
+                      "peak": "IMAD.WIDE.U32 issue rate (tools/imad_peak.cu) / 504 per mixed addition"})
+        else:
+            gbs = r["units"] / t / 1e9
+            e.update({"achieved_GBps": gbs, "hbm_frac": gbs / hbm_peak})
+            key = next((k for k in sorted(KERNEL_MODEL, key=len, reverse=True) if k in name), None)
+            if key and int_peak:
+                bpi, mpi = KERNEL_MODEL[key]
+                mm = r["units"] / bpi * mpi / t
+                e.update({"modmul_per_s": mm, "int_frac": mm / int_peak})
+            e["bound"] = "int_pipe" if e.get("int_frac", 0) > e["hbm_frac"] else "hbm"
+            e["frac"] = max(e.get("int_frac", 0), e["hbm_frac"])
+        out.append(e)
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -137,43 +191,22 @@ def run_gpu(args):
     from spartan_parallel_b200 import parallel
 
     numa = parallel.bind_host_to_gpu(local)  # before any pinned allocation (first-touch pages)
+    dev = torch.device("cuda", local)
     if world > 1:
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     ctx = sp.Context(local)
-    X, Q = 1 << args.log_x, args.proofs
-    N = X * Q
-    nx, nq = args.log_x, log2(Q)
-    rng = np.random.default_rng(0x5EED0000 + rank)
-
-    # witness: u random, v = u * roll(u) computed with the library (no CPU field code here)
-    t_setup = time.time()
-    u = random_canonical(rng, N)
-    du = sp.DensePolynomial.new(ctx, u)
-    u_next = np.ascontiguousarray(np.roll(u.reshape(Q, X, 4), -1, axis=1).reshape(N, 4))
-    dun = sp.DensePolynomial.new(ctx, u_next)
-    dv = sp.vec_op(ctx, "mul", du, dun)
-    v = dv.to_host()
-    del du, dun, dv, u_next
-    # pinned host copies for the end-to-end leg
-    hu = torch.from_numpy(u.view(np.int64)).pin_memory()
-    hv = torch.from_numpy(v.view(np.int64)).pin_memory()
-    u_pin, v_pin = hu.numpy().view(np.uint64), hv.numpy().view(np.uint64)
+    scaling = args.scaling or "strong"
+    X = 1 << args.log_x
+    nx = args.log_x
+    ng = log2(world)
+    assert world & (world - 1) == 0, "world size must be a power of two"
+    comm = parallel.ShmComm(device=dev) if world > 1 else parallel.LocalComm()
+    peer = parallel.PeerTable(ctx, comm, 2 * X) if world > 1 else None  # the rq-bound Z table: W * Y scalars
     A, B, Cm = synthetic_matrices(X, ONE)
     inst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A], [B], [Cm])
-    # challenges are common to all ranks (in production they come from rank 0's transcript)
-    crng = np.random.default_rng(0xC4A11E46E)
-    ng = log2(world)
-    tau_q, tau_x = challenges(crng, nq + ng), challenges(crng, nx)
-    ch1, ch2 = challenges(crng, nx + nq + ng), challenges(crng, 1 + nx)
-    r_abc = challenges(crng, 3)
-    setup_s = time.time() - t_setup
-
-    comm = parallel.ShmComm(device=torch.device("cuda", local)) if world > 1 else parallel.LocalComm()
-    peer = parallel.PeerTable(ctx, comm, 2 * X) if world > 1 else None  # the rq-bound Z table: W * Y scalars
-
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     trace, tracing = [], [False]
-
     nosync_trace = bool(os.environ.get("SPG_BENCH_TRACE_NOSYNC"))  # development: host timestamps in the timed loop
 
     def mark(name):
@@ -183,50 +216,17 @@ def run_gpu(args):
         elif nosync_trace:
             trace.append((name, time.perf_counter()))
 
-    def one_pass(secs):
-        """The hot path for one batch: everything R1CSProof::prove does on tables."""
-        mark("start")
-        z = sp.ZMat(ctx, [Q], [X], secs)
-        rx = ch1[:nx][::-1].copy()
-        if world == 1:
-            sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
-            sc1.set_claim(ZERO)  # claim_phase1 = 0 (src/r1csproof.rs:330); the synthetic witness satisfies the instance
-            sc1.run_rounds(ch1[:sc1.num_rounds])  # C loop: eval -> host -> bind per round, no Python in between
-            c1 = sc1.final()
-            sc1.free()
-            sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[nx:nx + nq], ch1[:0], r_abc[0], r_abc[1], r_abc[2])
-        else:
-            # one proof over Q * world proofs: shards exchange 3 scalars per round, then one
-            # all-gather of the rq-bound Z table; phase 2 (independent of Q) runs replicated
-            sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, tau_q, tau_x, satisfied=True)
-            mark("phase1 create")
-            sc1.run_rounds(ch1[:sc1.num_rounds])
-            mark("phase1 rounds (local C loop + tail)")
-            c1 = sc1.final()
-            sc1.free()
-            mark("phase1 final")
-            zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q, peer)
-            mark("Z bind + peer all-reduce")
-            sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
-        mark("phase2 create")
-        sc2.run_rounds(ch2[:sc2.num_rounds])
-        c2 = sc2.final()
-        mark("phase2 rounds")
-        sc2.free()
-        z.free()
-        mark("free")
-        return c1, c2
-
-    def upload(asynchronous=False):
-        return [sp.ProverWitnessSecInfo(ctx, [Q], [X], u_pin, asynchronous), sp.ProverWitnessSecInfo(ctx, [Q], [X], v_pin, asynchronous)]
-
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ctx.sync()
+
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
 
     def timed(fn, steps):
         barrier()
@@ -241,62 +241,196 @@ def run_gpu(args):
         wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
         barrier()
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1])
+        return max_over_ranks(ms, wall * 1e3)
+
+    class Shard:
+        """This rank's slice of one batch of Q_total proofs (proofs rank * Q .. rank * Q + Q - 1)."""
+
+        def __init__(self, Q_total, seed):
+            self.Q_total, self.Q = Q_total, Q_total // world
+            assert self.Q >= 1 and self.Q * world == Q_total, f"{Q_total} proofs do not split over {world} ranks"
+            Q, N = self.Q, X * self.Q
+            self.N, self.nq = N, log2(Q)
+            rng = np.random.default_rng(seed + rank)
+            # witness: u random, v = u * roll(u) computed with the library (no CPU field code here)
+            u = random_canonical(rng, N)
+            du = sp.DensePolynomial.new(ctx, u)
+            u_next = np.ascontiguousarray(np.roll(u.reshape(Q, X, 4), -1, axis=1).reshape(N, 4))
+            dun = sp.DensePolynomial.new(ctx, u_next)
+            dv = sp.vec_op(ctx, "mul", du, dun)
+            v = dv.to_host()
+            del du, dun, dv, u_next
+            # pinned host copies for the end-to-end leg
+            self.hu = torch.from_numpy(u.view(np.int64)).pin_memory()
+            self.hv = torch.from_numpy(v.view(np.int64)).pin_memory()
+            self.u_pin, self.v_pin = self.hu.numpy().view(np.uint64), self.hv.numpy().view(np.uint64)
+            # challenges are common to all ranks (in production they come from rank 0's transcript)
+            crng = np.random.default_rng(0xC4A11E46E)
+            nq = self.nq
+            self.tau_q, self.tau_x = challenges(crng, nq + ng), challenges(crng, nx)
+            self.ch1, self.ch2 = challenges(crng, nx + nq + ng), challenges(crng, 1 + nx)
+            self.r_abc = challenges(crng, 3)
+
+        def upload(self, asynchronous=False):
+            Q = self.Q
+            return [sp.ProverWitnessSecInfo(ctx, [Q], [X], self.u_pin, asynchronous),
+                    sp.ProverWitnessSecInfo(ctx, [Q], [X], self.v_pin, asynchronous)]
+
+        def one_pass(self, secs):
+            """The hot path for one batch: everything R1CSProof::prove does on tables."""
+            Q, nq, ch1, ch2, r_abc = self.Q, self.nq, self.ch1, self.ch2, self.r_abc
+            mark("start")
+            z = sp.ZMat(ctx, [Q], [X], secs)
+            rx = ch1[:nx][::-1].copy()
+            if world == 1:
+                sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, self.tau_q[:0], self.tau_q, self.tau_x)
+                sc1.set_claim(ZERO)  # claim_phase1 = 0 (src/r1csproof.rs:330); the synthetic witness satisfies the instance
+                sc1.run_rounds(ch1[:sc1.num_rounds])  # C loop: eval -> host -> bind per round, no Python in between
+                c1 = sc1.final()
+                sc1.free()
+                sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[nx:nx + nq], ch1[:0], r_abc[0], r_abc[1], r_abc[2])
+            else:
+                # one proof over Q * world proofs: shards exchange 3 scalars per round, then one
+                # modular all-reduce of the rq-bound Z table; phase 2 (independent of Q) runs replicated
+                sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, self.tau_q, self.tau_x, satisfied=True)
+                mark("phase1 create")
+                sc1.run_rounds(ch1[:sc1.num_rounds])
+                mark("phase1 rounds (local C loop + tail)")
+                c1 = sc1.final()
+                sc1.free()
+                mark("phase1 final")
+                zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q, peer)
+                mark("Z bind + peer all-reduce")
+                sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
+            mark("phase2 create")
+            sc2.run_rounds(ch2[:sc2.num_rounds])
+            c2 = sc2.final()
+            mark("phase2 rounds")
+            sc2.free()
+            z.free()
+            mark("free")
+            return c1, c2
+
+        def measure_resident(self, steps, warmup, profile=True):
+            secs = self.upload()
+            for _ in range(warmup):
+                first = self.one_pass(secs)
+            launches0 = ctx.launches
+            if profile:
+                ctx.profile_begin()
+            del trace[:]
+            ms, wall = timed(lambda: self.one_pass(secs), steps)
+            prof = ctx.profile_end() if profile else []
+            launches = (ctx.launches - launches0) // max(steps, 1)
+            for s in secs:
+                s.free()
+            return {"ms": ms / steps, "wall_ms": wall / steps, "prof": prof, "launches": int(launches), "first": first}
+
+        def measure_e2e(self, steps, warmup):
+            """host buffers in, claims out, every batch's copies inside the timed region. Batches are
+            double-buffered: the H2D copy of batch i+1 (copy stream) overlaps the proving of batch i
+            (compute stream); the first batch's copy is not overlapped."""
+            outs = []
+
+            def run(k):
+                nxt = self.upload(True)
+                for i in range(k):
+                    cur, nxt = nxt, (self.upload(True) if i + 1 < k else None)
+                    outs.append(self.one_pass(cur))
+                    for s in cur:
+                        s.free()
+
+            run(min(warmup, 2))
+            ms, _ = timed(lambda: run(steps), 1)
+            return ms / steps, outs[-1]
+
+    t_setup = time.time()
+    Q_main = args.proofs if scaling == "strong" else args.proofs * world
+    main = Shard(Q_main, 0x5EED0000)
+    setup_s = time.time() - t_setup
+    total_units = X * Q_main
+
+    # ---- N > 1: the sharded path must reproduce the unsharded one bit for bit (C3, 2^16 x 256)
+    parity = None
+    if world > 1 and not args.no_parity:
+        try:
+            parity = sharded_equals_unsharded(sp, parallel, ctx, comm, rank, world, 16, 256)
+        except Exception as e:
+            parity = {"ok": False, "error": str(e)[:200]}
+        ok = max_over_ranks(0.0 if parity.get("ok") else 1.0)[0] == 0.0
+        parity["ok"] = ok
 
     # ---- device-resident leg
-    secs = upload()
-    for _ in range(args.warmup):
-        first = one_pass(secs)
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("SPG_NO_CLOCKS"):
         sampler.start()
-    launches0 = ctx.launches
-    no_prof = bool(os.environ.get("SPG_BENCH_NO_PROFILE"))  # development: without per-launch events
-    if not no_prof:
-        ctx.profile_begin()
-    del trace[:]
-    ms_dev, wall_dev = timed(lambda: one_pass(secs), args.steps)
-    prof = [] if no_prof else ctx.profile_end()
+    res = main.measure_resident(args.steps, args.warmup, profile=not os.environ.get("SPG_BENCH_NO_PROFILE"))
     if nosync_trace and rank in (0, world - 1):
         print(f"[rank {rank}] timed loop, host clock, no syncs: " + ", ".join(f"{n}: {(t - trace[i][1]) * 1e3:.2f}" for i, (n, t) in enumerate(trace[1:])),
               file=sys.stderr, flush=True)
-        print(f"[rank {rank}] cpus {len(os.sched_getaffinity(0))} loadavg {os.getloadavg()}", file=sys.stderr, flush=True)
-    launches = (ctx.launches - launches0) // max(args.steps, 1)
-    for s in secs:
-        s.free()
-
-    # ---- end-to-end leg: host buffers in, claims out, every batch's copies inside the timed
-    # region. Batches are double-buffered: the H2D copy of batch i+1 (copy stream) overlaps the
-    # proving of batch i (compute stream); the first batch's copy is not overlapped.
-    e2e_out = []
-
-    def e2e_run(steps):
-        nxt = upload(True)
-        for i in range(steps):
-            cur, nxt = nxt, (upload(True) if i + 1 < steps else None)
-            e2e_out.append(one_pass(cur))
-            for s in cur:
-                s.free()
-
+    # ---- end-to-end leg
     if args.no_e2e:  # development runs only: the reported line then carries no end-to-end number
-        ms_e2e, last = float("nan"), first
+        e2e_ms, last = float("nan"), res["first"]
     else:
-        e2e_run(min(args.warmup, 2))
-        ms_e2e, wall_e2e = timed(lambda: e2e_run(args.steps), 1)
-        last = e2e_out[-1]
+        e2e_ms, last = main.measure_e2e(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    assert np.array_equal(first[0], last[0]) and np.array_equal(first[1], last[1])
+    assert np.array_equal(res["first"][0], last[0]) and np.array_equal(res["first"][1], last[1])
     if args.trace_phases:  # wall clock per phase of one more pass, every rank, to stderr (syncs between phases)
-        secs = upload()
+        secs = main.upload()
         barrier()
         del trace[:]
         tracing[0] = True
-        one_pass(secs)
+        main.one_pass(secs)
         tracing[0] = False
         print(f"[rank {rank}] " + ", ".join(f"{n}: {(t - trace[i][1]) * 1e3:.2f} ms" for i, (n, t) in enumerate(trace[1:])), file=sys.stderr, flush=True)
+        for s_ in secs:
+            s_.free()
+
+    # ---- witness commitment (polycommit): DensePolynomial::commit of both sections, rows sharded
+    # over the ranks exactly like the proofs (a rank's proofs are a contiguous row range), 32 bytes
+    # per row gathered over NCCL. Generators and their window tables are setup (SNARKGens).
+    from spartan_parallel_b200 import host
+
+    commit = None
+    gens = None
+    ell = nx + log2(Q_main)
+    rows_total, R = 1 << (ell // 2), 1 << (ell - ell // 2)
+    rows_local = rows_total // world
+    if not args.no_commit and rows_local >= 1 and (main.N % R) == 0:
+        t0 = time.perf_counter()
+        gens = host.R1CSGens(ctx, b"gens_r1cs_sat", X * Q_main)
+        pc = gens.gens_pc()
+        pc.prepare(R)
+        ctx.sync()
+        gens_s = time.perf_counter() - t0
+        secs = main.upload()
+        polys = [s.poly_w(0) for s in secs]
+
+        def commit_all():
+            out = []
+            for poly in polys:
+                mine = pc.commit_poly_rows(poly, rows_local, 0, rows_local)
+                if world > 1:
+                    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+                    full = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+                    dist.all_gather_into_tensor(full, t)
+                    mine = full.cpu().numpy().tobytes()
+                out.append(mine)
+            return out
+
+        first_c = commit_all()
+        ctx.profile_begin()
+        reps = 3
+        ms_c, wall_c = timed(commit_all, reps)
+        prof_c = ctx.profile_end()
+        assert commit_all() == first_c
+        info = pc.info()
+        commit = {"seconds": wall_c * 1e-3 / reps, "device_ms": ms_c / reps, "sections": 2, "scalars": 2 * X * Q_main,
+                  "rows_per_section": rows_total, "cols": R, "rows_per_rank": rows_local,
+                  "scalars_per_s": 2 * X * Q_main / (wall_c * 1e-3 / reps), **info,
+                  "setup_s": gens_s, "prof": prof_c,
+                  "what": "DensePolynomial::commit (src/dense_mlpoly.rs:214-239) of the two witness sections, compressed row commitments on the host"
+                          + ("" if world == 1 else f"; rows sharded over {world} ranks, all-gather of 32 B per row inside the timed region")}
         for s_ in secs:
             s_.free()
 
@@ -304,25 +438,58 @@ def run_gpu(args):
     full_proof = None
     if world == 1 and not args.no_full_proof:
         try:
-            from spartan_parallel_b200 import host
-
-            gens = host.R1CSGens(ctx, b"gens_r1cs_sat", N)
-            secs = upload()
+            if gens is None:
+                gens = host.R1CSGens(ctx, b"gens_r1cs_sat", main.N)
+            secs = main.upload()
             seed = np.array([1, 2, 3, 4], dtype=np.uint64)
-            times = []
+            Q = main.Q
+            times, stages = [], None
             for _ in range(3):
+                host.timings_reset()
                 t0 = time.perf_counter()
-                blob, _ = host.r1cs_prove(ctx, inst, secs, [Q], Q, [X], X, b"bench", b"gens_r1cs_sat", seed, N, gens)
+                blob, _ = host.r1cs_prove(ctx, inst, secs, [Q], Q, [X], X, b"bench", b"gens_r1cs_sat", seed, main.N, gens)
                 times.append(time.perf_counter() - t0)
+                stages = host.timings()
             for s in secs:
                 s.free()
-            gens.free()
+            st = {}
+            for k, v in stages:
+                st[k] = st.get(k, 0.0) + v * 1e-3
+            g = lambda *ks: sum(st.get(k, 0.0) for k in ks)
             full_proof = {"seconds": min(times[1:]), "proof_bytes": len(blob),
+                          "timers": {"prove_sc_phase_one": g("z_mat + SpMV + sc1 setup", "phase-1 rounds (zk)"),
+                                     "sigma_protocols_between_phases": g("sigma protocols"),
+                                     "prove_sc_phase_two": g("sc2 setup (ABC, Z bind)", "phase-2 rounds (zk)"),
+                                     "polyeval": g("witness evaluations", "opening proofs"),
+                                     "serialization": g("tail + serialization")},
                           "what": "R1CSProof::prove end to end for the same batch (witness resident): both ZK sumchecks with their "
                                   "per-round sigma protocols on the host mirror, witness evaluations, Hyrax openings with the bullet "
-                                  "reduction MSMs on the device; excludes witness commitment and generator setup"}
+                                  "reduction MSMs on the device; timers are the reference's labels (src/r1csproof.rs:274,421,518) "
+                                  "from the last of 3 runs, `seconds` the best of the last 2"}
         except Exception as e:  # never lose the bench line over the extra measurement
             full_proof = {"error": str(e)[:200]}
+    if gens is not None:
+        gens.free()
+        gens = None
+
+    # ---- sparse-polynomial evaluation proof (memory-check product trees), C5's second half
+    sparse = None
+    if world == 1 and args.with_sparse:
+        try:
+            sparse = sparse_leg(sp, host, ctx, args.sparse_log_nnz)
+        except Exception as e:
+            sparse = {"error": str(e)[:200]}
+
+    # ---- N > 1 in strong mode: the weak figure (proofs per GPU fixed) as an extra
+    weak = None
+    if world > 1 and scaling == "strong" and not args.no_weak:
+        del main.hu, main.hv, main.u_pin, main.v_pin
+        w = Shard(args.proofs * world, 0x5EED1000)
+        k = max(3, args.steps // 4)
+        r = w.measure_resident(k, 3, profile=False)
+        weak = {"value": X * w.Q_total / (r["ms"] * 1e-3), "unit": "constraints/s", "ms_per_step": r["ms"], "steps": k,
+                "workload": f"X=2^{args.log_x} x Q={args.proofs} proofs PER GPU ({w.Q_total} in the batch)"}
+        del w
 
     if world > 1:  # orderly teardown of the peer mappings, the mailbox and the process group
         try:
@@ -333,9 +500,7 @@ def run_gpu(args):
             pass
     if rank != 0:
         return
-    step_ms = ms_dev / args.steps
-    e2e_ms = ms_e2e / args.steps
-    total_units = N * world
+    step_ms, prof = res["ms"], res["prof"]
     value = total_units / (step_ms * 1e-3)
     e2e_value = total_units / (e2e_ms * 1e-3)
     peaks = {}
@@ -345,9 +510,10 @@ def run_gpu(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    int_peak = None
+    int_peak = imad_peak = None
     try:
-        int_peak = json.load(open(os.path.join(ROOT, "profiles", "r1_imad_peak.json")))["modmul_lazy_ilp2_t256_per_s"]
+        ip = json.load(open(os.path.join(ROOT, "profiles", "r1_imad_peak.json")))
+        int_peak, imad_peak = ip["modmul_lazy_ilp2_t256_per_s"], ip["imad_wide_carry_per_s"]
     except Exception:
         pass
     dom = max(prof, key=lambda r: r["total_ms"]) if prof else None
@@ -360,50 +526,209 @@ def run_gpu(args):
                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_ms,
                     "launches_per_step": dom["launches"] / args.steps,
-                    "share_of_step": dom["total_ms"] / ms_dev}
-        if "k_rows_rolled" in dom["kernel"]:
-            # fused bind + eval item: 576 algorithmic bytes, 10 Montgomery products
-            # (6 binds + 2 products + 2 eq-weighted accumulations)
-            mm = dom["units"] / 576.0 * 10.0 / (dom["total_ms"] * 1e-3)
-            roofline["int_pipe"] = {"achieved_modmul_per_s": mm, "peak_modmul_per_s": int_peak,
-                                    "frac": (mm / int_peak) if int_peak else None,
+                    "share_of_step": dom["total_ms"] / (step_ms * args.steps)}
+        key = next((k for k in sorted(KERNEL_MODEL, key=len, reverse=True) if k in dom["kernel"]), None)
+        if key and int_peak:
+            bpi, mpi = KERNEL_MODEL[key]
+            mm = dom["units"] / bpi * mpi / (dom["total_ms"] * 1e-3)
+            roofline["int_pipe"] = {"achieved_modmul_per_s": mm, "peak_modmul_per_s": int_peak, "frac": mm / int_peak,
                                     "peak_source": "tools/imad_peak.cu in-register fq_mul_lazy rate (profiles/r1_imad_peak.json)"}
-        # DRAM traffic of the largest launch of this kernel from the committed ncu --set full capture
+        tr = ncu_traffic(dom["kernel"])
+        if tr:
+            roofline["traffic"], roofline["traffic_note"] = tr
+    by_kernel = kernel_rooflines(prof, hbm_peak, int_peak, imad_peak)
+    for e in by_kernel:
+        e["ms_per_step"] = e.pop("total_ms") / args.steps
+        e["launches_per_step"] = e.pop("launches") / args.steps
+    if commit:
+        cp = commit.pop("prof")
+        for e in kernel_rooflines(cp, hbm_peak, int_peak, imad_peak):
+            e["ms_per_commit"] = e.pop("total_ms") / 3
+            e["launches_per_commit"] = e.pop("launches") / 3
+            e["leg"] = "polycommit"
+            by_kernel.append(e)
+    if sparse and "prof" in sparse:
+        for e in kernel_rooflines(sparse.pop("prof"), hbm_peak, int_peak, imad_peak)[:6]:
+            e["leg"] = "sparse proof"
+            by_kernel.append(e)
+    cpu = cpu_baseline_sample(args, threads=1)
+    # BASELINE metric (1): prove time
+    prove_time = {"polycommit": commit["seconds"] if commit else None}
+    if world == 1:
+        prove_time["R1CSProof::prove"] = full_proof.get("seconds") if full_proof else None
+        if full_proof and "timers" in full_proof:
+            prove_time.update(full_proof["timers"])
+        if sparse and "seconds" in sparse:
+            prove_time["SparseMatPolyEvalProof::prove"] = sparse["seconds"]
+            prove_time.update(sparse.get("timers", {}))
+        parts = [prove_time["polycommit"], prove_time["R1CSProof::prove"], prove_time.get("SparseMatPolyEvalProof::prove", 0.0)]
+        prove_time["what"] = "witness commitment + R1CSProof::prove" + (" + SparseMatPolyEvalProof::prove (3 matrices x 2^%d non-zeros)" % args.sparse_log_nnz if sparse and "seconds" in sparse else "") + ", wall clock, witness resident in HBM"
+    else:
+        prove_time["sumcheck_table_pass"] = step_ms * 1e-3
+        parts = [prove_time["polycommit"], prove_time["sumcheck_table_pass"]]
+        prove_time["what"] = ("sharded legs only: witness commitment (rows over ranks) + the table pass of both sumchecks; the transcript-side "
+                              "host mirror (sigma protocols, openings) drives one GPU and is timed at N = 1")
+    prove_time_s = sum(parts) if all(p is not None for p in parts) else None
+    shard_note = ("single GPU" if world == 1 else
+                  f"one batch of {Q_main} proofs sharded by proof index over {world} ranks ({main.Q} per rank): per-round exchange of 3 scalars per rank "
+                  "through host shared memory (the values already live in pinned host memory) + one modular all-reduce of the rq-bound Z table as a "
+                  "kernel over NVLink peer memory (CUDA IPC; rank r sums chunk r with P2P loads and writes it to every peer with P2P stores)")
+    line = {
+        "metric": "sumcheck_constraints_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "u256 (F_q, 8x32-bit Montgomery limbs)", "data": "synthetic",
+        "config": {"workload": f"data-parallel R1CS batch, X=2^{args.log_x} constraints x Q={Q_main} proofs in total ({main.Q} per GPU), P=1 instance, W=2 sections (BASELINE configs[4] shape)",
+                   "constraints_per_step": total_units, "sharding": shard_note,
+                   "e2e_pipeline": "double-buffered: the H2D copy of batch i+1 overlaps the proving of batch i; all copies are inside the timed region",
+                   "l2": f"inputs ({2 * main.N * 32 / 2**30:.2f} GiB per GPU per step) exceed the 126 MB L2; no flush needed",
+                   "challenges": "precomputed per-round challenges replayed by a C loop (spg_sc1_run_rounds / spg_sc2_run_rounds); every round still returns its 3 evaluations to the host (96 B) before the bind with that round's challenge (32 B) is issued; `value` is therefore the rate of the table work, `prove_time` the whole protocol",
+                   "phases": "z_mat + SpMV + phase-1 rounds + ABC/Z tables + phase-2 rounds"},
+        "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(2 * main.N * 32 * world), "d2h_bytes_per_step": int(96 * (2 * nx + main.nq + ng + 1) + 7 * 32)},
+        "gpu_launches": res["launches"], "full_proof": full_proof, "wall_ms_per_step": res["wall_ms"],
+        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse,
+        "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
+        "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s, "host_affinity": numa,
+    }
+    if parity is not None:
+        line["parity"] = bool(parity.get("ok"))
+        line["parity_check"] = parity
+    if weak is not None:
+        line["weak"] = weak
+    emit(line)
+
+
+def ncu_traffic(kernel_name):
+    """dram bytes of the largest launch of this kernel from the newest committed `ncu --set full`
+    summary under profiles/ (a cross-reference measured under the profiler, not part of this run)."""
+    import glob
+
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_full*.txt")), reverse=True):
         try:
             rd = wr = None
             seen = False
-            for ln in open(os.path.join(ROOT, "profiles", "r1e_ncu_full.txt")):
+            for ln in open(path):
                 if ln.startswith("== launch"):
-                    if seen:
+                    if seen and rd and wr:
                         break
-                    seen = "k_rows_rolled" in ln
+                    seen = kernel_name.split("<")[0] in ln
+                    rd = wr = None
                 elif seen and ln.startswith("dram__bytes_read.sum ="):
                     rd = float(ln.split("=")[1].split()[0]) * 1e9
                 elif seen and ln.startswith("dram__bytes_write.sum ="):
                     wr = float(ln.split("=")[1].split()[0]) * 1e9
-            if rd and wr and "k_rows_rolled" in dom["kernel"]:
-                roofline["traffic"] = rd + wr
-                roofline["traffic_note"] = f"largest launch (ncu --set full, profiles/r1e_ncu_full.txt); its algorithmic bytes: {dom['max_units']:.4g}"
+            if seen and rd and wr:
+                best = (rd + wr, f"largest launch of {kernel_name.split('<')[0]} in {os.path.basename(path)} (ncu --set full, captured separately)")
+                break
         except Exception:
-            pass
-    cpu = cpu_baseline_sample(args, threads=1)
-    line = {
-        "metric": "sumcheck_constraints_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u256 (F_q, 8x32-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": f"data-parallel R1CS batch, X=2^{args.log_x} constraints x Q={Q} proofs per GPU, P=1 instance, W=2 sections (BASELINE configs[4] shape)",
-                   "constraints_per_step": total_units, "sharding": ("single GPU" if world == 1 else f"one batch of {Q * world} proofs sharded by proof index over {world} ranks: per-round exchange of 3 scalars per rank through host shared memory (the values already live in pinned host memory) + one modular all-reduce of the rq-bound Z table as a kernel over NVLink peer memory (CUDA IPC; rank r sums chunk r with P2P loads and writes it to every peer with P2P stores)"),
-                   "e2e_pipeline": "double-buffered: the H2D copy of batch i+1 overlaps the proving of batch i; all copies are inside the timed region",
-                   "l2": "inputs (>= 4 GiB/step) exceed the 126 MB L2; no flush needed",
-                   "challenges": "precomputed per-round challenges replayed by a C loop (spg_sc1_run_rounds / spg_sc2_run_rounds); every round still returns its 3 evaluations to the host (96 B) before the bind with that round's challenge (32 B) is issued",
-                   "phases": "z_mat + SpMV + phase-1 rounds + ABC/Z tables + phase-2 rounds"},
-        "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(2 * N * 32), "d2h_bytes_per_step": int(96 * (2 * nx + nq + ng + 1) + 7 * 32)},
-        "gpu_launches": int(launches), "full_proof": full_proof, "wall_ms_per_step": wall_dev / args.steps,
-        "prove_time_s": step_ms * 1e-3, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s, "host_affinity": numa,
-    }
-    emit(line)
+            continue
+    return best
+
+
+def sharded_equals_unsharded(sp, parallel, ctx, comm, rank, world, log_x, Q):
+    """BASELINE config C3 (X = 2^16, Q = 256) proven sharded over all ranks and unsharded on this
+    rank's own GPU from the same seeded batch: every round polynomial of both sumchecks and both
+    claim vectors must be bit-identical (src/sumcheck.rs:1166-1275, src/r1csproof.rs:469-501)."""
+    X, Ql = 1 << log_x, Q // world
+    nq = log2(Q)
+    rng = np.random.default_rng(77)  # the same stream on every rank
+    u = random_canonical(rng, X * Q)
+    du = sp.DensePolynomial.new(ctx, u)
+    dun = sp.DensePolynomial.new(ctx, np.ascontiguousarray(np.roll(u.reshape(Q, X, 4), -1, axis=1).reshape(X * Q, 4)))
+    v = sp.vec_op(ctx, "mul", du, dun).to_host()
+    del du, dun
+    A, B, Cm = synthetic_matrices(X, ONE)
+    inst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A], [B], [Cm])
+    tau_q, tau_x = challenges(rng, nq), challenges(rng, log_x)
+    ch1, ch2, r_abc = challenges(rng, log_x + nq), challenges(rng, 1 + log_x), challenges(rng, 3)
+    none = ch1[:0]
+    rx = ch1[:log_x][::-1].copy()
+    secs = [sp.ProverWitnessSecInfo(ctx, [Q], [X], u), sp.ProverWitnessSecInfo(ctx, [Q], [X], v)]
+    z = sp.ZMat(ctx, [Q], [X], secs)
+    sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, none, tau_q, tau_x)
+    want1, wantc1 = sc1.run_rounds(ch1), None
+    wantc1 = sc1.final()
+    sc1.free()
+    sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[log_x:], none, *r_abc)
+    want2 = sc2.run_rounds(ch2)
+    wantc2 = sc2.final()
+    sc2.free()
+    z.free()
+    for s_ in secs:
+        s_.free()
+    lo, hi = rank * Ql * X, (rank + 1) * Ql * X
+    secs = [sp.ProverWitnessSecInfo(ctx, [Ql], [X], u[lo:hi]), sp.ProverWitnessSecInfo(ctx, [Ql], [X], v[lo:hi])]
+    z = sp.ZMat(ctx, [Ql], [X], secs)
+    peer = parallel.PeerTable(ctx, comm, 2 * X)
+    sh = parallel.gpu_phase1(ctx, comm, inst, z, Ql, X, X, tau_q, tau_x, satisfied=True)
+    got1 = sh.run_rounds(ch1)
+    gotc1 = sh.final()
+    sh.free()
+    zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[log_x:], Ql, peer)
+    sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, none, *r_abc)
+    got2 = sc2.run_rounds(ch2)
+    gotc2 = sc2.final()
+    sc2.free()
+    peer.close()
+    z.free()
+    for s_ in secs:
+        s_.free()
+    inst.free()
+    ok = (np.array_equal(got1, want1) and np.array_equal(gotc1, wantc1) and np.array_equal(got2, want2)
+          and np.array_equal(gotc2, wantc2))
+    return {"ok": bool(ok), "config": f"C3: X=2^{log_x} x Q={Q} sharded over {world} ranks vs unsharded on each rank's GPU",
+            "compared": f"{len(want1)} + {len(want2)} round polynomials, 4 + 3 final claims, bit for bit"}
+
+
+def sparse_leg(sp, host, ctx, lg):
+    """SparseMatPolynomial::multi_commit + SparseMatPolyEvalProof::prove (src/sparse_mlpoly.rs:566-586,
+    1497-1564) for three matrices of 2^lg non-zeros over 2^lg rows x 2^(lg+1) columns."""
+    batch, nvx, nvy = 3, lg, lg + 1
+    rng = np.random.default_rng(3)
+    nnz = 1 << lg
+    polys = []
+    for _ in range(batch):
+        rows = rng.integers(0, 1 << nvx, size=nnz).astype(np.uint32)
+        cols = rng.integers(0, 1 << nvy, size=nnz).astype(np.uint32)
+        polys.append((rows, cols, random_canonical(rng, nnz)))
+    rx, ry = challenges(rng, nvx), challenges(rng, nvy)
+    hrx, hry = sp.EqPolynomial(ctx, rx).evals().to_host(), sp.EqPolynomial(ctx, ry).evals().to_host()
+    evals = []
+    for rows, cols, vals in polys:  # M_i(rx, ry) on the device
+        a, b, v = sp.DensePolynomial.new(ctx, hrx[rows]), sp.DensePolynomial.new(ctx, hry[cols]), sp.DensePolynomial.new(ctx, vals)
+        evals.append(sp.dot(ctx, sp.vec_op(ctx, "mul", a, b), v))
+    seed = np.array([1, 2, 3, 4], dtype=np.uint64)
+    best, stages, prof = None, None, []
+    t0 = time.perf_counter()
+    gens = host.SparseGens(ctx, b"gens_sparse_poly", nvx, nvy, nnz, batch)  # setup: SNARKGens::new
+    gens_s = time.perf_counter() - t0
+    for it in range(3):
+        host.timings_reset()
+        if it == 2:
+            ctx.profile_begin()
+        t0 = time.perf_counter()
+        comm, proof = host.sparse_prove(ctx, polys, nvx, nvy, rx, ry, np.stack(evals), b"bench", b"gens_sparse_poly", seed, gens)
+        dt = time.perf_counter() - t0
+        if it == 2:
+            prof = ctx.profile_end()
+        if it and (best is None or dt < best):
+            best, stages = dt, host.timings()
+    st = {}
+    for k, v in stages:
+        st[k] = st.get(k, 0.0) + v * 1e-3
+    g = lambda *ks: sum(st.get("sparse: " + k, 0.0) for k in ks)
+    pre = g("dense representation", "generators", "multi_commit")
+    gens.free()
+    return {"gens_setup_s": gens_s, "seconds": best - pre, "with_preprocessing_s": best, "proof_bytes": len(proof), "commitment_bytes": len(comm),
+            "timers": {"commit_nondet_witness": g("eq tables + derefs", "derefs commitment"),
+                       "build_layered_network": g("hash layers + trees"),
+                       "evalproof_layered_network": g("tree evals + dotp", "product-circuit sumchecks"),
+                       "hash_layer_evals_and_openings": g("hash-layer evals + 3 openings")},
+            "preprocessing": {"dense_representation": g("dense representation"), "generators": g("generators"), "multi_commit": g("multi_commit")},
+            "prof": prof,
+            "what": f"3 matrices x 2^{lg} non-zeros; `seconds` = SparseMatPolyEvalProof::prove (timers: src/sparse_mlpoly.rs:1522-1545), "
+                    "preprocessing (SNARK::encode: dense representation, generators, multi_commit) reported apart"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -445,14 +770,21 @@ def set_oracle_threads(n):
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the same path on the host cores: the OpenMP C
+    restatement of its loops (oracle/; the Rust crate cannot be built here or on the GPU box:
+    no cargo). Same config as the GPU arm (X = 2^20 x Q = 64 by default); a pass takes ~20 s on
+    16 cores, so the number of timed passes is capped by --ref-budget-s and reported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     from oracle import cbind as O
+    from oracle import r1cs as R
 
     O.lib()
-    X, Q = 1 << min(args.log_x, args.cpu_log_x), min(args.proofs, args.cpu_proofs)
+    log_x = args.ref_log_x if args.ref_log_x is not None else args.log_x
+    Q = args.ref_proofs if args.ref_proofs is not None else args.proofs
+    X = 1 << log_x
     host_cores = os.cpu_count() or 1
     # the reference's default build is single-threaded (rayon is optional and only used in
     # commit_inner); the restatement's (q, x) loops are OpenMP-parallel. Use whichever thread
@@ -460,21 +792,42 @@ def run_reference(args):
     probe = {}
     for n in sorted({1, host_cores}):
         set_oracle_threads(n)
-        probe[n] = oracle_pass(1 << min(16, args.cpu_log_x), min(8, Q))
+        probe[n] = oracle_pass(1 << min(16, log_x), min(8, Q))
     cores = min(probe, key=probe.get)
     set_oracle_threads(cores)
-    for _ in range(min(args.warmup, 1)):
-        oracle_pass(X, Q)
-    t = [oracle_pass(X, Q) for _ in range(args.steps)]
+    # one synthetic batch, reused by every pass (generation is not part of the path)
+    inst = R.synthetic_instance(X)
+    secs = R.synthetic_witness(X, [Q], seed=1)
+    rng = np.random.default_rng(1)
+    nx, nq = log2(X), log2(Q)
+    tau_q, tau_x = challenges(rng, nq), challenges(rng, nx)
+    ch1, ch2 = challenges(rng, nx + nq), challenges(rng, 1 + nx)
+    r_abc = challenges(rng, 3)
+
+    def one():
+        t0 = time.perf_counter()
+        R.prove_tables(inst, 1, Q, [Q], X, [X], secs, tau_q[:0], tau_q, tau_x, ch1, r_abc, ch2)
+        return time.perf_counter() - t0
+
+    t_first = one()  # warm-up pass (page faults, thread pool); also sizes the run
+    steps = int(max(2, min(args.steps, args.ref_budget_s // max(t_first, 1e-3))))
+    warm = 1
+    t = [one() for _ in range(steps)]
     dt = float(np.mean(t))
     val = X * Q / dt
-    sample = f"X=2^{log2(X)} x Q={Q} ({X * Q} constraints) per step of the X=2^{args.log_x} x Q={args.proofs} workload"
+    same = (log_x == args.log_x and Q == args.proofs)
+    sample = (f"the whole X=2^{log_x} x Q={Q} batch ({X * Q} constraints) per step" if same else
+              f"X=2^{log_x} x Q={Q} ({X * Q} constraints) per step of the X=2^{args.log_x} x Q={args.proofs} workload")
     line = {
         "impl": "reference", "metric": "sumcheck_constraints_per_sec", "value": val, "unit": "constraints/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling or "strong",
         "vs_baseline": None, "dtype": "u256 (F_q, 4x64-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": f"data-parallel R1CS batch, X=2^{args.log_x} constraints x Q={args.proofs} proofs per GPU, P=1 instance, W=2 sections (BASELINE configs[4] shape)",
-                   "note": "the Rust crate cannot be built here (no cargo); this arm times the C restatement of its loops (oracle/) on the host cores",
+        "config": {"workload": f"data-parallel R1CS batch, X=2^{args.log_x} constraints x Q={args.proofs} proofs in total, P=1 instance, W=2 sections (BASELINE configs[4] shape)",
+                   "constraints_per_step": X * Q,
+                   "note": "the Rust crate cannot be built here (no cargo on either box); this arm times the C restatement of its loops (oracle/) on the host cores; "
+                           f"timed passes capped at {steps} by --ref-budget-s {args.ref_budget_s} (a pass takes {t_first:.1f} s)",
+                   "phases": "z_mat + SpMV + phase-1 rounds + ABC/Z tables + phase-2 rounds",
                    "thread_probe_s": {str(k): v for k, v in probe.items()}},
         "cpu_baseline": {"value": val, "unit": "constraints/s", "cores": cores, "kind": "port", "sample": sample, "host_cores": host_cores},
         "e2e": {"value": val, "unit": "constraints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -510,10 +863,20 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-x", type=int, default=20)
-    ap.add_argument("--proofs", type=int, default=64)
-    ap.add_argument("--cpu-log-x", type=int, default=18)
+    ap.add_argument("--proofs", type=int, default=64, help="proofs in the batch (strong scaling) / per GPU (--scaling weak)")
+    ap.add_argument("--scaling", choices=["strong", "weak"], default=None,
+                    help="N > 1: strong (default) splits the batch of --proofs over the ranks; weak keeps --proofs per GPU")
+    ap.add_argument("--cpu-log-x", type=int, default=18, help="bounded CPU sample inside the GPU arm's line")
     ap.add_argument("--cpu-proofs", type=int, default=16)
-    ap.add_argument("--no-full-proof", action="store_true", help="skip the extra whole-proof timing")
+    ap.add_argument("--ref-log-x", type=int, default=None, help="--impl reference: default = the GPU arm's config")
+    ap.add_argument("--ref-proofs", type=int, default=None)
+    ap.add_argument("--ref-budget-s", type=float, default=240.0, help="--impl reference: wall-clock budget of the timed passes")
+    ap.add_argument("--no-full-proof", action="store_true", help="skip the whole-proof timing")
+    ap.add_argument("--no-commit", action="store_true", help="skip the witness-commitment leg")
+    ap.add_argument("--no-sparse", dest="with_sparse", action="store_false", help="skip the sparse-polynomial evaluation proof leg")
+    ap.add_argument("--sparse-log-nnz", type=int, default=20)
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded == unsharded check (C3)")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1, strong mode: skip the extra weak-scaling figure")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the end-to-end leg")
     ap.add_argument("--trace-phases", action="store_true", help="development: per-phase wall clock of one extra pass on stderr")
     args = ap.parse_args()

@@ -196,6 +196,14 @@ int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, 
 int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges,
                                spg_fq *evals_out, void *mailbox, size_t slot_stride, int rank,
                                int world, uint64_t *calls);
+/* One exchange through the same mailbox: every rank contributes nbytes (<= slot_stride - 64) and
+ * receives all ranks' contributions in rank order (out: world * nbytes). Release / acquire
+ * ordering on the sequence words; waits are bounded (SPG_MAILBOX_TIMEOUT_S, default 120 s) and
+ * a rank that fails poisons its slots (spg_mailbox_poison, done automatically on error) so
+ * that its peers return SPG_ESTATE instead of spinning forever. */
+int spg_mailbox_all_gather(void *mailbox, size_t slot_stride, int rank, int world, uint64_t *calls,
+                           const void *data, size_t nbytes, void *out);
+void spg_mailbox_poison(void *mailbox, size_t slot_stride, int rank, int world);
 /* (tau_claim, Az, Bz, Cz) after the last bind, :1372-1377 */
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]);
 /* copy the current Az/Bz/Cz tables back in natural ragged order (tests) */

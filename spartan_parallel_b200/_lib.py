@@ -128,6 +128,7 @@ def _proto(L):
         "spg_poly_commit": [P, P, P, SZ, P],
         "spg_commit_batch": [P, P, P, SZ, P, SZ, P],
         "spg_poly_commit_rows": [P, P, P, SZ, SZ, SZ, P],
+        "spg_mailbox_all_gather": [P, SZ, INT, INT, P, P, SZ, P],
         "spg_gens_prepare": [P, P, SZ],
         "spg_gens_info": [P, P],
         "spg_debug_fe8_selftest": [P, SZ, C.c_uint64, P],
@@ -151,6 +152,8 @@ def _proto(L):
         if f is not None:
             f.restype = SZ
             f.argtypes = [P]
+    L.spg_mailbox_poison.restype = None
+    L.spg_mailbox_poison.argtypes = [P, SZ, INT, INT]
     L.spg_ctx_launch_count.restype = C.c_uint64
     L.spg_ctx_launch_count.argtypes = [P]
     L.spg_ctx_stream.restype = P

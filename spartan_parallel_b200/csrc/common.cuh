@@ -104,6 +104,29 @@ struct spg_vec {
 
 namespace spg {
 
+// Every entry point that takes a context or a handle runs on that context's device, whatever
+// device the calling thread had current (another host thread than the creating one -- current
+// device is per thread and defaults to 0 --, a library that switched devices in between, one
+// process holding several contexts), and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const spg_ctx *ctx) {
+    if (!ctx) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+template <typename H>
+static inline const spg_ctx *ctx_of(const H *h) {
+  return h ? h->ctx : nullptr;
+}
+static inline const spg_ctx *ctx_of(const spg_ctx *c) { return c; }
+
 // launch bookkeeping: every kernel goes through this so gpu_launches is exact
 #define SPG_LAUNCH(ctx, kernel, grid, block, smem, ...)                       \
   do {                                                                        \

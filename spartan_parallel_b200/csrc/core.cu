@@ -269,6 +269,7 @@ void spg_ctx_destroy(spg_ctx *ctx) {
 }
 
 int spg_ctx_sync(spg_ctx *ctx) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx, "null ctx");
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
@@ -277,6 +278,7 @@ int spg_ctx_sync(spg_ctx *ctx) {
 uint64_t spg_ctx_launch_count(const spg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int spg_ctx_profile_begin(spg_ctx *ctx) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx, "null ctx");
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   for (auto &r : ctx->prof) {
@@ -289,6 +291,7 @@ int spg_ctx_profile_begin(spg_ctx *ctx) {
 }
 
 int spg_ctx_profile_end(spg_ctx *ctx, char *out, size_t cap) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && cap > 2, "spg_ctx_profile_end: bad buffer");
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->profiling = false;
@@ -375,11 +378,13 @@ void spg_host_free(void *p) {
 }
 
 int spg_vec_alloc(spg_ctx *ctx, size_t n, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out, "spg_vec_alloc: null argument");
   return vec_new(ctx, n, out);
 }
 
 int spg_vec_upload(spg_ctx *ctx, const spg_fq *host, size_t n, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && (host || n == 0), "spg_vec_upload: null argument");
   spg_vec *v = nullptr;
   SPG_TRY(vec_new(ctx, n, &v));
@@ -396,6 +401,7 @@ int spg_vec_upload(spg_ctx *ctx, const spg_fq *host, size_t n, spg_vec **out) {
 }
 
 int spg_vec_wrap(spg_ctx *ctx, void *device_ptr, size_t n, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && device_ptr, "spg_vec_wrap: null argument");
   SPG_CHECK(((uintptr_t)device_ptr & 31) == 0, "spg_vec_wrap: pointer must be 32-byte aligned");
   spg_vec *v = new (std::nothrow) spg_vec();
@@ -409,6 +415,7 @@ int spg_vec_wrap(spg_ctx *ctx, void *device_ptr, size_t n, spg_vec **out) {
 }
 
 int spg_vec_download(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_fq *host) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && (host || n == 0), "spg_vec_download: null argument");
   SPG_CHECK(offset + n <= v->n, "spg_vec_download: range [%zu, %zu) exceeds length %zu", offset,
             offset + n, v->n);
@@ -423,6 +430,7 @@ size_t spg_vec_len(const spg_vec *v) { return v ? v->n : 0; }
 void *spg_vec_device_ptr(const spg_vec *v) { return v ? (void *)v->d : nullptr; }
 
 void spg_vec_free(spg_vec *v) {
+  spg::DeviceGuard _dev(spg::ctx_of(v));
   if (!v) return;
   if (v->owned && v->d) dev_free(v->ctx, v->d);
   delete v;

@@ -160,6 +160,7 @@ struct spg_cubic {
 extern "C" {
 
 int spg_prodtree_build(spg_ctx *ctx, const spg_vec *leaves, spg_prodtree **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && leaves && out, "spg_prodtree_build: null argument");
   size_t n = leaves->n;
   SPG_CHECK(is_pow2(n) && n >= 2, "spg_prodtree_build: length %zu must be a power of two >= 2", n);
@@ -201,6 +202,7 @@ int spg_prodtree_build(spg_ctx *ctx, const spg_vec *leaves, spg_prodtree **out) 
 size_t spg_prodtree_num_layers(const spg_prodtree *t) { return t ? t->num_layers : 0; }
 
 int spg_prodtree_layer(spg_prodtree *t, size_t layer, spg_vec **left, spg_vec **right) {
+  spg::DeviceGuard _dev(spg::ctx_of(t));
   SPG_CHECK(t && left && right, "spg_prodtree_layer: null argument");
   SPG_CHECK(layer < t->num_layers, "spg_prodtree_layer: layer %zu out of range (%zu)", layer, t->num_layers);
   *left = t->left[layer];
@@ -209,6 +211,7 @@ int spg_prodtree_layer(spg_prodtree *t, size_t layer, spg_vec **left, spg_vec **
 }
 
 int spg_prodtree_evaluate(spg_ctx *ctx, spg_prodtree *t, spg_fq *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && t && out, "spg_prodtree_evaluate: null argument");
   // left_vec[last][0] * right_vec[last][0]; the last layer (two scalars) sits at 2n - 4
   fq h[2];
@@ -222,6 +225,7 @@ int spg_prodtree_evaluate(spg_ctx *ctx, spg_prodtree *t, spg_fq *out) {
 }
 
 void spg_prodtree_destroy(spg_prodtree *t) {
+  spg::DeviceGuard _dev(spg::ctx_of(t));
   if (!t) return;
   for (spg_vec *v : t->left) spg_vec_free(v);
   for (spg_vec *v : t->right) spg_vec_free(v);
@@ -232,6 +236,7 @@ void spg_prodtree_destroy(spg_prodtree *t) {
 int spg_cubic_create(spg_ctx *ctx, size_t npar, spg_vec *const *A_par, spg_vec *const *B_par,
                      spg_vec *C_par, size_t nseq, spg_vec *const *A_seq, spg_vec *const *B_seq,
                      spg_vec *const *C_seq, const spg_fq *coeffs, spg_cubic **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && coeffs, "spg_cubic_create: null argument");
   SPG_CHECK(npar + nseq >= 1 && npar + nseq <= 24, "spg_cubic_create: %zu triples (1..24 supported)", npar + nseq);
   SPG_CHECK(npar == 0 || (A_par && B_par && C_par), "spg_cubic_create: null parallel tables");
@@ -268,6 +273,7 @@ int spg_cubic_create(spg_ctx *ctx, size_t npar, spg_vec *const *A_par, spg_vec *
 }
 
 int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && e, "spg_cubic_round_eval: null argument");
   if (s->len < 2 || s->evaluated) {
     set_error(s->evaluated ? "spg_cubic_round_eval: round already evaluated" : "spg_cubic_round_eval: all rounds are done");
@@ -305,6 +311,7 @@ int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]) {
 }
 
 int spg_cubic_round_bind(spg_cubic *s, const spg_fq *r) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && r, "spg_cubic_round_bind: null argument");
   if (!s->evaluated) {
     set_error("spg_cubic_round_bind: round has not been evaluated");
@@ -337,6 +344,7 @@ int spg_cubic_round_bind(spg_cubic *s, const spg_fq *r) {
 }
 
 int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && claims, "spg_cubic_final: null argument");
   if (s->len != 1) {
     set_error("spg_cubic_final: tables still have %zu entries", s->len);
@@ -357,12 +365,14 @@ int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
 }
 
 void spg_cubic_destroy(spg_cubic *s) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   if (!s) return;
   delete s;
 }
 
 int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const uint64_t *ts, size_t n,
                    const spg_fq *gamma, const spg_fq *tau, int ts_plus_one, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && val && gamma && tau && out, "spg_hash_layer: null argument");
   SPG_CHECK(val->n >= n, "spg_hash_layer: val has %zu entries, need %zu", val->n, n);
   spg_vec *o = nullptr;
@@ -392,6 +402,7 @@ int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const
 }
 
 int spg_deref(spg_ctx *ctx, const uint64_t *addr, size_t n, const spg_vec *mem, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && addr && mem && out, "spg_deref: null argument");
   for (size_t i = 0; i < n; i++)
     SPG_CHECK(addr[i] < mem->n, "spg_deref: address %llu at %zu exceeds %zu memory cells",

@@ -232,6 +232,7 @@ using namespace spg;
 extern "C" {
 
 int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_vec *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && a && out, "spg_fq_vec_op: null argument");
   SPG_CHECK(op >= 0 && op <= 6, "spg_fq_vec_op: unknown op %d", op);
   bool binary = op <= 2;
@@ -254,6 +255,7 @@ int spg_fq_vec_op(spg_ctx *ctx, int op, const spg_vec *a, const spg_vec *b, spg_
 }
 
 int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && (host_wide || n == 0), "spg_fq_from_u512: null argument");
   spg_vec *v = nullptr;
   SPG_TRY(vec_new(ctx, n, &v));
@@ -270,6 +272,7 @@ int spg_fq_from_u512(spg_ctx *ctx, const uint64_t *host_wide, size_t n, spg_vec 
 }
 
 int spg_eq_evals(spg_ctx *ctx, const spg_fq *r, size_t ell, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && (r || ell == 0), "spg_eq_evals: null argument");
   SPG_CHECK(ell <= 34, "spg_eq_evals: ell = %zu too large", ell);
   size_t n = (size_t)1 << ell;
@@ -292,6 +295,7 @@ int spg_eq_evals(spg_ctx *ctx, const spg_fq *r, size_t ell, spg_vec **out) {
 }
 
 int spg_dense_bound_top(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && r, "spg_dense_bound_top: null argument");
   SPG_CHECK(v->n >= 2 && is_pow2(v->n), "spg_dense_bound_top: length %zu is not a power of two >= 2", v->n);
   size_t n = v->n / 2;
@@ -303,6 +307,7 @@ int spg_dense_bound_top(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
 }
 
 int spg_dense_bound_bot(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && r, "spg_dense_bound_bot: null argument");
   SPG_CHECK(v->n >= 2 && is_pow2(v->n), "spg_dense_bound_bot: length %zu is not a power of two >= 2", v->n);
   SPG_CHECK(v->owned, "spg_dense_bound_bot: vector must be library-owned");
@@ -319,6 +324,7 @@ int spg_dense_bound_bot(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
 }
 
 int spg_dense_evaluate(spg_ctx *ctx, const spg_vec *v, const spg_fq *r, size_t ell, spg_fq *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && out && (r || ell == 0), "spg_dense_evaluate: null argument");
   SPG_CHECK(v->n == ((size_t)1 << ell), "spg_dense_evaluate: len %zu != 2^%zu", v->n, ell);
   SPG_TRY(dense_evaluate_device(ctx, v->d, v->n, r, ell, ctx->d_result));
@@ -326,6 +332,7 @@ int spg_dense_evaluate(spg_ctx *ctx, const spg_vec *v, const spg_fq *r, size_t e
 }
 
 int spg_dot(spg_ctx *ctx, const spg_vec *a, const spg_vec *b, spg_fq *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && a && b && out, "spg_dot: null argument");
   SPG_CHECK(a->n == b->n, "spg_dot: length mismatch");
   int grid = grid_for(ctx, a->n, 256, 4);
@@ -336,6 +343,7 @@ int spg_dot(spg_ctx *ctx, const spg_vec *a, const spg_vec *b, spg_fq *out) {
 }
 
 int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_size, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && L && out, "spg_dense_bound_L: null argument");
   SPG_CHECK(L_size && v->n % L_size == 0, "spg_dense_bound_L: L_size %zu does not divide len %zu", L_size, v->n);
   size_t Rs = v->n / L_size;
@@ -362,6 +370,7 @@ int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_
 extern "C" {
 
 int spg_peer_alloc(spg_ctx *ctx, size_t n, spg_vec **out, uint8_t handle[64]) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && handle && n, "spg_peer_alloc: null argument");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   fq *d = nullptr;
@@ -384,6 +393,7 @@ int spg_peer_alloc(spg_ctx *ctx, size_t n, spg_vec **out, uint8_t handle[64]) {
 }
 
 int spg_peer_free(spg_vec *v) {
+  spg::DeviceGuard _dev(spg::ctx_of(v));
   if (!v) return SPG_OK;
   void *d = v->d;
   spg_vec_free(v);
@@ -392,6 +402,7 @@ int spg_peer_free(spg_vec *v) {
 }
 
 int spg_peer_open(spg_ctx *ctx, const uint8_t handle[64], void **ptr) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && handle && ptr, "spg_peer_open: null argument");
   cudaIpcMemHandle_t h;
   memcpy(&h, handle, 64);
@@ -405,6 +416,7 @@ int spg_peer_close(void *ptr) {
 }
 
 int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && peer_ptrs, "spg_peer_sum: null argument");
   SPG_CHECK(world >= 1 && world <= 16 && rank >= 0 && rank < world, "spg_peer_sum: bad rank %d of %d", rank, world);
   SPG_CHECK(n % (size_t)world == 0, "spg_peer_sum: %zu scalars do not split over %d ranks", n, world);

@@ -20,6 +20,8 @@
 // concurrently resident blocks share a handful of chunks, so table reads are L2 hits. The next
 // table entry is fetched before the current addition is computed (its address depends only on
 // the scalar's digits).
+#include <atomic>
+
 #include "common.cuh"
 #include "ed25519.cuh"
 #include "fe8.cuh"
@@ -337,6 +339,16 @@ k_msm_finish_tree(const ge8 *__restrict__ partial, size_t nblk, const fq *__rest
   if (threadIdx.x == 0) store_compressed(acc, out + 32 * i);
 }
 
+// profiling only: the number of non-zero scalars (zero scalars cost no additions)
+__global__ void k_count_nonzero(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_stride,
+                                unsigned long long *__restrict__ count) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mine = 0;
+  for (; t < L * R; t += (size_t)gridDim.x * blockDim.x) mine += !fq_is_zero(fq_load(scalars + (t / R) * row_stride + t % R));
+  mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, mine);
+}
+
 // ---------------------------------------------------------------- fe8 self-test
 // random and edge operands through fe8_{mul,add,sub} and the mixed / full point additions,
 // compared with the ten-limb code of ed25519.cuh (which the CPU tests pin to the oracle)
@@ -431,25 +443,28 @@ namespace {
 
 size_t table_bytes_for(size_t slots, const Win &w) { return slots * (size_t)w.wins * w.ent * sizeof(niels8); }
 
-// Largest window width in [8, 13] whose table fits the budget: SPG_MSM_TABLE_GIB (default 40)
-// and at most 30 % of the device's memory. Wider windows mean fewer additions per scalar
-// (32 at c = 8, 26 at 10, 24 at 11, 22 at 12, 20 at 13) and a table that doubles with each bit.
+// Largest window width in [8, 13] whose table fits the budget. Wider windows mean fewer additions
+// per scalar (32 at c = 8, 26 at 10, 24 at 11, 22 at 12, 20 at 13) and a table that doubles with each
+// bit. Budget of one table: SPG_MSM_TABLE_GIB (default 40), and at most 60 % of what is left of the
+// process-wide allowance for tables (45 % of the device's memory) and of the memory free right now.
+std::atomic<size_t> g_table_bytes{0};
 Win pick_window(size_t slots) {
+  if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
+    int c = atoi(e);
+    if (c >= 5 && c <= 16) return make_win(c);
+  }
   double gib = 40.0;
   if (const char *e = getenv("SPG_MSM_TABLE_GIB")) gib = atof(e);
   size_t budget = (size_t)(gib * 1073741824.0);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-    if (budget > total_b * 3 / 10) budget = total_b * 3 / 10;
-    if (budget > free_b * 6 / 10) budget = free_b * 6 / 10;
+    size_t allowance = total_b / 100 * 45, used = g_table_bytes.load();
+    size_t left = allowance > used ? allowance - used : 0;
+    if (budget > left / 10 * 6) budget = left / 10 * 6;
+    if (budget > free_b / 10 * 6) budget = free_b / 10 * 6;
   }
-  int lo = 8, hi = 13;
-  if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
-    int c = atoi(e);
-    if (c >= 5 && c <= 16) return make_win(c);
-  }
-  Win best = make_win(lo);
-  for (int c = lo + 1; c <= hi; c++) {
+  Win best = make_win(8);
+  for (int c = 9; c <= 13; c++) {
     Win w = make_win(c);
     if (table_bytes_for(slots, w) <= budget && w.wins < best.wins) best = w;
   }
@@ -483,11 +498,15 @@ int build_table(spg_gens *g, size_t R) {
     cudaFree(t);
     return rc;
   }
-  if (g->table) cudaFree(g->table);
+  if (g->table) {
+    cudaFree(g->table);
+    g_table_bytes -= g->table_bytes;
+  }
   g->table = t;
   g->tab_R = R;
   g->win = win;
   g->table_bytes = bytes;
+  g_table_bytes += bytes;
   return SPG_OK;
 }
 
@@ -500,7 +519,19 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
             uint8_t *d_out) {
   spg_ctx *ctx = g->ctx;
   const Win win = g->win;
-  const double adds = (double)win.wins;
+  // work units of the launch = point additions: windows per scalar x non-zero scalars (counted
+  // only while profiling; otherwise every scalar is assumed non-zero)
+  double adds = (double)win.wins;
+  if (ctx->profiling && L * R >= 4096) {
+    unsigned long long *d_cnt = nullptr, h_cnt = 0;
+    if (dev_alloc(ctx, &d_cnt, sizeof(*d_cnt)) == cudaSuccess) {
+      cudaMemsetAsync(d_cnt, 0, sizeof(*d_cnt), ctx->stream);
+      k_count_nonzero<<<grid_for(ctx, L * R, 256), 256, 0, ctx->stream>>>(scalars, L, R, row_stride, d_cnt);
+      cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream);
+      if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) adds *= (double)h_cnt / ((double)L * (double)R);
+      dev_free(ctx, d_cnt);
+    }
+  }
   if (L <= 16 && R >= 256) {
     size_t nblk = (R + WIDE_BASES - 1) / WIDE_BASES;
     ge8 *partial = nullptr;
@@ -604,6 +635,7 @@ struct spg_bullet {
 extern "C" {
 
 int spg_bullet_create(spg_ctx *ctx, const spg_gens *gens, size_t n, spg_bullet **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens && out, "spg_bullet_create: null argument");
   SPG_CHECK(n >= 2 && (n & (n - 1)) == 0 && n <= gens->n, "spg_bullet_create: n = %zu must be a power of two <= %zu generators", n,
             gens->n);
@@ -626,6 +658,7 @@ int spg_bullet_create(spg_ctx *ctx, const spg_gens *gens, size_t n, spg_bullet *
 }
 
 int spg_bullet_lr(spg_bullet *b, size_t nk, const spg_fq *a, const spg_fq blinds[2], uint8_t out_LR[64]) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
   SPG_CHECK(b && a && blinds && out_LR, "spg_bullet_lr: null argument");
   SPG_CHECK(nk >= 2 && nk <= b->n && (nk & (nk - 1)) == 0, "spg_bullet_lr: bad round size %zu", nk);
   spg_ctx *ctx = b->ctx;
@@ -638,6 +671,7 @@ int spg_bullet_lr(spg_bullet *b, size_t nk, const spg_fq *a, const spg_fq blinds
 }
 
 int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_inv) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
   SPG_CHECK(b && u && u_inv, "spg_bullet_fold: null argument");
   SPG_CHECK(nk >= 2 && nk <= b->n && (nk & (nk - 1)) == 0, "spg_bullet_fold: bad round size %zu", nk);
   fq fu, fi;
@@ -648,11 +682,13 @@ int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_i
 }
 
 int spg_bullet_final(spg_bullet *b, uint8_t out_G[32]) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
   SPG_CHECK(b && out_G, "spg_bullet_final: null argument");
   return msm_rows(b->gens, b->s, 1, b->n, b->n, nullptr, out_G);
 }
 
 void spg_bullet_destroy(spg_bullet *b) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
   if (!b) return;
   dev_free(b->ctx, b->s);
   dev_free(b->ctx, b->rows);
@@ -662,6 +698,7 @@ void spg_bullet_destroy(spg_bullet *b) {
 }
 
 int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, spg_gens **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && compressed && out, "spg_gens_upload: null argument");
   SPG_CHECK(n_plus_1 >= 2, "spg_gens_upload: need at least one generator and h");
   spg_gens *g = new (std::nothrow) spg_gens();
@@ -698,6 +735,7 @@ int spg_gens_upload(spg_ctx *ctx, const uint8_t *compressed, size_t n_plus_1, sp
 }
 
 int spg_gens_from_uniform(spg_ctx *ctx, const uint8_t *uniform, size_t n_plus_1, spg_gens **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && uniform && out, "spg_gens_from_uniform: null argument");
   SPG_CHECK(n_plus_1 >= 2, "spg_gens_from_uniform: need at least one generator and h");
   spg_gens *g = new (std::nothrow) spg_gens();
@@ -723,19 +761,25 @@ int spg_gens_from_uniform(spg_ctx *ctx, const uint8_t *uniform, size_t n_plus_1,
 }
 
 void spg_gens_destroy(spg_gens *g) {
+  spg::DeviceGuard _dev(spg::ctx_of(g));
   if (!g) return;
   if (g->bases) cudaFree(g->bases);
-  if (g->table) cudaFree(g->table);
+  if (g->table) {
+    cudaFree(g->table);
+    g_table_bytes -= g->table_bytes;
+  }
   delete g;
 }
 
 int spg_poly_commit(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size,
                     uint8_t *out_compressed) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   return spg_poly_commit_rows(ctx, gens, poly, L_size, 0, L_size, out_compressed);
 }
 
 int spg_poly_commit_rows(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly, size_t L_size, size_t row0,
                          size_t nrows, uint8_t *out_compressed) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens && poly && out_compressed, "spg_poly_commit: null argument");
   SPG_CHECK(L_size >= 1 && poly->n % L_size == 0, "spg_poly_commit: L_size %zu does not divide len %zu", L_size, poly->n);
   SPG_CHECK(row0 <= L_size && nrows <= L_size - row0, "spg_poly_commit_rows: rows [%zu, %zu) of %zu", row0, row0 + nrows, L_size);
@@ -745,6 +789,7 @@ int spg_poly_commit_rows(spg_ctx *ctx, const spg_gens *gens, const spg_vec *poly
 }
 
 int spg_gens_prepare(spg_ctx *ctx, spg_gens *gens, size_t R) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens, "spg_gens_prepare: null argument");
   SPG_CHECK(R >= 1 && R <= gens->n, "spg_gens_prepare: %zu bases requested, %zu generators", R, gens->n);
   return ensure_table(gens, R);
@@ -760,6 +805,7 @@ int spg_gens_info(const spg_gens *gens, size_t out[4]) {
 }
 
 int spg_debug_fe8_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_bad) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out_bad && n >= 1, "spg_debug_fe8_selftest: bad argument");
   unsigned int *d_bad = nullptr;
   SPG_CUDA(dev_alloc(ctx, &d_bad, sizeof(unsigned int)));
@@ -776,6 +822,7 @@ int spg_debug_fe8_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_
 
 int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, size_t len,
                      const spg_fq *blinds, size_t count, uint8_t *out_compressed) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens && scalars && out_compressed, "spg_commit_batch: null argument");
   SPG_CHECK(len >= 1 && count >= 1, "spg_commit_batch: empty batch");
   fq *d_s = nullptr, *d_b = nullptr;

@@ -215,6 +215,7 @@ extern "C" {
 int spg_r1cs_create(spg_ctx *ctx, size_t num_instances, size_t max_num_cons, const size_t *num_cons,
                     size_t num_vars, const size_t *nnz, const uint32_t *rows, const uint32_t *cols,
                     const spg_fq *vals, spg_r1cs **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && num_cons && nnz, "spg_r1cs_create: null argument");
   SPG_CHECK(num_instances >= 1, "spg_r1cs_create: need at least one instance");
   // R1CSInstance::new asserts (src/r1csinstance.rs:105-117)
@@ -261,6 +262,7 @@ int spg_r1cs_create(spg_ctx *ctx, size_t num_instances, size_t max_num_cons, con
 }
 
 void spg_r1cs_destroy(spg_r1cs *r) {
+  spg::DeviceGuard _dev(spg::ctx_of(r));
   if (!r) return;
   for (auto &c : r->by_row) free_csx(c);
   for (auto &c : r->by_col) free_csx(c);
@@ -269,6 +271,7 @@ void spg_r1cs_destroy(spg_r1cs *r) {
 
 int spg_r1cs_multi_evaluate(spg_ctx *ctx, const spg_r1cs *inst, const spg_fq *rx, size_t nrx,
                             const spg_fq *ry, size_t nry, spg_fq *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && inst && out, "spg_r1cs_multi_evaluate: null argument");
   SPG_CHECK(((size_t)1 << nrx) == inst->max_num_cons && ((size_t)1 << nry) == inst->num_vars,
             "spg_r1cs_multi_evaluate: |rx| = %zu, |ry| = %zu do not match %zu x %zu", nrx, nry,
@@ -350,15 +353,18 @@ static int witness_upload_impl(spg_ctx *ctx, size_t num_instances, const size_t 
 
 int spg_witness_upload(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
                        const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   return witness_upload_impl(ctx, num_instances, num_proofs, num_inputs, host_w_mat, false, out);
 }
 
 int spg_witness_upload_async(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
                              const size_t *num_inputs, const spg_fq *host_w_mat, spg_witness **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   return witness_upload_impl(ctx, num_instances, num_proofs, num_inputs, host_w_mat, true, out);
 }
 
 void spg_witness_destroy(spg_witness *w) {
+  spg::DeviceGuard _dev(spg::ctx_of(w));
   if (!w) return;
   if (w->ready) {
     // a section freed before anyone consumed it: the free below is stream-ordered on the
@@ -373,6 +379,7 @@ void spg_witness_destroy(spg_witness *w) {
 }
 
 int spg_witness_poly(spg_witness *w, size_t p, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(w));
   SPG_CHECK(w && out, "spg_witness_poly: null argument");
   SPG_CHECK(p < w->num_instances, "spg_witness_poly: instance %zu out of range", p);
   SPG_TRY(witness_wait(w));
@@ -387,6 +394,7 @@ int spg_witness_poly(spg_witness *w, size_t p, spg_vec **out) {
 
 int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs, const size_t *num_inputs,
                    size_t num_witness_secs, spg_witness *const *witness_secs, spg_zmat **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out && num_proofs && num_inputs && witness_secs, "spg_zmat_build: null argument");
   // asserts of R1CSProof::prove (src/r1csproof.rs:240-263)
   SPG_CHECK(num_witness_secs >= 1 && num_witness_secs <= 16, "spg_zmat_build: num_witness_secs must be in 1..=16");
@@ -433,6 +441,7 @@ int spg_zmat_build(spg_ctx *ctx, size_t num_instances, const size_t *num_proofs,
 }
 
 void spg_zmat_destroy(spg_zmat *z) {
+  spg::DeviceGuard _dev(spg::ctx_of(z));
   if (!z) return;
   if (z->views) dev_free(z->ctx, z->views);
   delete z;

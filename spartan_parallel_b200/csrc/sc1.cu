@@ -709,6 +709,7 @@ int spg_sc1_create_from_tables(spg_ctx *ctx, size_t num_instances, const size_t 
                                const spg_fq *Az, const spg_fq *Bz, const spg_fq *Cz,
                                const spg_fq *tau_p, const spg_fq *tau_q, const spg_fq *tau_x,
                                spg_sc1 **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(Az && Bz && Cz, "spg_sc1_create_from_tables: null table");
   spg_sc1 *s = nullptr;
   SPG_TRY(sc1_alloc_common(ctx, num_instances, num_proofs, max_num_proofs, num_cons, max_num_cons,
@@ -736,6 +737,7 @@ int spg_sc1_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
                    const size_t *num_proofs, size_t max_num_proofs, const size_t *num_cons,
                    size_t max_num_cons, size_t max_num_inputs, const spg_fq *tau_p,
                    const spg_fq *tau_q, const spg_fq *tau_x, spg_sc1 **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(inst && z, "spg_sc1_create: null instance / z_mat");
   SPG_CHECK(max_num_cons == inst->max_num_cons, "spg_sc1_create: max_num_cons %zu != instance's %zu",
             max_num_cons, inst->max_num_cons);
@@ -841,6 +843,7 @@ hfq cubic_at(const hfq &e0, const hfq &e1, const hfq &e2, const hfq &e3, const h
 }  // namespace
 
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && e, "spg_sc1_round_eval: null argument");
   if (s->round >= spg_sc1_num_rounds(s)) {
     set_error("spg_sc1_round_eval: all %zu rounds are done", spg_sc1_num_rounds(s));
@@ -996,6 +999,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
 }
 
 int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && r, "spg_sc1_round_bind: null argument");
   if (!s->evaluated) {
     set_error("spg_sc1_round_bind: round %zu has not been evaluated", s->round);
@@ -1094,6 +1098,7 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
 }
 
 int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && challenges && evals_out, "spg_sc1_run_rounds: null argument");
   static const bool trace = getenv("SPG_TRACE_ROUNDS") != nullptr;
   for (size_t j = 0; j < num_rounds; j++) {
@@ -1110,40 +1115,96 @@ int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, 
   return SPG_OK;
 }
 
-// Rounds of a proof whose proofs are sharded over `world` processes of one host (one GPU
-// each): every rank evaluates its shard, the 3 partial evaluations are exchanged through a
-// shared-memory mailbox and summed with Scalar::add, and every rank binds with the same
-// challenge. The mailbox is the one spartan_parallel_b200.parallel.ShmComm maps:
+// ---------------------------------------------------------------- host mailbox of a sharded proof
+// The mailbox is the shared-memory segment spartan_parallel_b200.parallel.ShmComm maps:
 //   slot(b, r) = mailbox + (b * world + r) * slot_stride; word 0 = sequence number, data at +64
 // double-buffered by the parity of the call counter *calls (shared with the Python side).
+// A rank that fails publishes the poison sequence in both of its slots, so that its peers
+// return an error instead of spinning forever; every wait also has a deadline
+// (SPG_MAILBOX_TIMEOUT_S, default 120 s).
+namespace {
+constexpr uint64_t MAILBOX_POISON = UINT64_MAX;
+
+double mailbox_timeout_s() {
+  static const double t = [] {
+    const char *e = getenv("SPG_MAILBOX_TIMEOUT_S");
+    double v = e ? atof(e) : 120.0;
+    return v > 0 ? v : 120.0;
+  }();
+  return t;
+}
+
+int mailbox_exchange(char *base, size_t slot_stride, int rank, int world, uint64_t c, const void *mine, size_t nbytes,
+                     void *out) {
+  size_t b = c & 1;
+  char *me = base + (b * world + rank) * slot_stride;
+  memcpy(me + 64, mine, nbytes);
+  __atomic_store_n((uint64_t *)me, c, __ATOMIC_RELEASE);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < world; r++) {
+    char *slot = base + (b * world + r) * slot_stride;
+    unsigned spins = 0;
+    for (;;) {
+      uint64_t seq = __atomic_load_n((uint64_t *)slot, __ATOMIC_ACQUIRE);
+      if (seq == c) break;
+      if (seq == MAILBOX_POISON) {
+        set_error("sharded proof: rank %d reported a failure (see its own error message)", r);
+        return SPG_ESTATE;
+      }
+      spin_pause();
+      if ((++spins & 0xfffu) == 0 &&
+          std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > mailbox_timeout_s()) {
+        set_error("sharded proof: rank %d did not publish exchange %llu within %.0f s", r, (unsigned long long)c,
+                  mailbox_timeout_s());
+        return SPG_ESTATE;
+      }
+    }
+    memcpy((char *)out + (size_t)r * nbytes, slot + 64, nbytes);
+  }
+  return SPG_OK;
+}
+}  // namespace
+
+void spg_mailbox_poison(void *mailbox, size_t slot_stride, int rank, int world) {
+  if (!mailbox || rank < 0 || rank >= world) return;
+  for (size_t b = 0; b < 2; b++)
+    __atomic_store_n((uint64_t *)((char *)mailbox + (b * world + rank) * slot_stride), MAILBOX_POISON, __ATOMIC_RELEASE);
+}
+
+int spg_mailbox_all_gather(void *mailbox, size_t slot_stride, int rank, int world, uint64_t *calls, const void *data,
+                           size_t nbytes, void *out) {
+  SPG_CHECK(mailbox && calls && data && out, "spg_mailbox_all_gather: null argument");
+  SPG_CHECK(world >= 1 && rank >= 0 && rank < world && slot_stride >= 64 + nbytes, "spg_mailbox_all_gather: bad mailbox geometry");
+  uint64_t c = ++*calls;
+  int rc = mailbox_exchange((char *)mailbox, slot_stride, rank, world, c, data, nbytes, out);
+  if (rc != SPG_OK) spg_mailbox_poison(mailbox, slot_stride, rank, world);
+  return rc;
+}
+
+// Rounds of a proof whose proofs are sharded over `world` processes of one host (one GPU
+// each): every rank evaluates its shard, the 3 partial evaluations are exchanged through the
+// mailbox and summed with Scalar::add, and every rank binds with the same challenge.
 int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out,
                                void *mailbox, size_t slot_stride, int rank, int world, uint64_t *calls) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && challenges && evals_out && mailbox && calls, "spg_sc1_run_rounds_sharded: null argument");
-  SPG_CHECK(world >= 1 && rank >= 0 && rank < world && slot_stride >= 64 + 3 * sizeof(spg_fq),
+  SPG_CHECK(world >= 1 && world <= 64 && rank >= 0 && rank < world && slot_stride >= 64 + 3 * sizeof(spg_fq),
             "spg_sc1_run_rounds_sharded: bad mailbox geometry");
   char *base = (char *)mailbox;
   static const bool trace = getenv("SPG_TRACE_ROUNDS") != nullptr;
-  for (size_t j = 0; j < num_rounds; j++) {
-    spg_fq part[3];
+  int rc = SPG_OK;
+  for (size_t j = 0; j < num_rounds && rc == SPG_OK; j++) {
+    spg_fq part[3], all[64 * 3];
     auto t0 = std::chrono::steady_clock::now();
-    SPG_TRY(spg_sc1_round_eval(s, part));
+    if ((rc = spg_sc1_round_eval(s, part)) != SPG_OK) break;
     auto t1 = std::chrono::steady_clock::now();
-    uint64_t c = ++*calls;
-    size_t b = c & 1;
-    char *mine = base + (b * world + rank) * slot_stride;
-    memcpy(mine + 64, part, sizeof part);
-    __atomic_store_n((uint64_t *)mine, c, __ATOMIC_RELEASE);
+    if ((rc = mailbox_exchange(base, slot_stride, rank, world, ++*calls, part, sizeof part, all)) != SPG_OK) break;
     hfq acc[3] = {hfq_zero(), hfq_zero(), hfq_zero()};
-    for (int r = 0; r < world; r++) {
-      char *slot = base + (b * world + r) * slot_stride;
-      while (__atomic_load_n((uint64_t *)slot, __ATOMIC_ACQUIRE) != c) spin_pause();
-      spg_fq v[3];
-      memcpy(v, slot + 64, sizeof v);
-      for (int t = 0; t < 3; t++) acc[t] = hfq_add(acc[t], hfq_from(v[t]));
-    }
+    for (int r = 0; r < world; r++)
+      for (int t = 0; t < 3; t++) acc[t] = hfq_add(acc[t], hfq_from(all[3 * r + t]));
     for (int t = 0; t < 3; t++) evals_out[3 * j + t] = hfq_to(acc[t]);
     auto t2 = std::chrono::steady_clock::now();
-    SPG_TRY(spg_sc1_round_bind(s, challenges + j));
+    rc = spg_sc1_round_bind(s, challenges + j);
     if (trace && rank == 0) {
       auto t3 = std::chrono::steady_clock::now();
       fprintf(stderr, "[spg] sharded round %zu: eval %.1f us, mailbox %.1f us, bind %.1f us\n", j,
@@ -1152,10 +1213,12 @@ int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *chal
               std::chrono::duration<double, std::micro>(t3 - t2).count());
     }
   }
-  return SPG_OK;
+  if (rc != SPG_OK) spg_mailbox_poison(mailbox, slot_stride, rank, world);  // peers abort instead of spinning
+  return rc;
 }
 
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && claims, "spg_sc1_final: null argument");
   if (s->round != spg_sc1_num_rounds(s)) {
     set_error("spg_sc1_final: %zu of %zu rounds bound", s->round, spg_sc1_num_rounds(s));
@@ -1177,6 +1240,7 @@ int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
 }
 
 int spg_sc1_debug_tables(spg_sc1 *s, spg_fq *Az, spg_fq *Bz, spg_fq *Cz, size_t cap, size_t *n) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && n, "spg_sc1_debug_tables: null argument");
   SPG_TRY(sc1_materialize(s));
   size_t total = 0;
@@ -1196,6 +1260,7 @@ int spg_sc1_debug_tables(spg_sc1 *s, spg_fq *Az, spg_fq *Bz, spg_fq *Cz, size_t 
 }
 
 void spg_sc1_destroy(spg_sc1 *s) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   if (!s) return;
   for (int b = 0; b < 2; b++)
     for (int k = 0; k < 3; k++) dev_free(s->ctx, s->tab[b][k]);

@@ -435,6 +435,7 @@ int spg_sc2_create(spg_ctx *ctx, const spg_r1cs *inst, const spg_zmat *z, size_t
                    size_t max_num_inputs, size_t num_witness_secs, const spg_fq *rx,
                    const spg_fq *rq_rev, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
                    const spg_fq *r_C, spg_sc2 **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(z, "spg_sc2_create: null z_mat");
   return sc2_build(ctx, inst, z, nullptr, num_instances, num_proofs, max_num_proofs, num_inputs, max_num_inputs,
                    num_witness_secs, rx, rq_rev, rp, r_A, r_B, r_C, out);
@@ -444,6 +445,7 @@ int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *z
                             const size_t *num_inputs, size_t max_num_inputs, size_t num_witness_secs,
                             const spg_fq *rx, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
                             const spg_fq *r_C, spg_sc2 **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(zrq, "spg_sc2_create_from_zrq: null Z_rq");
   return sc2_build(ctx, inst, nullptr, zrq, num_instances, nullptr, 1, num_inputs, max_num_inputs, num_witness_secs,
                    rx, nullptr, rp, r_A, r_B, r_C, out);
@@ -451,6 +453,7 @@ int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *z
 
 int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
                      spg_vec *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && z && out && (rq_rev || nq == 0), "spg_zmat_bind_rq: null argument");
   std::vector<size_t> off(z->P);
   size_t total = 0;
@@ -465,6 +468,7 @@ int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size
 size_t spg_sc2_num_rounds(const spg_sc2 *s) { return s ? s->ny + s->nw + s->np : 0; }
 
 int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && e, "spg_sc2_round_eval: null argument");
   if (s->round >= spg_sc2_num_rounds(s)) {
     set_error("spg_sc2_round_eval: all rounds are done");
@@ -502,6 +506,7 @@ int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]) {
 }
 
 int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && r, "spg_sc2_round_bind: null argument");
   if (!s->evaluated) {
     set_error("spg_sc2_round_bind: round %zu has not been evaluated", s->round);
@@ -549,6 +554,7 @@ int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r) {
 }
 
 int spg_sc2_run_rounds(spg_sc2 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && challenges && evals_out, "spg_sc2_run_rounds: null argument");
   for (size_t j = 0; j < num_rounds; j++) {
     SPG_TRY(spg_sc2_round_eval(s, evals_out + 3 * j));
@@ -558,6 +564,7 @@ int spg_sc2_run_rounds(spg_sc2 *s, size_t num_rounds, const spg_fq *challenges, 
 }
 
 int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && claims, "spg_sc2_final: null argument");
   if (s->round != spg_sc2_num_rounds(s)) {
     set_error("spg_sc2_final: %zu of %zu rounds bound", s->round, spg_sc2_num_rounds(s));
@@ -573,6 +580,7 @@ int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]) {
 }
 
 void spg_sc2_destroy(spg_sc2 *s) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   if (!s) return;
   for (int b = 0; b < 2; b++)
     for (int k = 0; k < 2; k++) dev_free(s->ctx, s->tab[b][k]);

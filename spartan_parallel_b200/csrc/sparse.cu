@@ -73,6 +73,7 @@ extern "C" {
 
 int spg_sparse_create(spg_ctx *ctx, size_t batch, size_t num_vars_x, size_t num_vars_y, const size_t *nnz,
                       const uint32_t *rows, const uint32_t *cols, const spg_fq *vals, spg_sparse **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && nnz && rows && cols && vals && out, "spg_sparse_create: null argument");
   SPG_CHECK(batch >= 1, "spg_sparse_create: empty batch");
   SPG_CHECK(num_vars_x < 32 && num_vars_y < 32, "spg_sparse_create: at most 2^31 rows/columns");
@@ -144,6 +145,7 @@ int spg_sparse_create(spg_ctx *ctx, size_t batch, size_t num_vars_x, size_t num_
 }
 
 void spg_sparse_destroy(spg_sparse *s) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   if (!s) return;
   cudaFree(s->d_row);
   cudaFree(s->d_col);
@@ -156,6 +158,7 @@ size_t spg_sparse_num_ops(const spg_sparse *s) { return s ? s->N : 0; }
 size_t spg_sparse_num_mem_cells(const spg_sparse *s) { return s ? s->M : 0; }
 
 int spg_sparse_view(spg_sparse *s, int kind, size_t i, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && out, "spg_sparse_view: null argument");
   size_t bN = s->batch * s->N;
   fq *p = nullptr;
@@ -177,6 +180,7 @@ int spg_sparse_view(spg_sparse *s, int kind, size_t i, spg_vec **out) {
 }
 
 int spg_sparse_deref(spg_ctx *ctx, const spg_sparse *s, const spg_vec *mem_rx, const spg_vec *mem_ry, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && s && mem_rx && mem_ry && out, "spg_sparse_deref: null argument");
   SPG_CHECK(mem_rx->n == s->M && mem_ry->n == s->M, "spg_sparse_deref: memories must have %zu cells (got %zu, %zu)", s->M,
             mem_rx->n, mem_ry->n);
@@ -192,6 +196,7 @@ int spg_sparse_deref(spg_ctx *ctx, const spg_sparse *s, const spg_vec *mem_rx, c
 
 int spg_hash_layer_fq(spg_ctx *ctx, const spg_vec *addr, const spg_vec *val, const spg_vec *ts, int ts_plus_one,
                       const spg_fq *gamma, const spg_fq *tau, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && val && gamma && tau && out, "spg_hash_layer_fq: null argument");
   size_t n = val->n;
   SPG_CHECK((!addr || addr->n == n) && (!ts || ts->n == n), "spg_hash_layer_fq: tables must share the length %zu", n);
@@ -212,6 +217,7 @@ int spg_hash_layer_fq(spg_ctx *ctx, const spg_vec *addr, const spg_vec *val, con
 }
 
 int spg_vec_clone(spg_ctx *ctx, const spg_vec *v, size_t offset, size_t n, spg_vec **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && out, "spg_vec_clone: null argument");
   SPG_CHECK(offset + n <= v->n, "spg_vec_clone: range [%zu, %zu) exceeds length %zu", offset, offset + n, v->n);
   spg_vec *o = nullptr;

@@ -180,6 +180,7 @@ extern "C" {
 int spg_perm_scan(spg_ctx *ctx, size_t n, const size_t *seg_len, size_t n_seg, const spg_vec *v, size_t v_off,
                   size_t v_stride, const spg_vec *x, size_t x_off, size_t x_stride, spg_vec *D, size_t D_off,
                   size_t D_stride, spg_vec *pi, size_t pi_off, size_t pi_stride) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && v && x && D && pi && seg_len, "spg_perm_scan: null argument");
   SPG_CHECK(n_seg >= 1 && n_seg <= (1u << 20), "spg_perm_scan: %zu segments", n_seg);
   SPG_CHECK(v_stride && x_stride && D_stride && pi_stride, "spg_perm_scan: zero stride");

@@ -38,10 +38,16 @@ def lib():
         L.sph_r1cs_gens_new.restype = C.c_void_p
         L.sph_r1cs_gens_free.argtypes = [C.c_void_p]
         L.sph_r1cs_gens_free.restype = None
+        L.sph_r1cs_gens_device_pc.argtypes = [C.c_void_p]
+        L.sph_r1cs_gens_device_pc.restype = C.c_void_p
         L.sph_sparse_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                       C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
+                                       C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_size_t)]
+        L.sph_sparse_gens_new.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.sph_sparse_gens_new.restype = C.c_void_p
+        L.sph_sparse_gens_free.argtypes = [C.c_void_p]
+        L.sph_sparse_gens_free.restype = None
         L.sph_timings.argtypes = [C.c_char_p, C.c_size_t]
         L.sph_timings.restype = C.c_size_t
         L.sph_timings_reset.restype = None
@@ -98,6 +104,16 @@ class R1CSGens:
         if not self.h:
             raise SpgError(f"sph_r1cs_gens_new: {lib().sph_last_error().decode('utf-8', 'replace')}")
 
+    def gens_pc(self):
+        """gens_pc.gens.gens_n on the device as a MultiCommitGens view (not owned): the bases of the
+        witness commitments (src/dense_mlpoly.rs:214-239) and of the openings' MSMs."""
+        from . import api
+
+        g = api.MultiCommitGens.__new__(api.MultiCommitGens)
+        g.ctx, g.h, g.n, g._borrowed = self.ctx, C.c_void_p(lib().sph_r1cs_gens_device_pc(self.h)), None, self
+        g.free = lambda: None
+        return g
+
     def free(self):
         if getattr(self, "h", None):
             lib().sph_r1cs_gens_free(self.h)
@@ -138,8 +154,30 @@ def r1cs_prove(ctx, inst, witness_secs, num_proofs, max_num_proofs, num_inputs, 
     return proof, outs
 
 
+class SparseGens:
+    """SparseMatPolyCommitmentGens::new (src/sparse_mlpoly.rs:289-316) with bases and window tables on the
+    device. Create once, reuse across proofs (like the reference's SNARKGens)."""
+
+    def __init__(self, ctx, label: bytes, num_vars_x: int, num_vars_y: int, max_nz: int, batch: int):
+        self.ctx = ctx
+        self.h = lib().sph_sparse_gens_new(ctx.h, label, num_vars_x, num_vars_y, max_nz, batch)
+        if not self.h:
+            raise SpgError(f"sph_sparse_gens_new: {lib().sph_last_error().decode('utf-8', 'replace')}")
+
+    def free(self):
+        if getattr(self, "h", None):
+            lib().sph_sparse_gens_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def sparse_prove(ctx, polys, num_vars_x: int, num_vars_y: int, rx, ry, evals, transcript_label: bytes, gens_label: bytes,
-                 tape_seed):
+                 tape_seed, gens: "SparseGens | None" = None):
     """SparseMatPolynomial::multi_commit + SparseMatPolyEvalProof::prove (src/sparse_mlpoly.rs:566-586,
     1509-1564) for a batch of matrices `polys` = [(rows, cols, vals), ...].
     Returns (SparseMatPolyCommitment bytes, SparseMatPolyEvalProof bytes), both in bincode layout."""
@@ -153,8 +191,8 @@ def sparse_prove(ctx, polys, num_vars_x: int, num_vars_y: int, rx, ry, evals, tr
     oc, ocl, op, opl = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     _check(lib().sph_sparse_prove(ctx.h, transcript_label, gens_label, p(seed), len(polys), num_vars_x, num_vars_y, p(nnz),
-                                  p(rows), p(cols), p(vals), p(rx_), p(ry_), p(ev), C.byref(oc), C.byref(ocl), C.byref(op),
-                                  C.byref(opl)), "sph_sparse_prove")
+                                  p(rows), p(cols), p(vals), p(rx_), p(ry_), p(ev), gens.h if gens else None, C.byref(oc),
+                                  C.byref(ocl), C.byref(op), C.byref(opl)), "sph_sparse_prove")
     comm, proof = C.string_at(oc, ocl.value), C.string_at(op, opl.value)
     lib().sph_free(oc)
     lib().sph_free(op)

@@ -67,6 +67,9 @@ void *sph_r1cs_gens_new(spg_ctx *ctx, const char *label, size_t num_vars) {
 }
 
 void sph_r1cs_gens_free(void *g) { delete (R1CSGens *)g; }
+// the device copy of gens_pc.gens.gens_n (the generators DensePolynomial::commit uses for the witness
+// sections, src/dense_mlpoly.rs:214-239); owned by the R1CSGens object
+spg_gens *sph_r1cs_gens_device_pc(void *g) { return g ? ((R1CSGens *)g)->d_pc : nullptr; }
 
 // R1CSProof::prove (src/r1csproof.rs:210-685). The caller owns the device handles.
 //   gens_handle: from sph_r1cs_gens_new, or NULL to derive host-only generators for this call
@@ -118,13 +121,33 @@ int sph_r1cs_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_
   }
 }
 
+// SparseMatPolyCommitmentGens::new (src/sparse_mlpoly.rs:289-316) with the bases and their window tables
+// resident on the device; created once and reused across proofs
+void *sph_sparse_gens_new(spg_ctx *ctx, const char *label, size_t num_vars_x, size_t num_vars_y, size_t max_nz,
+                          size_t batch) {
+  try {
+    std::unique_ptr<SparseGens> g(new SparseGens(ctx, label, num_vars_x, num_vars_y, max_nz, batch));
+    check(spg_gens_prepare(ctx, g->d_ops, g->ops.n), "spg_gens_prepare");
+    check(spg_gens_prepare(ctx, g->d_mem, g->mem.n), "spg_gens_prepare");
+    check(spg_gens_prepare(ctx, g->d_derefs, g->derefs.n), "spg_gens_prepare");
+    return g.release();
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+void sph_sparse_gens_free(void *g) { delete (SparseGens *)g; }
+
 // SparseMatPolynomial::multi_commit + SparseMatPolyEvalProof::prove (src/sparse_mlpoly.rs:566-586, 1509-1564)
 // for `batch` matrices given as concatenated (row, col, val) entries, nnz[i] each.
 //   out_comm: bincode of SparseMatPolyCommitment; out_proof: bincode of SparseMatPolyEvalProof (malloc'ed)
+//   gens_handle: from sph_sparse_gens_new (created once, like the reference's SNARKGens), or NULL to
+//   derive the generators inside this call
 int sph_sparse_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_label, const uint64_t tape_seed[4],
                      size_t batch, size_t num_vars_x, size_t num_vars_y, const size_t *nnz, const uint32_t *rows,
                      const uint32_t *cols, const spg_fq *vals, const spg_fq *rx, const spg_fq *ry, const spg_fq *evals,
-                     uint8_t **out_comm, size_t *out_comm_len, uint8_t **out_proof, size_t *out_proof_len) {
+                     const void *gens_handle, uint8_t **out_comm, size_t *out_comm_len, uint8_t **out_proof,
+                     size_t *out_proof_len) {
   spg_sparse *sp = nullptr;
   try {
     size_t max_nz = 0;
@@ -132,7 +155,9 @@ int sph_sparse_prove(spg_ctx *ctx, const char *transcript_label, const char *gen
     Trace tr;
     check(spg_sparse_create(ctx, batch, num_vars_x, num_vars_y, nnz, rows, cols, vals, &sp), "spg_sparse_create");
     tr.lap("sparse: dense representation");
-    SparseGens gens(ctx, gens_label, num_vars_x, num_vars_y, max_nz, batch);
+    std::unique_ptr<SparseGens> own;
+    if (!gens_handle) own.reset(new SparseGens(ctx, gens_label, num_vars_x, num_vars_y, max_nz, batch));
+    const SparseGens &gens = gens_handle ? *(const SparseGens *)gens_handle : *own;
     tr.lap("sparse: generators");
     SparseCommitment c = sparse_commit(ctx, sp, batch, gens);
     tr.lap("sparse: multi_commit");

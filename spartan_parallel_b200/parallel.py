@@ -141,18 +141,28 @@ class ShmComm(TorchComm):
         self.slot_stride = self.SLOT + 64
 
     def all_gather(self, arr: np.ndarray) -> np.ndarray:
+        """Through the C helper (spg_mailbox_all_gather): the same release / acquire ordering as the
+        C round loop (plain numpy stores are ordered only on x86), a deadline on every wait, and a
+        poisoned slot when a rank fails so that its peers raise instead of spinning forever."""
+        import ctypes as C
+
+        from ._lib import check, lib
+
         a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1)
         assert a.size * 8 <= self.SLOT
-        self.calls += 1
-        b = self.calls & 1
-        self.data[b, self.rank, : a.size] = a
-        self.seq[b, self.rank] = self.calls
-        out = np.empty((self.world,) + arr.shape, dtype=np.uint64)
-        for r in range(self.world):
-            while self.seq[b, r] != self.calls:
-                pass
-            out[r] = self.data[b, r, : a.size].reshape(arr.shape)
-        return out
+        calls = C.c_uint64(self.calls)
+        out = np.empty((self.world, a.size), dtype=np.uint64)
+        rc = lib().spg_mailbox_all_gather(C.c_void_p(self.addr), self.slot_stride, self.rank, self.world, C.byref(calls),
+                                          a.ctypes.data_as(C.c_void_p), a.size * 8, out.ctypes.data_as(C.c_void_p))
+        self.calls = int(calls.value)
+        check(rc, "spg_mailbox_all_gather")
+        return out.reshape((self.world,) + tuple(np.shape(arr)))
+
+    def poison(self):
+        """Called by a rank that is about to fail: peers blocked in an exchange return an error."""
+        from ._lib import lib
+
+        lib().spg_mailbox_poison(self.addr, self.slot_stride, self.rank, self.world)
 
     def close(self):
         try:

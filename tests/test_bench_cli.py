@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-log-x", "10", "--cpu-proofs", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+                          "--ref-log-x", "10", "--ref-proofs", "2"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, out.stdout
@@ -19,6 +19,24 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["unit"] == "constraints/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] >= 1 and d["ms_per_step"] > 0 and d["config"]["constraints_per_step"] == 2048
+
+
+def test_kernel_roofline_table():
+    """the per-kernel roofline arithmetic of bench.py on a synthetic profile"""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    prof = [{"kernel": "k_rows_rolled", "launches": 2, "total_ms": 2.0, "units": 576.0 * 1e7, "max_ms": 1, "max_units": 1},
+            {"kernel": "k_msm_rows", "launches": 1, "total_ms": 100.0, "units": 1.4e9, "max_ms": 1, "max_units": 1},
+            {"kernel": "k_unknown", "launches": 1, "total_ms": 1.0, "units": 1e9, "max_ms": 1, "max_units": 1}]
+    out = {e["kernel"]: e for e in bench.kernel_rooflines(prof, 6550.4, 8.459e10, 9.113e12)}
+    r = out["k_rows_rolled"]
+    assert abs(r["achieved_GBps"] - 576.0 * 1e7 / 2e-3 / 1e9) < 1e-6 and abs(r["modmul_per_s"] - 1e8 / 2e-3) < 1
+    assert r["bound"] == "int_pipe" and abs(r["frac"] - 5e10 / 8.459e10) < 1e-9
+    m = out["k_msm_rows"]
+    assert abs(m["point_adds_per_s"] - 1.4e10) < 1 and abs(m["frac"] - 1.4e10 * 504 / 9.113e12) < 1e-9
+    assert out["k_unknown"]["bound"] == "hbm" and "int_frac" not in out["k_unknown"]
 
 
 def test_reference_arm_other_ranks_do_nothing():
