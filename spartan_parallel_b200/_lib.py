@@ -29,7 +29,7 @@ def declared_symbols() -> list[str]:
     """Every function name declared in include/spgpu.h."""
     text = open(HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(spg_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(spg_[A-Za-z0-9_]+)\s*\(", text)))
 
 
 def lib() -> C.CDLL:
