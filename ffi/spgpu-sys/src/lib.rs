@@ -434,6 +434,53 @@ extern "C" {
         rank: c_int,
         n: usize,
     ) -> c_int;
+    pub fn spg_wit_perm_w0(
+        ctx: *mut spg_ctx,
+        tau: *const spg_fq,
+        r: *const spg_fq,
+        used: usize,
+        total: usize,
+        out: *mut *mut spg_vec,
+    ) -> c_int;
+    pub fn spg_wit_block(
+        ctx: *mut spg_ctx,
+        exec_mode: c_int,
+        vars: *const spg_vec,
+        rows: usize,
+        vars_width: usize,
+        perm_w0: *const spg_vec,
+        tau: *const spg_fq,
+        r: *const spg_fq,
+        num_inputs_unpadded: usize,
+        io_width: usize,
+        phy_ops: usize,
+        vir_ops: usize,
+        w2_width: usize,
+        seg_len: *const usize,
+        n_seg: usize,
+        w2_out: *mut *mut spg_vec,
+        w3_out: *mut *mut spg_vec,
+    ) -> c_int;
+    pub fn spg_wit_mem(
+        ctx: *mut spg_ctx,
+        mems: *const spg_vec,
+        rows: usize,
+        in_width: usize,
+        tau: *const spg_fq,
+        r: *const spg_fq,
+        mem_width: usize,
+        w2_out: *mut *mut spg_vec,
+        w3_out: *mut *mut spg_vec,
+    ) -> c_int;
+    pub fn spg_wit_shift(
+        ctx: *mut spg_ctx,
+        w3: *const spg_vec,
+        rows: usize,
+        width: usize,
+        seg_len: *const usize,
+        n_seg: usize,
+        out: *mut *mut spg_vec,
+    ) -> c_int;
     pub fn spg_gens_upload(
         ctx: *mut spg_ctx,
         compressed: *const u8,

@@ -340,6 +340,31 @@ int spg_peer_open(spg_ctx *ctx, const uint8_t handle[64], void **ptr);
 int spg_peer_close(void *ptr);
 int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n);
 
+/* ---------------------------------------------------------------- derived witness sections (f2)
+ * What SNARK::prove computes from the primary sections (block_vars, exec_inputs, the memory
+ * lists) and the two challenges (comb_tau, comb_r) right before committing: with these on the
+ * device only the primary sections cross the host boundary. Tables are row-major, exactly the
+ * flattened lists the reference commits (src/lib.rs:1424, 1443, 1630, 1655).
+ *  spg_wit_perm_w0: perm_w0 = (tau, r, r^2, ..., r^(used-1), 0 ...), src/lib.rs:1328-1338
+ *    (used = 2 * num_inputs_unpadded, total = num_ios).
+ *  spg_wit_block: exec_mode = 0: block_w2 and block_w3 of ONE instance (src/lib.rs:1511-1613):
+ *    vars = block_vars_mat[p] (rows x vars_width; inputs first, memory operations from io_width
+ *    on), w2 rows of w2_width scalars, w3 rows of 8 = (v, x, pi, D, pi_phy, D_phy, pi_vir, D_vir).
+ *    exec_mode = 1: perm_exec_w2 / perm_exec_w3 (src/lib.rs:1346-1400): vars = exec_inputs,
+ *    w2_width = num_ios, w3 columns 4, 5 = w2[0], w2[1], no memory operations.
+ *    seg_len: rows per proving instance (the (pi, D) recurrences restart at each).
+ *  spg_wit_mem: mem_gen, src/lib.rs:832-880: mems rows (v, _, addr, data, ...).
+ *  spg_wit_shift: w3_shifted, src/lib.rs:1667-1676: each instance's rows 1.. and a zero row. */
+int spg_wit_perm_w0(spg_ctx *ctx, const spg_fq *tau, const spg_fq *r, size_t used, size_t total, spg_vec **out);
+int spg_wit_block(spg_ctx *ctx, int exec_mode, const spg_vec *vars, size_t rows, size_t vars_width,
+                  const spg_vec *perm_w0, const spg_fq *tau, const spg_fq *r, size_t num_inputs_unpadded,
+                  size_t io_width, size_t phy_ops, size_t vir_ops, size_t w2_width, const size_t *seg_len,
+                  size_t n_seg, spg_vec **w2_out, spg_vec **w3_out);
+int spg_wit_mem(spg_ctx *ctx, const spg_vec *mems, size_t rows, size_t in_width, const spg_fq *tau,
+                const spg_fq *r, size_t mem_width, spg_vec **w2_out, spg_vec **w3_out);
+int spg_wit_shift(spg_ctx *ctx, const spg_vec *w3, size_t rows, size_t width, const size_t *seg_len,
+                  size_t n_seg, spg_vec **out);
+
 /* ---------------------------------------------------------------- commitments (a16)
  * MultiCommitGens::new is host-side setup (src/commitments.rs:15-33); the caller
  * passes the n+1 generators as compressed ristretto points (G[0..n], h). */

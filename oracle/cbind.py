@@ -90,6 +90,13 @@ def _proto(L):
     L.odense_evaluate.argtypes = [_P, _SZ, _P, _SZ]
     L.odense_bound_L.restype = None
     L.odense_bound_L.argtypes = [_P, _SZ, _P, _P]
+    for name in ("owit_perm_w0", "owit_exec", "owit_block", "owit_mem", "owit_shift"):
+        getattr(L, name).restype = None
+    L.owit_perm_w0.argtypes = [_P, _P, _SZ, _SZ, _P]
+    L.owit_exec.argtypes = [_P, _SZ, _SZ, _P, _P, _SZ, _SZ, _P, _P]
+    L.owit_block.argtypes = [_P, _SZ, _SZ, _P, _P, _P, _SZ, _SZ, _SZ, _SZ, _SZ, _P, _P]
+    L.owit_mem.argtypes = [_P, _SZ, _SZ, _P, _P, _SZ, _P, _P]
+    L.owit_shift.argtypes = [_P, _SZ, _SZ, _P]
     L.owit_perm_fill.restype = None
     L.owit_perm_fill.argtypes = [_P, _SZ, _P, _SZ, _SZ, _SZ, _SZ, _SZ]
     L.odot.restype = Fq
@@ -339,6 +346,48 @@ def perm_fill(w3, seg_len, width=8, v_col=0, x_col=1, pi_col=2, d_col=3):
     assert w3.shape[0] == int(seg.sum()) * width
     lib().owit_perm_fill(_ptr(w3), width, _ptr(seg), seg.size, v_col, x_col, pi_col, d_col)
     return w3
+
+
+def wit_perm_w0(tau, r, used: int, total: int):
+    """perm_w0 (src/lib.rs:1328-1338)"""
+    out = np.zeros((total, 4), dtype=np.uint64)
+    lib().owit_perm_w0(_ptr(fq_array(tau)), _ptr(fq_array(r)), used, total, _ptr(out))
+    return out
+
+
+def wit_exec(inputs, w0, tau, n: int, num_ios: int):
+    """perm_exec_w2, perm_exec_w3 (src/lib.rs:1346-1400); inputs: (rows, in_width, 4)"""
+    a = fq_array(inputs)
+    rows, in_width = a.shape[0], a.shape[1]
+    w2, w3 = np.zeros((rows, num_ios, 4), dtype=np.uint64), np.zeros((rows, 8, 4), dtype=np.uint64)
+    lib().owit_exec(_ptr(a), rows, in_width, _ptr(fq_array(w0)), _ptr(fq_array(tau)), n, num_ios, _ptr(w2), _ptr(w3))
+    return w2, w3
+
+
+def wit_block(vars_, w0, tau, r, n: int, io_width: int, phy_ops: int, vir_ops: int, w2_width: int):
+    """block_w2, block_w3 of one instance (src/lib.rs:1511-1613); vars_: (rows, vars_width, 4)"""
+    a = fq_array(vars_)
+    rows, width = a.shape[0], a.shape[1]
+    w2, w3 = np.zeros((rows, w2_width, 4), dtype=np.uint64), np.zeros((rows, 8, 4), dtype=np.uint64)
+    lib().owit_block(_ptr(a), rows, width, _ptr(fq_array(w0)), _ptr(fq_array(tau)), _ptr(fq_array(r)), n, io_width, phy_ops,
+                     vir_ops, w2_width, _ptr(w2), _ptr(w3))
+    return w2, w3
+
+
+def wit_mem(mems, tau, r, mem_width: int):
+    """mem_gen (src/lib.rs:832-880); mems: (rows, in_width, 4)"""
+    a = fq_array(mems)
+    rows, width = a.shape[0], a.shape[1]
+    w2, w3 = np.zeros((rows, mem_width, 4), dtype=np.uint64), np.zeros((rows, 8, 4), dtype=np.uint64)
+    lib().owit_mem(_ptr(a), rows, width, _ptr(fq_array(tau)), _ptr(fq_array(r)), mem_width, _ptr(w2), _ptr(w3))
+    return w2, w3
+
+
+def wit_shift(w3):
+    a = fq_array(w3)
+    out = np.zeros_like(a)
+    lib().owit_shift(_ptr(a), a.shape[0], a.shape[1], _ptr(out))
+    return out
 
 
 def dot(a, b):

@@ -16,6 +16,7 @@ from .api import (  # noqa: F401
     DensePolynomial,
     EqPolynomial,
     MultiCommitGens,
+    MultiSparseMatPolynomialAsDense,
     ProductCircuit,
     ProverWitnessSecInfo,
     R1CSInstance,
@@ -31,5 +32,9 @@ from .api import (  # noqa: F401
     host_sum,
     sumcheck_phase1,
     vec_op,
+    wit_block,
+    wit_mem,
+    wit_perm_w0,
+    wit_shift,
     zmat_bind_rq,
 )

@@ -178,6 +178,41 @@ def perm_scan(ctx: Context, w3: DensePolynomial, seg_len, width: int = 8, v_col:
     return w3
 
 
+def wit_perm_w0(ctx: Context, tau, r, used: int, total: int) -> DensePolynomial:
+    """perm_w0 = (tau, r, r^2, ...) (src/lib.rs:1328-1338)."""
+    h = C.c_void_p()
+    check(ctx.L.spg_wit_perm_w0(ctx.h, _ptr(_fq(tau)), _ptr(_fq(r)), used, total, C.byref(h)), "spg_wit_perm_w0")
+    return DensePolynomial(ctx, h)
+
+
+def wit_block(ctx: Context, vars_: DensePolynomial, rows: int, vars_width: int, perm_w0: DensePolynomial, tau, r,
+              num_inputs_unpadded: int, io_width: int = 0, phy_ops: int = 0, vir_ops: int = 0, w2_width: int | None = None,
+              seg_len=None, exec_mode: bool = False):
+    """block_w2 / block_w3 of one instance (src/lib.rs:1511-1613), or with exec_mode perm_exec_w2 /
+    perm_exec_w3 (src/lib.rs:1346-1400). Returns (w2, w3) as device polynomials (row-major)."""
+    seg = _sz([rows] if seg_len is None else seg_len)
+    a, b = C.c_void_p(), C.c_void_p()
+    check(ctx.L.spg_wit_block(ctx.h, int(exec_mode), vars_.h, rows, vars_width, perm_w0.h, _ptr(_fq(tau)), _ptr(_fq(r)),
+                              num_inputs_unpadded, io_width, phy_ops, vir_ops, w2_width, _ptr(seg), seg.size, C.byref(a), C.byref(b)),
+          "spg_wit_block")
+    return DensePolynomial(ctx, a), DensePolynomial(ctx, b)
+
+
+def wit_mem(ctx: Context, mems: DensePolynomial, rows: int, in_width: int, tau, r, mem_width: int):
+    """mem_gen's w2 and w3 (src/lib.rs:832-880)."""
+    a, b = C.c_void_p(), C.c_void_p()
+    check(ctx.L.spg_wit_mem(ctx.h, mems.h, rows, in_width, _ptr(_fq(tau)), _ptr(_fq(r)), mem_width, C.byref(a), C.byref(b)), "spg_wit_mem")
+    return DensePolynomial(ctx, a), DensePolynomial(ctx, b)
+
+
+def wit_shift(ctx: Context, w3: DensePolynomial, rows: int, width: int = 8, seg_len=None) -> DensePolynomial:
+    """w3_shifted (src/lib.rs:1667-1676): per instance, rows 1.. followed by a zero row."""
+    seg = _sz([rows] if seg_len is None else seg_len)
+    h = C.c_void_p()
+    check(ctx.L.spg_wit_shift(ctx.h, w3.h, rows, width, _ptr(seg), seg.size, C.byref(h)), "spg_wit_shift")
+    return DensePolynomial(ctx, h)
+
+
 def from_u512(ctx: Context, wide) -> DensePolynomial:
     wide = np.ascontiguousarray(wide, dtype=np.uint64)
     assert wide.shape[-1] == 8
@@ -619,6 +654,45 @@ def deref(ctx: Context, addr, mem: DensePolynomial) -> DensePolynomial:
     h = C.c_void_p()
     check(ctx.L.spg_deref(ctx.h, _ptr(a), len(a), mem.h, C.byref(h)), "spg_deref")
     return DensePolynomial(ctx, h)
+
+
+class MultiSparseMatPolynomialAsDense:
+    """SparseMatPolynomial::multi_sparse_to_dense_rep (src/sparse_mlpoly.rs:368-425) on the device:
+    padded address vectors, read / audit timestamps (AddrTimestamps::new, :222-253) and values of a
+    batch of sparse matrices `polys` = [(rows, cols, vals), ...]."""
+
+    KINDS = {"row_addr": 0, "row_read_ts": 1, "col_addr": 2, "col_read_ts": 3, "val": 4, "row_audit_ts": 5,
+             "col_audit_ts": 6, "comb_ops": 7, "comb_mem": 8}
+
+    def __init__(self, ctx: Context, polys, num_vars_x: int, num_vars_y: int):
+        self.ctx = ctx
+        nnz = _sz([len(p[0]) for p in polys])
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(p[0], dtype=np.uint32) for p in polys]))
+        cols = np.ascontiguousarray(np.concatenate([np.asarray(p[1], dtype=np.uint32) for p in polys]))
+        vals = _fq(np.concatenate([np.asarray(p[2], dtype=np.uint64).reshape(-1, 4) for p in polys]))
+        h = C.c_void_p()
+        check(ctx.L.spg_sparse_create(ctx.h, len(polys), num_vars_x, num_vars_y, _ptr(nnz), _ptr(rows), _ptr(cols), _ptr(vals),
+                                      C.byref(h)), "spg_sparse_create")
+        self.h = h
+        self.batch = len(polys)
+        self.num_ops = int(ctx.L.spg_sparse_num_ops(h))
+        self.num_mem_cells = int(ctx.L.spg_sparse_num_mem_cells(h))
+
+    def view(self, kind: str, i: int = 0) -> DensePolynomial:
+        v = C.c_void_p()
+        check(self.ctx.L.spg_sparse_view(self.h, self.KINDS[kind], i, C.byref(v)), "spg_sparse_view")
+        return DensePolynomial(self.ctx, v, owner=self)
+
+    def free(self):
+        if getattr(self, "h", None):
+            self.ctx.L.spg_sparse_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class BulletReduction:

@@ -8,9 +8,68 @@
 // val[b] | zero pad], each block N scalars, which is exactly DensePolynomial::merge's order
 // (:409-416), so the polynomial that is committed and the per-poly tables the sumchecks
 // read are the same memory. comb_mem = [row_audit_ts | col_audit_ts].
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 
 namespace spg {
+
+// ---------------------------------------------------------------- AddrTimestamps::new on the device
+// The reference walks the operations in order with one counter per memory cell
+// (src/sparse_mlpoly.rs:222-253): read_ts[k] = number of EARLIER operations on the same address,
+// audit_ts[a] = number of operations on a. Order-dependent but not sequential: a STABLE sort of the
+// operation indices by address (CUB radix sort over the address bits; the one library primitive in
+// this backend, preprocessing only) puts each address's operations in a run, in index order, and
+// the timestamp is the position inside the run.
+__global__ void k_iota_u32(uint32_t *__restrict__ v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+// keys: sorted addresses, idx: the operations in that order. run start by binary search (the keys are
+// L2 resident); the last element of a run writes the cell's final counter.
+__global__ void k_run_ranks(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ idx, size_t n,
+                            uint32_t *__restrict__ read_ts, uint32_t *__restrict__ audit) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t key = keys[i];
+    size_t lo = 0, hi = i;  // first position holding `key`
+    while (lo < hi) {
+      size_t mid = (lo + hi) >> 1;
+      if (keys[mid] < key) lo = mid + 1;
+      else hi = mid;
+    }
+    uint32_t rank = (uint32_t)(i - lo);
+    read_ts[idx[i]] = rank;
+    if (i + 1 == n || keys[i + 1] != key) audit[key] = rank + 1;
+  }
+}
+
+// read_ts[n] and audit[cells] (zeroed here) from addr[n] < cells; all device pointers
+int addr_timestamps(spg_ctx *ctx, const uint32_t *d_addr, size_t n, size_t cells, uint32_t *d_read_ts, uint32_t *d_audit) {
+  uint32_t *buf = nullptr;  // keys_out | idx_in | idx_out
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int end_bit = (int)log2u(cells);
+  if (end_bit < 1) end_bit = 1;
+  SPG_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_addr, (uint32_t *)nullptr, (const uint32_t *)nullptr,
+                                           (uint32_t *)nullptr, (int)n, 0, end_bit, ctx->stream));
+  SPG_CUDA(dev_alloc(ctx, &buf, 3 * n * sizeof(uint32_t)));
+  cudaError_t e = dev_alloc_bytes(ctx, &tmp, tmp_bytes ? tmp_bytes : 16);
+  if (e != cudaSuccess) {
+    dev_free(ctx, buf);
+    return cuda_fail(e, "sort scratch", __FILE__, __LINE__);
+  }
+  uint32_t *keys_out = buf, *idx_in = buf + n, *idx_out = buf + 2 * n;
+  int rc = [&]() -> int {
+    SPG_LAUNCH(ctx, k_iota_u32, grid_for(ctx, n, 256), 256, 0, idx_in, n);
+    SPG_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, d_addr, keys_out, idx_in, idx_out, (int)n, 0, end_bit, ctx->stream));
+    ctx->launches += 4;  // CUB's histogram + onesweep passes (a lower bound; not launched through SPG_LAUNCH)
+    SPG_CUDA(cudaMemsetAsync(d_audit, 0, cells * sizeof(uint32_t), ctx->stream));
+    SPG_LAUNCH(ctx, k_run_ranks, grid_for(ctx, n, 256), 256, 0, keys_out, idx_out, n, d_read_ts, d_audit);
+    return SPG_OK;
+  }();
+  dev_free(ctx, tmp);
+  dev_free(ctx, buf);
+  return rc;
+}
 
 __device__ __forceinline__ fq fq_from_u32_dev(unsigned int v) {
   // Scalar::from(u64) = [v,0,0,0] * R^2 (ristretto255.rs:212-216)
@@ -84,11 +143,13 @@ int spg_sparse_create(spg_ctx *ctx, size_t batch, size_t num_vars_x, size_t num_
   }
   size_t M = (size_t)1 << (num_vars_x > num_vars_y ? num_vars_x : num_vars_y);
   SPG_CHECK(batch * N < ((size_t)1 << 32), "spg_sparse_create: batch * N = %zu exceeds 2^32 timestamps", batch * N);
-  // integer side on the host: padded address vectors and the read / audit timestamps
-  // (AddrTimestamps::new, :222-253: one counter per memory cell running across the batch)
+  // integer side: the host only pads the address vectors; the read / audit timestamps
+  // (AddrTimestamps::new, :222-253: one counter per memory cell running across the batch) are
+  // computed on the device from them (addr_timestamps above)
   size_t bN = batch * N;
-  std::vector<uint32_t> h(4 * bN, 0), audit(2 * M, 0);
-  uint32_t *h_row = h.data(), *h_rrts = h_row + bN, *h_col = h_rrts + bN, *h_crts = h_col + bN;
+  SPG_CHECK(bN < ((size_t)1 << 31), "spg_sparse_create: batch * N = %zu operations exceed 2^31", bN);
+  std::vector<uint32_t> h(2 * bN, 0);
+  uint32_t *h_row = h.data(), *h_col = h_row + bN;
   size_t pos = 0;
   for (size_t i = 0; i < batch; i++) {
     for (size_t k = 0; k < nnz[i]; k++, pos++) {
@@ -97,10 +158,6 @@ int spg_sparse_create(spg_ctx *ctx, size_t batch, size_t num_vars_x, size_t num_
       h_row[i * N + k] = rows[pos];
       h_col[i * N + k] = cols[pos];
     }
-  }
-  for (size_t k = 0; k < bN; k++) {
-    h_rrts[k] = audit[h_row[k]]++;
-    h_crts[k] = audit[M + h_col[k]]++;
   }
   spg_sparse *s = new (std::nothrow) spg_sparse();
   if (!s) return SPG_ENOMEM;
@@ -122,24 +179,34 @@ int spg_sparse_create(spg_ctx *ctx, size_t batch, size_t num_vars_x, size_t num_
     spg_sparse_destroy(s);
     return cuda_fail(e, "cudaMalloc(sparse)", __FILE__, __LINE__);
   }
-  SPG_CUDA(cudaMemcpyAsync(d_int, h.data(), 4 * bN * 4, cudaMemcpyHostToDevice, ctx->stream));
-  SPG_CUDA(cudaMemcpyAsync(d_audit, audit.data(), 2 * M * 4, cudaMemcpyHostToDevice, ctx->stream));
-  SPG_CUDA(cudaMemcpyAsync(s->d_row, d_int, bN * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  SPG_CUDA(cudaMemcpyAsync(s->d_col, d_int + 2 * bN, bN * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  SPG_LAUNCH(ctx, k_from_u32, grid_for(ctx, 4 * bN, 256), 256, 0, d_int, 4 * bN, s->comb_ops);
-  SPG_LAUNCH(ctx, k_from_u32, grid_for(ctx, 2 * M, 256), 256, 0, d_audit, 2 * M, s->comb_mem);
-  // val[b][N] (zero padded), then the zero tail of the merged polynomial
-  SPG_CUDA(cudaMemsetAsync(s->comb_ops + 4 * bN, 0, (s->comb_ops_len - 4 * bN) * sizeof(fq), ctx->stream));
-  pos = 0;
-  for (size_t i = 0; i < batch; i++) {
-    if (nnz[i])
-      SPG_CUDA(cudaMemcpyAsync(s->comb_ops + 4 * bN + i * N, vals + pos, nnz[i] * sizeof(fq), cudaMemcpyHostToDevice,
-                               ctx->stream));
-    pos += nnz[i];
-  }
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  int rc = [&]() -> int {
+    // d_int = [row_addr | row_read_ts | col_addr | col_read_ts], d_audit = [row cells | col cells]
+    SPG_CUDA(cudaMemcpyAsync(d_int, h_row, bN * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(d_int + 2 * bN, h_col, bN * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_TRY(addr_timestamps(ctx, d_int, bN, M, d_int + bN, d_audit));
+    SPG_TRY(addr_timestamps(ctx, d_int + 2 * bN, bN, M, d_int + 3 * bN, d_audit + M));
+    SPG_CUDA(cudaMemcpyAsync(s->d_row, d_int, bN * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(s->d_col, d_int + 2 * bN, bN * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    SPG_LAUNCH(ctx, k_from_u32, grid_for(ctx, 4 * bN, 256), 256, 0, d_int, 4 * bN, s->comb_ops);
+    SPG_LAUNCH(ctx, k_from_u32, grid_for(ctx, 2 * M, 256), 256, 0, d_audit, 2 * M, s->comb_mem);
+    // val[b][N] (zero padded), then the zero tail of the merged polynomial
+    SPG_CUDA(cudaMemsetAsync(s->comb_ops + 4 * bN, 0, (s->comb_ops_len - 4 * bN) * sizeof(fq), ctx->stream));
+    pos = 0;
+    for (size_t i = 0; i < batch; i++) {
+      if (nnz[i])
+        SPG_CUDA(cudaMemcpyAsync(s->comb_ops + 4 * bN + i * N, vals + pos, nnz[i] * sizeof(fq), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+      pos += nnz[i];
+    }
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SPG_OK;
+  }();
   cudaFree(d_int);
   cudaFree(d_audit);
+  if (rc != SPG_OK) {
+    spg_sparse_destroy(s);
+    return rc;
+  }
   *out = s;
   return SPG_OK;
 }

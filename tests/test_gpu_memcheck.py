@@ -104,3 +104,41 @@ def test_cubic_batched(ctx, logn, npar, nseq):
     got = sc.final()
     want = [x[0] for x in oa] + [x[0] for x in ob] + ([oc[0]] if npar else []) + [x[0] for x in oas] + [x[0] for x in obs] + [x[0] for x in ocs]
     assert np.array_equal(got, np.stack(want))
+
+
+def test_addr_timestamps_on_device(ctx):
+    """AddrTimestamps::new (src/sparse_mlpoly.rs:222-253) computed on the device (stable sort by
+    address + position in the run) against the reference's sequential counters: heavy repeats of a
+    few addresses, address 0 shared with the zero padding of the shorter matrices, cells never
+    touched, and the counters running ACROSS the matrices of the batch."""
+    import spartan_parallel_b200 as sp
+
+    rng = np.random.default_rng(91)
+    nvx, nvy = 6, 9
+    nnz = [300, 1, 512, 77]
+    polys = []
+    for n in nnz:
+        rows = rng.integers(0, 1 << nvx, size=n).astype(np.uint32)
+        cols = rng.integers(0, 1 << nvy, size=n).astype(np.uint32)
+        rows[: n // 3] = 5          # one hot row
+        cols[n // 2:] = 0           # address 0 is also what the padding reads
+        polys.append((rows, cols, rand_scalars(n, 92 + n)))
+    d = sp.MultiSparseMatPolynomialAsDense(ctx, polys, nvx, nvy)
+    N, M = d.num_ops, d.num_mem_cells
+    assert N == 512 and M == 1 << nvy
+    for side, col in (("row", 0), ("col", 1)):
+        audit = [0] * M
+        for i, p in enumerate(polys):
+            addr = np.zeros(N, dtype=np.int64)
+            addr[: len(p[col])] = p[col]
+            want_ts = []
+            for a in addr:
+                want_ts.append(audit[a])
+                audit[a] += 1
+            got_addr = d.view(f"{side}_addr", i).to_host()
+            got_ts = d.view(f"{side}_read_ts", i).to_host()
+            assert np.array_equal(got_addr, np.stack([O.from_u64(int(a)) for a in addr])), (side, i)
+            assert np.array_equal(got_ts, np.stack([O.from_u64(t) for t in want_ts])), (side, i)
+        got_audit = d.view(f"{side}_audit_ts").to_host()
+        assert np.array_equal(got_audit, np.stack([O.from_u64(t) for t in audit])), side
+    d.free()

@@ -76,3 +76,37 @@ def test_affine_composition_equals_the_recurrence():
         b_q = (x[q] - a_q) % Q
         A, B = a_q * A % Q, (a_q * B + b_q) % Q
         assert A == 0 and B == D[q]  # the last row has A = 0, so every suffix map is constant
+
+
+def test_derived_sections_satisfy_their_relations():
+    """oracle restatement of block_w2 / block_w3 (src/lib.rs:1511-1613): the relations the block
+    R1CS checks on those columns -- x = v (tau - sum w2[3..] - in[2]), PMC chain, pi = v D,
+    D[q] = x[q] (pi[q+1] + 1 - v[q+1]) -- recomputed independently with python integers"""
+    from tests.helpers import rand_scalars
+
+    q_mod = (1 << 252) + 27742317777372353535851937790883648493
+    rows, n, phy, vir = 6, 3, 2, 1
+    tau, r = rand_scalars(2, 400)
+    io_width, vars_width, w2_width = 2 * n, 16, 16
+    w0 = O.wit_perm_w0(tau, r, 2 * n, 8)
+    vars_ = rand_scalars(rows * vars_width, 401).reshape(rows, vars_width, 4)
+    for q in range(rows):
+        vars_[q, 0] = O.ONE if q < 4 else 0
+    w2, w3 = O.wit_block(vars_, w0, tau, r, n, io_width, phy, vir, w2_width)
+    I = lambda a: O.to_int(a)
+    t, rr = I(tau), I(r)
+    assert [I(x) for x in w0[:6]] == [t] + [pow(rr, k, q_mod) for k in range(1, 6)]
+    for q in range(rows):
+        v = I(vars_[q, 0])
+        s = sum(I(w2[q, i]) for i in range(3, 2 * n)) % q_mod
+        assert I(w3[q, 1]) == v * (t - s - I(vars_[q, 2])) % q_mod
+        chain = v
+        for i in range(phy):
+            pmr = rr * I(vars_[q, io_width + 2 * i + 1]) % q_mod
+            chain = chain * (t - I(vars_[q, io_width + 2 * i]) - pmr) % q_mod
+            assert I(w2[q, 2 * n + 2 * i]) == pmr and I(w2[q, 2 * n + 2 * i + 1]) == chain
+        for (pi_c, d_c, x) in ((2, 3, I(w3[q, 1])), (4, 5, chain)):
+            nxt = (I(w3[q + 1, pi_c]) + 1 - I(w3[q + 1, 0])) % q_mod if q + 1 < rows else 1
+            assert I(w3[q, d_c]) == x * nxt % q_mod and I(w3[q, pi_c]) == v * I(w3[q, d_c]) % q_mod
+    sh = O.wit_shift(w3)
+    assert np.array_equal(sh[:-1], w3[1:]) and not sh[-1].any()

@@ -521,6 +521,9 @@ def main():
     open(B("src/gpu.rs"), "w").write(GPU_RS)
 
     diff = subprocess.run(["diff", "-ruN", "a", "b"], cwd=tmp, capture_output=True, text=True).stdout
+    import re
+
+    diff = re.sub(r"^(---|\+\+\+) (\S+)\t.*$", r"\1 \2", diff, flags=re.M)  # no timestamps: reproducible
     header = ("# Feature-gated call sites for the reference crate (scroll-tech/spartan-parallel): routes the table work of\n"
               "# R1CSProof::prove, DensePolynomial::commit and ProductCircuit::new through libspgpu.so.\n"
               "# Generated by tools/make_gpu_patch.py; apply from the crate root with `git apply ffi/gpu-feature.patch`\n"
