@@ -480,6 +480,13 @@ def run_gpu(args):
         except Exception as e:
             sparse = {"error": str(e)[:200]}
 
+    witness_gen = None
+    if world == 1 and not args.no_witness_gen:
+        try:
+            witness_gen = witness_gen_leg(sp, ctx)
+        except Exception as e:
+            witness_gen = {"error": str(e)[:200]}
+
     # ---- N > 1 in strong mode: the weak figure (proofs per GPU fixed) as an extra
     weak = None
     if world > 1 and scaling == "strong" and not args.no_weak:
@@ -586,7 +593,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * main.N * 32 * world), "d2h_bytes_per_step": int(96 * (2 * nx + main.nq + ng + 1) + 7 * 32)},
         "gpu_launches": res["launches"], "full_proof": full_proof, "wall_ms_per_step": res["wall_ms"],
-        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse,
+        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse, "witness_gen": witness_gen,
         "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
         "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s, "host_affinity": numa,
     }
@@ -679,6 +686,38 @@ def sharded_equals_unsharded(sp, parallel, ctx, comm, rank, world, log_x, Q):
           and np.array_equal(gotc2, wantc2))
     return {"ok": bool(ok), "config": f"C3: X=2^{log_x} x Q={Q} sharded over {world} ranks vs unsharded on each rank's GPU",
             "compared": f"{len(want1)} + {len(want2)} round polynomials, 4 + 3 final claims, bit for bit"}
+
+
+def witness_gen_leg(sp, ctx, log_rows=18, n=16, phy=4, vir=2):
+    """SNARK::prove's derived block sections on the device (src/lib.rs:1481-1613, 1667-1676): block_w2,
+    block_w3 and block_w3_shifted computed from block_vars, so that only the primary section crosses
+    PCIe. Reports the device time next to the bytes that no longer need uploading."""
+    rows = 1 << log_rows
+    io_width = 2 * n
+    vars_width = 1 << (io_width + 2 * phy + 4 * vir - 1).bit_length()
+    w2_width = 1 << (2 * n + 2 * phy + 4 * vir - 1).bit_length()
+    rng = np.random.default_rng(11)
+    vars_ = random_canonical(rng, rows * vars_width)
+    vars_[::vars_width] = ONE  # validity column
+    tau, r = challenges(rng, 2)
+    d_vars = sp.DensePolynomial.new(ctx, vars_)
+    w0 = sp.wit_perm_w0(ctx, tau, r, 2 * n, 2 * n)
+    best = None
+    for _ in range(4):
+        ctx.sync()
+        t0 = time.perf_counter()
+        w2, w3 = sp.wit_block(ctx, d_vars, rows, vars_width, w0, tau, r, n, io_width, phy, vir, w2_width)
+        sh = sp.wit_shift(ctx, w3, rows)
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        w2.free(); w3.free(); sh.free()
+    primary, derived = rows * vars_width * 32, rows * (w2_width + 16) * 32
+    return {"seconds": best, "rows": rows, "primary_bytes": primary, "derived_bytes_not_uploaded": derived,
+            "derived_share_of_upload": derived / (primary + derived), "derived_GBps": derived / best / 1e9,
+            "what": f"block_w2 ({w2_width} wide), block_w3 and block_w3_shifted of one block instance with {rows} executions, "
+                    f"{n} inputs, {phy} physical and {vir} virtual memory operations, derived on the device from block_vars "
+                    f"({vars_width} wide); PCIe moves ~54 GB/s, so uploading them instead would take {derived / 54e9:.3f} s"}
 
 
 def sparse_leg(sp, host, ctx, lg):
@@ -875,6 +914,7 @@ def main():
     ap.add_argument("--no-commit", action="store_true", help="skip the witness-commitment leg")
     ap.add_argument("--no-sparse", dest="with_sparse", action="store_false", help="skip the sparse-polynomial evaluation proof leg")
     ap.add_argument("--sparse-log-nnz", type=int, default=20)
+    ap.add_argument("--no-witness-gen", action="store_true", help="skip the derived-witness-section leg")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded == unsharded check (C3)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong mode: skip the extra weak-scaling figure")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the end-to-end leg")

@@ -569,6 +569,126 @@ def polyeval_verify_batched(proofs, num_proofs_list, num_inputs_list, gens: DotP
     return True
 
 
+def _factored(r):
+    """EqPolynomial::compute_factored_evals (src/dense_mlpoly.rs:122-130)."""
+    left = len(r) // 2
+    one = ONE.reshape(1, 4)
+    L = O.eq_evals(np.stack(r[:left])) if left else one
+    R = O.eq_evals(np.stack(r[left:])) if len(r) - left else one
+    return L, R
+
+
+def _key(v):
+    return tuple(int(x) for x in np.asarray(v, dtype=np.uint64).reshape(-1))
+
+
+def polyeval_prove_batched_points(poly, r_list, Zr_list, gens: DotProductProofGens, t, tape):
+    """PolyEvalProof::prove_batched_points (src/dense_mlpoly.rs:531-622), zero blinds: several points
+    on one polynomial; points sharing the left half of r share L and are combined by powers of c."""
+    t.append_protocol_name(b"polynomial evaluation proof")
+    left = len(r_list[0]) // 2
+    index_map, L_list, R_list, Zc_list = {}, [], [], []
+    c_base = t.challenge_scalar(b"challenge_c")
+    c = ONE
+    for i, r in enumerate(r_list):
+        Li, Ri = _factored(list(r))
+        k = _key(np.stack(r[:left])) if left else ()
+        if k in index_map:
+            c = mul(c, c_base)
+            idx = index_map[k]
+            R_list[idx] = O.vec_add(R_list[idx], O.vec_mul(np.tile(c, (Ri.shape[0], 1)), Ri))
+            Zc_list[idx] = add(Zc_list[idx], mul(c, Zr_list[i]))
+        else:
+            index_map[k] = len(L_list)
+            L_list.append(Li)
+            R_list.append(Ri)
+            Zc_list.append(Zr_list[i])
+    proofs = []
+    for i in range(len(L_list)):
+        LZ = O.dense_bound_L(poly, L_list[i])
+        pr, _, _ = dplog_prove(gens, t, tape, list(LZ), ZERO, list(R_list[i]), Zc_list[i], ZERO)
+        proofs.append(pr)
+    return proofs
+
+
+def polyeval_prove_batched_instances(polys, r_list, Zr_list, gens: DotProductProofGens, t, tape):
+    """PolyEvalProof::prove_batched_instances (src/dense_mlpoly.rs:689-780), zero blinds: one point per
+    polynomial (padded with leading zeros or trimmed to the polynomial's size); instances with the same
+    size and R are combined."""
+    t.append_protocol_name(b"polynomial evaluation proof")
+    index_map, LZ_list, Zc_list, R_list = {}, [], [], []
+    c_base = t.challenge_scalar(b"challenge_c")
+    c = ONE
+    for i, poly in enumerate(polys):
+        nv = log2(poly.shape[0])
+        r = list(r_list[i])
+        r = [ZERO] * (nv - len(r)) + r if nv >= len(r) else r[len(r) - nv:]
+        L, R = _factored(r)
+        k = (nv, _key(R))
+        LZ = O.dense_bound_L(poly, L)
+        if k in index_map:
+            c = mul(c, c_base)
+            idx = index_map[k]
+            LZ_list[idx] = O.vec_add(LZ_list[idx], O.vec_mul(np.tile(c, (LZ.shape[0], 1)), LZ))
+            Zc_list[idx] = add(Zc_list[idx], mul(c, Zr_list[i]))
+        else:
+            index_map[k] = len(LZ_list)
+            Zc_list.append(Zr_list[i])
+            R_list.append(R)
+            LZ_list.append(LZ)
+    proofs = []
+    for i in range(len(LZ_list)):
+        pr, _, _ = dplog_prove(gens, t, tape, list(LZ_list[i]), ZERO, list(R_list[i]), Zc_list[i], ZERO)
+        proofs.append(pr)
+    return proofs
+
+
+def polyeval_prove_uni_batched_instances(polys, r, Zr, gens: DotProductProofGens, t, tape):
+    """PolyEvalProof::prove_uni_batched_instances (src/dense_mlpoly.rs:1046-1130): the polynomials read as
+    univariate ones, opened at the single point r; returns (proof, C_Zr_prime)."""
+    t.append_protocol_name(b"polynomial evaluation proof")
+    max_nv = max(log2(p.shape[0]) for p in polys)
+    R_size = 1 << (max_nv - max_nv // 2)
+    R, rb = [], ONE
+    for _ in range(R_size):
+        R.append(rb)
+        rb = mul(rb, r)
+    L_map = {}
+    c_base = t.challenge_scalar(b"challenge_c")
+    c = ONE
+    LZ_comb = np.zeros((R_size, 4), dtype=np.uint64)
+    Zr_comb = ZERO
+    for i, poly in enumerate(polys):
+        nv = log2(poly.shape[0])
+        if nv not in L_map:
+            Ls, Rs = 1 << (nv // 2), 1 << (nv - nv // 2)
+            r_base = ONE
+            for _ in range(Rs):
+                r_base = mul(r_base, r)
+            L, lb = [], ONE
+            for _ in range(Ls):
+                L.append(lb)
+                lb = mul(lb, r_base)
+            L_map[nv] = np.stack(L)
+        LZ = O.dense_bound_L(poly, L_map[nv])
+        pad = np.zeros((R_size, 4), dtype=np.uint64)
+        pad[: LZ.shape[0]] = O.vec_mul(np.tile(c, (LZ.shape[0], 1)), LZ)
+        LZ_comb = O.vec_add(LZ_comb, pad)
+        Zr_comb = add(Zr_comb, mul(c, Zr[i]))
+        c = mul(c, c_base)
+    pr, _, Cy = dplog_prove(gens, t, tape, list(LZ_comb), ZERO, R, Zr_comb, ZERO)
+    return pr, Cy
+
+
+def serialize_polyeval_proofs(proofs) -> bytes:
+    """bincode of Vec<PolyEvalProof>"""
+    w = Writer()
+    w.u64(len(proofs))
+    for pr in proofs:
+        w_dplog(w, pr)
+    return bytes(w.b)
+
+
 def poly_commit(Z, gens_n: G.MultiCommitGens):
     """DensePolynomial::commit with zero blinds (src/dense_mlpoly.rs:199-239)."""
     ell = log2(Z.shape[0])

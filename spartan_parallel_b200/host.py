@@ -48,6 +48,9 @@ def lib():
         L.sph_sparse_gens_new.restype = C.c_void_p
         L.sph_sparse_gens_free.argtypes = [C.c_void_p]
         L.sph_sparse_gens_free.restype = None
+        L.sph_polyeval_prove.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                         C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                         C.c_void_p]
         L.sph_timings.argtypes = [C.c_char_p, C.c_size_t]
         L.sph_timings.restype = C.c_size_t
         L.sph_timings_reset.restype = None
@@ -197,3 +200,30 @@ def sparse_prove(ctx, polys, num_vars_x: int, num_vars_y: int, rx, ry, evals, tr
     lib().sph_free(oc)
     lib().sph_free(op)
     return comm, proof
+
+
+def polyeval_prove(ctx, variant: str, polys, r, Zr, transcript_label: bytes, gens_label: bytes, tape_seed, gens_n: int):
+    """PolyEvalProof::prove_batched_points ("points": one polynomial, r = list of points),
+    ::prove_batched_instances ("instances": one point per polynomial) or ::prove_uni_batched_instances
+    ("uni": r = one scalar) over device polynomials (src/dense_mlpoly.rs:531, 689, 1046).
+    Returns the bincode bytes (and C_Zr_prime for "uni")."""
+    v = {"points": 0, "instances": 1, "uni": 2}[variant]
+    hs = (C.c_void_p * len(polys))(*[p.h for p in polys])
+    Zr_ = np.ascontiguousarray(np.asarray(Zr, dtype=np.uint64).reshape(-1, 4))
+    if v == 2:
+        num_points, r_len = len(polys), 1
+        r_ = np.ascontiguousarray(np.tile(np.asarray(r, dtype=np.uint64).reshape(1, 4), (num_points, 1)))
+    else:
+        num_points = len(r)
+        r_len = len(r[0])
+        assert all(len(x) == r_len for x in r), "points must have equal length (pad on the caller's side)"
+        r_ = np.ascontiguousarray(np.asarray([np.asarray(x, dtype=np.uint64).reshape(r_len, 4) for x in r], dtype=np.uint64).reshape(-1, 4))
+    seed = np.ascontiguousarray(tape_seed, dtype=np.uint64)
+    out, out_len = C.c_void_p(), C.c_size_t()
+    extra = np.zeros(32, dtype=np.uint8)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _check(lib().sph_polyeval_prove(ctx.h, v, transcript_label, gens_label, p(seed), gens_n, len(polys), hs, num_points, r_len, p(r_), p(Zr_),
+                                    C.byref(out), C.byref(out_len), p(extra)), "sph_polyeval_prove")
+    blob = C.string_at(out, out_len.value)
+    lib().sph_free(out)
+    return (blob, extra.tobytes()) if v == 2 else blob

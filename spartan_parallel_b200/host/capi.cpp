@@ -121,6 +121,68 @@ int sph_r1cs_prove(spg_ctx *ctx, const char *transcript_label, const char *gens_
   }
 }
 
+// The PolyEvalProof variants other than the disjoint-rounds one R1CSProof::prove uses (src/dense_mlpoly.rs:531,
+// 689, 1046), over device-resident polynomials.
+//   variant 0: prove_batched_points  (polys[0]; num_points points of r_len scalars each, Zr per point)
+//   variant 1: prove_batched_instances (num_polys polynomials, one point of r_len scalars and one Zr each)
+//   variant 2: prove_uni_batched_instances (num_polys polynomials, the single scalar r[0], one Zr each);
+//              out_extra receives C_Zr_prime
+// gens: DotProductProofGens::new(gens_n, gens_label) with the bases on the device.
+// out: bincode of Vec<PolyEvalProof> (variants 0, 1) or of one PolyEvalProof (variant 2); free with sph_free.
+int sph_polyeval_prove(spg_ctx *ctx, int variant, const char *transcript_label, const char *gens_label,
+                       const uint64_t tape_seed[4], size_t gens_n, size_t num_polys, spg_vec *const *polys, size_t num_points,
+                       size_t r_len, const spg_fq *r, const spg_fq *Zr, uint8_t **out, size_t *out_len, uint8_t out_extra[32]) {
+  spg_gens *dev = nullptr;
+  try {
+    DotProductProofGens gens;
+    if (gens_n >= 256) {
+      gens = DotProductProofGens::on_device(ctx, gens_n, gens_label, &dev);
+    } else {
+      gens = DotProductProofGens(gens_n, gens_label);
+      std::vector<uint8_t> c = gens.gens_n.compressed();
+      check(spg_gens_upload(ctx, c.data(), gens.gens_n.n + 1, &dev), "spg_gens_upload");
+      gens.attach_device(ctx, dev);
+    }
+    ProofTranscript t(transcript_label);
+    hfq seed{{tape_seed[0], tape_seed[1], tape_seed[2], tape_seed[3]}};
+    RandomTape tape("proof", Scalar(seed));
+    std::vector<std::vector<Scalar>> r_list(num_points);
+    std::vector<Scalar> Zr_list;
+    for (size_t i = 0; i < num_points; i++) {
+      for (size_t k = 0; k < r_len; k++) r_list[i].push_back(Scalar::from_fq(r[i * r_len + k]));
+      Zr_list.push_back(Scalar::from_fq(Zr[i]));
+    }
+    std::vector<const spg_vec *> pl(polys, polys + num_polys);
+    Writer w;
+    if (variant == 0) {
+      auto proofs = prove_batched_points(ctx, pl.at(0), r_list, Zr_list, gens, t, tape);
+      w.u64(proofs.size());
+      for (auto &p : proofs) p.write(w);
+    } else if (variant == 1) {
+      if (num_points != num_polys) throw std::runtime_error("prove_batched_instances: one point per polynomial");
+      auto proofs = prove_batched_instances(ctx, pl, r_list, Zr_list, gens, t, tape);
+      w.u64(proofs.size());
+      for (auto &p : proofs) p.write(w);
+    } else if (variant == 2) {
+      if (num_points != num_polys || r_len != 1) throw std::runtime_error("prove_uni_batched_instances: one scalar point, one Zr per polynomial");
+      auto pr = prove_uni_batched_instances(ctx, pl, r_list[0][0], Zr_list, gens, t, tape);
+      pr.first.write(w);
+      if (out_extra) memcpy(out_extra, pr.second.b, 32);
+    } else {
+      throw std::runtime_error("sph_polyeval_prove: unknown variant");
+    }
+    spg_gens_destroy(dev);
+    *out_len = w.out.size();
+    *out = (uint8_t *)malloc(w.out.size());
+    memcpy(*out, w.out.data(), w.out.size());
+    return 0;
+  } catch (const std::exception &e) {
+    spg_gens_destroy(dev);
+    g_err = e.what();
+    return -1;
+  }
+}
+
 // SparseMatPolyCommitmentGens::new (src/sparse_mlpoly.rs:289-316) with the bases and their window tables
 // resident on the device; created once and reused across proofs
 void *sph_sparse_gens_new(spg_ctx *ctx, const char *label, size_t num_vars_x, size_t num_vars_y, size_t max_nz,

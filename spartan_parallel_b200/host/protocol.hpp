@@ -665,6 +665,158 @@ inline std::vector<DotProductProofLog> prove_batched_instances_disjoint_rounds(
   return proofs;
 }
 
+// ---------------------------------------------------------------- the other opening variants
+// PolyEvalProof::prove_batched_points / prove_batched_instances / prove_uni_batched_instances
+// (src/dense_mlpoly.rs:531-622, 689-780, 1046-1130; called from src/lib.rs:2587, 2657, 2673), zero blinds as at
+// every call site. The polynomials stay on the device: `poly.bound(&L)` is spg_dense_bound_L, the dot-product
+// proofs' MSMs run there as well; the grouping, the random linear combinations and the transcript are host work.
+inline std::vector<Scalar> bound_L_dev(spg_ctx *ctx, const spg_vec *pv, const std::vector<Scalar> &L) {
+  spg_vec *out = nullptr;
+  std::vector<spg_fq> Lf;
+  for (auto &s : L) Lf.push_back(s.to_fq());
+  check(spg_dense_bound_L(ctx, pv, Lf.data(), Lf.size(), &out), "spg_dense_bound_L");
+  size_t n = spg_vec_len(out);
+  std::vector<spg_fq> h(n);
+  check(spg_vec_download(ctx, out, 0, n, h.data()), "spg_vec_download");
+  spg_vec_free(out);
+  std::vector<Scalar> r;
+  for (auto &x : h) r.push_back(Scalar::from_fq(x));
+  return r;
+}
+// EqPolynomial::compute_factored_evals (src/dense_mlpoly.rs:122-130)
+inline std::pair<std::vector<Scalar>, std::vector<Scalar>> factored_evals(const std::vector<Scalar> &r) {
+  size_t left = r.size() / 2;
+  return {eq_evals_host(std::vector<Scalar>(r.begin(), r.begin() + left)), eq_evals_host(std::vector<Scalar>(r.begin() + left, r.end()))};
+}
+inline std::vector<uint64_t> limbs_key(const std::vector<Scalar> &v, size_t from, size_t to) {
+  std::vector<uint64_t> k;
+  for (size_t i = from; i < to; i++) {
+    spg_fq f = v[i].to_fq();
+    k.insert(k.end(), f.l, f.l + 4);
+  }
+  return k;
+}
+
+inline std::vector<DotProductProofLog> prove_batched_points(spg_ctx *ctx, const spg_vec *poly,
+                                                            const std::vector<std::vector<Scalar>> &r_list,
+                                                            const std::vector<Scalar> &Zr_list, const DotProductProofGens &gens,
+                                                            ProofTranscript &t, RandomTape &tape) {
+  t.append_protocol_name("polynomial evaluation proof");
+  size_t left = r_list.at(0).size() / 2;
+  std::map<std::vector<uint64_t>, size_t> index_map;
+  std::vector<std::vector<Scalar>> L_list, R_list;
+  std::vector<Scalar> Zc_list;
+  Scalar c_base = t.challenge_scalar("challenge_c");
+  Scalar c = Scalar::one();
+  for (size_t i = 0; i < r_list.size(); i++) {
+    auto LR = factored_evals(r_list[i]);
+    auto key = limbs_key(r_list[i], 0, left);
+    auto it = index_map.find(key);
+    if (it != index_map.end()) {
+      c *= c_base;
+      size_t idx = it->second;
+      for (size_t j = 0; j < LR.second.size(); j++) R_list[idx][j] = R_list[idx][j] + c * LR.second[j];
+      Zc_list[idx] += c * Zr_list[i];
+    } else {
+      index_map[key] = L_list.size();
+      L_list.push_back(LR.first);
+      R_list.push_back(LR.second);
+      Zc_list.push_back(Zr_list[i]);
+    }
+  }
+  std::vector<DotProductProofLog> proofs;
+  for (size_t i = 0; i < L_list.size(); i++) {
+    std::vector<Scalar> LZ = bound_L_dev(ctx, poly, L_list[i]);
+    proofs.push_back(DotProductProofLog::prove(gens, t, tape, LZ, Scalar::zero(), R_list[i], Zc_list[i], Scalar::zero()));
+  }
+  return proofs;
+}
+
+inline std::vector<DotProductProofLog> prove_batched_instances(spg_ctx *ctx, const std::vector<const spg_vec *> &polys,
+                                                               const std::vector<std::vector<Scalar>> &r_list,
+                                                               const std::vector<Scalar> &Zr_list, const DotProductProofGens &gens,
+                                                               ProofTranscript &t, RandomTape &tape) {
+  t.append_protocol_name("polynomial evaluation proof");
+  std::map<std::pair<size_t, std::vector<uint64_t>>, size_t> index_map;
+  std::vector<std::vector<Scalar>> LZ_list, R_list;
+  std::vector<Scalar> Zc_list;
+  Scalar c_base = t.challenge_scalar("challenge_c");
+  Scalar c = Scalar::one();
+  for (size_t i = 0; i < polys.size(); i++) {
+    size_t nv = log2z(spg_vec_len(polys[i]));
+    std::vector<Scalar> r;
+    if (nv >= r_list[i].size()) {
+      r.assign(nv - r_list[i].size(), Scalar::zero());
+      r.insert(r.end(), r_list[i].begin(), r_list[i].end());
+    } else {
+      r.assign(r_list[i].end() - nv, r_list[i].end());
+    }
+    auto LR = factored_evals(r);
+    auto key = std::make_pair(nv, limbs_key(LR.second, 0, LR.second.size()));
+    std::vector<Scalar> LZ = bound_L_dev(ctx, polys[i], LR.first);
+    auto it = index_map.find(key);
+    if (it != index_map.end()) {
+      c *= c_base;
+      size_t idx = it->second;
+      for (size_t j = 0; j < LZ.size(); j++) LZ_list[idx][j] = LZ_list[idx][j] + c * LZ[j];
+      Zc_list[idx] += c * Zr_list[i];
+    } else {
+      index_map[key] = LZ_list.size();
+      Zc_list.push_back(Zr_list[i]);
+      R_list.push_back(LR.second);
+      LZ_list.push_back(LZ);
+    }
+  }
+  std::vector<DotProductProofLog> proofs;
+  for (size_t i = 0; i < LZ_list.size(); i++)
+    proofs.push_back(DotProductProofLog::prove(gens, t, tape, LZ_list[i], Scalar::zero(), R_list[i], Zc_list[i], Scalar::zero()));
+  return proofs;
+}
+
+inline std::pair<DotProductProofLog, Compressed> prove_uni_batched_instances(spg_ctx *ctx, const std::vector<const spg_vec *> &polys,
+                                                                            const Scalar &r, const std::vector<Scalar> &Zr,
+                                                                            const DotProductProofGens &gens, ProofTranscript &t,
+                                                                            RandomTape &tape) {
+  t.append_protocol_name("polynomial evaluation proof");
+  size_t max_nv = 0;
+  for (auto *p : polys) max_nv = std::max(max_nv, log2z(spg_vec_len(p)));
+  size_t R_size = (size_t)1 << (max_nv - max_nv / 2);
+  std::vector<Scalar> R;
+  Scalar rb = Scalar::one();
+  for (size_t i = 0; i < R_size; i++) {
+    R.push_back(rb);
+    rb *= r;
+  }
+  std::map<size_t, std::vector<Scalar>> L_map;
+  Scalar c_base = t.challenge_scalar("challenge_c");
+  Scalar c = Scalar::one();
+  std::vector<Scalar> LZ_comb(R_size, Scalar::zero());
+  Scalar Zr_comb = Scalar::zero();
+  for (size_t i = 0; i < polys.size(); i++) {
+    size_t nv = log2z(spg_vec_len(polys[i]));
+    if (!L_map.count(nv)) {
+      size_t Ls = (size_t)1 << (nv / 2), Rs = (size_t)1 << (nv - nv / 2);
+      Scalar r_base = Scalar::one();
+      for (size_t k = 0; k < Rs; k++) r_base *= r;
+      std::vector<Scalar> L;
+      Scalar lb = Scalar::one();
+      for (size_t k = 0; k < Ls; k++) {
+        L.push_back(lb);
+        lb *= r_base;
+      }
+      L_map[nv] = L;
+    }
+    std::vector<Scalar> LZ = bound_L_dev(ctx, polys[i], L_map[nv]);
+    for (size_t j = 0; j < LZ.size() && j < R_size; j++) LZ_comb[j] = LZ_comb[j] + c * LZ[j];
+    Zr_comb += c * Zr[i];
+    c *= c_base;
+  }
+  DotProductProofLog pr = DotProductProofLog::prove(gens, t, tape, LZ_comb, Scalar::zero(), R, Zr_comb, Scalar::zero());
+  // C_Zr_prime = the Cy the dot-product proof committed to (src/nizk/mod.rs:470)
+  Compressed Cy = commit(Zr_comb, Scalar::zero(), gens.gens_1).compress();
+  return {pr, Cy};
+}
+
 // ---------------------------------------------------------------- R1CSProof::prove (src/r1csproof.rs:210-685)
 struct R1CSProofOut {
   std::vector<uint8_t> bytes;                 // bincode layout of R1CSProof (src/r1csproof.rs:25-43)
