@@ -91,6 +91,7 @@ extern "C" {
     pub fn spg_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn spg_host_free(p: *mut c_void);
     pub fn spg_vec_alloc(ctx: *mut spg_ctx, n: usize, out: *mut *mut spg_vec) -> c_int;
+    pub fn spg_vec_zero(ctx: *mut spg_ctx, v: *mut spg_vec) -> c_int;
     pub fn spg_vec_upload(ctx: *mut spg_ctx, host: *const spg_fq, n: usize, out: *mut *mut spg_vec) -> c_int;
     pub fn spg_vec_wrap(
         ctx: *mut spg_ctx,
@@ -255,6 +256,7 @@ extern "C" {
         out: *mut c_void,
     ) -> c_int;
     pub fn spg_mailbox_poison(mailbox: *mut c_void, slot_stride: usize, rank: c_int, world: c_int);
+    pub fn spg_sc1_set_row_weights(s: *mut spg_sc1, weights: *const spg_fq, n_rows: usize) -> c_int;
     pub fn spg_sc1_final(s: *mut spg_sc1, claims: *mut spg_fq) -> c_int;
     pub fn spg_sc1_debug_tables(
         s: *mut spg_sc1,
@@ -304,6 +306,14 @@ extern "C" {
         rq_rev: *const spg_fq,
         nq: usize,
         scale: *const spg_fq,
+        out: *mut spg_vec,
+    ) -> c_int;
+    pub fn spg_zmat_bind_weights(
+        ctx: *mut spg_ctx,
+        z: *const spg_zmat,
+        weights: *const spg_fq,
+        n_weights: usize,
+        out_off: *const usize,
         out: *mut spg_vec,
     ) -> c_int;
     pub fn spg_sc2_num_rounds(s: *const spg_sc2) -> usize;

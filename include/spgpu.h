@@ -76,6 +76,8 @@ void spg_host_free(void *p);
 /* ---------------------------------------------------------------- vectors
  * DensePolynomial (src/dense_mlpoly.rs:19-24). */
 int spg_vec_alloc(spg_ctx *ctx, size_t n, spg_vec **out);
+/* v[i] = 0 */
+int spg_vec_zero(spg_ctx *ctx, spg_vec *v);
 int spg_vec_upload(spg_ctx *ctx, const spg_fq *host, size_t n, spg_vec **out);
 /* wrap caller-owned device memory (e.g. a torch tensor); not freed by spg_vec_free */
 int spg_vec_wrap(spg_ctx *ctx, void *device_ptr, size_t n, spg_vec **out);
@@ -204,6 +206,12 @@ int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *chal
 int spg_mailbox_all_gather(void *mailbox, size_t slot_stride, int rank, int world, uint64_t *calls,
                            const void *data, size_t nbytes, void *out);
 void spg_mailbox_poison(void *mailbox, size_t slot_stride, int rank, int world);
+/* Sharded proofs whose rows (instance, proof) are spread over ranks in any way: a rank creates the
+ * prover over ITS rows and replaces the row weights eq_p[p] * eq_q[q] of the x rounds by the global
+ * eq weights of those rows (n_rows = sum_p num_proofs[p], table order); call before the first round.
+ * The q and p rounds then run on the gathered per-row scalars (spg_sc1_debug_tables after the x
+ * rounds -> spg_sc1_create_from_tables with num_cons = 1). */
+int spg_sc1_set_row_weights(spg_sc1 *s, const spg_fq *weights, size_t n_rows);
 /* (tau_claim, Az, Bz, Cz) after the last bind, :1372-1377 */
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]);
 /* copy the current Az/Bz/Cz tables back in natural ragged order (tests) */
@@ -231,6 +239,12 @@ int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *z
  * on its own: out[p][w][y] = scale * sum_q eq_lsb(rq_rev, q) z[p][q][w][y]; scale may be NULL (= 1). */
 int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
                      spg_vec *out);
+/* the same sum with explicit per-row weights (sum_p num_proofs[p], instance major) instead of the eq
+ * table of rq: the sharded counterpart of spg_sc1_set_row_weights. out_off (may be NULL): where
+ * instance p's W * num_inputs[p] scalars go inside `out` (a rank that owns some of the batch's
+ * instances writes them at their place in the batch-wide table). */
+int spg_zmat_bind_weights(spg_ctx *ctx, const spg_zmat *z, const spg_fq *weights, size_t n_weights,
+                          const size_t *out_off, spg_vec *out);
 size_t spg_sc2_num_rounds(const spg_sc2 *s);
 int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]);
 int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r);

@@ -1,0 +1,61 @@
+"""The smallest program that launches every hot kernel once at the BASELINE size, for ncu:
+one table pass (z_mat, fused SpMV + round 0, phase-1 rounds, Z bind, phase-2 rounds) at
+X = 2^20 x Q = 64 and one witness commitment (8192 rows x 8192 generators; --no-commit skips it).
+usage: python scripts/ncu_target.py [--no-commit] [--log-x 20] [--proofs 64]"""
+import argparse
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import spartan_parallel_b200 as sp
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--no-commit", action="store_true")
+ap.add_argument("--log-x", type=int, default=20)
+ap.add_argument("--proofs", type=int, default=64)
+args = ap.parse_args()
+ctx = sp.Context(0)
+X, Q = 1 << args.log_x, args.proofs
+N, nx, nq = X * Q, args.log_x, Q.bit_length() - 1
+rng = np.random.default_rng(5)
+
+
+def canon(n):
+    a = rng.integers(0, 1 << 64, size=(max(n, 1), 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    return a[:n]
+
+
+u = canon(N)
+du = sp.DensePolynomial.new(ctx, u)
+dun = sp.DensePolynomial.new(ctx, np.ascontiguousarray(np.roll(u.reshape(Q, X, 4), -1, axis=1).reshape(N, 4)))
+v = sp.vec_op(ctx, "mul", du, dun).to_host()
+del du, dun
+rows = np.arange(X, dtype=np.uint32)
+ones = np.tile(sp.api.ONE, (X, 1))
+inst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [(rows, rows, ones)], [(rows, ((rows + 1) % X).astype(np.uint32), ones)],
+                       [(rows, (rows + X).astype(np.uint32), ones)])
+secs = [sp.ProverWitnessSecInfo(ctx, [Q], [X], u), sp.ProverWitnessSecInfo(ctx, [Q], [X], v)]
+z = sp.ZMat(ctx, [Q], [X], secs)
+tau_q, tau_x, ch1, ch2, r_abc = canon(nq), canon(nx), canon(nx + nq), canon(1 + nx), canon(3)
+sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
+sc1.set_claim(np.zeros(4, dtype=np.uint64))
+sc1.run_rounds(ch1)
+c1 = sc1.final()
+sc1.free()
+sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, ch1[:nx][::-1].copy(), ch1[nx:], ch1[:0], *r_abc)
+sc2.run_rounds(ch2)
+c2 = sc2.final()
+sc2.free()
+if not args.no_commit:
+    ell = nx + nq
+    L, R = 1 << (ell // 2), 1 << (ell - ell // 2)
+    base = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
+    gens = sp.MultiCommitGens.from_uniform(ctx, hashlib.shake_256(b"gens_r1cs_sat" + base).digest(64 * (R + 1)))
+    rows_c = gens.commit_poly(secs[0].poly_w(0), L)
+    print("commit rows", len(rows_c), gens.info())
+ctx.sync()
+print("ok", ctx.launches, "launches")

@@ -37,4 +37,5 @@ from .api import (  # noqa: F401
     wit_perm_w0,
     wit_shift,
     zmat_bind_rq,
+    zmat_bind_weights,
 )

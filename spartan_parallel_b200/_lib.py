@@ -129,6 +129,9 @@ def _proto(L):
         "spg_commit_batch": [P, P, P, SZ, P, SZ, P],
         "spg_poly_commit_rows": [P, P, P, SZ, SZ, SZ, P],
         "spg_mailbox_all_gather": [P, SZ, INT, INT, P, P, SZ, P],
+        "spg_sc1_set_row_weights": [P, P, SZ],
+        "spg_zmat_bind_weights": [P, P, P, SZ, P, P],
+        "spg_vec_zero": [P, P],
         "spg_wit_perm_w0": [P, P, P, SZ, SZ, PP],
         "spg_wit_block": [P, INT, P, SZ, SZ, P, P, P, SZ, SZ, SZ, SZ, SZ, P, SZ, PP, PP],
         "spg_wit_mem": [P, P, SZ, SZ, P, P, SZ, PP, PP],

@@ -122,6 +122,9 @@ class DensePolynomial:
     def device_ptr(self) -> int:
         return int(self.ctx.L.spg_vec_device_ptr(self.h) or 0)
 
+    def zero(self):
+        check(self.ctx.L.spg_vec_zero(self.ctx.h, self.h), "spg_vec_zero")
+
     def to_host(self) -> np.ndarray:
         out = np.empty((len(self), 4), dtype=np.uint64)
         check(self.ctx.L.spg_vec_download(self.ctx.h, self.h, 0, len(self), _ptr(out)), "spg_vec_download")
@@ -287,6 +290,12 @@ class SumcheckPhase1:
         check(self.ctx.L.spg_sc1_run_rounds_sharded(self.h, ch.shape[0], _ptr(ch), _ptr(out), C.c_void_p(mailbox_addr),
                                                     slot_stride, rank, world, _ptr(calls)), "spg_sc1_run_rounds_sharded")
         return out
+
+    def set_row_weights(self, weights):
+        """caller-supplied row weights for the x rounds (spg_sc1_set_row_weights): a rank of a sharded
+        proof passes the global eq_p * eq_q weights of the rows it owns"""
+        w = _fq(weights)
+        check(self.ctx.L.spg_sc1_set_row_weights(self.h, _ptr(w), w.shape[0]), "spg_sc1_set_row_weights")
 
     def set_claim(self, claim):
         """The prover's `claim` argument (src/sumcheck.rs:1069; zero in R1CSProof::prove): lets round 0
@@ -490,6 +499,18 @@ def zmat_bind_rq(ctx: Context, z: "ZMat", rq_rev, scale=None, out: DensePolynomi
         out = DensePolynomial.empty(ctx, total)
     sc = None if scale is None else _fq(scale)
     check(ctx.L.spg_zmat_bind_rq(ctx.h, z.h, _ptr(rq), rq.shape[0], _ptr(sc), out.h), "spg_zmat_bind_rq")
+    return out
+
+
+def zmat_bind_weights(ctx: Context, z: "ZMat", weights, out: DensePolynomial | None = None, out_off=None) -> DensePolynomial:
+    """sum_q weights[p][q] * Z[p][q][w][y] with explicit per-row weights (spg_zmat_bind_weights);
+    out_off places instance p's table at out[out_off[p]:] (a batch-wide table)."""
+    w = _fq(weights)
+    total = sum(len(z.witness_secs) * y for y in z.num_inputs)
+    if out is None:
+        out = DensePolynomial.empty(ctx, total)
+    off = None if out_off is None else _sz(out_off)
+    check(ctx.L.spg_zmat_bind_weights(ctx.h, z.h, _ptr(w), w.shape[0], _ptr(off), out.h), "spg_zmat_bind_weights")
     return out
 
 

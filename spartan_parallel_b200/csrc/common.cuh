@@ -108,10 +108,14 @@ namespace spg {
 // device the calling thread had current (another host thread than the creating one -- current
 // device is per thread and defaults to 0 --, a library that switched devices in between, one
 // process holding several contexts), and leaves the caller's current device as it found it.
+// Contexts that exist right now. Handles may outlive their context (a host language's finalisers run
+// in no particular order at exit): such a handle's destroy function must not touch the dead context --
+// its device memory went with spg_ctx_destroy -- and only frees its own host-side struct.
+bool ctx_alive(const spg_ctx *ctx);
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(const spg_ctx *ctx) {
-    if (!ctx) return;
+    if (!ctx || !ctx_alive(ctx)) return;
     int cur = -1;
     if (cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device && cudaSetDevice(ctx->device) == cudaSuccess) prev = cur;
   }

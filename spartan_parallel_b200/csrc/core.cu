@@ -1,12 +1,23 @@
 // Context, device vectors, error reporting and the shared reduction kernels.
 #include <atomic>
 #include <chrono>
+#include <mutex>
+#include <unordered_set>
 
 #include "common.cuh"
 
 namespace spg {
 
 static thread_local char g_err[512] = "";
+
+// live contexts (see DeviceGuard): never destroyed, so handle finalisers that run during process exit
+// can still consult it
+static std::mutex &g_live_mu = *new std::mutex();
+static std::unordered_set<const spg_ctx *> &g_live = *new std::unordered_set<const spg_ctx *>();
+bool ctx_alive(const spg_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  return g_live.count(ctx) != 0;
+}
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -48,6 +59,7 @@ cudaError_t dev_alloc_bytes(spg_ctx *ctx, void **p, size_t bytes) {
 
 void dev_free(spg_ctx *ctx, void *p) {
   if (!p) return;
+  if (!ctx_alive(ctx)) return;  // the context (and with it this memory) is already gone
   for (auto &b : ctx->big)
     if (b.p == p) {
       b.busy = false;
@@ -244,12 +256,20 @@ int spg_ctx_create(int device, spg_ctx **out) {
   *ctx->h_flag = 0;
   int rc = ensure_partials(ctx, (size_t)ctx->sm_count * 16 * 8);
   if (rc != SPG_OK) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    g_live.insert(ctx);
+  }
   *out = ctx;
   return SPG_OK;
 }
 
 void spg_ctx_destroy(spg_ctx *ctx) {
   if (!ctx) return;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    if (!g_live.erase(ctx)) return;  // not a live context (destroyed twice)
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto &b : ctx->big) cudaFreeAsync(b.p, ctx->stream);
@@ -381,6 +401,13 @@ int spg_vec_alloc(spg_ctx *ctx, size_t n, spg_vec **out) {
   spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && out, "spg_vec_alloc: null argument");
   return vec_new(ctx, n, out);
+}
+
+int spg_vec_zero(spg_ctx *ctx, spg_vec *v) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
+  SPG_CHECK(ctx && v, "spg_vec_zero: null argument");
+  if (v->n) SPG_CUDA(cudaMemsetAsync(v->d, 0, v->n * sizeof(fq), ctx->stream));
+  return SPG_OK;
 }
 
 int spg_vec_upload(spg_ctx *ctx, const spg_fq *host, size_t n, spg_vec **out) {

@@ -369,7 +369,7 @@ void spg_witness_destroy(spg_witness *w) {
   if (w->ready) {
     // a section freed before anyone consumed it: the free below is stream-ordered on the
     // compute stream, so the copy must be ordered before it
-    cudaStreamWaitEvent(w->ctx->stream, w->ready, 0);
+    if (spg::ctx_alive(w->ctx)) cudaStreamWaitEvent(w->ctx->stream, w->ready, 0);
     cudaEventDestroy(w->ready);
   }
   for (spg_vec *v : w->views)

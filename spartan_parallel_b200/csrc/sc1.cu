@@ -795,6 +795,25 @@ int spg_sc1_set_claim(spg_sc1 *s, const spg_fq *claim) {
   return SPG_OK;
 }
 
+// Replaces the row weights RW[p][q] = eq_p[p] * eq_q[q] of the x rounds by caller-supplied ones (one
+// per (instance, proof) row, in table order). A rank of a sharded proof that owns an arbitrary subset of
+// the batch's rows passes the GLOBAL eq weights of its rows here; the q and p rounds of such a
+// proof run on the gathered per-row scalars (parallel.ShardedRows), not on this handle.
+int spg_sc1_set_row_weights(spg_sc1 *s, const spg_fq *weights, size_t n_rows) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
+  SPG_CHECK(s && weights, "spg_sc1_set_row_weights: null argument");
+  if (s->round != 0 || s->evaluated) {
+    set_error("spg_sc1_set_row_weights: must be called before the first round");
+    return SPG_ESTATE;
+  }
+  size_t rows = 0;
+  for (size_t p = 0; p < s->P; p++) rows += s->Q[p];
+  SPG_CHECK(n_rows == rows, "spg_sc1_set_row_weights: %zu weights for %zu rows", n_rows, rows);
+  SPG_CUDA(cudaMemcpyAsync(s->RWx, weights, rows * sizeof(fq), cudaMemcpyHostToDevice, s->ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(s->ctx->stream));  // the caller's buffer may be pageable and short-lived
+  return SPG_OK;
+}
+
 size_t spg_sc1_num_rounds(const spg_sc1 *s) { return s ? s->nx + s->nq + s->np : 0; }
 
 namespace {

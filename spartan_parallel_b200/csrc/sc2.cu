@@ -465,6 +465,41 @@ int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size
   return z_bind_rq_all(ctx, z, rq_rev, nq, scale, out->d, off);
 }
 
+// out[p][w][y] = sum_q weights[p][q] * Z[p][q][w][y] with explicit weights (sum_p Q_p of them, instance
+// major): what spg_zmat_bind_rq computes when weights[p][q] = eq(rq, q), for a rank of a sharded proof
+// whose rows are an arbitrary subset of the batch (it passes the global eq weights of its own rows).
+int spg_zmat_bind_weights(spg_ctx *ctx, const spg_zmat *z, const spg_fq *weights, size_t n_weights, const size_t *out_off,
+                          spg_vec *out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
+  SPG_CHECK(ctx && z && weights && out, "spg_zmat_bind_weights: null argument");
+  std::vector<size_t> off(z->P), woff(z->P);
+  size_t total = 0, rows = 0;
+  for (size_t p = 0; p < z->P; p++) {
+    off[p] = out_off ? out_off[p] : total;
+    woff[p] = rows;
+    total += z->W * z->num_inputs[p];
+    rows += z->num_proofs[p];
+    SPG_CHECK(off[p] + z->W * z->num_inputs[p] <= out->n, "spg_zmat_bind_weights: instance %zu runs past the output (%zu entries)", p, out->n);
+  }
+  SPG_CHECK(out_off || out->n == total, "spg_zmat_bind_weights: output has %zu entries, expected %zu", out->n, total);
+  SPG_CHECK(n_weights == rows, "spg_zmat_bind_weights: %zu weights for %zu rows", n_weights, rows);
+  fq *dW = nullptr;
+  SPG_CUDA(dev_alloc(ctx, &dW, rows * sizeof(fq)));
+  int rc = [&]() -> int {
+    SPG_CUDA(cudaMemcpyAsync(dW, weights, rows * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t p = 0; p < z->P; p++) {
+      size_t WY = z->W * z->num_inputs[p];
+      ctx->next_units = 32.0 * (double)WY * (double)(z->num_proofs[p] + 1);
+      SPG_LAUNCH(ctx, k_z_bind_rq, (unsigned)((WY + ZB - 1) / ZB), ZB, 0, z->views + p * z->W, dW + woff[p], z->num_proofs[p],
+                 z->W, log2u(z->num_inputs[p]), out->d + off[p]);
+    }
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SPG_OK;
+  }();
+  dev_free(ctx, dW);
+  return rc;
+}
+
 size_t spg_sc2_num_rounds(const spg_sc2 *s) { return s ? s->ny + s->nw + s->np : 0; }
 
 int spg_sc2_round_eval(spg_sc2 *s, spg_fq e[3]) {

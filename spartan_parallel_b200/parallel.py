@@ -369,3 +369,213 @@ def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local, peer: "PeerTable | None" 
         acc = acc2
     ctx.sync()
     return acc
+
+
+# ---------------------------------------------------------------------------------------------
+# Several instances with different numbers of proofs (BASELINE config C4; src/lib.rs:1156-1270 sorts
+# them by num_proofs): the (instance, proof) ROWS of the batch are spread over the ranks. The x rounds
+# touch each row on its own, so a rank proves its rows with the global eq weights eq_p[p] * eq_q[q]
+# handed to the engine (spg_sc1_set_row_weights); after the x rounds every row is one scalar per
+# table, those are gathered, and the q and p rounds (sum_p Q_p entries: negligible) run on every
+# rank alike. Unlike ShardedPhase1 nothing ties a rank to a bit pattern of q, so instances with fewer
+# proofs than ranks are no special case.
+def next_pow2(n: int) -> int:
+    return 1 if n <= 1 else 1 << (n - 1).bit_length()
+
+
+def partition_rows(num_proofs, world: int):
+    """blocks[rank] = [(instance p, first proof, count)]: instance p's proofs are cut into
+    min(world, Q_p) equal blocks, dealt to the ranks starting at rank p (so that instances with fewer
+    proofs than ranks do not pile up on rank 0). Counts are powers of two like the Q_p."""
+    blocks = [[] for _ in range(world)]
+    for p, Q in enumerate(num_proofs):
+        per = max(1, Q // world)
+        nblk = Q // per
+        stride = max(1, world // nblk)
+        for b in range(nblk):
+            blocks[(b * stride + p) % world].append((p, b * per, per))
+    for r in range(world):
+        blocks[r].sort()
+    return blocks
+
+
+def host_eq(a, b) -> np.ndarray:
+    """eq(a, b) = a b + (1 - a)(1 - b) for two scalars, through the library's host helpers"""
+    one_minus = lambda t: api.host_eq_weight(np.asarray(t, dtype=np.uint64).reshape(1, 4), 0)
+    return api.host_sum(np.stack([api.host_mul(a, b), api.host_mul(one_minus(a), one_minus(b))]).reshape(2, 1, 4))[0]
+
+
+def row_weights(blocks_of_rank, tau_p, tau_q):
+    """eq_p[p] * eq_q[q] for the rows of one rank. eq_p is the reference's table order (index MSB <->
+    tau_p[0], p is never bit-reversed); eq_q pairs bit k of the natural proof index with tau_q[k]."""
+    tau_p = np.asarray(tau_p, dtype=np.uint64).reshape(-1, 4)
+    tau_q = np.asarray(tau_q, dtype=np.uint64).reshape(-1, 4)
+    tp = tau_p[::-1].copy()
+    out = []
+    for p, q0, cnt in blocks_of_rank:
+        wp = api.host_eq_weight(tp, p)
+        for q in range(q0, q0 + cnt):
+            out.append(api.host_mul(wp, api.host_eq_weight(tau_q, q)))
+    return np.stack(out) if out else np.zeros((0, 4), dtype=np.uint64)
+
+
+class ShardedRows:
+    """Phase-1 sumcheck of a multi-instance batch whose rows are spread over the ranks.
+
+    ``make_engine(blocks, weights)`` returns this rank's prover over its rows (round_eval /
+    round_bind / debug_tables; on a GPU ``api.SumcheckPhase1`` with set_row_weights) or None when
+    the rank owns no row; ``make_tail(Az, Bz, Cz)`` builds the prover of the q and p rounds from the
+    gathered per-row scalars (set_scale / round_eval / round_bind / final)."""
+
+    def __init__(self, comm, num_proofs, max_num_cons: int, tau_p, tau_q, tau_x, make_engine, make_tail):
+        self.comm = comm
+        self.num_proofs = list(num_proofs)
+        P = len(self.num_proofs)
+        self.nx, self.nq, self.np_ = log2(max_num_cons), log2(max(self.num_proofs)), log2(next_pow2(P))
+        self.tau_x = np.asarray(tau_x, dtype=np.uint64).reshape(-1, 4)
+        self.blocks = partition_rows(self.num_proofs, comm.world)
+        self.mine = self.blocks[comm.rank]
+        self.engine = make_engine(self.mine, row_weights(self.mine, tau_p, tau_q)) if self.mine else None
+        self.make_tail = make_tail
+        self.tail = None
+        self.round = 0
+        self.num_rounds = self.nx + self.nq + self.np_
+        self.rx = []
+
+    def round_eval(self) -> np.ndarray:
+        if self.round < self.nx:
+            part = self.engine.round_eval() if self.engine is not None else np.zeros((3, 4), dtype=np.uint64)
+            return api.host_sum(self.comm.all_gather(np.asarray(part, dtype=np.uint64).reshape(3, 4)))
+        return self._tail().round_eval()
+
+    def round_bind(self, r):
+        r = np.asarray(r, dtype=np.uint64).reshape(4)
+        if self.round < self.nx:
+            if self.engine is not None:
+                self.engine.round_bind(r)
+            self.rx.append(r)
+        else:
+            self._tail().round_bind(r)
+        self.round += 1
+
+    def run_rounds(self, challenges) -> np.ndarray:
+        ch = np.asarray(challenges, dtype=np.uint64).reshape(-1, 4)
+        out = []
+        if (self.round == 0 and self.nx and self.engine is not None and hasattr(self.engine, "run_rounds_sharded")
+                and isinstance(self.comm, ShmComm) and all(self.blocks)):
+            # every rank owns rows: the x rounds run in the C loop (eval, mailbox, bind; no Python in between)
+            calls = np.array([self.comm.calls], dtype=np.uint64)
+            out.extend(self.engine.run_rounds_sharded(ch[: self.nx], self.comm.addr, self.comm.slot_stride, self.comm.rank,
+                                                      self.comm.world, calls))
+            self.comm.calls = int(calls[0])
+            self.rx = [ch[j] for j in range(self.nx)]
+            self.round = self.nx
+        while self.round < self.num_rounds:
+            j = self.round
+            out.append(self.round_eval())
+            self.round_bind(ch[j])
+        return np.stack(out)
+
+    def _tail(self):
+        if self.tail is None:
+            n_rows = [sum(c for _, _, c in b) for b in self.blocks]
+            cap = max(n_rows)
+            mine = np.zeros((3, cap, 4), dtype=np.uint64)
+            if self.engine is not None:
+                tabs = self.engine.debug_tables()
+                for k in range(3):
+                    mine[k, : n_rows[self.comm.rank]] = np.asarray(tabs[k], dtype=np.uint64).reshape(-1, 4)[: n_rows[self.comm.rank]]
+            # one exchange of 3 scalars per row; through torch.distributed: it may exceed a mailbox slot
+            allr = TorchComm.all_gather(self.comm, mine) if self.comm.world > 1 else mine[None]
+            off, tot = [], 0
+            for Q in self.num_proofs:
+                off.append(tot)
+                tot += Q
+            tabs = np.zeros((3, tot, 4), dtype=np.uint64)
+            for r, blk in enumerate(self.blocks):
+                pos = 0
+                for p, q0, cnt in blk:
+                    tabs[:, off[p] + q0: off[p] + q0 + cnt] = allr[r][:, pos: pos + cnt]
+                    pos += cnt
+            # the x rounds left the scalar prefix prod_j eq(tau_x[j], r_j) with the host
+            cx = api.ONE.copy()
+            for j in range(self.nx):
+                cx = api.host_mul(cx, host_eq(self.tau_x[j], self.rx[j]))
+            self.tail = self.make_tail(tabs[0], tabs[1], tabs[2])
+            self.tail.set_scale(cx)
+        return self.tail
+
+    def final(self) -> np.ndarray:
+        return self._tail().final()
+
+    def free(self):
+        for eng in (self.engine, self.tail):
+            if eng is not None and hasattr(eng, "free"):
+                eng.free()
+        self.engine = self.tail = None
+
+
+def gpu_phase1_rows(ctx, comm, mats, num_cons, max_num_cons, num_vars, secs, num_proofs, num_inputs, max_num_inputs,
+                    tau_p, tau_q, tau_x, satisfied: bool = False):
+    """ShardedRows on this rank's GPU. mats: (A_list, B_list, C_list) of host COO triples, one per
+    instance (or one shared); secs: witness sections as objects with .num_inputs and .w_mat[p][q]
+    (host arrays; a section with one instance / one proof is shared, as in the reference).
+    Returns (prover, z_local, blocks of this rank): the caller keeps z_local for the Z bind."""
+    empty = np.zeros((0, 4), dtype=np.uint64)
+    P = len(num_proofs)
+    state = {}
+
+    def make_engine(blocks, weights):
+        ps = sorted({p for p, _, _ in blocks})
+        assert len(ps) == len(blocks), "one block per instance and rank"
+        shared = len(mats[0]) == 1
+        sel = [0] if shared else ps
+        inst = api.R1CSInstance(ctx, len(sel), max_num_cons, [num_cons[0 if shared else p] for p in sel], num_vars,
+                                [mats[0][i] for i in sel], [mats[1][i] for i in sel], [mats[2][i] for i in sel])
+        Ql = [c for _, _, c in blocks]
+        dsecs = []
+        for ws in secs:
+            single = len(ws.w_mat) == 1
+            src_p = [0] if single else ps
+            nq, rows = [], []
+            for k, p in enumerate(src_p):
+                short = len(ws.w_mat[p]) == 1
+                if single or short:
+                    q0, cnt = 0, 1
+                else:
+                    _, q0, cnt = blocks[k]
+                nq.append(cnt)
+                rows.extend(ws.w_mat[p][q0: q0 + cnt])
+            dsecs.append(api.ProverWitnessSecInfo(ctx, nq, [ws.num_inputs[p] for p in src_p], np.concatenate(rows)))
+        z = api.ZMat(ctx, Ql, [num_inputs[p] for p in ps], dsecs)
+        sc = api.sumcheck_phase1(ctx, inst, z, Ql, max(Ql), [num_cons[0 if shared else p] for p in ps], max_num_cons,
+                                 max_num_inputs, np.tile(api.ONE, (log2(next_pow2(len(ps))), 1)), np.tile(api.ONE, (log2(max(Ql)), 1)), tau_x)
+        sc.set_row_weights(weights)
+        if satisfied:
+            sc.set_claim(np.zeros(4, dtype=np.uint64))
+        state.update(z=z, inst=inst, secs=dsecs)
+        return sc
+
+    def make_tail(Az, Bz, Cz):
+        return api.SumcheckPhase1.from_tables(ctx, list(num_proofs), max(num_proofs), [1] * P, 1, Az, Bz, Cz, tau_p, tau_q, empty)
+
+    sh = ShardedRows(comm, num_proofs, max_num_cons, tau_p, tau_q, tau_x, make_engine, make_tail)
+    sh._state = state  # keeps the rank-local instance, sections and z_mat alive
+    return sh, state.get("z"), sh.mine
+
+
+def gpu_bind_rq_rows(ctx, comm, z_local, blocks, rq_rev, num_inputs, W: int, peer: "PeerTable"):
+    """Z bound to rq for a row-sharded batch: this rank's rows weighted by eq(rq, q) land at their
+    instances' places in the batch-wide [p][w][y] table (zeros elsewhere), then the modular all-reduce
+    over peer memory. peer.n = W * sum_p num_inputs[p]."""
+    rq_rev = np.asarray(rq_rev, dtype=np.uint64).reshape(-1, 4)
+    off, tot = [], 0
+    for y in num_inputs:
+        off.append(tot)
+        tot += W * y
+    assert peer.n == tot
+    peer.poly.zero()
+    if blocks:
+        w = np.stack([api.host_eq_weight(rq_rev, q) for _, q0, cnt in blocks for q in range(q0, q0 + cnt)])
+        api.zmat_bind_weights(ctx, z_local, w, peer.poly, [off[p] for p, _, _ in blocks])
+    return peer.all_reduce() if comm.world > 1 else peer.poly
