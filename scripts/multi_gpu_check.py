@@ -27,6 +27,8 @@ def main():
         check(ctx, comm, shm, rank, world, log_x)
     if "--full" in sys.argv:
         full_size(ctx, shm, rank, world)
+    if "--c4" in sys.argv:
+        c4_rows(ctx, shm, rank, world)
     dist.barrier()
     if rank == 0:
         print(f"multi-GPU parity ok: world={world}, every round bit-exact on every rank (per-round driver and C round loop)")
@@ -92,6 +94,49 @@ def full_size(ctx, shm, rank, world):
     peer.close()
     if rank == 0:
         print(f"C3 (2^16 x 256) sharded over {world} GPUs == unsharded: every round and claim bit-identical")
+
+
+def c4_rows(ctx, shm, rank, world):
+    """BASELINE config C4 at full size (P = 5 instances of 2^12 constraints, Q_p = {64,16,16,4,1}, W = 5
+    sections with a single one, ragged inputs) with its (instance, proof) rows spread over the ranks
+    (parallel.ShardedRows) against the oracle's unsharded run: every round of both sumchecks and all
+    final claims, on every rank."""
+    from tests.helpers import random_instance, random_witness_secs
+
+    P, W, Ymax = 5, 5, 1 << 12
+    num_proofs = [64, 16, 16, 4, 1]
+    num_cons = [1 << 12] * P
+    Y = [1 << 12, 1 << 12, 1 << 11, 1 << 12, 1 << 11]
+    inst = random_instance(P, num_cons, W, Ymax, Y, nnz=3 << 12, seed=204)
+    kinds = ["full", "single", "full", "full", "full"]
+    sec_inputs = [Y, [1 << 10] * P, [1 << 12, 1 << 13, 1 << 11, 1 << 12, 1 << 10], [8] * P, [8] * P]
+    secs = random_witness_secs(P, num_proofs, W, sec_inputs, kinds, seed=205)
+    np_, nq, nx, ny, nw = 3, 6, 12, 12, 3
+    big = rand_scalars(64, 2040)
+    tau_p, tau_q, tau_x = big[:np_], big[8:8 + nq], big[16:16 + nx]
+    ch1, ch2, r_abc = rand_scalars(np_ + nq + nx, 2041), rand_scalars(np_ + nw + ny, 2042), rand_scalars(3, 2043)
+    want = R.prove_tables(inst, P, 64, num_proofs, Ymax, Y, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
+    mats = ([inst.mats[3 * i] for i in range(P)], [inst.mats[3 * i + 1] for i in range(P)], [inst.mats[3 * i + 2] for i in range(P)])
+    sh, z_local, mine = parallel.gpu_phase1_rows(ctx, shm, mats, num_cons, 1 << 12, inst.num_vars, secs, num_proofs, Y, Ymax,
+                                                 tau_p, tau_q, tau_x)
+    got1 = sh.run_rounds(ch1)
+    assert np.array_equal(got1, np.stack(want.evals1)), f"rank {rank}: row-sharded C4 phase 1 differs"
+    assert np.array_equal(sh.final(), want.claims1), f"rank {rank}: row-sharded C4 phase-1 claims differ"
+    peer = parallel.PeerTable(ctx, shm, W * sum(Y))
+    zrq = parallel.gpu_bind_rq_rows(ctx, shm, z_local, mine, ch1[nx:nx + nq], Y, W, peer)
+    dinst = sp.R1CSInstance(ctx, P, 1 << 12, num_cons, inst.num_vars, *mats)
+    rx = ch1[:nx][::-1].copy()
+    sc2 = sp.SumcheckPhase2.from_zrq(ctx, dinst, zrq, Y, Ymax, W, rx, ch1[nx + nq:], *r_abc)
+    got2 = sc2.run_rounds(ch2)
+    assert np.array_equal(got2, np.stack(want.evals2)), f"rank {rank}: row-sharded C4 phase 2 differs"
+    assert np.array_equal(sc2.final(), want.claims2), f"rank {rank}: row-sharded C4 phase-2 claims differ"
+    sc2.free()
+    sh.free()
+    peer.close()
+    if rank == 0:
+        print(f"C4 (P = 5, Q_p = {num_proofs}, 2^12 constraints, W = 5) row-sharded over {world} GPUs == oracle: "
+              f"{len(got1)} + {len(got2)} rounds and all claims bit-identical; rows per rank "
+              f"{[sum(c for _, _, c in b) for b in sh.blocks]}")
 
 
 def check(ctx, comm, shm, rank, world, log_x):
