@@ -822,12 +822,20 @@ namespace {
 void build_tile_segs(spg_sc1 *s, int phase, int fused, unsigned long long *tiles_out, unsigned long long *out_total) {
   unsigned long long in_off = 0, out_off = 0, tiles = 0, rw = 0;
   s->segs.resize(s->P);
+  // tile size: 1024 items while that still gives every SM several blocks; smaller tiles (down to
+  // one item per thread) for the later rounds and for shards with few rows, which otherwise run
+  // on a handful of blocks (8 rows of 2^12 items: 32 blocks of 1024 instead of 256 of 128)
+  unsigned long long total_items = 0;
+  for (size_t p = 0; p < s->P; p++) total_items += (unsigned long long)(phase == 0 ? s->Q[p] : 1) << (s->loglen[p] - (fused ? 2 : 1));
+  unsigned log_tile = ROWS_LOG_TILE;
+  const unsigned long long want_blocks = (unsigned long long)s->ctx->sm_count * 8;
+  while (log_tile > 7 && (total_items >> log_tile) < want_blocks) log_tile--;
   for (size_t p = 0; p < s->P; p++) {
     Seg &g = s->segs[p];
     unsigned ll = s->loglen[p];
     unsigned long long rows = phase == 0 ? s->Q[p] : 1;
     unsigned li = ll - (fused ? 2 : 1);
-    unsigned lt = li > (unsigned)ROWS_LOG_TILE ? li - ROWS_LOG_TILE : 0;
+    unsigned lt = li > log_tile ? li - log_tile : 0;
     g.in_off = in_off;
     g.out_off = out_off;
     g.item_start = tiles;
