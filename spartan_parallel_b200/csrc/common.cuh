@@ -161,6 +161,50 @@ template <typename T>
 static inline cudaError_t dev_alloc(spg_ctx *ctx, T **p, size_t bytes) {
   return dev_alloc_bytes(ctx, (void **)p, bytes);
 }
+// Scope guards for the temporaries of an entry point: every early return (SPG_CUDA / SPG_TRY /
+// SPG_CHECK) releases them, so a failed call does not pin pool blocks or leak output vectors.
+struct DevTmp {
+  spg_ctx *ctx;
+  void *p = nullptr;
+  explicit DevTmp(spg_ctx *c) : ctx(c) {}
+  ~DevTmp() {
+    if (p) dev_free(ctx, p);
+  }
+  cudaError_t alloc(size_t bytes) { return dev_alloc_bytes(ctx, &p, bytes); }
+  template <typename T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+  DevTmp(const DevTmp &) = delete;
+  DevTmp &operator=(const DevTmp &) = delete;
+};
+struct CudaTmp {  // plain cudaMalloc'ed scratch
+  void *p = nullptr;
+  ~CudaTmp() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+  template <typename T>
+  T *as() const {
+    return static_cast<T *>(p);
+  }
+  CudaTmp() = default;
+  CudaTmp(const CudaTmp &) = delete;
+  CudaTmp &operator=(const CudaTmp &) = delete;
+};
+struct VecOut {  // an output vector that is freed unless released
+  spg_vec *v = nullptr;
+  ~VecOut();
+  spg_vec *release() {
+    spg_vec *r = v;
+    v = nullptr;
+    return r;
+  }
+  VecOut() = default;
+  VecOut(const VecOut &) = delete;
+  VecOut &operator=(const VecOut &) = delete;
+};
+
 int ensure_partials(spg_ctx *ctx, size_t n_fq);
 int vec_new(spg_ctx *ctx, size_t n, spg_vec **out);
 

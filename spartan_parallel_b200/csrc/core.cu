@@ -68,6 +68,10 @@ void dev_free(spg_ctx *ctx, void *p) {
   cudaFreeAsync(p, ctx->stream);
 }
 
+VecOut::~VecOut() {
+  if (v) spg_vec_free(v);
+}
+
 void prof_begin(spg_ctx *ctx, const char *name, cudaEvent_t *a, cudaEvent_t *b) {
   auto get = [&]() {
     cudaEvent_t e = nullptr;

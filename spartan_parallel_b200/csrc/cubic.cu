@@ -375,16 +375,16 @@ int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const
   spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && val && gamma && tau && out, "spg_hash_layer: null argument");
   SPG_CHECK(val->n >= n, "spg_hash_layer: val has %zu entries, need %zu", val->n, n);
-  spg_vec *o = nullptr;
-  SPG_TRY(vec_new(ctx, n, &o));
-  unsigned long long *d_addr = nullptr, *d_ts = nullptr;
+  VecOut o;
+  SPG_TRY(vec_new(ctx, n, &o.v));
+  DevTmp t_addr(ctx), t_ts(ctx);
   if (addr) {
-    SPG_CUDA(dev_alloc(ctx, &d_addr, n * 8));
-    SPG_CUDA(cudaMemcpyAsync(d_addr, addr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(t_addr.alloc(n * 8));
+    SPG_CUDA(cudaMemcpyAsync(t_addr.p, addr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (ts) {
-    SPG_CUDA(dev_alloc(ctx, &d_ts, n * 8));
-    SPG_CUDA(cudaMemcpyAsync(d_ts, ts, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(t_ts.alloc(n * 8));
+    SPG_CUDA(cudaMemcpyAsync(t_ts.p, ts, n * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   hfq g = hfq_from(*gamma);
   hfq g2 = hfq_mul(g, g);
@@ -393,11 +393,10 @@ int spg_hash_layer(spg_ctx *ctx, const uint64_t *addr, const spg_vec *val, const
   memcpy(&fg2, &g2, 32);
   memcpy(&ft, tau, 32);
   ctx->next_units = (double)n * (32.0 + 32.0 + (addr ? 8 : 0) + (ts ? 8 : 0));
-  SPG_LAUNCH(ctx, k_hash_layer, grid_for(ctx, n, 256), 256, 0, d_addr, val->d, d_ts, n, fg, fg2, ft, ts_plus_one, o->d);
+  SPG_LAUNCH(ctx, k_hash_layer, grid_for(ctx, n, 256), 256, 0, t_addr.as<unsigned long long>(), val->d,
+             t_ts.as<unsigned long long>(), n, fg, fg2, ft, ts_plus_one, o.v->d);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (d_addr) dev_free(ctx, d_addr);
-  if (d_ts) dev_free(ctx, d_ts);
-  *out = o;
+  *out = o.release();
   return SPG_OK;
 }
 
@@ -407,15 +406,14 @@ int spg_deref(spg_ctx *ctx, const uint64_t *addr, size_t n, const spg_vec *mem, 
   for (size_t i = 0; i < n; i++)
     SPG_CHECK(addr[i] < mem->n, "spg_deref: address %llu at %zu exceeds %zu memory cells",
               (unsigned long long)addr[i], i, mem->n);
-  spg_vec *o = nullptr;
-  SPG_TRY(vec_new(ctx, n, &o));
-  unsigned long long *d_addr = nullptr;
-  SPG_CUDA(dev_alloc(ctx, &d_addr, (n ? n : 1) * 8));
-  SPG_CUDA(cudaMemcpyAsync(d_addr, addr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-  SPG_LAUNCH(ctx, k_deref, grid_for(ctx, n, 256), 256, 0, d_addr, n, mem->d, o->d);
+  VecOut o;
+  SPG_TRY(vec_new(ctx, n, &o.v));
+  DevTmp t_addr(ctx);
+  SPG_CUDA(t_addr.alloc((n ? n : 1) * 8));
+  SPG_CUDA(cudaMemcpyAsync(t_addr.p, addr, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SPG_LAUNCH(ctx, k_deref, grid_for(ctx, n, 256), 256, 0, t_addr.as<unsigned long long>(), n, mem->d, o.v->d);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  dev_free(ctx, d_addr);
-  *out = o;
+  *out = o.release();
   return SPG_OK;
 }
 

@@ -314,11 +314,12 @@ int spg_dense_bound_bot(spg_ctx *ctx, spg_vec *v, const spg_fq *r) {
   size_t n = v->n / 2;
   fq rr;
   memcpy(&rr, r, sizeof rr);
-  fq *tmp = nullptr;
-  SPG_CUDA(dev_alloc(ctx, &tmp, n * sizeof(fq)));
-  SPG_LAUNCH(ctx, k_bound_bot, grid_for(ctx, n, 256), 256, 0, v->d, tmp, n, rr);
+  DevTmp tmp(ctx);
+  SPG_CUDA(tmp.alloc(n * sizeof(fq)));
+  SPG_LAUNCH(ctx, k_bound_bot, grid_for(ctx, n, 256), 256, 0, v->d, tmp.as<fq>(), n, rr);
   dev_free(ctx, v->d);
-  v->d = tmp;
+  v->d = tmp.as<fq>();
+  tmp.p = nullptr;  // now owned by the vector
   v->n = v->cap = n;
   return SPG_OK;
 }
@@ -347,21 +348,19 @@ int spg_dense_bound_L(spg_ctx *ctx, const spg_vec *v, const spg_fq *L, size_t L_
   SPG_CHECK(ctx && v && L && out, "spg_dense_bound_L: null argument");
   SPG_CHECK(L_size && v->n % L_size == 0, "spg_dense_bound_L: L_size %zu does not divide len %zu", L_size, v->n);
   size_t Rs = v->n / L_size;
-  spg_vec *o = nullptr;
-  SPG_TRY(vec_new(ctx, Rs, &o));
+  VecOut o;
+  SPG_TRY(vec_new(ctx, Rs, &o.v));
   size_t slab = 64;
   size_t nslabs = (L_size + slab - 1) / slab;
-  fq *dL = nullptr, *partial = nullptr;
-  SPG_CUDA(dev_alloc(ctx, &dL, L_size * sizeof(fq)));
-  SPG_CUDA(dev_alloc(ctx, &partial, nslabs * Rs * sizeof(fq)));
-  SPG_CUDA(cudaMemcpyAsync(dL, L, L_size * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  DevTmp tL(ctx), tpart(ctx);
+  SPG_CUDA(tL.alloc(L_size * sizeof(fq)));
+  SPG_CUDA(tpart.alloc(nslabs * Rs * sizeof(fq)));
+  SPG_CUDA(cudaMemcpyAsync(tL.p, L, L_size * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   dim3 grid((unsigned)((Rs + 127) / 128), (unsigned)nslabs);
-  SPG_LAUNCH(ctx, k_bound_L_partial, grid, 128, 0, v->d, dL, L_size, Rs, slab, partial);
-  SPG_LAUNCH(ctx, k_sum_slabs, (unsigned)((Rs + 127) / 128), 128, 0, partial, nslabs, Rs, o->d);
+  SPG_LAUNCH(ctx, k_bound_L_partial, grid, 128, 0, v->d, tL.as<fq>(), L_size, Rs, slab, tpart.as<fq>());
+  SPG_LAUNCH(ctx, k_sum_slabs, (unsigned)((Rs + 127) / 128), 128, 0, tpart.as<fq>(), nslabs, Rs, o.v->d);
   SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  dev_free(ctx, dL);
-  dev_free(ctx, partial);
-  *out = o;
+  *out = o.release();
   return SPG_OK;
 }
 

@@ -825,17 +825,14 @@ int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, 
   spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens && scalars && out_compressed, "spg_commit_batch: null argument");
   SPG_CHECK(len >= 1 && count >= 1, "spg_commit_batch: empty batch");
-  fq *d_s = nullptr, *d_b = nullptr;
-  SPG_CUDA(dev_alloc(ctx, &d_s, len * count * sizeof(fq)));
-  SPG_CUDA(cudaMemcpyAsync(d_s, scalars, len * count * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  DevTmp t_s(ctx), t_b(ctx);
+  SPG_CUDA(t_s.alloc(len * count * sizeof(fq)));
+  SPG_CUDA(cudaMemcpyAsync(t_s.p, scalars, len * count * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   if (blinds) {
-    SPG_CUDA(dev_alloc(ctx, &d_b, count * sizeof(fq)));
-    SPG_CUDA(cudaMemcpyAsync(d_b, blinds, count * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(t_b.alloc(count * sizeof(fq)));
+    SPG_CUDA(cudaMemcpyAsync(t_b.p, blinds, count * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   }
-  int rc = msm_rows(const_cast<spg_gens *>(gens), d_s, count, len, len, d_b, out_compressed);
-  dev_free(ctx, d_s);
-  if (d_b) dev_free(ctx, d_b);
-  return rc;
+  return msm_rows(const_cast<spg_gens *>(gens), t_s.as<fq>(), count, len, len, t_b.as<fq>(), out_compressed);
 }
 
 }  // extern "C"

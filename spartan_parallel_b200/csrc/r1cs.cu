@@ -277,9 +277,10 @@ int spg_r1cs_multi_evaluate(spg_ctx *ctx, const spg_r1cs *inst, const spg_fq *rx
             "spg_r1cs_multi_evaluate: |rx| = %zu, |ry| = %zu do not match %zu x %zu", nrx, nry,
             inst->max_num_cons, inst->num_vars);
   size_t nx = (size_t)1 << nrx, ny = (size_t)1 << nry;
-  fq *tabs = nullptr, *d_r = nullptr;
-  SPG_CUDA(cudaMalloc(&tabs, (nx + ny + (nx > ny ? nx : ny)) * sizeof(fq)));
-  SPG_CUDA(cudaMalloc(&d_r, (nrx + nry + 1) * sizeof(fq)));
+  CudaTmp t_tabs, t_r;
+  SPG_CUDA(t_tabs.alloc((nx + ny + (nx > ny ? nx : ny)) * sizeof(fq)));
+  SPG_CUDA(t_r.alloc((nrx + nry + 1) * sizeof(fq)));
+  fq *tabs = t_tabs.as<fq>(), *d_r = t_r.as<fq>();
   SPG_CUDA(cudaMemcpyAsync(d_r, rx, nrx * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   SPG_CUDA(cudaMemcpyAsync(d_r + nrx, ry, nry * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
   fq *trx = tabs, *try_ = tabs + nx, *scratch = tabs + nx + ny;
@@ -298,9 +299,7 @@ int spg_r1cs_multi_evaluate(spg_ctx *ctx, const spg_r1cs *inst, const spg_fq *rx
       rc = fetch_result(ctx, (int)cnt, out + (m - (cnt - 1)));
     }
   }
-  cudaStreamSynchronize(ctx->stream);
-  cudaFree(tabs);
-  cudaFree(d_r);
+  cudaStreamSynchronize(ctx->stream);  // before the guards free the tables
   return rc;
 }
 
