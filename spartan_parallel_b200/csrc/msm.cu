@@ -15,7 +15,7 @@
 //   C_i = sum_j sum_w sign(d) T[j][w][|d|-1],   d = digit_w(s_ij) in [-(2^(c-1)-1), 2^(c-1)]
 // at 7 field multiplications per entry (mixed addition). The window width c (8..13) is the
 // largest whose table fits the memory budget: 8192 bases take 3.2 GB at c = 8 (32 additions
-// per scalar) and 35 GB at c = 12 (22 additions); see pick_window.
+// per scalar), 35 GB at c = 12 (22 additions) and 64 GB at c = 13 (20 additions); see pick_window.
 // One thread owns (row i, chunk of bases); a block is 128 consecutive rows of the same chunk and
 // concurrently resident blocks share a handful of chunks, so table reads are L2 hits. The next
 // table entry is fetched before the current addition is computed (its address depends only on
@@ -445,20 +445,21 @@ size_t table_bytes_for(size_t slots, const Win &w) { return slots * (size_t)w.wi
 
 // Largest window width in [8, 13] whose table fits the budget. Wider windows mean fewer additions
 // per scalar (32 at c = 8, 26 at 10, 24 at 11, 22 at 12, 20 at 13) and a table that doubles with each
-// bit. Budget of one table: SPG_MSM_TABLE_GIB (default 40), and at most 60 % of what is left of the
-// process-wide allowance for tables (45 % of the device's memory) and of the memory free right now.
+// bit. Budget of one table: SPG_MSM_TABLE_GIB (default 64: 8193 bases at c = 13 take 60 GiB of a B200's
+// 180 GB), and at most 60 % of what is left of the process-wide allowance for tables (60 % of the
+// device's memory) and of the memory free right now.
 std::atomic<size_t> g_table_bytes{0};
 Win pick_window(size_t slots) {
   if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
     int c = atoi(e);
     if (c >= 5 && c <= 16) return make_win(c);
   }
-  double gib = 40.0;
+  double gib = 64.0;
   if (const char *e = getenv("SPG_MSM_TABLE_GIB")) gib = atof(e);
   size_t budget = (size_t)(gib * 1073741824.0);
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
-    size_t allowance = total_b / 100 * 45, used = g_table_bytes.load();
+    size_t allowance = total_b / 100 * 60, used = g_table_bytes.load();
     size_t left = allowance > used ? allowance - used : 0;
     if (budget > left / 10 * 6) budget = left / 10 * 6;
     if (budget > free_b / 10 * 6) budget = free_b / 10 * 6;
