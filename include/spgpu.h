@@ -181,6 +181,12 @@ int spg_sc1_set_scale(spg_sc1 *s, const spg_fq *c);
  * reference's whenever the claim really is the sum over the tables, i.e. for a satisfying
  * witness; without this call every round is exact for arbitrary tables. Call before round 0. */
 int spg_sc1_set_claim(spg_sc1 *s, const spg_fq *claim);
+/* the same, and the first round verifies the claim against the tables (three evaluation points
+ * instead of two): SPG_EINVAL from spg_sc1_round_eval if the claim is not the true sum, e.g. for a
+ * witness that does not satisfy the instance. Applies to tables the row-tiled kernels handle
+ * (every row of at least 2^8 constraints); smaller tables evaluate three points anyway and ignore
+ * the supplied claim's value. */
+int spg_sc1_set_claim_checked(spg_sc1 *s, const spg_fq *claim);
 size_t spg_sc1_num_rounds(const spg_sc1 *s);
 /* e = (eval_point_0, eval_point_2, eval_point_3) of the current round, :1166-1245 */
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]);

@@ -297,6 +297,12 @@ class SumcheckPhase1:
         w = _fq(weights)
         check(self.ctx.L.spg_sc1_set_row_weights(self.h, _ptr(w), w.shape[0]), "spg_sc1_set_row_weights")
 
+    def set_claim_checked(self, claim):
+        """set_claim, and the first round checks the claim against the tables (SpgError if it is not the
+        true sum, e.g. an unsatisfied witness)"""
+        c = _fq(np.asarray(claim, dtype=np.uint64).reshape(4))
+        check(self.ctx.L.spg_sc1_set_claim_checked(self.h, _ptr(c)), "spg_sc1_set_claim_checked")
+
     def set_claim(self, claim):
         """The prover's `claim` argument (src/sumcheck.rs:1069; zero in R1CSProof::prove): lets round 0
         use e(1) = claim - e(0) like the reference does. Exact iff the claim is the true sum."""

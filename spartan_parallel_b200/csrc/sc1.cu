@@ -487,6 +487,8 @@ struct spg_sc1 {
   // the true running claim s_{j-1}(r_{j-1}) (= e(0) + e(1) of the current round), maintained
   // from the evaluations this object itself produced: exact for any input tables
   bool claim_known = false;
+  bool check_claim = false;  // verify a supplied claim against the tables in the first round (spg_sc1_set_claim_checked)
+  hfq supplied_claim;
   hfq claim;
   hfq last_e[3];
   // the same claim divided by the scalar prefix c of the current round: with
@@ -814,6 +816,18 @@ int spg_sc1_set_row_weights(spg_sc1 *s, const spg_fq *weights, size_t n_rows) {
   return SPG_OK;
 }
 
+// spg_sc1_set_claim plus a check: the first round evaluates three points (like a prover without a
+// claim), which yields the true sum over the tables; if it differs from `claim` the round returns
+// SPG_EINVAL instead of emitting a proof that cannot verify. Costs one evaluation point of the first
+// round. With a plain spg_sc1_set_claim a wrong claim (an unsatisfied witness) goes unnoticed here --
+// as it does in the reference, whose verifier rejects the proof later.
+int spg_sc1_set_claim_checked(spg_sc1 *s, const spg_fq *claim) {
+  SPG_TRY(spg_sc1_set_claim(s, claim));
+  s->check_claim = true;
+  s->supplied_claim = hfq_from(*claim);
+  return SPG_OK;
+}
+
 size_t spg_sc1_num_rounds(const spg_sc1 *s) { return s ? s->nx + s->nq + s->np : 0; }
 
 namespace {
@@ -922,7 +936,8 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
     const fq *S = s_table(s, phase, n_phase - j - 1);
     const fq *RW = phase == 0 ? s->RWx : s->Ap;
     bool done = false;
-    if (s->cached_kind == 0 && s->claim_known && rows_eligible(s, 0) && !hfq_is_zero(hfq_mul(c, tau))) {
+    const bool verify_now = s->check_claim && s->round == 0;  // then the three-point path below yields the true sum
+    if (s->cached_kind == 0 && s->claim_known && !verify_now && rows_eligible(s, 0) && !hfq_is_zero(hfq_mul(c, tau))) {
       // the claim is known (spg_sc1_set_claim, or tracked from earlier rounds): two points suffice
       unsigned long long tiles = 0, out_total = 0;
       build_tile_segs(s, phase, 0, &tiles, &out_total);
@@ -1011,6 +1026,10 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       ev[1] = hfq_mul(hfq_mul(c, line[1]), G2);
       ev[2] = hfq_mul(hfq_mul(c, line[2]), G3);
       s->claim = hfq_add(ev[0], hfq_mul(hfq_mul(c, tau), G1));  // e(0) + e(1): the true claim
+      if (verify_now && !hfq_eq(s->claim, s->supplied_claim)) {
+        set_error("spg_sc1_round_eval: the supplied claim is not the sum over the tables (the witness does not satisfy the instance?)");
+        return SPG_EINVAL;
+      }
       s->claim_known = true;
       s->lastG[0] = G0;
       s->lastG[1] = G1;

@@ -198,3 +198,39 @@ def test_golden_round_tables(ctx):
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tables_p3_ragged.npz"))
     assert np.array_equal(np.stack(e1), g["evals1"]) and np.array_equal(np.asarray(c1), g["claims1"])
     assert np.array_equal(np.stack(e2), g["evals2"]) and np.array_equal(np.asarray(c2), g["claims2"])
+
+
+def test_checked_claim_detects_an_unsatisfied_witness(ctx):
+    """spg_sc1_set_claim_checked: same rounds as the plain prover for a satisfying witness; a witness
+    with one wrong entry makes the first round return an error instead of an unverifiable proof"""
+    import spartan_parallel_b200 as sp
+
+    X, Q = 1 << 9, 4
+    inst = R.synthetic_instance(X)
+    secs = R.synthetic_witness(X, [Q], seed=17)
+    A, B, Cm = inst.mats
+    dinst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A], [B], [Cm])
+    big = rand_scalars(64, 170)
+    tau_q, tau_x, ch = big[8:10], big[16:25], rand_scalars(11, 171)
+
+    def prover(w_secs):
+        dsecs = [sp.ProverWitnessSecInfo(ctx, [Q], [X], np.concatenate(ws.w_mat[0])) for ws in w_secs]
+        z = sp.ZMat(ctx, [Q], [X], dsecs)
+        sc = sp.sumcheck_phase1(ctx, dinst, z, [Q], Q, [X], X, X, big[:0], tau_q, tau_x)
+        sc._hold = (dsecs, z)
+        return sc
+
+    plain, checked = prover(secs), prover(secs)
+    plain.set_claim(O.ZERO)
+    checked.set_claim_checked(O.ZERO)
+    for j in range(plain.num_rounds):
+        assert np.array_equal(plain.round_eval(), checked.round_eval()), j
+        plain.round_bind(ch[j])
+        checked.round_bind(ch[j])
+    assert np.array_equal(plain.final(), checked.final())
+    bad = R.synthetic_witness(X, [Q], seed=17)
+    bad[1].w_mat[0][2][5] = O.add(bad[1].w_mat[0][2][5], O.ONE)  # v of proof 2, constraint 5
+    sc = prover(bad)
+    sc.set_claim_checked(O.ZERO)
+    with pytest.raises(sp.SpgError, match="not the sum over the tables"):
+        sc.round_eval()
