@@ -258,6 +258,14 @@ extern "C" {
     ) -> c_int;
     pub fn spg_mailbox_poison(mailbox: *mut c_void, slot_stride: usize, rank: c_int, world: c_int);
     pub fn spg_sc1_set_row_weights(s: *mut spg_sc1, weights: *const spg_fq, n_rows: usize) -> c_int;
+    pub fn spg_sc1_host_tail_eval(
+        state: *const spg_fq,
+        G: usize,
+        len: usize,
+        scale: *const spg_fq,
+        e: *mut spg_fq,
+    ) -> c_int;
+    pub fn spg_sc1_host_tail_bind(state: *mut spg_fq, G: usize, len: usize, r: *const spg_fq) -> c_int;
     pub fn spg_sc1_final(s: *mut spg_sc1, claims: *mut spg_fq) -> c_int;
     pub fn spg_sc1_debug_tables(
         s: *mut spg_sc1,

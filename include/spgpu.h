@@ -218,6 +218,15 @@ void spg_mailbox_poison(void *mailbox, size_t slot_stride, int rank, int world);
  * The q and p rounds then run on the gathered per-row scalars (spg_sc1_debug_tables after the x
  * rounds -> spg_sc1_create_from_tables with num_cons = 1). */
 int spg_sc1_set_row_weights(spg_sc1 *s, const spg_fq *weights, size_t n_rows);
+/* The last log2(G) rounds of a proof sharded over G <= 64 ranks, on the host: after the rounds each
+ * rank runs alone every table is one scalar per rank, and combining G scalars is mailbox-side work
+ * like the per-round sum of partial evaluations (no device prover is stood up for them).
+ * state = [E | A | B | C], G scalars each: E = eq table of the rank bits (index bit k <-> tau_q[nq_local
+ * + k]), A, B, C = the gathered Az, Bz, Cz scalars in rank order. A round evaluates on the first
+ * `len` entries of each (len = G >> round) and binds them in place to len / 2.
+ * e = scale * sum E(t) (A(t) B(t) - C(t)) at t = 0, 2, 3. */
+int spg_sc1_host_tail_eval(const spg_fq *state, size_t G, size_t len, const spg_fq *scale, spg_fq e[3]);
+int spg_sc1_host_tail_bind(spg_fq *state, size_t G, size_t len, const spg_fq *r);
 /* (tau_claim, Az, Bz, Cz) after the last bind, :1372-1377 */
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]);
 /* copy the current Az/Bz/Cz tables back in natural ragged order (tests) */

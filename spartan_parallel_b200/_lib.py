@@ -130,6 +130,8 @@ def _proto(L):
         "spg_poly_commit_rows": [P, P, P, SZ, SZ, SZ, P],
         "spg_mailbox_all_gather": [P, SZ, INT, INT, P, P, SZ, P],
         "spg_sc1_set_row_weights": [P, P, SZ],
+        "spg_sc1_host_tail_eval": [P, SZ, SZ, P, P],
+        "spg_sc1_host_tail_bind": [P, SZ, SZ, P],
         "spg_sc1_set_claim_checked": [P, P],
         "spg_zmat_bind_weights": [P, P, P, SZ, P, P],
         "spg_vec_zero": [P, P],

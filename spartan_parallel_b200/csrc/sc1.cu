@@ -1280,6 +1280,51 @@ int spg_sc1_run_rounds_sharded(spg_sc1 *s, size_t num_rounds, const spg_fq *chal
   return rc;
 }
 
+// The cross-rank end of a sharded proof. After the rounds a rank can run alone, every table of a
+// proof sharded over G ranks is one scalar per rank; the last log2(G) rounds combine those G
+// scalars. Like the per-round sum of the ranks' partial evaluations they run on the host, next to the
+// mailbox the scalars arrived through: G <= 64 entries, microseconds of exact field arithmetic,
+// against ~0.2 ms for standing up a device prover for them. Natural order, low bit first, the eq table
+// of the rank bits bound along with the tables (the reference binds its eq tables the same way,
+// src/sumcheck.rs:1265-1275):
+//   e_j(t) = scale * sum_i E_j(t)[i] * (A_j(t)[i] * B_j(t)[i] - C_j(t)[i]),  t = 0, 2, 3.
+// state: [E | A | B | C], G scalars each, overwritten in place; round j works on the first G >> j of each.
+int spg_sc1_host_tail_eval(const spg_fq *state, size_t G, size_t len, const spg_fq *scale, spg_fq e[3]) {
+  SPG_CHECK(state && scale && e, "spg_sc1_host_tail_eval: null argument");
+  SPG_CHECK(is_pow2(G) && G <= 64 && is_pow2(len) && len >= 2 && len <= G, "spg_sc1_host_tail_eval: bad sizes %zu / %zu", len, G);
+  hfq acc[3] = {hfq_zero(), hfq_zero(), hfq_zero()};
+  for (size_t i = 0; i < len / 2; i++) {
+    hfq lo[4], d[4];
+    for (int k = 0; k < 4; k++) {
+      lo[k] = hfq_from(state[k * G + 2 * i]);
+      d[k] = hfq_sub(hfq_from(state[k * G + 2 * i + 1]), lo[k]);
+    }
+    for (int pt = 0; pt < 3; pt++) {
+      if (pt >= 1)
+        for (int k = 0; k < 4; k++) {
+          lo[k] = hfq_add(lo[k], d[k]);
+          if (pt == 1) lo[k] = hfq_add(lo[k], d[k]);  // 0 -> 2, then 2 -> 3
+        }
+      acc[pt] = hfq_add(acc[pt], hfq_mul(lo[0], hfq_sub(hfq_mul(lo[1], lo[2]), lo[3])));
+    }
+  }
+  hfq sc = hfq_from(*scale);
+  for (int pt = 0; pt < 3; pt++) e[pt] = hfq_to(hfq_mul(sc, acc[pt]));
+  return SPG_OK;
+}
+
+int spg_sc1_host_tail_bind(spg_fq *state, size_t G, size_t len, const spg_fq *r) {
+  SPG_CHECK(state && r, "spg_sc1_host_tail_bind: null argument");
+  SPG_CHECK(is_pow2(G) && G <= 64 && is_pow2(len) && len >= 2 && len <= G, "spg_sc1_host_tail_bind: bad sizes %zu / %zu", len, G);
+  hfq rr = hfq_from(*r);
+  for (int k = 0; k < 4; k++)
+    for (size_t i = 0; i < len / 2; i++) {
+      hfq lo = hfq_from(state[k * G + 2 * i]), hi = hfq_from(state[k * G + 2 * i + 1]);
+      state[k * G + i] = hfq_to(hfq_add(lo, hfq_mul(rr, hfq_sub(hi, lo))));
+    }
+  return SPG_OK;
+}
+
 int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
   spg::DeviceGuard _dev(spg::ctx_of(s));
   SPG_CHECK(s && claims, "spg_sc1_final: null argument");

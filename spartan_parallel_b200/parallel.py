@@ -321,6 +321,50 @@ class ShardedPhase1:
         self.engine = self.tail = None
 
 
+class HostTail:
+    """The last log2(G) rounds of a sharded proof on G gathered scalars per table, on the host through
+    spg_sc1_host_tail_eval / _bind (see include/spgpu.h): same interface as the device prover."""
+
+    def __init__(self, Az, Bz, Cz, tau_high):
+        import ctypes as C
+
+        from ._lib import lib
+
+        self.L, self.C = lib(), C
+        G = Az.shape[0]
+        self.G, self.len = G, G
+        tau_high = np.asarray(tau_high, dtype=np.uint64).reshape(-1, 4)
+        E = np.stack([api.host_eq_weight(tau_high, i) for i in range(G)])
+        self.state = np.ascontiguousarray(np.concatenate([E, Az, Bz, Cz]).astype(np.uint64))
+        self.scale = api.ONE.copy()
+
+    def set_scale(self, c):
+        self.scale = np.ascontiguousarray(np.asarray(c, dtype=np.uint64).reshape(4))
+
+    def round_eval(self):
+        from ._lib import check
+
+        e = np.empty((3, 4), dtype=np.uint64)
+        p = lambda a: a.ctypes.data_as(self.C.c_void_p)
+        check(self.L.spg_sc1_host_tail_eval(p(self.state), self.G, self.len, p(self.scale), p(e)), "spg_sc1_host_tail_eval")
+        return e
+
+    def round_bind(self, r):
+        from ._lib import check
+
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.uint64).reshape(4))
+        p = lambda a: a.ctypes.data_as(self.C.c_void_p)
+        check(self.L.spg_sc1_host_tail_bind(p(self.state), self.G, self.len, p(r)), "spg_sc1_host_tail_bind")
+        self.len //= 2
+
+    def final(self):
+        s = self.state.reshape(4, self.G, 4)
+        return np.stack([api.host_mul(self.scale, s[0, 0]), s[1, 0], s[2, 0], s[3, 0]])
+
+    def free(self):
+        pass
+
+
 def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, satisfied: bool = False) -> ShardedPhase1:
     """ShardedPhase1 on this rank's GPU. satisfied=True asserts that the witness satisfies the
     instance: Az*Bz - Cz then vanishes entry by entry, so every shard's own sum is zero and the
@@ -335,6 +379,8 @@ def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, sat
 
     def make_tail(Az, Bz, Cz, tau_high):
         G = Az.shape[0]
+        if G <= 64 and not os.environ.get("SPG_DEVICE_TAIL"):
+            return HostTail(Az, Bz, Cz, tau_high)
         return api.SumcheckPhase1.from_tables(ctx, [G], G, [1], 1, Az, Bz, Cz, empty, tau_high, empty)
 
     return ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)

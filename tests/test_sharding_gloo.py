@@ -51,7 +51,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, Q_local, X, use_shm=False):
+def _worker(rank, world, port, Q_local, X, use_shm=False, host_tail=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -80,6 +80,8 @@ def _worker(rank, world, port, Q_local, X, use_shm=False):
 
         def make_tail(a, b, c, tau_high):
             G = a.shape[0]
+            if host_tail:  # the library's host-side tail (spg_sc1_host_tail_*), what gpu_phase1 uses for G <= 64
+                return parallel.HostTail(a, b, c, tau_high)
             return OracleEngine(mk_sc1(0, log2(G), G, 1, a, b, c, tau_high, tau_x[:0]))
 
         sh = parallel.ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)
@@ -121,6 +123,12 @@ def _worker(rank, world, port, Q_local, X, use_shm=False):
 @pytest.mark.parametrize("world,Q_local,X", [(2, 4, 8), (4, 2, 4), (2, 1, 16)])
 def test_sharded_phase1_matches_unsharded(world, Q_local, X):
     mp.spawn(_worker, args=(world, _free_port(), Q_local, X), nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,Q_local,X", [(2, 4, 8), (4, 2, 4), (8, 1, 2)])
+def test_host_tail_matches_unsharded(world, Q_local, X):
+    """the cross-rank rounds on the host (parallel.HostTail over spg_sc1_host_tail_eval / _bind)"""
+    mp.spawn(_worker, args=(world, _free_port(), Q_local, X, False, True), nprocs=world, join=True)
 
 
 def test_shared_memory_mailbox():
