@@ -27,7 +27,11 @@ $(LIB): $(OBJ)
 oracle:
 	$(MAKE) -C oracle
 
-tools: build/imad_peak
+tools: build/imad_peak build/round_latency
+
+build/round_latency: tools/round_latency.cu $(PKG)/csrc/fq.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ $<
 
 build/imad_peak: tools/imad_peak.cu $(PKG)/csrc/fq.cuh
 	@mkdir -p build
