@@ -625,3 +625,41 @@ def gpu_bind_rq_rows(ctx, comm, z_local, blocks, rq_rev, num_inputs, W: int, pee
         w = np.stack([api.host_eq_weight(rq_rev, q) for _, q0, cnt in blocks for q in range(q0, q0 + cnt)])
         api.zmat_bind_weights(ctx, z_local, w, peer.poly, [off[p] for p, _, _ in blocks])
     return peer.all_reduce() if comm.world > 1 else peer.poly
+
+
+# ---------------------------------------------------------------------------------------------
+# Live Fiat-Shamir transcript over a sharded proof. Only one rank owns the transcript (merlin state,
+# RandomTape, the per-round sigma protocol); the others need nothing but the challenge of each round.
+# The leader wraps the sharded prover so that its round_bind first publishes r_j through the same
+# exchange the evaluations use; followers replay the rounds with the challenges they receive.
+class LeaderRounds:
+    """round_eval / round_bind / final of a sharded prover (ShardedPhase1 or ShardedRows) for the rank
+    that runs the transcript: hand it to the code that drives an unsharded prover (the ZK sumcheck
+    glue of the host)."""
+
+    def __init__(self, sharded, comm):
+        self.sh, self.comm = sharded, comm
+        self.num_rounds = sharded.num_rounds
+
+    def round_eval(self):
+        return self.sh.round_eval()
+
+    def round_bind(self, r):
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.uint64).reshape(4))
+        self.comm.all_gather(r)  # broadcast: the followers take the leader's entry
+        self.sh.round_bind(r)
+
+    def final(self):
+        return self.sh.final()
+
+
+def follow_rounds(sharded, comm, leader: int = 0):
+    """The other ranks' side of LeaderRounds: take part in every round's exchange, bind with the
+    challenge the leader publishes. Returns the challenges (every rank ends with the same r)."""
+    out = []
+    for _ in range(sharded.num_rounds):
+        sharded.round_eval()
+        r = comm.all_gather(np.zeros(4, dtype=np.uint64))[leader]
+        sharded.round_bind(r)
+        out.append(r)
+    return np.stack(out) if out else np.zeros((0, 4), dtype=np.uint64)

@@ -125,6 +125,65 @@ def test_sharded_phase1_matches_unsharded(world, Q_local, X):
     mp.spawn(_worker, args=(world, _free_port(), Q_local, X), nprocs=world, join=True)
 
 
+def _live_worker(rank, world, port, Q_local, X):
+    """a live transcript on rank 0 (the oracle's ZK sumcheck glue: merlin, tape, per-round dot-product
+    proofs) over the sharded prover; the other ranks follow the challenges it publishes"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import protocol as P
+        from spartan_parallel_b200 import parallel
+
+        Q = Q_local * world
+        nx, nq = log2(X), log2(Q)
+        N = Q * X
+        Az, Bz, Cz = rand_scalars(N, 1), rand_scalars(N, 2), rand_scalars(N, 3)
+        tau_q, tau_x = rand_scalars(max(nq, 1), 4)[:nq], rand_scalars(max(nx, 1), 5)[:nx]
+        lo, hi = rank * Q_local * X, (rank + 1) * Q_local * X
+        comm = parallel.TorchComm()
+        make_engine = lambda tq: OracleEngine(mk_sc1(nx, log2(Q_local), Q_local, X, Az[lo:hi], Bz[lo:hi], Cz[lo:hi], tq, tau_x))
+        make_tail = lambda a, b, c, th: parallel.HostTail(a, b, c, th)
+        sh = parallel.ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)
+        gens = P.R1CSGens(b"gens_live", 16)
+        seed = rand_scalars(1, 9)[0]
+        # the claim of these random tables (they satisfy nothing): sum of eq(tau, (q, x)) * (Az Bz - Cz), natural
+        # bit k of q / x pairing with tau_q[k] / tau_x[k]
+        import spartan_parallel_b200 as sp
+
+        claim = O.ZERO
+        for q in range(Q):
+            wq = sp.host_eq_weight(tau_q, q)
+            for x in range(X):
+                i = q * X + x
+                w = O.mul(wq, sp.host_eq_weight(tau_x, x))
+                claim = O.add(claim, O.mul(w, O.sub(O.mul(Az[i], Bz[i]), Cz[i])))
+        if rank == 0:
+            t, tape = P.Transcript(b"live"), P.RandomTape(b"proof", seed)
+            got, r_got, _ = P.zk_sumcheck_prove(claim, O.ZERO, nx + nq, parallel.LeaderRounds(sh, comm), gens.gens_1, gens.gens_4, t, tape)
+            t2, tape2 = P.Transcript(b"live"), P.RandomTape(b"proof", seed)
+            want, r_want, _ = P.zk_sumcheck_prove(claim, O.ZERO, nx + nq, OracleEngine(mk_sc1(nx, nq, Q, X, Az, Bz, Cz, tau_q, tau_x)),
+                                                  gens.gens_1, gens.gens_4, t2, tape2)
+            assert got["comm_polys"] == want["comm_polys"] and got["comm_evals"] == want["comm_evals"]
+            assert all(np.array_equal(a, b) for a, b in zip(r_got, r_want))
+            # and the proof is one the verifier accepts for that claim
+            tv = P.Transcript(b"live")
+            ok = P.zk_sumcheck_verify(got, P.commit1(claim, O.ZERO, gens.gens_1).compress(), nx + nq, gens.gens_1, gens.gens_4, tv)
+            assert ok is not None and ok is not False
+            rs = np.stack(r_got)
+        else:
+            rs = parallel.follow_rounds(sh, comm)
+        allr = comm.all_gather(rs)
+        assert all(np.array_equal(allr[0], allr[k]) for k in range(world)), "every rank ends with the leader's challenges"
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,Q_local,X", [(2, 2, 4), (4, 1, 4)])
+def test_live_transcript_over_sharded_prover(world, Q_local, X):
+    mp.spawn(_live_worker, args=(world, _free_port(), Q_local, X), nprocs=world, join=True)
+
+
 @pytest.mark.parametrize("world,Q_local,X", [(2, 4, 8), (4, 2, 4), (8, 1, 2)])
 def test_host_tail_matches_unsharded(world, Q_local, X):
     """the cross-rank rounds on the host (parallel.HostTail over spg_sc1_host_tail_eval / _bind)"""
