@@ -386,6 +386,19 @@ class R1CSInstance:
               "spg_r1cs_multi_evaluate")
         return out
 
+    def multi_evaluate_bound_rp(self, rp, rx, ry):
+        """R1CSInstance::multi_evaluate_bound_rp (src/r1csinstance.rs:597-629): the per-instance evaluations
+        and the three MLEs over the instance index of the A, B and C evaluations at rp (zero padded to a
+        power of two like DensePolynomial::new)."""
+        ev = self.multi_evaluate(rx, ry)
+        rp = _fq(np.asarray(rp, dtype=np.uint64).reshape(-1, 4))
+        bound = []
+        for m in range(3):
+            poly = DensePolynomial.new(self.ctx, ev[m::3])
+            bound.append(poly.evaluate(rp))
+            poly.free()
+        return ev, tuple(bound)
+
     def free(self):
         if getattr(self, "h", None):
             self.ctx.L.spg_r1cs_destroy(self.h)

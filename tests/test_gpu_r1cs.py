@@ -234,3 +234,22 @@ def test_checked_claim_detects_an_unsatisfied_witness(ctx):
     sc.set_claim_checked(O.ZERO)
     with pytest.raises(sp.SpgError, match="not the sum over the tables"):
         sc.round_eval()
+
+
+def test_multi_evaluate_bound_rp(ctx):
+    """R1CSInstance::multi_evaluate_bound_rp (src/r1csinstance.rs:597-629) for 3 instances (padded to 4)"""
+    import spartan_parallel_b200 as sp
+
+    inst = random_instance(3, [32, 16, 32], 3, 16, [16, 8, 16], nnz=70, seed=33)
+    A = [inst.mats[3 * i] for i in range(3)]
+    B = [inst.mats[3 * i + 1] for i in range(3)]
+    Cm = [inst.mats[3 * i + 2] for i in range(3)]
+    d = sp.R1CSInstance(ctx, 3, 32, [32, 16, 32], inst.num_vars, A, B, Cm)
+    rx, ry, rp = rand_scalars(5, 1), rand_scalars(log2(inst.num_vars), 2), rand_scalars(2, 3)
+    ev, bound = d.multi_evaluate_bound_rp(rp, rx, ry)
+    trx, try_ = O.eq_evals(rx), O.eq_evals(ry)
+    want = [O.sparse_evaluate_with_tables(*inst.mats[m], trx, try_) for m in range(9)]
+    assert all(np.array_equal(ev[m], want[m]) for m in range(9))
+    for k in range(3):
+        col = np.stack([want[3 * i + k] for i in range(3)] + [O.ZERO])
+        assert np.array_equal(bound[k], O.dense_evaluate(col, rp)), k
