@@ -203,6 +203,7 @@ def run_gpu(args):
     assert world & (world - 1) == 0, "world size must be a power of two"
     comm = parallel.ShmComm(device=dev) if world > 1 else parallel.LocalComm()
     peer = parallel.PeerTable(ctx, comm, 2 * X) if world > 1 else None  # the rq-bound Z table: W * Y scalars
+    shard_y = world > 1 and not args.replicated_phase2  # W = 2 sections, world a power of two >= 2: chunks stay inside a section
     A, B, Cm = synthetic_matrices(X, ONE)
     inst = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A], [B], [Cm])
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -291,7 +292,7 @@ def run_gpu(args):
                 sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, rx, ch1[nx:nx + nq], ch1[:0], r_abc[0], r_abc[1], r_abc[2])
             else:
                 # one proof over Q * world proofs: shards exchange 3 scalars per round, then one
-                # modular all-reduce of the rq-bound Z table; phase 2 (independent of Q) runs replicated
+                # modular reduction of the rq-bound Z table over peer memory; phase 2 (independent of Q) is cut over y
                 sc1 = parallel.gpu_phase1(ctx, comm, inst, z, Q, X, X, self.tau_q, self.tau_x, satisfied=True)
                 mark("phase1 create")
                 sc1.run_rounds(ch1[:sc1.num_rounds])
@@ -299,9 +300,12 @@ def run_gpu(args):
                 c1 = sc1.final()
                 sc1.free()
                 mark("phase1 final")
-                zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q, peer)
-                mark("Z bind + peer all-reduce")
-                sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
+                zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[nx:nx + nq + ng], Q, peer, scatter=shard_y)
+                mark("Z bind + peer reduce")
+                if shard_y:  # phase 2 cut over y: each rank builds and folds 1/world of the ABC and Z tables
+                    sc2 = parallel.gpu_phase2_sharded(ctx, comm, inst, zrq, X, 2, rx, r_abc[0], r_abc[1], r_abc[2])
+                else:
+                    sc2 = sp.SumcheckPhase2.from_zrq(ctx, inst, zrq, [X], X, 2, rx, ch1[:0], r_abc[0], r_abc[1], r_abc[2])
             mark("phase2 create")
             sc2.run_rounds(ch2[:sc2.num_rounds])
             c2 = sc2.final()
@@ -579,7 +583,9 @@ def run_gpu(args):
     shard_note = ("single GPU" if world == 1 else
                   f"one batch of {Q_main} proofs sharded by proof index over {world} ranks ({main.Q} per rank): per-round exchange of 3 scalars per rank "
                   "through host shared memory (the values already live in pinned host memory) + one modular all-reduce of the rq-bound Z table as a "
-                  "kernel over NVLink peer memory (CUDA IPC; rank r sums chunk r with P2P loads and writes it to every peer with P2P stores)")
+                  "kernel over NVLink peer memory (CUDA IPC; rank r sums chunk r with P2P loads" +
+                  ("; phase 2 is sharded over y the same way: rank r builds and folds chunk r of the ABC and Z tables, the last log2(N) rounds run on the gathered scalars)"
+                   if shard_y else " and writes it to every peer with P2P stores; phase 2 replicated)"))
     line = {
         "metric": "sumcheck_constraints_per_sec", "value": value, "unit": "constraints/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling,
@@ -677,13 +683,19 @@ def sharded_equals_unsharded(sp, parallel, ctx, comm, rank, world, log_x, Q):
     got2 = sc2.run_rounds(ch2)
     gotc2 = sc2.final()
     sc2.free()
+    ok_y = True
+    if world <= 2 * X and (2 * X) % world == 0 and world % 2 == 0:  # the y-sharded phase 2 must agree as well
+        zrq = parallel.gpu_bind_rq_sharded(ctx, comm, z, ch1[log_x:], Ql, peer, scatter=True)
+        sy = parallel.gpu_phase2_sharded(ctx, comm, inst, zrq, X, 2, rx, *r_abc)
+        ok_y = np.array_equal(sy.run_rounds(ch2), want2) and np.array_equal(sy.final(), wantc2)
+        sy.free()
     peer.close()
     z.free()
     for s_ in secs:
         s_.free()
     inst.free()
     ok = (np.array_equal(got1, want1) and np.array_equal(gotc1, wantc1) and np.array_equal(got2, want2)
-          and np.array_equal(gotc2, wantc2))
+          and np.array_equal(gotc2, wantc2) and ok_y)
     return {"ok": bool(ok), "config": f"C3: X=2^{log_x} x Q={Q} sharded over {world} ranks vs unsharded on each rank's GPU",
             "compared": f"{len(want1)} + {len(want2)} round polynomials, 4 + 3 final claims, bit for bit"}
 
@@ -916,6 +928,7 @@ def main():
     ap.add_argument("--sparse-log-nnz", type=int, default=20)
     ap.add_argument("--no-witness-gen", action="store_true", help="skip the derived-witness-section leg")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded == unsharded check (C3)")
+    ap.add_argument("--replicated-phase2", action="store_true", help="N > 1: run phase 2 replicated on every rank instead of sharded over y")
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong mode: skip the extra weak-scaling figure")
     ap.add_argument("--no-e2e", action="store_true", help="development: skip the end-to-end leg")
     ap.add_argument("--trace-phases", action="store_true", help="development: per-phase wall clock of one extra pass on stderr")

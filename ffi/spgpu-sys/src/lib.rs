@@ -309,6 +309,46 @@ extern "C" {
         r_C: *const spg_fq,
         out: *mut *mut spg_sc2,
     ) -> c_int;
+    pub fn spg_sc2_create_slice(
+        ctx: *mut spg_ctx,
+        inst: *const spg_r1cs,
+        zrq: *const spg_vec,
+        max_num_inputs: usize,
+        num_witness_secs: usize,
+        flat_off: usize,
+        flat_len: usize,
+        rx: *const spg_fq,
+        r_A: *const spg_fq,
+        r_B: *const spg_fq,
+        r_C: *const spg_fq,
+        out: *mut *mut spg_sc2,
+    ) -> c_int;
+    pub fn spg_sc2_run_rounds_sharded(
+        s: *mut spg_sc2,
+        num_rounds: usize,
+        challenges: *const spg_fq,
+        evals_out: *mut spg_fq,
+        mailbox: *mut c_void,
+        slot_stride: usize,
+        rank: c_int,
+        world: c_int,
+        calls: *mut u64,
+    ) -> c_int;
+    pub fn spg_sc2_host_tail_eval(
+        state: *const spg_fq,
+        G: usize,
+        len: usize,
+        mode: c_int,
+        scale: *const spg_fq,
+        e: *mut spg_fq,
+    ) -> c_int;
+    pub fn spg_sc2_host_tail_bind(
+        state: *mut spg_fq,
+        G: usize,
+        len: usize,
+        mode: c_int,
+        r: *const spg_fq,
+    ) -> c_int;
     pub fn spg_zmat_bind_rq(
         ctx: *mut spg_ctx,
         z: *const spg_zmat,
@@ -447,6 +487,13 @@ extern "C" {
     pub fn spg_peer_open(ctx: *mut spg_ctx, handle: *const u8, ptr: *mut *mut c_void) -> c_int;
     pub fn spg_peer_close(ptr: *mut c_void) -> c_int;
     pub fn spg_peer_sum(
+        ctx: *mut spg_ctx,
+        peer_ptrs: *const *mut c_void,
+        world: c_int,
+        rank: c_int,
+        n: usize,
+    ) -> c_int;
+    pub fn spg_peer_reduce_scatter(
         ctx: *mut spg_ctx,
         peer_ptrs: *const *mut c_void,
         world: c_int,

@@ -250,6 +250,21 @@ int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *z
                             const size_t *num_inputs, size_t max_num_inputs, size_t num_witness_secs,
                             const spg_fq *rx, const spg_fq *rp, const spg_fq *r_A, const spg_fq *r_B,
                             const spg_fq *r_C, spg_sc2 **out);
+/* A y-sharded phase 2 (one instance, G ranks, G a multiple of the power-of-two number of witness
+ * sections): rank r owns entries [flat_off, flat_off + flat_len) of the flat [w][y] tables (flat_len =
+ * W * Y / G) and proves them as a (P = 1, W = 1, Y = flat_len) prover -- the summand has no weight over
+ * (w, y), so the partial round evaluations of the ranks simply add. The ABC slice is built from the
+ * instance, the Z slice is read from zrq at flat_off (spg_peer_reduce_scatter leaves it there).
+ * spg_sc2_run_rounds_sharded runs the log2(flat_len) local rounds with the mailbox exchange; the remaining
+ * log2(G) rounds run on the gathered scalars on the host: state = [B | C] (G each, flat (w, y_high) order),
+ * mode 0 = a y round (adjacent pairs), mode 1 = a w round (top bit first). */
+int spg_sc2_create_slice(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *zrq, size_t max_num_inputs,
+                         size_t num_witness_secs, size_t flat_off, size_t flat_len, const spg_fq *rx,
+                         const spg_fq *r_A, const spg_fq *r_B, const spg_fq *r_C, spg_sc2 **out);
+int spg_sc2_run_rounds_sharded(spg_sc2 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out,
+                               void *mailbox, size_t slot_stride, int rank, int world, uint64_t *calls);
+int spg_sc2_host_tail_eval(const spg_fq *state, size_t G, size_t len, int mode, const spg_fq *scale, spg_fq e[3]);
+int spg_sc2_host_tail_bind(spg_fq *state, size_t G, size_t len, int mode, const spg_fq *r);
 /* Z_poly.bound_poly_vars_rq (src/r1csproof.rs:478, src/custom_dense_mlpoly.rs:222-244, 300-304)
  * on its own: out[p][w][y] = scale * sum_q eq_lsb(rq_rev, q) z[p][q][w][y]; scale may be NULL (= 1). */
 int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
@@ -368,6 +383,9 @@ int spg_peer_free(spg_vec *v);
 int spg_peer_open(spg_ctx *ctx, const uint8_t handle[64], void **ptr);
 int spg_peer_close(void *ptr);
 int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n);
+/* the same reduction, but the sum of chunk r stays with rank r only (half the NVLink traffic): for a
+ * consumer that is sharded the same way (spg_sc2_create_slice) */
+int spg_peer_reduce_scatter(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n);
 
 /* ---------------------------------------------------------------- derived witness sections (f2)
  * What SNARK::prove computes from the primary sections (block_vars, exec_inputs, the memory

@@ -132,6 +132,11 @@ def _proto(L):
         "spg_sc1_set_row_weights": [P, P, SZ],
         "spg_sc1_host_tail_eval": [P, SZ, SZ, P, P],
         "spg_sc1_host_tail_bind": [P, SZ, SZ, P],
+        "spg_sc2_create_slice": [P, P, P, SZ, SZ, SZ, SZ, P, P, P, P, PP],
+        "spg_sc2_run_rounds_sharded": [P, SZ, P, P, P, SZ, INT, INT, P],
+        "spg_sc2_host_tail_eval": [P, SZ, SZ, INT, P, P],
+        "spg_sc2_host_tail_bind": [P, SZ, SZ, INT, P],
+        "spg_peer_reduce_scatter": [P, P, INT, INT, SZ],
         "spg_sc1_set_claim_checked": [P, P],
         "spg_zmat_bind_weights": [P, P, P, SZ, P, P],
         "spg_vec_zero": [P, P],

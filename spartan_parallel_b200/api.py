@@ -561,6 +561,28 @@ class SumcheckPhase2:
                                    _ptr(_fq(r_C)), C.byref(h)), "spg_sc2_create")
         self.h = h
 
+    @classmethod
+    def slice(cls, ctx: Context, inst: R1CSInstance, zrq: DensePolynomial, max_num_inputs, num_witness_secs: int,
+              flat_off: int, flat_len: int, rx, r_A, r_B, r_C) -> "SumcheckPhase2":
+        """one rank's chunk [flat_off, flat_off + flat_len) of a y-sharded phase 2 (spg_sc2_create_slice)"""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        h = C.c_void_p()
+        f = lambda v: _fq(np.asarray(v, dtype=np.uint64).reshape(-1, 4))
+        check(ctx.L.spg_sc2_create_slice(ctx.h, inst.h, zrq.h, max_num_inputs, num_witness_secs, flat_off, flat_len, _ptr(f(rx)),
+                                         _ptr(f(r_A)), _ptr(f(r_B)), _ptr(f(r_C)), C.byref(h)), "spg_sc2_create_slice")
+        self.h = h
+        self._keep = (inst, zrq)
+        return self
+
+    def run_rounds_sharded(self, challenges, mailbox_addr: int, slot_stride: int, rank: int, world: int, calls: np.ndarray):
+        """local rounds with the mailbox exchange in one C loop (spg_sc2_run_rounds_sharded)"""
+        ch = _fq(np.asarray(challenges, dtype=np.uint64).reshape(-1, 4))
+        out = np.empty((ch.shape[0], 3, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_sc2_run_rounds_sharded(self.h, ch.shape[0], _ptr(ch), _ptr(out), C.c_void_p(mailbox_addr), slot_stride,
+                                                    rank, world, _ptr(calls)), "spg_sc2_run_rounds_sharded")
+        return out
+
     @property
     def num_rounds(self) -> int:
         return int(self.ctx.L.spg_sc2_num_rounds(self.h))

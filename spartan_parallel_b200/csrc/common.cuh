@@ -205,6 +205,10 @@ struct VecOut {  // an output vector that is freed unless released
   VecOut &operator=(const VecOut &) = delete;
 };
 
+// one exchange through the host mailbox of a sharded proof (csrc/sc1.cu): publish `mine`, collect all ranks'
+int mailbox_exchange(char *base, size_t slot_stride, int rank, int world, uint64_t c, const void *mine, size_t nbytes,
+                     void *out);
+
 int ensure_partials(spg_ctx *ctx, size_t n_fq);
 int vec_new(spg_ctx *ctx, size_t n, spg_vec **out);
 

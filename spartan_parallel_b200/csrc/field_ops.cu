@@ -186,12 +186,14 @@ __global__ void k_sum_slabs(const fq *__restrict__ partial, size_t nslabs, size_
 struct PeerPtrs {
   fq *p[16];
 };
-__global__ void k_peer_sum(const __grid_constant__ PeerPtrs P, int world, size_t begin, size_t count) {
+// scatter_only: the sum of chunk `begin` stays with its owner (P.p[0]) -- a reduce-scatter, half the traffic
+__global__ void k_peer_sum(const __grid_constant__ PeerPtrs P, int world, size_t begin, size_t count, int scatter_only) {
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) {
     size_t i = begin + t;
     fq acc = fq_load_cg(P.p[0] + i);
     for (int r = 1; r < world; r++) acc = fq_add(acc, fq_load_cg(P.p[r] + i));
-    for (int r = 0; r < world; r++) fq_store(P.p[r] + i, acc);
+    const int nw = scatter_only ? 1 : world;
+    for (int r = 0; r < nw; r++) fq_store(P.p[r] + i, acc);
   }
 }
 
@@ -414,7 +416,14 @@ int spg_peer_close(void *ptr) {
   return SPG_OK;
 }
 
+static int peer_sum_impl(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n, int scatter_only);
 int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n) {
+  return peer_sum_impl(ctx, peer_ptrs, world, rank, n, 0);
+}
+int spg_peer_reduce_scatter(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n) {
+  return peer_sum_impl(ctx, peer_ptrs, world, rank, n, 1);
+}
+static int peer_sum_impl(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n, int scatter_only) {
   spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && peer_ptrs, "spg_peer_sum: null argument");
   SPG_CHECK(world >= 1 && world <= 16 && rank >= 0 && rank < world, "spg_peer_sum: bad rank %d of %d", rank, world);
@@ -426,8 +435,8 @@ int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size
   for (int r = 0, k = 1; r < world; r++)
     if (r != rank) P.p[k++] = (fq *)peer_ptrs[r];
   size_t chunk = n / world;
-  ctx->next_units = 64.0 * (double)chunk * (double)(world - 1);
-  SPG_LAUNCH(ctx, k_peer_sum, grid_for(ctx, chunk, 256), 256, 0, P, world, (size_t)rank * chunk, chunk);
+  ctx->next_units = (scatter_only ? 32.0 : 64.0) * (double)chunk * (double)(world - 1);
+  SPG_LAUNCH(ctx, k_peer_sum, grid_for(ctx, chunk, 256), 256, 0, P, world, (size_t)rank * chunk, chunk, scatter_only);
   return SPG_OK;
 }
 

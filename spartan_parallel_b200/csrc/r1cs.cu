@@ -49,18 +49,19 @@ __device__ __forceinline__ fq spmv_col(const CsxView &M, uint32_t c, const fq *_
 }
 
 // out[w * num_cols + y] = r_A * sum_A + r_B * sum_B + r_C * sum_C over column w*max_cols + y
+// (entries [t0, t0 + count) of the table only: a rank of a y-sharded phase 2 builds its own slice)
 __global__ void k_abc_table(CsxView A, CsxView B, CsxView C, const fq *__restrict__ rx,
-                            size_t num_segs, unsigned int log_max_cols, unsigned int log_cols,
+                            size_t t0, size_t count, unsigned int log_max_cols, unsigned int log_cols,
                             fq rA, fq rB, fq rC, fq *__restrict__ out) {
-  size_t total = num_segs << log_cols;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (size_t)gridDim.x * blockDim.x) {
+  for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < count;
+       l += (size_t)gridDim.x * blockDim.x) {
+    size_t t = t0 + l;
     size_t w = t >> log_cols, y = t & (((size_t)1 << log_cols) - 1);
     uint32_t c = (uint32_t)((w << log_max_cols) + y);
     fq a = fq_mul(rA, spmv_col(A, c, rx));
     fq b = fq_mul(rB, spmv_col(B, c, rx));
     fq cc = fq_mul(rC, spmv_col(C, c, rx));
-    fq_store(out + t, fq_add(fq_add(a, b), cc));
+    fq_store(out + l, fq_add(fq_add(a, b), cc));
   }
 }
 
@@ -189,9 +190,25 @@ int r1cs_abc_table(spg_ctx *ctx, const spg_r1cs *inst, const fq *evals_rx, size_
     }
     size_t items = num_segs * num_cols[p];
     SPG_LAUNCH(ctx, k_abc_table, grid_for(ctx, items, 128), 128, 0, view(inst->by_col[3 * p]),
-               view(inst->by_col[3 * p + 1]), view(inst->by_col[3 * p + 2]), evals_rx, num_segs, log_max,
+               view(inst->by_col[3 * p + 1]), view(inst->by_col[3 * p + 2]), evals_rx, (size_t)0, items, log_max,
                log2u(num_cols[p]), rA, rB, rC, out + out_off[p]);
   }
+  return SPG_OK;
+}
+
+// entries [t0, t0 + count) of instance 0's [w][y] table (num_cols = max_num_cols columns per segment)
+int r1cs_abc_slice(spg_ctx *ctx, const spg_r1cs *inst, const fq *evals_rx, size_t num_segs, size_t max_num_cols,
+                   size_t t0, size_t count, const spg_fq *r_A, const spg_fq *r_B, const spg_fq *r_C, fq *out) {
+  fq rA, rB, rC;
+  memcpy(&rA, r_A, 32);
+  memcpy(&rB, r_B, 32);
+  memcpy(&rC, r_C, 32);
+  unsigned log_max = log2u(max_num_cols);
+  SPG_CHECK(t0 + count <= num_segs * max_num_cols, "abc_slice: [%zu, %zu) exceeds the table", t0, t0 + count);
+  for (int m = 0; m < 3; m++)
+    if (inst->by_col[m].nnz) SPG_CHECK((inst->max_col[m] >> log_max) < num_segs, "abc_slice: column %u addresses segment >= %zu", inst->max_col[m], num_segs);
+  SPG_LAUNCH(ctx, k_abc_table, grid_for(ctx, count, 128), 128, 0, view(inst->by_col[0]), view(inst->by_col[1]),
+             view(inst->by_col[2]), evals_rx, t0, count, log_max, log_max, rA, rB, rC, out);
   return SPG_OK;
 }
 

@@ -170,4 +170,8 @@ int r1cs_abc_table(spg_ctx *ctx, const spg_r1cs *inst, const fq *evals_rx, size_
                    size_t max_num_cols, const size_t *num_cols, const size_t *out_off,
                    const spg_fq *r_A, const spg_fq *r_B, const spg_fq *r_C, fq *out);
 
+// entries [t0, t0 + count) of a shared / single instance's ABC table (the y-sharded phase 2)
+int r1cs_abc_slice(spg_ctx *ctx, const spg_r1cs *inst, const fq *evals_rx, size_t num_segs, size_t max_num_cols,
+                   size_t t0, size_t count, const spg_fq *r_A, const spg_fq *r_B, const spg_fq *r_C, fq *out);
+
 }  // namespace spg

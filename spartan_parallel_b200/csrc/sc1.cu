@@ -1185,7 +1185,8 @@ int spg_sc1_run_rounds(spg_sc1 *s, size_t num_rounds, const spg_fq *challenges, 
 // A rank that fails publishes the poison sequence in both of its slots, so that its peers
 // return an error instead of spinning forever; every wait also has a deadline
 // (SPG_MAILBOX_TIMEOUT_S, default 120 s).
-namespace {
+extern "C++" {
+namespace spg {
 constexpr uint64_t MAILBOX_POISON = UINT64_MAX;
 
 double mailbox_timeout_s() {
@@ -1226,7 +1227,8 @@ int mailbox_exchange(char *base, size_t slot_stride, int rank, int world, uint64
   }
   return SPG_OK;
 }
-}  // namespace
+}  // namespace spg
+}  // extern "C++"
 
 void spg_mailbox_poison(void *mailbox, size_t slot_stride, int rank, int world) {
   if (!mailbox || rank < 0 || rank >= world) return;

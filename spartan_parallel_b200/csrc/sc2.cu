@@ -451,6 +451,127 @@ int spg_sc2_create_from_zrq(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *z
                    rx, nullptr, rp, r_A, r_B, r_C, out);
 }
 
+// One rank's slice of a y-sharded phase 2 (single instance): the flat [w][y] tables are cut into
+// `flat_len`-entry chunks, rank r owns entries [flat_off, flat_off + flat_len) -- one contiguous y
+// range of one witness section. The summand eq_p * ABC * Z carries no weight over (w, y), so the
+// rank runs the unchanged round kernels on its chunk as a (P = 1, W = 1, Y = flat_len) prover: the ABC
+// slice is built here from the CSC arrays, the Z slice is read from `zrq` at flat_off (where the
+// reduce-scatter over peer memory leaves this rank's sums). After log2(flat_len) rounds the
+// chunk is one scalar per table; the remaining y and w rounds run on the gathered scalars
+// (spg_sc2_host_tail_*).
+int spg_sc2_create_slice(spg_ctx *ctx, const spg_r1cs *inst, const spg_vec *zrq, size_t max_num_inputs,
+                         size_t num_witness_secs, size_t flat_off, size_t flat_len, const spg_fq *rx, const spg_fq *r_A,
+                         const spg_fq *r_B, const spg_fq *r_C, spg_sc2 **out) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
+  SPG_CHECK(ctx && inst && zrq && out && r_A && r_B && r_C, "spg_sc2_create_slice: null argument");
+  SPG_CHECK(inst->num_instances == 1, "spg_sc2_create_slice: one instance only");
+  SPG_CHECK(is_pow2(max_num_inputs) && is_pow2(flat_len) && flat_len >= 1 && flat_len <= max_num_inputs && flat_off % flat_len == 0,
+            "spg_sc2_create_slice: chunk [%zu, +%zu) must be an aligned power-of-two part of one section", flat_off, flat_len);
+  size_t total = num_witness_secs * max_num_inputs;
+  SPG_CHECK(next_pow2(num_witness_secs) * max_num_inputs == inst->num_vars, "spg_sc2_create_slice: W' * Y != num_vars");
+  SPG_CHECK(flat_off + flat_len <= total && zrq->n >= total, "spg_sc2_create_slice: chunk exceeds the %zu-entry tables", total);
+  size_t nx = log2u(inst->max_num_cons), X = inst->max_num_cons;
+  SPG_CHECK(nx == 0 || rx, "spg_sc2_create_slice: null rx");
+  spg_sc2 *s = new (std::nothrow) spg_sc2();
+  if (!s) return SPG_ENOMEM;
+  s->ctx = ctx;
+  s->P = s->Pp = 1;
+  s->W = s->Wp = 1;
+  s->ny = log2u(flat_len);
+  s->nw = s->np = 0;
+  s->Y.assign(1, flat_len);
+  s->p_len = 1;
+  s->cap = flat_len;
+  auto fail = [&](int code) {
+    spg_sc2_destroy(s);
+    return code;
+  };
+  for (int b = 0; b < 2; b++)
+    for (int k = 0; k < 2; k++)
+      if (dev_alloc(ctx, &s->tab[b][k], s->cap * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 slice tables", __FILE__, __LINE__));
+  if (dev_alloc(ctx, &s->A, sizeof(fq)) != cudaSuccess || dev_alloc(ctx, &s->d_segs, sizeof(Seg)) != cudaSuccess)
+    return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 slice aux", __FILE__, __LINE__));
+  DevTmp scr(ctx);
+  if (scr.alloc((2 * X + nx + 8) * sizeof(fq)) != cudaSuccess) return fail(cuda_fail(cudaErrorMemoryAllocation, "sc2 slice scratch", __FILE__, __LINE__));
+  fq *evals_rx = scr.as<fq>(), *eq_scratch = evals_rx + X, *d_r = eq_scratch + X;
+  int rc = SPG_OK;
+  if (nx && cudaMemcpyAsync(d_r, rx, nx * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "rx upload", __FILE__, __LINE__));
+  if ((rc = eq_evals_device(ctx, d_r, rx, nx, evals_rx, eq_scratch)) != SPG_OK) return fail(rc);
+  if ((rc = r1cs_abc_slice(ctx, inst, evals_rx, num_witness_secs, max_num_inputs, flat_off, flat_len, r_A, r_B, r_C, s->tab[0][0])) != SPG_OK) return fail(rc);
+  if (cudaMemcpyAsync(s->tab[0][1], zrq->d + flat_off, flat_len * sizeof(fq), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "Z slice copy", __FILE__, __LINE__));
+  if ((rc = eq_evals_device(ctx, d_r, nullptr, 0, s->A, eq_scratch)) != SPG_OK) return fail(rc);  // A = [1]
+  s->loglen.assign(1, log2u(flat_len));
+  *out = s;
+  return SPG_OK;
+}
+
+// local rounds of a y-sharded phase 2: evaluate, exchange the 3 partial evaluations through the host
+// mailbox, add, bind (the phase-2 twin of spg_sc1_run_rounds_sharded)
+int spg_sc2_run_rounds_sharded(spg_sc2 *s, size_t num_rounds, const spg_fq *challenges, spg_fq *evals_out, void *mailbox,
+                               size_t slot_stride, int rank, int world, uint64_t *calls) {
+  spg::DeviceGuard _dev(spg::ctx_of(s));
+  SPG_CHECK(s && challenges && evals_out && mailbox && calls, "spg_sc2_run_rounds_sharded: null argument");
+  SPG_CHECK(world >= 1 && world <= 64 && rank >= 0 && rank < world && slot_stride >= 64 + 3 * sizeof(spg_fq),
+            "spg_sc2_run_rounds_sharded: bad mailbox geometry");
+  int rc = SPG_OK;
+  for (size_t j = 0; j < num_rounds && rc == SPG_OK; j++) {
+    spg_fq part[3], all[64 * 3];
+    if ((rc = spg_sc2_round_eval(s, part)) != SPG_OK) break;
+    if ((rc = mailbox_exchange((char *)mailbox, slot_stride, rank, world, ++*calls, part, sizeof part, all)) != SPG_OK) break;
+    hfq acc[3] = {hfq_zero(), hfq_zero(), hfq_zero()};
+    for (int r = 0; r < world; r++)
+      for (int t = 0; t < 3; t++) acc[t] = hfq_add(acc[t], hfq_from(all[3 * r + t]));
+    for (int t = 0; t < 3; t++) evals_out[3 * j + t] = hfq_to(acc[t]);
+    rc = spg_sc2_round_bind(s, challenges + j);
+  }
+  if (rc != SPG_OK) spg_mailbox_poison(mailbox, slot_stride, rank, world);
+  return rc;
+}
+
+// The cross-rank end of a y-sharded phase 2, on the host like spg_sc1_host_tail_*: state = [B | C], G
+// scalars each in flat (w, y_high) order; e(t) = scale * sum B(t) C(t), t = 0, 2, 3. mode 0 binds the low
+// bit (adjacent pairs: the remaining y rounds), mode 1 the TOP bit (pairs i, i + len/2: the w rounds, which
+// the reference binds top first, src/custom_dense_mlpoly.rs:247-264).
+int spg_sc2_host_tail_eval(const spg_fq *state, size_t G, size_t len, int mode, const spg_fq *scale, spg_fq e[3]) {
+  SPG_CHECK(state && scale && e, "spg_sc2_host_tail_eval: null argument");
+  SPG_CHECK(is_pow2(G) && G <= 64 && is_pow2(len) && len >= 2 && len <= G, "spg_sc2_host_tail_eval: bad sizes %zu / %zu", len, G);
+  hfq acc[3] = {hfq_zero(), hfq_zero(), hfq_zero()};
+  size_t half = len / 2;
+  for (size_t i = 0; i < half; i++) {
+    size_t i0 = mode ? i : 2 * i, i1 = mode ? i + half : 2 * i + 1;
+    hfq lo[2], d[2];
+    for (int k = 0; k < 2; k++) {
+      lo[k] = hfq_from(state[k * G + i0]);
+      d[k] = hfq_sub(hfq_from(state[k * G + i1]), lo[k]);
+    }
+    for (int pt = 0; pt < 3; pt++) {
+      if (pt >= 1)
+        for (int k = 0; k < 2; k++) {
+          lo[k] = hfq_add(lo[k], d[k]);
+          if (pt == 1) lo[k] = hfq_add(lo[k], d[k]);
+        }
+      acc[pt] = hfq_add(acc[pt], hfq_mul(lo[0], lo[1]));
+    }
+  }
+  hfq sc = hfq_from(*scale);
+  for (int pt = 0; pt < 3; pt++) e[pt] = hfq_to(hfq_mul(sc, acc[pt]));
+  return SPG_OK;
+}
+
+int spg_sc2_host_tail_bind(spg_fq *state, size_t G, size_t len, int mode, const spg_fq *r) {
+  SPG_CHECK(state && r, "spg_sc2_host_tail_bind: null argument");
+  SPG_CHECK(is_pow2(G) && G <= 64 && is_pow2(len) && len >= 2 && len <= G, "spg_sc2_host_tail_bind: bad sizes %zu / %zu", len, G);
+  hfq rr = hfq_from(*r);
+  size_t half = len / 2;
+  for (int k = 0; k < 2; k++)
+    for (size_t i = 0; i < half; i++) {
+      size_t i0 = mode ? i : 2 * i, i1 = mode ? i + half : 2 * i + 1;
+      hfq lo = hfq_from(state[k * G + i0]), hi = hfq_from(state[k * G + i1]);
+      state[k * G + i] = hfq_to(hfq_add(lo, hfq_mul(rr, hfq_sub(hi, lo))));
+    }
+  return SPG_OK;
+}
+
 int spg_zmat_bind_rq(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq, const spg_fq *scale,
                      spg_vec *out) {
   spg::DeviceGuard _dev(spg::ctx_of(ctx));

@@ -231,6 +231,18 @@ class PeerTable:
         self.comm.barrier()  # every chunk has been written everywhere
         return self.poly
 
+    def reduce_scatter(self):
+        """like all_reduce, but rank r only receives the sums of chunk r (entries [r * n / G, (r + 1) * n / G)
+        of its own table): half the NVLink traffic, for a consumer sharded the same way (ShardedPhase2)"""
+        from ._lib import check
+
+        self.ctx.sync()
+        self.comm.barrier()
+        check(self.ctx.L.spg_peer_reduce_scatter(self.ctx.h, self._ptrs, self.comm.world, self.comm.rank, self.n), "spg_peer_reduce_scatter")
+        self.ctx.sync()
+        self.comm.barrier()  # peers have finished reading this rank's table before it is overwritten again
+        return self.poly
+
     def close(self):
         if getattr(self, "_vec", None) is None:
             return
@@ -365,6 +377,119 @@ class HostTail:
         pass
 
 
+class HostTail2:
+    """The last log2(G) rounds of a y-sharded phase 2 on the gathered scalars (spg_sc2_host_tail_*): first
+    the remaining y rounds (adjacent pairs), then the w rounds (top bit first)."""
+
+    def __init__(self, B, C_, n_y_rounds: int):
+        import ctypes as C
+
+        from ._lib import lib
+
+        self.L, self.C = lib(), C
+        self.G = self.len = B.shape[0]
+        self.state = np.ascontiguousarray(np.concatenate([B, C_]).astype(np.uint64))
+        self.scale = api.ONE.copy()
+        self.n_y, self.done = n_y_rounds, 0
+
+    def set_scale(self, c):
+        self.scale = np.ascontiguousarray(np.asarray(c, dtype=np.uint64).reshape(4))
+
+    def round_eval(self):
+        from ._lib import check
+
+        e = np.empty((3, 4), dtype=np.uint64)
+        p = lambda a: a.ctypes.data_as(self.C.c_void_p)
+        check(self.L.spg_sc2_host_tail_eval(p(self.state), self.G, self.len, int(self.done >= self.n_y), p(self.scale), p(e)),
+              "spg_sc2_host_tail_eval")
+        return e
+
+    def round_bind(self, r):
+        from ._lib import check
+
+        r = np.ascontiguousarray(np.asarray(r, dtype=np.uint64).reshape(4))
+        p = lambda a: a.ctypes.data_as(self.C.c_void_p)
+        check(self.L.spg_sc2_host_tail_bind(p(self.state), self.G, self.len, int(self.done >= self.n_y), p(r)), "spg_sc2_host_tail_bind")
+        self.len //= 2
+        self.done += 1
+
+    def final(self):
+        s = self.state.reshape(2, self.G, 4)
+        return np.stack([self.scale, s[0, 0], s[1, 0]])
+
+
+class ShardedPhase2:
+    """Phase-2 sumcheck of one instance sharded over y: rank r owns chunk r of the flat [w][y] tables
+    (W sections of Y inputs, W a power of two dividing the world size). The summand eq_p * ABC * Z has no
+    weight over (w, y), so the ranks' partial round evaluations add; after the log2(chunk) local rounds
+    the per-rank scalars are gathered and the last log2(G) rounds run on the host (HostTail2).
+
+    ``make_engine(flat_off, flat_len)`` returns the rank-local prover (round_eval / round_bind / final;
+    ``api.SumcheckPhase2.slice`` on a GPU)."""
+
+    def __init__(self, comm, W: int, Y: int, make_engine):
+        self.comm = comm
+        G = comm.world
+        assert W & (W - 1) == 0 and G % W == 0 and (W * Y) % G == 0, "y-sharding needs W | G | W * Y"
+        self.flat_len = W * Y // G
+        self.n_local = log2(self.flat_len)
+        self.n_y_tail = log2(Y) - self.n_local
+        self.num_rounds = log2(Y) + log2(W)
+        self.engine = make_engine(comm.rank * self.flat_len, self.flat_len)
+        self.tail = None
+        self.round = 0
+
+    def round_eval(self) -> np.ndarray:
+        if self.round < self.n_local:
+            return api.host_sum(self.comm.all_gather(self.engine.round_eval()))
+        return self._tail().round_eval()
+
+    def round_bind(self, r):
+        if self.round < self.n_local:
+            self.engine.round_bind(r)
+        else:
+            self._tail().round_bind(r)
+        self.round += 1
+
+    def run_rounds(self, challenges) -> np.ndarray:
+        ch = np.asarray(challenges, dtype=np.uint64).reshape(-1, 4)
+        out = []
+        if self.round == 0 and self.n_local and hasattr(self.engine, "run_rounds_sharded") and isinstance(self.comm, ShmComm):
+            calls = np.array([self.comm.calls], dtype=np.uint64)
+            out.extend(self.engine.run_rounds_sharded(ch[: self.n_local], self.comm.addr, self.comm.slot_stride, self.comm.rank,
+                                                      self.comm.world, calls))
+            self.comm.calls = int(calls[0])
+            self.round = self.n_local
+        while self.round < self.num_rounds:
+            j = self.round
+            out.append(self.round_eval())
+            self.round_bind(ch[j])
+        return np.stack(out)
+
+    def _tail(self):
+        if self.tail is None:
+            claims = np.asarray(self.engine.final(), dtype=np.uint64).reshape(3, 4)
+            allc = self.comm.all_gather(claims)  # (G, 3, 4), rank order = flat (w, y_high) order
+            self.tail = HostTail2(allc[:, 1].copy(), allc[:, 2].copy(), self.n_y_tail)
+            self.tail.set_scale(claims[0])  # eq_p bound so far (one instance: 1)
+        return self.tail
+
+    def final(self) -> np.ndarray:
+        return self._tail().final()
+
+    def free(self):
+        if self.engine is not None and hasattr(self.engine, "free"):
+            self.engine.free()
+        self.engine = None
+
+
+def gpu_phase2_sharded(ctx, comm, inst, zrq, max_num_inputs: int, W: int, rx, r_A, r_B, r_C) -> ShardedPhase2:
+    """ShardedPhase2 on this rank's GPU; zrq holds this rank's reduce-scattered chunk in place
+    (PeerTable.reduce_scatter)."""
+    return ShardedPhase2(comm, W, max_num_inputs,
+                         lambda off, n: api.SumcheckPhase2.slice(ctx, inst, zrq, max_num_inputs, W, off, n, rx, r_A, r_B, r_C))
+
+
 def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, satisfied: bool = False) -> ShardedPhase1:
     """ShardedPhase1 on this rank's GPU. satisfied=True asserts that the witness satisfies the
     instance: Az*Bz - Cz then vanishes entry by entry, so every shard's own sum is zero and the
@@ -386,7 +511,7 @@ def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, sat
     return ShardedPhase1(comm, Q_local, X, tau_q, tau_x, make_engine, make_tail)
 
 
-def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local, peer: "PeerTable | None" = None):
+def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local, peer: "PeerTable | None" = None, scatter: bool = False):
     """Z bound to rq over all shards: local bind scaled by the rank's eq weight, then the modular
     sum over ranks -- over peer memory when a PeerTable is given (one kernel per rank, 2 (G-1)/G
     of a table over NVLink), else one NCCL all-gather of the partial tables + device additions."""
@@ -398,7 +523,7 @@ def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local, peer: "PeerTable | None" 
     if peer is not None and comm.world > 1:
         assert peer.n == total
         api.zmat_bind_rq(ctx, z, rq_rev[:nql], api.host_eq_weight(rq_rev[nql:], comm.rank), peer.poly)
-        return peer.all_reduce()
+        return peer.reduce_scatter() if scatter else peer.all_reduce()
     dev = torch.device("cuda", ctx.device)
     mine = torch.empty((total, 4), dtype=torch.int64, device=dev)
     out = api.DensePolynomial.wrap(ctx, mine.data_ptr(), total, owner=mine)
