@@ -440,6 +440,10 @@ int spg_gens_info(const spg_gens *gens, size_t out[4]);
  * GF(2^255-19) arithmetic of the commitment kernels, compared on the device with the ten-limb
  * code; *out_bad = OR of the failing checks' bits (0 = all agree). */
 int spg_debug_fe8_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_bad);
+/* F_q wide-range forms (csrc/fq.cuh: differences made non-negative by adding 2q / 6q, one fold into
+ * [0, 2q)) as the row kernels use them, on n operand tuples that include every edge combination of
+ * {0, 1, q-1, q, q+1, 2q-1}, against canonical arithmetic; *out_bad = OR of the failing checks (0 = pass) */
+int spg_debug_fq_wide_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_bad);
 /* Commitments::commit for a batch of short vectors sharing the bases (sumcheck
  * round polynomials etc.): out[i] = sum_j s[i*len+j] G[j] + blind[i] h */
 int spg_commit_batch(spg_ctx *ctx, const spg_gens *gens, const spg_fq *scalars, size_t len,

@@ -147,6 +147,7 @@ def _proto(L):
         "spg_gens_prepare": [P, P, SZ],
         "spg_gens_info": [P, P],
         "spg_debug_fe8_selftest": [P, SZ, C.c_uint64, P],
+        "spg_debug_fq_wide_selftest": [P, SZ, C.c_uint64, P],
     }
     for name, args in sigs.items():
         f = getattr(L, name, None)

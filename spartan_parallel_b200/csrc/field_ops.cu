@@ -227,6 +227,76 @@ int dense_evaluate_device(spg_ctx *ctx, const fq *Z, size_t n, const spg_fq *r, 
   return rc;
 }
 
+
+// Self-test of the wide-range forms of fq.cuh (fq_sub_plus2q / fq_sub_plus6q / fq_fold2q and fq_mul_lazy
+// on operands beyond [0, 2q)): the bind and the two evaluation terms exactly as k_rows_rolled computes
+// them, on operands in [0, 2q) that include the edges (0, 1, q - 1, q, q + 1, 2q - 1), against the same
+// quantities from canonical arithmetic (fq_add / fq_sub / fq_mul on canonicalised operands).
+__global__ void k_fq_wide_selftest(size_t n, uint64_t seed, unsigned int *__restrict__ bad) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  uint64_t st = seed + 0x9E3779B97F4A7C15ull * (t + 1);
+  auto rnd = [&]() {
+    st += 0x9E3779B97F4A7C15ull;
+    uint64_t z = st;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  };
+  const uint32_t Q[8] = {SPG_Q0, SPG_Q1, SPG_Q2, SPG_Q3, 0, 0, 0, SPG_Q7};
+  const uint32_t Q2[8] = {SPG_2Q0, SPG_2Q1, SPG_2Q2, SPG_2Q3, 0, 0, 0, SPG_2Q7};
+  // value number `sel` of [0, 2q): edges for sel < 6, else uniform below 2q
+  auto pick = [&](unsigned sel) {
+    fq x = fq_zero();
+    if (sel == 1) x.v[0] = 1;
+    else if (sel >= 2 && sel <= 4) {  // q - 1, q, q + 1
+      for (int i = 0; i < 8; i++) x.v[i] = Q[i];
+      x.v[0] += sel - 3;                // limb 0 of q is far from 0 and 2^32 - 1: no carry
+    } else if (sel == 5) {              // 2q - 1
+      for (int i = 0; i < 8; i++) x.v[i] = Q2[i];
+      x.v[0] -= 1;
+    } else if (sel >= 6) {
+      for (int i = 0; i < 8; i += 2) {
+        uint64_t r = rnd();
+        x.v[i] = (uint32_t)r;
+        x.v[i + 1] = (uint32_t)(r >> 32);
+      }
+      x.v[7] &= 0x1fffffffu;            // < 2^253 < 2q ... then fold anything >= 2q
+      x = fq_fold2q(x);
+    }
+    return x;
+  };
+  unsigned m = (unsigned)(t % 1296);  // 6^4 edge combinations for (lo, hi, other, acc), the rest random
+  bool edges = t < 4 * 1296;
+  fq lo = pick(edges ? m % 6 : 6), hi = pick(edges ? (m / 6) % 6 : 6), ot = pick(edges ? (m / 36) % 6 : 6),
+     acc = pick(edges ? (m / 216) % 6 : 6);
+  fq r = fq_canon(pick(6)), w = fq_canon(pick(edges ? 2 + (unsigned)(t / 1296) % 4 : 6));
+  unsigned int err = 0;
+  fq clo = fq_canon(lo), chi = fq_canon(hi), cot = fq_canon(ot), cacc = fq_canon(acc);
+  // bind
+  fq v = fq_fold2q(fq_raw_add(lo, fq_mul_lazy(r, fq_sub_plus2q(hi, lo))));
+  fq want = fq_add(clo, fq_mul(r, fq_sub(chi, clo)));
+  if (!fq_equal(fq_canon(v), want)) err |= 1;
+  // t = 0 term: acc + w (a0 b0 - c0) with (a0, b0, c0) = (lo, hi, ot)
+  fq e0 = fq_fold2q(fq_raw_add(acc, fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(lo, hi), ot))));
+  fq want0 = fq_add(cacc, fq_mul(w, fq_sub(fq_mul(clo, chi), cot)));
+  if (!fq_equal(fq_canon(e0), want0)) err |= 2;
+  // t = 2 term with a = (lo, hi), b = (hi, ot), c = (ot, lo)
+  fq a2 = fq_raw_add(hi, fq_sub_plus2q(hi, lo)), b2 = fq_raw_add(ot, fq_sub_plus2q(ot, hi)), c2 = fq_raw_add(lo, fq_sub_plus2q(lo, ot));
+  fq e2 = fq_fold2q(fq_raw_add(acc, fq_mul_lazy(w, fq_sub_plus6q(fq_mul_lazy(a2, b2), c2))));
+  fq ca2 = fq_sub(fq_add(chi, chi), clo), cb2 = fq_sub(fq_add(cot, cot), chi), cc2 = fq_sub(fq_add(clo, clo), cot);
+  fq want2 = fq_add(cacc, fq_mul(w, fq_sub(fq_mul(ca2, cb2), cc2)));
+  if (!fq_equal(fq_canon(e2), want2)) err |= 4;
+  // the folded values really are below 2q (fq_canon of something >= 2q would not be canonical)
+  fq q_minus_1 = pick(2);
+  auto below_q = [&](const fq &x) {  // x <= q - 1
+    fq d = fq_sub_plus(q_minus_1, x, 0, 0, 0, 0, 0);
+    return (d.v[7] >> 31) == 0;      // no wrap: q - 1 - x >= 0 (both far below 2^255)
+  };
+  if (!below_q(fq_canon(v)) || !below_q(fq_canon(e0)) || !below_q(fq_canon(e2))) err |= 8;
+  if (err) atomicOr(bad, err);
+}
+
 }  // namespace spg
 
 using namespace spg;
@@ -437,6 +507,18 @@ static int peer_sum_impl(spg_ctx *ctx, void *const *peer_ptrs, int world, int ra
   size_t chunk = n / world;
   ctx->next_units = (scatter_only ? 32.0 : 64.0) * (double)chunk * (double)(world - 1);
   SPG_LAUNCH(ctx, k_peer_sum, grid_for(ctx, chunk, 256), 256, 0, P, world, (size_t)rank * chunk, chunk, scatter_only);
+  return SPG_OK;
+}
+
+int spg_debug_fq_wide_selftest(spg_ctx *ctx, size_t n, uint64_t seed, uint32_t *out_bad) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
+  SPG_CHECK(ctx && out_bad && n >= 1, "spg_debug_fq_wide_selftest: bad argument");
+  DevTmp d_bad(ctx);
+  SPG_CUDA(d_bad.alloc(sizeof(unsigned int)));
+  SPG_CUDA(cudaMemsetAsync(d_bad.p, 0, sizeof(unsigned int), ctx->stream));
+  SPG_LAUNCH(ctx, k_fq_wide_selftest, (unsigned)((n + 127) / 128), 128, 0, n, seed, d_bad.as<unsigned int>());
+  SPG_CUDA(cudaMemcpyAsync(out_bad, d_bad.p, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
   return SPG_OK;
 }
 

@@ -187,15 +187,17 @@ k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restric
     fq b0 = fq_load_stream(T1 + idx), b1 = fq_load_stream(T1 + idx + 1);
     fq c0 = fq_load_stream(T2 + idx), c1 = fq_load_stream(T2 + idx + 1);
     fq w = fq_load(S + it);
+    // wide-range forms (fq.cuh), bounds as in k_rows_rolled: table entries are canonical here, w is
+    // canonical, acc stays in [0, 2q)
     // t = 0
-    acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a0, b0), c0)));
+    acc[0] = fq_fold2q(fq_raw_add(acc[0], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(a0, b0), c0))));
     if (NE == 3)  // t = 1
-      acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a1, b1), c1)));
-    // t = 2: 2*hi - lo
-    fq a2 = fq_add_lazy(a1, fq_sub_lazy(a1, a0));
-    fq b2 = fq_add_lazy(b1, fq_sub_lazy(b1, b0));
-    fq c2 = fq_add_lazy(c1, fq_sub_lazy(c1, c0));
-    acc[NE - 1] = fq_add_lazy(acc[NE - 1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a2, b2), c2)));
+      acc[1] = fq_fold2q(fq_raw_add(acc[1], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(a1, b1), c1))));
+    // t = 2: 2*hi - lo + 2q in (0, 4q)
+    fq a2 = fq_raw_add(a1, fq_sub_plus2q(a1, a0));
+    fq b2 = fq_raw_add(b1, fq_sub_plus2q(b1, b0));
+    fq c2 = fq_raw_add(c1, fq_sub_plus2q(c1, c0));
+    acc[NE - 1] = fq_fold2q(fq_raw_add(acc[NE - 1], fq_mul_lazy(w, fq_sub_plus6q(fq_mul_lazy(a2, b2), c2))));
   }
 #pragma unroll
   for (int k = 0; k < NE; k++) acc[k] = fq_canon(acc[k]);
@@ -216,7 +218,17 @@ k_rows(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restric
 // 22 % of its stall samples were no_instructions) and measured 5.99 ms per pass at 2^20 x 64; this
 // loop is 21 KB and takes 5.69 ms. The loads of the next (table, pair) are issued
 // before the current product, across items too, so the rolled loop does not expose one DRAM
-// latency per bind.
+// latency per bind. (Two binds per trip with the operand registers ping-ponging removes the 22
+// register copies at the end of a trip, 7 % of the bind's instructions, and measured SLOWER: 5.53 ms
+// against 5.41 ms.)
+//
+// Ranges (fq.cuh, wide-range forms): the tables may come in unreduced, in [0, 2q) -- that is how this
+// kernel leaves them when LAZY_OUT, i.e. when the host knows the next bind is this kernel again -- so
+// the bind is d = hi - lo + 2q in (0, 4q), r d / R + q < 1.25 q, lo + that < 3.25 q, folded once into
+// [0, 2q); the last launch of a run (LAZY_OUT = false) also canonicalises. The evaluation adds 2q or 6q
+// instead of correcting conditionally; bounds are stated line by line. Against the form with a
+// conditional correction after every add and sub this is ~220 fewer ALU instructions per item.
+template <bool LAZY_OUT>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_rows_rolled(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__restrict__ T2,
               fq *__restrict__ O0, fq *__restrict__ O1, fq *__restrict__ O2, const Seg *__restrict__ segs,
@@ -258,7 +270,8 @@ k_rows_rolled(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__
           nhi = fq_load_stream(Tn + nidx + 1);
         }
       }
-      fq v = fq_canon(fq_add_lazy(lo, fq_mul_lazy(r, fq_sub_lazy(hi, lo))));
+      fq v = fq_fold2q(fq_raw_add(lo, fq_mul_lazy(r, fq_sub_plus2q(hi, lo))));
+      if (!LAZY_OUT) v = fq_canon(v);
       fq *To = (k >> 1) == 0 ? O0 : ((k >> 1) == 1 ? O1 : O2);
       fq_store(To + o + (k & 1), v);
       stash[k * RB] = v;
@@ -267,13 +280,17 @@ k_rows_rolled(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__
     }
     fq w = fq_load(S + it);
     {
+      // all six in [0, 2q); w (suffix eq table) is canonical; acc stays in [0, 2q)
       fq a0 = stash[0], b0 = stash[2 * RB], c0 = stash[4 * RB];
-      acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a0, b0), c0)));
+      // a0 b0 / R + q < 1.25 q; - c0 + 2q: (0, 3.25 q); w * that / R + q < 1.21 q; acc + that < 3.21 q
+      acc[0] = fq_fold2q(fq_raw_add(acc[0], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(a0, b0), c0))));
       fq a1 = stash[RB], b1 = stash[3 * RB], c1 = stash[5 * RB];
-      fq a2 = fq_add_lazy(a1, fq_sub_lazy(a1, a0));
-      fq b2 = fq_add_lazy(b1, fq_sub_lazy(b1, b0));
-      fq c2 = fq_add_lazy(c1, fq_sub_lazy(c1, c0));
-      acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a2, b2), c2)));
+      // 2 x1 - x0 + 2q in (0, 6q)
+      fq a2 = fq_raw_add(a1, fq_sub_plus2q(a1, a0));
+      fq b2 = fq_raw_add(b1, fq_sub_plus2q(b1, b0));
+      fq c2 = fq_raw_add(c1, fq_sub_plus2q(c1, c0));
+      // a2 b2 / R + q < 3.26 q; - c2 + 6q: (0, 9.26 q); w * that / R + q < 1.58 q; acc + that < 3.58 q
+      acc[1] = fq_fold2q(fq_raw_add(acc[1], fq_mul_lazy(w, fq_sub_plus6q(fq_mul_lazy(a2, b2), c2))));
     }
   }
   acc[0] = fq_canon(acc[0]);
@@ -285,6 +302,16 @@ k_rows_rolled(const fq *__restrict__ T0, const fq *__restrict__ T1, const fq *__
     acc[1] = fq_mul(rw, acc[1]);
   }
   finish_block<2>(fa, acc, sm);
+}
+
+// tables left in [0, 2q) by k_rows_rolled<true> -> canonical (only when the bind that follows is not the
+// one the host predicted, e.g. fusing was switched off in between)
+__global__ void k_canon3(fq *__restrict__ T0, fq *__restrict__ T1, fq *__restrict__ T2, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    fq_store(T0 + i, fq_canon(fq_load(T0 + i)));
+    fq_store(T1 + i, fq_canon(fq_load(T1 + i)));
+    fq_store(T2 + i, fq_canon(fq_load(T2 + i)));
+  }
 }
 
 // First round with the SpMV fused in (multiply_vec_block + round 0 in one pass): the block
@@ -348,12 +375,13 @@ k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__re
     fq_store_stream(O1 + idx, lo3[1]); fq_store_stream(O1 + idx + 1, hi3[1]);
     fq_store_stream(O2 + idx, lo3[2]); fq_store_stream(O2 + idx + 1, hi3[2]);
     fq w = fq_load(S + it);
-    acc[0] = fq_add_lazy(acc[0], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(lo3[0], lo3[1]), lo3[2])));
-    if (NE == 3) acc[1] = fq_add_lazy(acc[1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(hi3[0], hi3[1]), hi3[2])));
-    fq a2 = fq_add_lazy(hi3[0], fq_sub_lazy(hi3[0], lo3[0]));
-    fq b2 = fq_add_lazy(hi3[1], fq_sub_lazy(hi3[1], lo3[1]));
-    fq c2 = fq_add_lazy(hi3[2], fq_sub_lazy(hi3[2], lo3[2]));
-    acc[NE - 1] = fq_add_lazy(acc[NE - 1], fq_mul_lazy(w, fq_sub_lazy(fq_mul_lazy(a2, b2), c2)));
+    // wide-range forms (fq.cuh), bounds as in k_rows_rolled; lo3 / hi3 are canonical
+    acc[0] = fq_fold2q(fq_raw_add(acc[0], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(lo3[0], lo3[1]), lo3[2]))));
+    if (NE == 3) acc[1] = fq_fold2q(fq_raw_add(acc[1], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(hi3[0], hi3[1]), hi3[2]))));
+    fq a2 = fq_raw_add(hi3[0], fq_sub_plus2q(hi3[0], lo3[0]));
+    fq b2 = fq_raw_add(hi3[1], fq_sub_plus2q(hi3[1], lo3[1]));
+    fq c2 = fq_raw_add(hi3[2], fq_sub_plus2q(hi3[2], lo3[2]));
+    acc[NE - 1] = fq_fold2q(fq_raw_add(acc[NE - 1], fq_mul_lazy(w, fq_sub_plus6q(fq_mul_lazy(a2, b2), c2))));
   }
 #pragma unroll
   for (int k = 0; k < NE; k++) acc[k] = fq_canon(acc[k]);
@@ -486,6 +514,8 @@ struct spg_sc1 {
   hfq cached[3];
   // the true running claim s_{j-1}(r_{j-1}) (= e(0) + e(1) of the current round), maintained
   // from the evaluations this object itself produced: exact for any input tables
+  bool tab_lazy = false;   // tab[cur] holds values in [0, 2q) (k_rows_rolled<true>); only k_rows_rolled reads those
+  size_t tab_lazy_n = 0;
   bool claim_known = false;
   bool check_claim = false;  // verify a supplied claim against the tables in the first round (spg_sc1_set_claim_checked)
   hfq supplied_claim;
@@ -692,8 +722,19 @@ int sc1_build_weights(spg_sc1 *s) {
   return SPG_OK;
 }
 
+// tables left in [0, 2q) by the fused bind: canonicalise in place (see k_canon3)
+int sc1_canon_tables(spg_sc1 *s) {
+  if (!s->tab_lazy) return SPG_OK;
+  spg_ctx *ctx = s->ctx;
+  SPG_LAUNCH(ctx, k_canon3, grid_for(ctx, s->tab_lazy_n, 256, 4), 256, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2],
+             s->tab_lazy_n);
+  s->tab_lazy = false;
+  return SPG_OK;
+}
+
 // runs the deferred multiply_vec_block (anything but the fused first round needs the tables)
 int sc1_materialize(spg_sc1 *s) {
+  if (s->tab_lazy) return sc1_canon_tables(s);  // (never together with a pending SpMV: that is round 0)
   if (!s->pend_inst) return SPG_OK;
   const spg_r1cs *inst = s->pend_inst;
   const spg_zmat *z = s->pend_z;
@@ -867,12 +908,13 @@ void build_tile_segs(spg_sc1 *s, int phase, int fused, unsigned long long *tiles
 }
 
 // the tiled kernels need every row to hold at least one item per thread of a block
-bool rows_eligible(const spg_sc1 *s, int fused) {
-  unsigned need = (fused ? 2 : 1) + 7;
+bool rows_eligible(const spg_sc1 *s, int fused, unsigned rounds_ahead = 0) {
+  unsigned need = (fused ? 2 : 1) + 7 + rounds_ahead;
   for (size_t p = 0; p < s->P; p++)
     if (s->loglen[p] < need) return false;
   return true;
 }
+
 
 // per-segment matrices and witness views for the fused first round
 SpmvSegs make_spmv_segs(const spg_sc1 *s) {
@@ -1103,7 +1145,11 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
     int nxt = s->cur ^ 1;
     unsigned long long items = 0, out_total = 0;
     const fq *RW = phase == 0 ? s->RWx : s->Ap;
-    if (s->fuse && next_same && s->claim_known && rows_eligible(s, 1)) {
+    bool rolled = s->fuse && next_same && s->claim_known && rows_eligible(s, 1);
+    if (s->tab_lazy && !rolled) SPG_TRY(sc1_canon_tables(s));
+    if (rolled) {
+      // the bind after this one is this kernel again iff the same conditions hold one round later
+      bool lazy_out = j + 2 < n_phase && rows_eligible(s, 1, 1);
       unsigned long long tiles = 0;
       build_tile_segs(s, phase, 1, &tiles, &out_total);
       SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
@@ -1112,9 +1158,16 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       SPG_TRY(ensure_partials(ctx, (size_t)tiles * 2));
       ctx->next_units = 288.0 * (double)out_total;  // per bound pair: 4 read + 2 written scalars x 3 tables
       FinishArgs fa = finish_args(ctx, tiles);
-      SPG_LAUNCH(ctx, k_rows_rolled, (unsigned)tiles, RB, ROWS_STASH_BYTES, s->tab[s->cur][0], s->tab[s->cur][1],
-                 s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P,
-                 make_pack(s->segs), rr, RW, Snext, fa);
+      if (lazy_out)
+        SPG_LAUNCH(ctx, k_rows_rolled<true>, (unsigned)tiles, RB, ROWS_STASH_BYTES, s->tab[s->cur][0], s->tab[s->cur][1],
+                   s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P,
+                   make_pack(s->segs), rr, RW, Snext, fa);
+      else
+        SPG_LAUNCH(ctx, k_rows_rolled<false>, (unsigned)tiles, RB, ROWS_STASH_BYTES, s->tab[s->cur][0], s->tab[s->cur][1],
+                   s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs, (int)s->P,
+                   make_pack(s->segs), rr, RW, Snext, fa);
+      s->tab_lazy = lazy_out;
+      s->tab_lazy_n = (size_t)out_total;
       spg_fq tmp[2];
       SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));
       s->cached[0] = hfq_from(tmp[0]);

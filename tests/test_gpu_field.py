@@ -113,3 +113,16 @@ def test_reference_dense_kat(ctx):
     Z = np.stack([O.from_u64(v) for v in (1, 2, 1, 4)])
     r = np.stack([O.from_u64(4), O.from_u64(3)])
     assert np.array_equal(sp.DensePolynomial.new(ctx, Z).evaluate(r), O.from_u64(28))
+
+
+def test_wide_range_forms_selftest(ctx):
+    """csrc/fq.cuh's wide-range forms (a - b + 2q / 6q without a condition, one fold into [0, 2q), products of
+    operands up to 6q) exactly as k_rows_rolled / k_rows / k_rows_spmv chain them, on every edge combination of
+    {0, 1, q-1, q, q+1, 2q-1} plus random operands below 2q, against canonical arithmetic on the device"""
+    import ctypes as C
+
+    from spartan_parallel_b200._lib import check
+
+    bad = C.c_uint32(0xFFFFFFFF)
+    check(ctx.L.spg_debug_fq_wide_selftest(ctx.h, 1 << 18, 2024, C.byref(bad)), "spg_debug_fq_wide_selftest")
+    assert bad.value == 0, f"failing checks: {bad.value:#x}"
