@@ -500,6 +500,21 @@ extern "C" {
         rank: c_int,
         n: usize,
     ) -> c_int;
+    pub fn spg_zmat_bind_rq_sharded(
+        ctx: *mut spg_ctx,
+        z: *const spg_zmat,
+        rq_rev: *const spg_fq,
+        nq_local: usize,
+        nq_total: usize,
+        peer_ptrs: *const *mut c_void,
+        world: c_int,
+        rank: c_int,
+        n: usize,
+        scatter_only: c_int,
+        mailbox: *mut c_void,
+        slot_stride: usize,
+        calls: *mut u64,
+    ) -> c_int;
     pub fn spg_wit_perm_w0(
         ctx: *mut spg_ctx,
         tau: *const spg_fq,

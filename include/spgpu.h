@@ -386,6 +386,13 @@ int spg_peer_sum(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size
 /* the same reduction, but the sum of chunk r stays with rank r only (half the NVLink traffic): for a
  * consumer that is sharded the same way (spg_sc2_create_slice) */
 int spg_peer_reduce_scatter(spg_ctx *ctx, void *const *peer_ptrs, int world, int rank, size_t n);
+/* the whole step between the phases of a proof sharded over the proof axis in one call: bind this rank's
+ * Z rows to rq_rev[0 .. nq_local) scaled by the eq weight of its shard index under rq_rev[nq_local .. nq_total)
+ * into peer_ptrs[rank], barrier (mailbox), spg_peer_sum or (scatter_only) spg_peer_reduce_scatter, barrier.
+ * Replaces Z_poly.bound_poly_vars_rq (src/r1csproof.rs:478) of the unsharded prover. */
+int spg_zmat_bind_rq_sharded(spg_ctx *ctx, const spg_zmat *z, const spg_fq *rq_rev, size_t nq_local, size_t nq_total,
+                             void *const *peer_ptrs, int world, int rank, size_t n, int scatter_only, void *mailbox,
+                             size_t slot_stride, uint64_t *calls);
 
 /* ---------------------------------------------------------------- derived witness sections (f2)
  * What SNARK::prove computes from the primary sections (block_vars, exec_inputs, the memory

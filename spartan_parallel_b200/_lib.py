@@ -137,6 +137,7 @@ def _proto(L):
         "spg_sc2_host_tail_eval": [P, SZ, SZ, INT, P, P],
         "spg_sc2_host_tail_bind": [P, SZ, SZ, INT, P],
         "spg_peer_reduce_scatter": [P, P, INT, INT, SZ],
+        "spg_zmat_bind_rq_sharded": [P, P, P, SZ, SZ, P, INT, INT, SZ, INT, P, SZ, P],
         "spg_sc1_set_claim_checked": [P, P],
         "spg_zmat_bind_weights": [P, P, P, SZ, P, P],
         "spg_vec_zero": [P, P],

@@ -522,6 +522,18 @@ def gpu_bind_rq_sharded(ctx, comm, z, rq_rev, Q_local, peer: "PeerTable | None" 
     total = sum(len(z.witness_secs) * y for y in z.num_inputs)
     if peer is not None and comm.world > 1:
         assert peer.n == total
+        if isinstance(comm, ShmComm):  # bind, barrier, peer sum, barrier in one C call (spg_zmat_bind_rq_sharded)
+            import ctypes as C
+
+            from ._lib import check
+
+            rq = np.ascontiguousarray(rq_rev)
+            calls = C.c_uint64(comm.calls)
+            rc = ctx.L.spg_zmat_bind_rq_sharded(ctx.h, z.h, rq.ctypes.data_as(C.c_void_p), nql, rq.shape[0], peer._ptrs, comm.world,
+                                                comm.rank, total, int(scatter), C.c_void_p(comm.addr), comm.slot_stride, C.byref(calls))
+            comm.calls = int(calls.value)
+            check(rc, "spg_zmat_bind_rq_sharded")
+            return peer.poly
         api.zmat_bind_rq(ctx, z, rq_rev[:nql], api.host_eq_weight(rq_rev[nql:], comm.rank), peer.poly)
         return peer.reduce_scatter() if scatter else peer.all_reduce()
     dev = torch.device("cuda", ctx.device)
