@@ -90,3 +90,33 @@ def test_run_rounds_equals_round_by_round(ctx):
     got = b.run_rounds(ch)
     assert np.array_equal(got, np.stack(want))
     assert np.array_equal(a.final(), b.final())
+
+
+def test_tables_read_between_fused_binds_are_canonical(ctx):
+    """The fused bind leaves its tables in [0, 2q) while the next bind is the same kernel (csrc/sc1.cu,
+    k_rows_rolled<true>). Anything else that reads them -- here spg_sc1_debug_tables in the middle of the
+    run -- must see canonical scalars (k_canon3), and the rounds after such a read must not change."""
+    import spartan_parallel_b200 as sp
+
+    X, Q = 1 << 13, 2
+    N = X * Q
+    Az, Bz, Cz = rand_scalars(N, 71), rand_scalars(N, 72), rand_scalars(N, 73)
+    tau_q, tau_x = rand_scalars(1, 74), rand_scalars(13, 75)
+    ch = rand_scalars(14, 76)
+    none = tau_q[:0]
+    ref = sp.SumcheckPhase1.from_tables(ctx, [Q], Q, [X], X, Az, Bz, Cz, none, tau_q, tau_x)
+    want = ref.run_rounds(ch)
+    want_final = ref.final()
+    sc = sp.SumcheckPhase1.from_tables(ctx, [Q], Q, [X], X, Az, Bz, Cz, none, tau_q, tau_x)
+    tabs = [t.reshape(Q, X, 4) for t in (Az, Bz, Cz)]
+    for j in range(14):
+        assert np.array_equal(sc.round_eval(), want[j]), f"round {j}"
+        sc.round_bind(ch[j])
+        if j < 3:  # after binds 1 and 2 the tables are held unreduced (rows of 2^12, 2^11 >= 2^10)
+            got = sc.debug_tables()
+            for k in range(3):
+                lo, hi = tabs[k][:, 0::2].reshape(-1, 4), tabs[k][:, 1::2].reshape(-1, 4)
+                bound = O.vec_add(lo, O.vec_mul(np.tile(ch[j], (lo.shape[0], 1)), O.vec_sub(hi, lo)))
+                tabs[k] = bound.reshape(Q, -1, 4)
+                assert np.array_equal(got[k], bound), f"table {k} after bind {j}"
+    assert np.array_equal(sc.final(), want_final)
