@@ -137,6 +137,7 @@ KERNEL_MODEL = {
     "k_rows_spmv": (288.0, 4.0),         # SpMV + round 0: z read + 3 tables written per pair, 2 products + 2 weighted sums
     "k_rows": (192.0, 4.0),
     "k_quad_bind_eval": (576.0, 13.0),
+    "k_quad_split": (576.0, 13.0),       # the same round with one item over eight lanes (late rounds: latency, not throughput)
     "k_pair_eval": (192.0, 7.0),
     "k_pair_bind": (288.0, 3.0),
     "k_z_bind_rq": (32.0, 74.0 / 104.0),  # one product per witness scalar read, as four-term dot products: 296 wide multiplies per 4 instead of 4 x 104

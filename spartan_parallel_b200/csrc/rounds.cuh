@@ -100,4 +100,158 @@ __device__ __forceinline__ void comb_accumulate(fq (&acc)[3], const fq &w, const
   acc[2] = fq_add(acc[2], fq_mul(w, f3));
 }
 
+// ---------------------------------------------------------------- late rounds: one item over eight lanes
+// A late round (tables of a few thousand scalars or less) is not throughput but a dependent chain: with
+// one item per thread, k_quad_bind_eval / k2_quad_bind_eval execute ~6700 dependent instructions (the
+// binds one after the other, three evaluation points, three accumulators reduced one after the other,
+// the in-kernel final reduction again) on one warp per scheduler, ~8 cycles each: 20 - 27 us at ONE block
+// (profiles/r2_ncu_launches.csv). Nothing in an item is sequential except bind -> evaluate, so here an
+// item is spread over eight lanes and every stage runs once:
+//   lane 0 .. 2 NT - 1   bind of (table l / 2, pair l % 2): z + x * y with (x, y, z) = (r, hi - lo, lo)
+//   lane 6               the item's weight, the same z + x * y with (RW[row], S[i], 0) or (A[p], 1, 0)
+//   lanes 0, 1, 2        after an exchange by shuffles: evaluation at t = 0, 2, 3 (the point is a
+//                        select of the addend -d, d, 2d on top of x1 -- no divergent branch)
+// and the three sums live in DIFFERENT lanes, so one butterfly reduces all three (the final reduction over
+// the blocks' partial sums is laid out the same way). ~1500 instructions end to end. Same values as the
+// per-thread kernels: exact arithmetic, canonical results.
+struct SplitTabs {
+  const fq *in[3];
+  fq *out[3];
+};
+constexpr int SPLIT_ITEMS_PER_BLOCK = 16;        // 128 threads / 8 lanes
+constexpr unsigned long long SPLIT_MAX_ITEMS = 4096;  // up to 256 blocks; beyond, one item per thread wins
+
+__device__ __forceinline__ fq fq_shfl(const fq &x, int src) {
+  fq y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) y.v[i] = __shfl_sync(0xffffffffu, x.v[i], src);
+  return y;
+}
+__device__ __forceinline__ fq fq_shfl_down(const fq &x, int off) {
+  fq y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) y.v[i] = __shfl_down_sync(0xffffffffu, x.v[i], off);
+  return y;
+}
+
+// x0 + t (x1 - x0) at t = 0, 2, 3 for lane role l = 0, 1, 2: x1 + {x0 - x1, d, 2d}
+__device__ __forceinline__ fq split_point(const fq &x0, const fq &x1, unsigned int l) {
+  fq d = fq_sub(x1, x0), nd = fq_sub(x0, x1), d2 = fq_add(d, d), s;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s.v[i] = l == 0 ? nd.v[i] : (l == 1 ? d.v[i] : d2.v[i]);
+  return fq_add(x1, s);
+}
+
+template <int NT, int COMB>
+__global__ void __launch_bounds__(128)
+k_quad_split(const __grid_constant__ SplitTabs T, const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk,
+             unsigned long long total_items, fq r, const fq *__restrict__ RW, const fq *__restrict__ Snext, FinishArgs fa) {
+  static_assert((NT == 3 && COMB == 1) || (NT == 2 && COMB == 2), "phase 1: three tables, A B - C; phase 2: two tables, B C");
+  __shared__ fq sm[4 * 4];  // [warp][point]
+  __shared__ int is_last;
+  const unsigned int lane = threadIdx.x & 31, l = lane & 7, warp = threadIdx.x >> 5;
+  const unsigned long long item = (unsigned long long)blockIdx.x * SPLIT_ITEMS_PER_BLOCK + (threadIdx.x >> 3);
+  const bool valid = item < total_items;
+  const Seg sg = pick_seg(pk, segs, nseg, valid ? item : 0);
+  const unsigned long long local = valid ? item - sg.item_start : 0;
+  const unsigned long long idx = sg.in_off + 4 * local, o = sg.out_off + 2 * local;
+  const bool is_bind = l < 2 * NT, is_weight = l == 6;
+  const unsigned int tab = is_bind ? l >> 1 : 0, pair = l & 1;
+  // operands of z + x * y
+  fq x = fq_zero(), y = fq_zero(), z = fq_zero();
+  if (valid && is_bind) {
+    const fq *p = T.in[tab] + idx + 2 * pair;
+    z = fq_load_stream(p);
+    y = fq_sub(fq_load_stream(p + 1), z);
+    x = r;
+  } else if (valid && is_weight) {
+    if (Snext) {  // phase 1: row weight times the suffix eq table of the remaining variables
+      unsigned int ql = sg.log_len - 2;
+      x = fq_load(RW + sg.rw_off + (local >> ql));
+      y = fq_load(Snext + (local & ((1ull << ql) - 1)));
+    } else {      // phase 2: the instance's eq_p weight
+      x = fq_load(RW + sg.rw_off);
+      y = fq_one();
+    }
+  }
+  const fq v = fq_add(z, fq_mul(x, y));
+  if (valid && is_bind) fq_store(T.out[tab] + o + pair, v);
+  // every lane of the group receives the bound values and the weight
+  const int base = lane & ~7u;
+  fq g[2 * NT];
+#pragma unroll
+  for (int k = 0; k < 2 * NT; k++) g[k] = fq_shfl(v, base + k);
+  const fq w = fq_shfl(v, base + 6);
+  fq f;
+  if (COMB == 1) {
+    fq a = split_point(g[0], g[1], l), b = split_point(g[2], g[3], l), c = split_point(g[4], g[5], l);
+    f = fq_sub(fq_mul(a, b), c);
+  } else {
+    fq b = split_point(g[0], g[1], l), c = split_point(g[2], g[3], l);
+    f = fq_mul(b, c);
+  }
+  fq acc = fq_mul(w, f);
+  if (!(valid && l < 3)) acc = fq_zero();
+  // lanes 8 j + k hold point k of item j: two butterfly steps leave the warp's sums in lanes 0 .. 2
+  acc = fq_add(acc, fq_shfl_down(acc, 8));
+  acc = fq_add(acc, fq_shfl_down(acc, 16));
+  if (lane < 3) sm[warp * 4 + lane] = acc;
+  __syncthreads();
+  fq mine[3] = {fq_zero(), fq_zero(), fq_zero()};
+  if (warp == 0) {
+    fq t = l < 3 ? sm[(lane >> 3) * 4 + l] : fq_zero();
+    t = fq_add(t, fq_shfl_down(t, 8));
+    t = fq_add(t, fq_shfl_down(t, 16));
+    mine[0] = t;
+    mine[1] = fq_shfl(t, 1);
+    mine[2] = fq_shfl(t, 2);
+  }
+  // ---- final reduction over the blocks (FinishArgs, common.cuh), the three sums side by side again
+  if (gridDim.x == 1 && fa.seq) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) fq_store(fa.result + k, mine[k]);
+      __threadfence_system();
+      *(volatile unsigned long long *)fa.flag = fa.seq;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) fq_store(fa.partials + (size_t)blockIdx.x * 3 + k, mine[k]);
+    int last = 0;
+    if (fa.seq) {
+      __threadfence();
+      last = atomicAdd(fa.counter, 1u) == gridDim.x - 1;
+    }
+    is_last = last;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const unsigned int k4 = threadIdx.x & 3;
+  fq a = fq_zero();
+  if (k4 < 3)
+    for (unsigned int b = threadIdx.x >> 2; b < gridDim.x; b += 32) a = fq_add(a, fq_load_cg(fa.partials + (size_t)b * 3 + k4));
+  a = fq_add(a, fq_shfl_down(a, 4));
+  a = fq_add(a, fq_shfl_down(a, 8));
+  a = fq_add(a, fq_shfl_down(a, 16));
+  if (lane < 3) sm[warp * 4 + lane] = a;  // (the first use of sm was consumed before the barrier above)
+  __syncthreads();
+  if (warp == 0) {
+    fq t = (lane < 16 && (lane & 3) < 3) ? sm[(lane >> 2) * 4 + (lane & 3)] : fq_zero();
+    t = fq_add(t, fq_shfl_down(t, 4));
+    t = fq_add(t, fq_shfl_down(t, 8));
+    fq s1 = fq_shfl(t, 1), s2 = fq_shfl(t, 2);
+    if (lane == 0) {
+      fq_store(fa.result + 0, t);
+      fq_store(fa.result + 1, s1);
+      fq_store(fa.result + 2, s2);
+      *fa.counter = 0;
+      __threadfence_system();
+      *(volatile unsigned long long *)fa.flag = fa.seq;
+    }
+  }
+}
+
 }  // namespace spg

@@ -1178,13 +1178,19 @@ int spg_sc1_round_bind(spg_sc1 *s, const spg_fq *r) {
       SPG_CHECK(out_total <= s->cap[nxt], "internal: bound table exceeds buffer");
       SPG_TRY(upload_segs(s));
       const fq *Snext = s_table(s, phase, n_phase - j - 2);
-      int grid = grid_for(ctx, items, RB, 4);
+      const bool split = items <= SPLIT_MAX_ITEMS;  // a late round: latency, not throughput (rounds.cuh)
+      int grid = split ? (int)((items + SPLIT_ITEMS_PER_BLOCK - 1) / SPLIT_ITEMS_PER_BLOCK) : grid_for(ctx, items, RB, 4);
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
       FinishArgs fa = finish_args(ctx, grid);
       ctx->next_units = 576.0 * (double)items;  // 4 read + 2 written scalars x 3 tables per item
-      SPG_LAUNCH(ctx, k_quad_bind_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
-                 s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs,
-                 (int)s->P, make_pack(s->segs), items, rr, RW, Snext, fa);
+      if (split) {
+        SplitTabs T = {{s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2]}, {s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2]}};
+        SPG_LAUNCH(ctx, (k_quad_split<3, 1>), grid, 128, 0, T, s->d_segs, (int)s->P, make_pack(s->segs), items, rr, RW, Snext, fa);
+      } else {
+        SPG_LAUNCH(ctx, k_quad_bind_eval<1>, grid, RB, 0, s->tab[s->cur][0], s->tab[s->cur][1],
+                   s->tab[s->cur][2], s->tab[nxt][0], s->tab[nxt][1], s->tab[nxt][2], s->d_segs,
+                   (int)s->P, make_pack(s->segs), items, rr, RW, Snext, fa);
+      }
       spg_fq tmp[3];
       SPG_TRY(finish_result(ctx, fa, grid, 3, tmp));
       for (int t = 0; t < 3; t++) s->cached[t] = hfq_from(tmp[t]);

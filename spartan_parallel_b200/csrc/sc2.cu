@@ -725,11 +725,18 @@ int spg_sc2_round_bind(spg_sc2 *s, const spg_fq *r) {
     if (next_same && minlen >= 2) {
       build_segs2(s, phase, 1, &items, &out_total);
       if (s->P > (size_t)SEG_INLINE) SPG_CUDA(cudaMemcpyAsync(s->d_segs, s->segs.data(), s->P * sizeof(Seg), cudaMemcpyHostToDevice, ctx->stream));
-      int grid = grid_for(ctx, items, RB2, 4);
+      const bool split = items <= SPLIT_MAX_ITEMS;  // a late round: latency, not throughput (rounds.cuh)
+      int grid = split ? (int)((items + SPLIT_ITEMS_PER_BLOCK - 1) / SPLIT_ITEMS_PER_BLOCK) : grid_for(ctx, items, RB2, 4);
       SPG_TRY(ensure_partials(ctx, (size_t)grid * 3));
       FinishArgs fa = finish_args(ctx, grid);
-      SPG_LAUNCH(ctx, k2_quad_bind_eval, grid, RB2, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[nxt][0],
-                 s->tab[nxt][1], s->d_segs, (int)s->P, make_pack(s->segs), items, rr, s->A, fa);
+      if (split) {
+        SplitTabs T = {{s->tab[s->cur][0], s->tab[s->cur][1], nullptr}, {s->tab[nxt][0], s->tab[nxt][1], nullptr}};
+        SPG_LAUNCH(ctx, (k_quad_split<2, 2>), grid, 128, 0, T, s->d_segs, (int)s->P, make_pack(s->segs), items, rr, s->A,
+                   (const fq *)nullptr, fa);
+      } else {
+        SPG_LAUNCH(ctx, k2_quad_bind_eval, grid, RB2, 0, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[nxt][0],
+                   s->tab[nxt][1], s->d_segs, (int)s->P, make_pack(s->segs), items, rr, s->A, fa);
+      }
       SPG_TRY(finish_result(ctx, fa, grid, 3, s->cached));
       s->have_cached = true;
     } else {
