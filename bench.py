@@ -142,6 +142,7 @@ KERNEL_MODEL = {
     "k_pair_bind": (288.0, 3.0),
     "k_z_bind_rq": (32.0, 74.0 / 104.0),  # one product per witness scalar read, as four-term dot products: 296 wide multiplies per 4 instead of 4 x 104
     "k_cubic_eval_rlc": (192.0, 6.0),
+    "k_cubic_eval_split": (192.0, 6.0),
     "k_multi_bind_top": (96.0, 1.0),
     "k_prod_layer": (96.0, 1.0),
     "k_hash_layer_fq": (128.0, 2.0),
@@ -771,13 +772,20 @@ def sparse_leg(sp, host, ctx, lg):
         st[k] = st.get(k, 0.0) + v * 1e-3
     g = lambda *ks: sum(st.get("sparse: " + k, 0.0) for k in ks)
     pre = g("dense representation", "generators", "multi_commit")
+    prove = g("eq tables + derefs", "derefs commitment", "hash layers + trees", "tree evals + dotp", "product-circuit sumchecks",
+              "hash-layer evals + 3 openings")
     gens.free()
-    return {"gens_setup_s": gens_s, "seconds": best - pre, "with_preprocessing_s": best, "proof_bytes": len(proof), "commitment_bytes": len(comm),
+    # `seconds` is SparseMatPolyEvalProof::prove itself (src/sparse_mlpoly.rs:1497-1564: it receives the dense
+    # representation built at encode time); what the python call adds on top -- marshalling the three COO
+    # matrices (120 MB) into the library -- is instance setup and reported apart
+    return {"gens_setup_s": gens_s, "seconds": prove, "with_preprocessing_s": prove + pre, "call_s": best,
+            "instance_marshalling_s": best - prove - pre, "proof_bytes": len(proof), "commitment_bytes": len(comm),
             "timers": {"commit_nondet_witness": g("eq tables + derefs", "derefs commitment"),
                        "build_layered_network": g("hash layers + trees"),
                        "evalproof_layered_network": g("tree evals + dotp", "product-circuit sumchecks"),
                        "hash_layer_evals_and_openings": g("hash-layer evals + 3 openings")},
             "preprocessing": {"dense_representation": g("dense representation"), "generators": g("generators"), "multi_commit": g("multi_commit")},
+            "stages_ms": {k: round(v * 1e3, 3) for k, v in st.items()},
             "prof": prof,
             "what": f"3 matrices x 2^{lg} non-zeros; `seconds` = SparseMatPolyEvalProof::prove (timers: src/sparse_mlpoly.rs:1522-1545), "
                     "preprocessing (SNARK::encode: dense representation, generators, multi_commit) reported apart"}

@@ -225,6 +225,8 @@ static inline int grid_for(const spg_ctx *ctx, size_t items, int block, int max_
 int reduce_partials(spg_ctx *ctx, const fq *partials, size_t nblocks, int width, fq *d_out);
 // fetch `width` scalars from the mapped result slot after a stream sync
 int fetch_result(spg_ctx *ctx, int width, spg_fq *out);
+// out[i] = *ptrs[i] for n device scalars, through the mapped result page (one tiny launch per 48)
+int gather_heads(spg_ctx *ctx, const fq *const *ptrs, size_t n, spg_fq *out);
 
 // Final reduction inside the round kernel: every block stores its partial sums; the block
 // that draws the last ticket adds all of them, writes the result to mapped host memory and then

@@ -215,6 +215,37 @@ int fetch_result(spg_ctx *ctx, int width, spg_fq *out) {
   return SPG_OK;
 }
 
+// First scalar of up to HEADS_PER_LAUNCH device tables -> the mapped result page, published through the
+// flag word like a round result: the final claims of a sumcheck (one scalar per bound table) reach the
+// host with one tiny launch instead of one cudaMemcpyAsync per table (25 - 43 copies of 32 bytes at
+// ~6 us each per product-circuit layer, 42 layers per sparse proof).
+constexpr int HEADS_PER_LAUNCH = 48;  // the page holds 56 scalars before the flag word
+struct HeadPtrs {
+  const fq *p[HEADS_PER_LAUNCH];
+};
+__global__ void k_gather_heads(const __grid_constant__ HeadPtrs P, int n, fq *__restrict__ result, unsigned long long *flag,
+                               unsigned long long seq) {
+  if ((int)threadIdx.x < n) {
+    fq_store(result + threadIdx.x, fq_load(P.p[threadIdx.x]));
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *(volatile unsigned long long *)flag = seq;
+}
+
+int gather_heads(spg_ctx *ctx, const fq *const *ptrs, size_t n, spg_fq *out) {
+  for (size_t base = 0; base < n; base += HEADS_PER_LAUNCH) {
+    int cnt = (int)(n - base < (size_t)HEADS_PER_LAUNCH ? n - base : (size_t)HEADS_PER_LAUNCH);
+    HeadPtrs P;
+    memset(&P, 0, sizeof P);
+    for (int i = 0; i < cnt; i++) P.p[i] = ptrs[base + i];
+    unsigned long long seq = ++ctx->seq;
+    SPG_LAUNCH(ctx, k_gather_heads, 1, 64, 0, P, cnt, ctx->d_result, ctx->d_flag, seq);
+    SPG_TRY(wait_flag(ctx, seq, cnt, out + base));
+  }
+  return SPG_OK;
+}
+
 }  // namespace spg
 
 using namespace spg;

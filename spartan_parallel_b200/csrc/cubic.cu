@@ -6,6 +6,7 @@
 // These tables are plain DensePolynomials bound with bound_poly_var_top: the pair
 // (i, i + n/2) is two perfectly coalesced streams, so the reference order is kept.
 #include "common.cuh"
+#include "rounds.cuh"
 
 namespace spg {
 
@@ -62,6 +63,46 @@ k_cubic_eval_rlc(const __grid_constant__ CubicPtrs P, const __grid_constant__ Cu
     for (int t = 0; t < 3; t++) acc[t] = fq_mul(ck, acc[t]);
   }
   finish_block<3>(fa, acc, sm);
+}
+
+// The same round on small tables, where it is a dependent chain and not throughput (rounds.cuh,
+// k_quad_split): one item over four lanes, lane l = 0, 1, 2 evaluating at t = 0, 2, 3, so the three
+// sums of a block are reduced by ONE butterfly, the triple's coefficient is applied by three lanes at
+// once, and the final reduction over the blocks runs side by side as well. A block works on one triple.
+constexpr int CUBIC_SPLIT_ITEMS = 32;  // items per 128-thread block
+__global__ void __launch_bounds__(128)
+k_cubic_eval_split(const __grid_constant__ CubicPtrs P, const __grid_constant__ CubicCoeffs K, int gx, size_t half, FinishArgs fa) {
+  __shared__ fq sm[4 * 4];
+  const unsigned int lane = threadIdx.x & 31, l = lane & 3, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x / gx, bx = blockIdx.x % gx;
+  const fq *__restrict__ A = P.A[k];
+  const fq *__restrict__ B = P.B[k];
+  const fq *__restrict__ C = P.C[k];
+  const size_t i = (size_t)bx * CUBIC_SPLIT_ITEMS + (threadIdx.x >> 2);
+  fq acc = fq_zero();
+  if (i < half && l < 3) {
+    fq a = split_point(fq_load(A + i), fq_load(A + i + half), l);
+    fq b = split_point(fq_load(B + i), fq_load(B + i + half), l);
+    fq c = split_point(fq_load(C + i), fq_load(C + i + half), l);
+    acc = fq_mul(fq_mul(a, b), c);
+  }
+  // lanes 4 j + l hold point l of item j
+  acc = fq_add(acc, fq_shfl_down(acc, 4));
+  acc = fq_add(acc, fq_shfl_down(acc, 8));
+  acc = fq_add(acc, fq_shfl_down(acc, 16));
+  if (lane < 3) sm[warp * 4 + lane] = acc;
+  __syncthreads();
+  fq mine[3] = {fq_zero(), fq_zero(), fq_zero()};
+  if (warp == 0) {
+    fq t = (lane < 16 && l < 3) ? sm[(lane >> 2) * 4 + l] : fq_zero();
+    t = fq_add(t, fq_shfl_down(t, 4));
+    t = fq_add(t, fq_shfl_down(t, 8));
+    t = fq_mul(K.c[k], t);  // lanes 0 .. 2: the three sums of this block, scaled by the triple's coefficient
+    mine[0] = t;
+    mine[1] = fq_shfl(t, 1);
+    mine[2] = fq_shfl(t, 2);
+  }
+  finish_block_lanes3(fa, mine, sm);
 }
 
 struct BindPtrs {
@@ -295,6 +336,9 @@ int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]) {
   int gx = grid_for(ctx, half, CB, 2);
   if (gx > 1024) gx = 1024;
   if ((size_t)gx * nt > 4096) gx = (int)(4096 / nt);  // keep the in-kernel final reduction (finish_args)
+  const size_t gx_split = (half + CUBIC_SPLIT_ITEMS - 1) / CUBIC_SPLIT_ITEMS;
+  const bool split = gx_split * nt <= 512;  // small tables: the lane-split kernel (latency, not throughput)
+  if (split) gx = (int)gx_split;
   size_t nblocks = (size_t)gx * nt;
   SPG_TRY(ensure_partials(ctx, nblocks * 3));
   CubicCoeffs K;
@@ -304,7 +348,10 @@ int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]) {
   }
   ctx->next_units = 192.0 * (double)half * (double)nt;
   FinishArgs fa = finish_args(ctx, nblocks);
-  SPG_LAUNCH(ctx, k_cubic_eval_rlc, (unsigned)nblocks, CB, 0, P, K, gx, half, fa);
+  if (split)
+    SPG_LAUNCH(ctx, k_cubic_eval_split, (unsigned)nblocks, 128, 0, P, K, gx, half, fa);
+  else
+    SPG_LAUNCH(ctx, k_cubic_eval_rlc, (unsigned)nblocks, CB, 0, P, K, gx, half, fa);
   SPG_TRY(finish_result(ctx, fa, nblocks, 3, e));
   s->evaluated = true;
   return SPG_OK;
@@ -358,10 +405,9 @@ int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
   for (auto v : s->A_seq) all.push_back(v);
   for (auto v : s->B_seq) all.push_back(v);
   for (auto v : s->C_seq) all.push_back(v);
-  for (size_t i = 0; i < all.size(); i++)
-    SPG_CUDA(cudaMemcpyAsync(&claims[i], all[i]->d, sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return SPG_OK;
+  std::vector<const fq *> heads;
+  for (auto v : all) heads.push_back(v->d);
+  return gather_heads(ctx, heads.data(), heads.size(), claims);
 }
 
 void spg_cubic_destroy(spg_cubic *s) {

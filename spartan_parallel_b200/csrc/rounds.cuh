@@ -142,13 +142,66 @@ __device__ __forceinline__ fq split_point(const fq &x0, const fq &x1, unsigned i
   return fq_add(x1, s);
 }
 
+// Final reduction over the blocks for kernels whose three sums are reduced side by side: `mine` (valid in
+// thread 0) = this block's sums; single block: published directly; else the block that draws the last
+// ticket adds the partial rows with thread t on sum t % 4 and one butterfly for all three (finish_block,
+// common.cuh, does the same with three block_sums one after the other). 128 threads, sm = fq[16].
+__device__ __forceinline__ void finish_block_lanes3(const FinishArgs &fa, const fq (&mine)[3], fq *sm) {
+  __shared__ int is_last;
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (gridDim.x == 1 && fa.seq) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) fq_store(fa.result + k, mine[k]);
+      __threadfence_system();
+      *(volatile unsigned long long *)fa.flag = fa.seq;
+    }
+    return;
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) fq_store(fa.partials + (size_t)blockIdx.x * 3 + k, mine[k]);
+    int last = 0;
+    if (fa.seq) {
+      __threadfence();
+      last = atomicAdd(fa.counter, 1u) == gridDim.x - 1;
+    }
+    is_last = last;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const unsigned int k4 = threadIdx.x & 3;
+  fq a = fq_zero();
+  if (k4 < 3)
+    for (unsigned int b = threadIdx.x >> 2; b < gridDim.x; b += 32) a = fq_add(a, fq_load_cg(fa.partials + (size_t)b * 3 + k4));
+  a = fq_add(a, fq_shfl_down(a, 4));
+  a = fq_add(a, fq_shfl_down(a, 8));
+  a = fq_add(a, fq_shfl_down(a, 16));
+  if (lane < 3) sm[warp * 4 + lane] = a;  // (the caller's use of sm was consumed before the barrier above)
+  __syncthreads();
+  if (warp == 0) {
+    fq t = (lane < 16 && (lane & 3) < 3) ? sm[(lane >> 2) * 4 + (lane & 3)] : fq_zero();
+    t = fq_add(t, fq_shfl_down(t, 4));
+    t = fq_add(t, fq_shfl_down(t, 8));
+    fq s1 = fq_shfl(t, 1), s2 = fq_shfl(t, 2);
+    if (lane == 0) {
+      fq_store(fa.result + 0, t);
+      fq_store(fa.result + 1, s1);
+      fq_store(fa.result + 2, s2);
+      *fa.counter = 0;
+      __threadfence_system();
+      *(volatile unsigned long long *)fa.flag = fa.seq;
+    }
+  }
+}
+
 template <int NT, int COMB>
 __global__ void __launch_bounds__(128)
 k_quad_split(const __grid_constant__ SplitTabs T, const Seg *__restrict__ segs, int nseg, const __grid_constant__ SegPack pk,
              unsigned long long total_items, fq r, const fq *__restrict__ RW, const fq *__restrict__ Snext, FinishArgs fa) {
   static_assert((NT == 3 && COMB == 1) || (NT == 2 && COMB == 2), "phase 1: three tables, A B - C; phase 2: two tables, B C");
   __shared__ fq sm[4 * 4];  // [warp][point]
-  __shared__ int is_last;
   const unsigned int lane = threadIdx.x & 31, l = lane & 7, warp = threadIdx.x >> 5;
   const unsigned long long item = (unsigned long long)blockIdx.x * SPLIT_ITEMS_PER_BLOCK + (threadIdx.x >> 3);
   const bool valid = item < total_items;
@@ -206,52 +259,7 @@ k_quad_split(const __grid_constant__ SplitTabs T, const Seg *__restrict__ segs, 
     mine[1] = fq_shfl(t, 1);
     mine[2] = fq_shfl(t, 2);
   }
-  // ---- final reduction over the blocks (FinishArgs, common.cuh), the three sums side by side again
-  if (gridDim.x == 1 && fa.seq) {
-    if (threadIdx.x == 0) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) fq_store(fa.result + k, mine[k]);
-      __threadfence_system();
-      *(volatile unsigned long long *)fa.flag = fa.seq;
-    }
-    return;
-  }
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) fq_store(fa.partials + (size_t)blockIdx.x * 3 + k, mine[k]);
-    int last = 0;
-    if (fa.seq) {
-      __threadfence();
-      last = atomicAdd(fa.counter, 1u) == gridDim.x - 1;
-    }
-    is_last = last;
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  const unsigned int k4 = threadIdx.x & 3;
-  fq a = fq_zero();
-  if (k4 < 3)
-    for (unsigned int b = threadIdx.x >> 2; b < gridDim.x; b += 32) a = fq_add(a, fq_load_cg(fa.partials + (size_t)b * 3 + k4));
-  a = fq_add(a, fq_shfl_down(a, 4));
-  a = fq_add(a, fq_shfl_down(a, 8));
-  a = fq_add(a, fq_shfl_down(a, 16));
-  if (lane < 3) sm[warp * 4 + lane] = a;  // (the first use of sm was consumed before the barrier above)
-  __syncthreads();
-  if (warp == 0) {
-    fq t = (lane < 16 && (lane & 3) < 3) ? sm[(lane >> 2) * 4 + (lane & 3)] : fq_zero();
-    t = fq_add(t, fq_shfl_down(t, 4));
-    t = fq_add(t, fq_shfl_down(t, 8));
-    fq s1 = fq_shfl(t, 1), s2 = fq_shfl(t, 2);
-    if (lane == 0) {
-      fq_store(fa.result + 0, t);
-      fq_store(fa.result + 1, s1);
-      fq_store(fa.result + 2, s2);
-      *fa.counter = 0;
-      __threadfence_system();
-      *(volatile unsigned long long *)fa.flag = fa.seq;
-    }
-  }
+  finish_block_lanes3(fa, mine, sm);
 }
 
 }  // namespace spg

@@ -1396,11 +1396,9 @@ int spg_sc1_final(spg_sc1 *s, spg_fq claims[4]) {
   spg_ctx *ctx = s->ctx;
   SPG_TRY(sc1_materialize(s));
   // with zero q rounds the x phase never re-keys the segments; everything is length one anyway
-  fq h[4];
-  SPG_CUDA(cudaMemcpyAsync(&h[0], s->Ap, sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  for (int k = 0; k < 3; k++)
-    SPG_CUDA(cudaMemcpyAsync(&h[1 + k], s->tab[s->cur][k], sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  spg_fq h[4];
+  const fq *heads[4] = {s->Ap, s->tab[s->cur][0], s->tab[s->cur][1], s->tab[s->cur][2]};
+  SPG_TRY(gather_heads(ctx, heads, 4, h));
   hfq ap;
   memcpy(&ap, &h[0], sizeof ap);
   claims[0] = hfq_to(hfq_mul(hfq_mul(hfq_mul(ap, s->cq), s->cx), s->scale));

@@ -773,11 +773,8 @@ int spg_sc2_final(spg_sc2 *s, spg_fq claims[3]) {
   }
   SPG_TRY(enter_w_phase(s));
   spg_ctx *ctx = s->ctx;
-  SPG_CUDA(cudaMemcpyAsync(&claims[0], s->A, sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaMemcpyAsync(&claims[1], s->tab[s->cur][0], sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaMemcpyAsync(&claims[2], s->tab[s->cur][1], sizeof(fq), cudaMemcpyDeviceToHost, ctx->stream));
-  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-  return SPG_OK;
+  const fq *heads[3] = {s->A, s->tab[s->cur][0], s->tab[s->cur][1]};
+  return gather_heads(ctx, heads, 3, claims);
 }
 
 void spg_sc2_destroy(spg_sc2 *s) {
