@@ -406,7 +406,7 @@ def run_gpu(args):
         t0 = time.perf_counter()
         gens = host.R1CSGens(ctx, b"gens_r1cs_sat", X * Q_main)
         pc = gens.gens_pc()
-        pc.prepare(R)
+        pc.prepare(R, rows_local)
         ctx.sync()
         gens_s = time.perf_counter() - t0
         secs = main.upload()
@@ -431,6 +431,12 @@ def run_gpu(args):
         prof_c = ctx.profile_end()
         assert commit_all() == first_c
         info = pc.info()
+        rows_tab = info.pop("rows_table")
+        if rows_tab["table_bytes"]:  # the many-row path served the commitment: report ITS window and additions
+            info = {"window_bits": rows_tab["window_bits"], "adds_per_scalar": rows_tab["adds_per_scalar"],
+                    "table_bytes": rows_tab["table_bytes"] + info["table_bytes"], "table_bases": rows_tab["table_bases"],
+                    "tables": "single-window table per base + Horner over the windows (k_msm_hrows) for the row commitments; "
+                              f"per-window table (c = {info['window_bits']}, {info['table_bytes']} bytes) for the few-row MSMs of the openings"}
         commit = {"seconds": wall_c * 1e-3 / reps, "device_ms": ms_c / reps, "sections": 2, "scalars": 2 * X * Q_main,
                   "rows_per_section": rows_total, "cols": R, "rows_per_rank": rows_local,
                   "scalars_per_s": 2 * X * Q_main / (wall_c * 1e-3 / reps), **info,

@@ -593,6 +593,8 @@ extern "C" {
     ) -> c_int;
     pub fn spg_gens_prepare(ctx: *mut spg_ctx, gens: *mut spg_gens, R: usize) -> c_int;
     pub fn spg_gens_info(gens: *const spg_gens, out: *mut usize) -> c_int;
+    pub fn spg_gens_prepare_rows(ctx: *mut spg_ctx, gens: *mut spg_gens, L: usize, R: usize) -> c_int;
+    pub fn spg_gens_info_rows(gens: *const spg_gens, out: *mut usize) -> c_int;
     pub fn spg_debug_fe8_selftest(ctx: *mut spg_ctx, n: usize, seed: u64, out_bad: *mut u32) -> c_int;
     pub fn spg_debug_fq_wide_selftest(ctx: *mut spg_ctx, n: usize, seed: u64, out_bad: *mut u32) -> c_int;
     pub fn spg_commit_batch(

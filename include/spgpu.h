@@ -443,6 +443,14 @@ int spg_gens_prepare(spg_ctx *ctx, spg_gens *gens, size_t R);
 /* out = {window bits c, windows per scalar (= point additions per non-zero scalar), table
  * bytes, bases covered}; zeros before the first table is built. */
 int spg_gens_info(const spg_gens *gens, size_t out[4]);
+/* The same as spg_gens_prepare for a commitment of L rows over R bases (DensePolynomial::commit,
+ * src/dense_mlpoly.rs:214-239): commitments with many rows use a second, single-window table per
+ * base (the window factor 2^(c w) is applied once per row by a Horner chain instead of being folded
+ * into the table: 15 additions per scalar at c = 17), which this call builds ahead as well. */
+int spg_gens_prepare_rows(spg_ctx *ctx, spg_gens *gens, size_t L, size_t R);
+/* spg_gens_info for that single-window table: {c, additions per non-zero scalar, bytes, bases};
+ * zeros while commitments with many rows go through the per-window table. */
+int spg_gens_info_rows(const spg_gens *gens, size_t out[4]);
 /* Development aid: n pseudo-random and edge-case operand pairs through the eight-limb
  * GF(2^255-19) arithmetic of the commitment kernels, compared on the device with the ten-limb
  * code; *out_bad = OR of the failing checks' bits (0 = all agree). */

@@ -44,7 +44,7 @@ def main():
         ctx.sync()
         t_gens = time.perf_counter() - t0
         t0 = time.perf_counter()
-        gens.prepare(R)
+        gens.prepare(R, L)
         t_table = time.perf_counter() - t0
         times = []
         first = None
@@ -58,6 +58,11 @@ def main():
             assert rows == first
         best = min(times[1:])
         info = gens.info()
+        rows_tab = info.pop("rows_table")
+        if rows_tab["table_bytes"]:  # the many-row path (single-window table + Horner) served the commitment
+            info = {"path": "k_msm_hrows", "per_window_table_bytes": info["table_bytes"], **rows_tab}
+        else:
+            info["path"] = "k_msm_rows"
         adds = info["adds_per_scalar"]
         print(json.dumps({"ell": ell, "rows": L, "cols": R, "gens_s": t_gens, "table_s": t_table, "first_call_s": times[0], "commit_s": best,
                           "scalars_per_s": n / best, "point_adds_per_s": n * adds / best, "adds_per_scalar": adds, **info}), flush=True)

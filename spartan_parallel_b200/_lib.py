@@ -147,6 +147,8 @@ def _proto(L):
         "spg_wit_shift": [P, P, SZ, SZ, P, SZ, PP],
         "spg_gens_prepare": [P, P, SZ],
         "spg_gens_info": [P, P],
+        "spg_gens_prepare_rows": [P, P, SZ, SZ],
+        "spg_gens_info_rows": [P, P],
         "spg_debug_fe8_selftest": [P, SZ, C.c_uint64, P],
         "spg_debug_fq_wide_selftest": [P, SZ, C.c_uint64, P],
     }

@@ -840,14 +840,21 @@ class MultiCommitGens:
         check(self.ctx.L.spg_poly_commit_rows(self.ctx.h, self.h, poly.h, L_size, row0, nrows, _ptr(out)), "spg_poly_commit_rows")
         return out[:32 * nrows].tobytes()
 
-    def prepare(self, R: int):
-        """Build the fixed-base tables for the first R generators now (setup, not prove time)."""
-        check(self.ctx.L.spg_gens_prepare(self.ctx.h, self.h, R), "spg_gens_prepare")
+    def prepare(self, R: int, rows: int | None = None):
+        """Build the fixed-base tables for the first R generators now (setup, not prove time);
+        with `rows`, also the single-window table a commitment of that many rows would use."""
+        if rows is None:
+            check(self.ctx.L.spg_gens_prepare(self.ctx.h, self.h, R), "spg_gens_prepare")
+        else:
+            check(self.ctx.L.spg_gens_prepare_rows(self.ctx.h, self.h, rows, R), "spg_gens_prepare_rows")
 
     def info(self) -> dict:
         o = np.zeros(4, dtype=np.uint64)
         check(self.ctx.L.spg_gens_info(self.h, _ptr(o)), "spg_gens_info")
-        return {"window_bits": int(o[0]), "adds_per_scalar": int(o[1]), "table_bytes": int(o[2]), "table_bases": int(o[3])}
+        d = {"window_bits": int(o[0]), "adds_per_scalar": int(o[1]), "table_bytes": int(o[2]), "table_bases": int(o[3])}
+        check(self.ctx.L.spg_gens_info_rows(self.h, _ptr(o)), "spg_gens_info_rows")
+        d["rows_table"] = {"window_bits": int(o[0]), "adds_per_scalar": int(o[1]), "table_bytes": int(o[2]), "table_bases": int(o[3])}
+        return d
 
     def commit_batch(self, scalars, blinds=None) -> list:
         """Commitments::commit for `count` vectors of equal length sharing these generators."""

@@ -241,6 +241,121 @@ k_msm_rows(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_stride
   partial[i * nchunks + k] = acc;
 }
 
+// ---------------------------------------------------------------- many rows: ONE window table per base + Horner
+// A polynomial commitment has thousands of rows over the same bases, so the factor 2^(c w) of
+// window w need not be folded into the table at all: with the single table H[j][d-1] = d G_j
+//   C_i = sum_w 2^(c w) S_{i,w},   S_{i,w} = sum_j sign(d) H[j][|d|-1],  d = digit_w(s_ij),
+// and the doublings (c per window and ROW, against R additions per window and row) are noise.
+// The table then costs R * 2^(c-1) entries instead of R * wins * 2^(c-1), which buys c = 17 --
+// 15 additions per scalar in 48 GiB for 8192 bases -- where the per-window table above stops at
+// c = 13 (20 additions, 60 GiB). One thread owns (row i, window w, chunk of bases) and keeps one
+// accumulator; the digits come from a recoding pre-pass (one Montgomery reduction per scalar, not
+// one per (scalar, window)); k_hsum adds the chunks, k_hfinish runs the Horner chain of a row.
+//
+// Recoding: s' = s + K with K = sum_{w < wins-1} 2^(c w + c - 1); the unsigned c-bit digits u_w of
+// s' give the signed digits d_w = u_w - 2^(c-1) in [-2^(c-1), 2^(c-1) - 1] for w < wins - 1, and
+// the top digit (no offset) stays non-negative and below 2^(c-1) + 1 because c * wins >= 254.
+// dg[(t * R) + j], t = w * L + i (window-major: the 32 tasks of a warp are 32 rows of ONE window, so
+// when the scalars are small -- addresses, timestamps, most of a real witness -- the warps of the high
+// windows find only zero digits and retire at once, instead of every warp running its additions with
+// the two or three lanes of the low windows active): magnitude | sign << 31 (0 = nothing to add).
+struct RecodeK {
+  uint32_t k[8];
+};
+__global__ void __launch_bounds__(256)
+k_hrecode(const fq *__restrict__ scalars, size_t L, size_t R, size_t row_stride, Win win, const __grid_constant__ RecodeK K,
+          uint32_t *__restrict__ dg) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L * R) return;
+  size_t i = idx / R, j = idx - i * R;
+  fq s = fq_from_mont(fq_load(scalars + i * row_stride + j));
+  asm("{\n\t"
+      "add.cc.u32  %0, %0, %8;\n\t"
+      "addc.cc.u32 %1, %1, %9;\n\t"
+      "addc.cc.u32 %2, %2, %10;\n\t"
+      "addc.cc.u32 %3, %3, %11;\n\t"
+      "addc.cc.u32 %4, %4, %12;\n\t"
+      "addc.cc.u32 %5, %5, %13;\n\t"
+      "addc.cc.u32 %6, %6, %14;\n\t"
+      "addc.u32    %7, %7, %15;\n\t"
+      "}"
+      : "+r"(s.v[0]), "+r"(s.v[1]), "+r"(s.v[2]), "+r"(s.v[3]), "+r"(s.v[4]), "+r"(s.v[5]), "+r"(s.v[6]), "+r"(s.v[7])
+      : "r"(K.k[0]), "r"(K.k[1]), "r"(K.k[2]), "r"(K.k[3]), "r"(K.k[4]), "r"(K.k[5]), "r"(K.k[6]), "r"(K.k[7]));
+  const uint32_t mask = (1u << win.c) - 1u;
+  uint32_t *out = dg + i * R + j;
+  const size_t wstride = L * R;
+#pragma unroll 1
+  for (int w = 0; w + 1 < win.wins; w++) {
+    int d = (int)(s.v[0] & mask) - (int)win.ent;
+#pragma unroll
+    for (int l = 0; l < 7; l++) s.v[l] = __funnelshift_r(s.v[l], s.v[l + 1], win.c);
+    s.v[7] >>= win.c;
+    out[(size_t)w * wstride] = d < 0 ? ((uint32_t)(-d) | 0x80000000u) : (uint32_t)d;
+  }
+  out[(size_t)(win.wins - 1) * wstride] = s.v[0];  // what is left: below 2^(c-1) + 1
+}
+
+// profiling only: the number of non-zero digits = the point additions k_msm_hrows performs
+__global__ void k_count_nonzero_u32(const uint32_t *__restrict__ dg, size_t n, unsigned long long *__restrict__ count) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int mine = 0;
+  for (; t < n; t += (size_t)gridDim.x * blockDim.x) mine += dg[t] != 0;
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, (unsigned long long)mine);
+}
+
+// partial[t * nchunks + k] = sum over bases j in chunk k of sign * H[j][mag - 1] for task t = (window, row)
+// (MINB = 4: 124 registers, 16 warps per SM; MINB = 3: 135 registers. SPG_MSM_HROWS_MINB=3 selects the latter.)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_msm_hrows(const uint32_t *__restrict__ dg, size_t ntasks, size_t R, const niels8 *__restrict__ htab, uint32_t ent,
+            size_t chunk, size_t nchunks, ge8 *__restrict__ partial) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t k = blockIdx.y;
+  if (t >= ntasks) return;
+  size_t j0 = k * chunk, j1 = j0 + chunk < R ? j0 + chunk : R;  // both multiples of four
+  const uint4 *__restrict__ d4 = reinterpret_cast<const uint4 *>(dg + t * R);
+  ge8 acc = ge8_identity();
+  niels8 cur;
+  bool have = false, cur_neg = false;
+  uint4 nx = j0 < j1 ? __ldg(d4 + j0 / 4) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+  for (size_t j = j0; j < j1; j += 4) {
+    uint4 q = nx;
+    if (j + 4 < j1) nx = __ldg(d4 + j / 4 + 1);
+#pragma unroll 1
+    for (int u = 0; u < 4; u++) {
+      uint32_t dv = q.x;
+      q.x = q.y;
+      q.y = q.z;
+      q.z = q.w;
+      uint32_t mag = dv & 0x7fffffffu;
+      if (mag) {
+        // fetch this entry now, add the previous one while the load is in flight
+        niels8 nxt = niels8_load(htab + (j + u) * (size_t)ent + (mag - 1));
+        if (have) acc = ge8_madd(acc, cur, cur_neg);
+        cur = nxt;
+        cur_neg = (dv >> 31) != 0;
+        have = true;
+      }
+    }
+  }
+  if (have) acc = ge8_madd(acc, cur, cur_neg);
+  partial[t * nchunks + k] = acc;
+}
+
+// S[i * wins + w] = sum over the chunks of task t = w * L + i
+__global__ void __launch_bounds__(128)
+k_hsum(const ge8 *__restrict__ partial, size_t L, size_t wins, size_t nchunks, ge8 *__restrict__ S) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L * wins) return;
+  ge8 acc = partial[t * nchunks];
+#pragma unroll 1
+  for (size_t k = 1; k < nchunks; k++) acc = ge8_add(acc, partial[t * nchunks + k]);
+  size_t w = t / L, i = t - w * L;
+  S[i * wins + w] = acc;
+}
+
 // few rows, many bases (the L / R vectors of a bullet reduction round, Cx of an opening):
 // WIDE_SPLIT threads per base, each adding a quarter of the base's windows (the additions of one
 // scalar are a dependent chain), a block sums its 128 points through shared memory.
@@ -307,6 +422,25 @@ __global__ void k_msm_finish(const ge8 *__restrict__ partial, size_t L, size_t n
   ge8 acc = partial[i * nchunks];
 #pragma unroll 1
   for (size_t k = 1; k < nchunks; k++) acc = ge8_add(acc, partial[i * nchunks + k]);
+  if (blinds) add_blind(acc, blinds[i], table, hslot, win);
+  store_compressed(acc, out + 32 * i);
+}
+
+// out[i] = compress(sum_w 2^(c w) S[i][w] + blind[i] * h): the Horner chain of one row, top window first
+// (c doublings and one addition per window; the blind uses the per-window table of h)
+__global__ void __launch_bounds__(64)
+k_hfinish(const ge8 *__restrict__ S, size_t L, Win hwin, const fq *__restrict__ blinds, const niels8 *__restrict__ table,
+          size_t hslot, Win win, uint8_t *__restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L) return;
+  const ge8 *Si = S + i * (size_t)hwin.wins;
+  ge8 acc = Si[hwin.wins - 1];
+#pragma unroll 1
+  for (int w = hwin.wins - 2; w >= 0; w--) {
+#pragma unroll 1
+    for (int b = 0; b < hwin.c; b++) acc = ge8_double(acc);
+    acc = ge8_add(acc, Si[w]);
+  }
   if (blinds) add_blind(acc, blinds[i], table, hslot, win);
   store_compressed(acc, out + 32 * i);
 }
@@ -437,6 +571,12 @@ struct spg_gens {
   size_t tab_R = 0;
   Win win = make_win(8);
   size_t table_bytes = 0;
+  // many-row commitments: one window per base, H[j][d-1] = d G_j for bases [0, htab_R) (Horner over the windows)
+  niels8 *htab = nullptr;
+  size_t htab_R = 0;
+  Win hwin = make_win(8);
+  size_t htab_bytes = 0;
+  bool htab_failed = false;  // no budget / allocation failed once: do not try again for the same R
 };
 
 namespace {
@@ -445,18 +585,13 @@ size_t table_bytes_for(size_t slots, const Win &w) { return slots * (size_t)w.wi
 
 // Largest window width in [8, 13] whose table fits the budget. Wider windows mean fewer additions
 // per scalar (32 at c = 8, 26 at 10, 24 at 11, 22 at 12, 20 at 13) and a table that doubles with each
-// bit. Budget of one table: SPG_MSM_TABLE_GIB (default 64: 8193 bases at c = 13 take 60 GiB of a B200's
-// 180 GB), and at most 60 % of what is left of the process-wide allowance for tables (60 % of the
-// device's memory) and of the memory free right now.
+// bit. Budget of one per-window table: SPG_MSM_TABLE_GIB (default 20: 8193 bases at c = 11 take 18 GiB;
+// the many-row commitments, where the additions per scalar decide the time, use the single-window
+// table below, and the few-row MSMs this table serves wait on latency, not on their 24 additions),
+// and at most 60 % of what is left of the process-wide allowance for tables (60 % of the device's
+// memory) and of the memory free right now.
 std::atomic<size_t> g_table_bytes{0};
-Win pick_window(size_t slots) {
-  if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
-    int c = atoi(e);
-    if (c >= 5 && c <= 16) return make_win(c);
-  }
-  double gib = 64.0;
-  if (const char *e = getenv("SPG_MSM_TABLE_GIB")) gib = atof(e);
-  size_t budget = (size_t)(gib * 1073741824.0);
+size_t clamp_table_budget(size_t budget) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
     size_t allowance = total_b / 100 * 60, used = g_table_bytes.load();
@@ -464,6 +599,16 @@ Win pick_window(size_t slots) {
     if (budget > left / 10 * 6) budget = left / 10 * 6;
     if (budget > free_b / 10 * 6) budget = free_b / 10 * 6;
   }
+  return budget;
+}
+Win pick_window(size_t slots) {
+  if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
+    int c = atoi(e);
+    if (c >= 5 && c <= 16) return make_win(c);
+  }
+  double gib = 20.0;
+  if (const char *e = getenv("SPG_MSM_TABLE_GIB")) gib = atof(e);
+  size_t budget = clamp_table_budget((size_t)(gib * 1073741824.0));
   Win best = make_win(8);
   for (int c = 9; c <= 13; c++) {
     Win w = make_win(c);
@@ -516,23 +661,183 @@ int ensure_table(spg_gens *g, size_t R) {
   return build_table(g, R);
 }
 
+// ---- the single-window table of the many-row path
+// Width: the largest c in [9, 17] whose table (R * 2^(c-1) entries of 96 bytes: 48 GiB for 8192 bases at
+// c = 17, 15 additions per scalar; 24 GiB at c = 16, 16 additions) fits SPG_MSM_HTABLE_GIB (default 48)
+// and the same allowance rules as above; 0 if none gives fewer additions than the per-window table.
+size_t htab_bytes_for(size_t R, int c) { return R * ((size_t)1 << (c - 1)) * sizeof(niels8); }
+int pick_hwindow(size_t R, int perwindow_wins) {
+  if (const char *e = getenv("SPG_MSM_HWINDOW")) {  // development / tests: force a width
+    int c = atoi(e);
+    if (c >= 5 && c <= 17) return c;
+  }
+  double gib = 48.0;
+  if (const char *e = getenv("SPG_MSM_HTABLE_GIB")) gib = atof(e);
+  size_t budget = clamp_table_budget((size_t)(gib * 1073741824.0));
+  int best = 0, best_wins = perwindow_wins;
+  for (int c = 9; c <= 17; c++) {
+    int wins = make_win(c).wins;
+    if (htab_bytes_for(R, c) <= budget && wins < best_wins) {
+      best = c;
+      best_wins = wins;
+    }
+  }
+  return best;
+}
+
+// Is a commitment of L rows over R bases one for the many-row path? (SPG_MSM_HORNER=0 switches it off,
+// SPG_MSM_HORNER_MIN sets the smallest L * R, default 2^22: below that the table build does not pay.)
+bool horner_wanted(size_t L, size_t R) {
+  static const bool enabled = [] {
+    const char *e = getenv("SPG_MSM_HORNER");
+    return !(e && *e == '0');
+  }();
+  if (!enabled || L < 128 || R < 16 || (R & 3) != 0) return false;
+  size_t min_scalars = (size_t)1 << 22;
+  if (const char *e = getenv("SPG_MSM_HORNER_MIN")) min_scalars = (size_t)strtoull(e, nullptr, 10);
+  return L * R >= min_scalars;
+}
+
+int build_htab(spg_gens *g, size_t R) {
+  spg_ctx *ctx = g->ctx;
+  int c = pick_hwindow(R, g->table ? g->win.wins : 1 << 30);
+  if (c == 0) {
+    g->htab_failed = true;
+    return SPG_OK;  // not an error: the per-window path serves the call
+  }
+  Win hw = make_win(c), one = hw;
+  one.wins = 1;  // table geometry: one window per base
+  niels8 *t = nullptr;
+  ge8 *wb = nullptr;
+  size_t bytes = htab_bytes_for(R, c);
+  if (cudaMalloc(&t, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    g->htab_failed = true;
+    return SPG_OK;
+  }
+  cudaError_t e = cudaMalloc(&wb, R * sizeof(ge8));
+  if (e != cudaSuccess) {
+    cudaFree(t);
+    return cuda_fail(e, "window bases", __FILE__, __LINE__);
+  }
+  int rc = [&]() -> int {
+    SPG_LAUNCH(ctx, k_window_bases, (unsigned)((R + 63) / 64), 64, 0, g->bases, R, one, wb);
+    size_t threads = R * (one.ent / TB);
+    SPG_LAUNCH(ctx, k_build_table, (unsigned)((threads + 63) / 64), 64, 0, wb, R, one, t);
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SPG_OK;
+  }();
+  cudaFree(wb);
+  if (rc != SPG_OK) {
+    cudaFree(t);
+    return rc;
+  }
+  if (g->htab) {
+    cudaFree(g->htab);
+    g_table_bytes -= g->htab_bytes;
+  }
+  g->htab = t;
+  g->htab_R = R;
+  g->hwin = hw;
+  g->htab_bytes = bytes;
+  g->htab_failed = false;
+  g_table_bytes += bytes;
+  return SPG_OK;
+}
+
+int ensure_htab(spg_gens *g, size_t R) {
+  if (g->htab && g->htab_R >= R) return SPG_OK;
+  if (g->htab_failed && !g->htab) return SPG_OK;
+  return build_htab(g, R);
+}
+
+// the many-row path: slabs of rows (the digits of a slab take at most ~1 GiB), see k_msm_hrows
+int run_msm_horner(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
+                   uint8_t *d_out, double nonzero_frac) {
+  spg_ctx *ctx = g->ctx;
+  const Win hw = g->hwin;
+  const size_t wins = (size_t)hw.wins;
+  static const int minb = [] {
+    const char *e = getenv("SPG_MSM_HROWS_MINB");
+    return e && *e == '3' ? 3 : 4;
+  }();
+  // the digits of a slab take at most 4 GiB (a whole 2^26-scalar section at c = 17): every slab ends with a
+  // partly filled last wave, so fewer slabs are better
+  size_t slab_bytes = (size_t)4 << 30;
+  if (const char *e = getenv("SPG_MSM_SLAB_BYTES")) slab_bytes = (size_t)strtoull(e, nullptr, 10);  // tests: several slabs
+  size_t slab = slab_bytes / (wins * R * sizeof(uint32_t));
+  if (slab < 1) slab = 1;
+  if (slab > L) slab = L;
+  // chunks of bases: a block's run time is proportional to its chunk (the tail of the grid is one block
+  // long) and k_hsum adds one partial per chunk and task (9 products against 7 per table entry), so the
+  // chunk is the largest of 256 / 128 / 64 bases that still gives ~16 waves of resident blocks
+  size_t task_blocks = (slab * wins + 127) / 128;
+  size_t want = (size_t)ctx->sm_count * minb * 16;
+  size_t chunk = 256;
+  if (const char *e = getenv("SPG_MSM_HROWS_CHUNK")) chunk = (size_t)strtoull(e, nullptr, 10) & ~(size_t)3;
+  else
+    while (chunk > 64 && task_blocks * ((R + chunk - 1) / chunk) < want) chunk /= 2;
+  if (chunk < 4) chunk = 4;
+  if (chunk > R) chunk = R;  // R is a multiple of four (horner_wanted)
+  size_t nchunks = (R + chunk - 1) / chunk;
+  RecodeK K;
+  memset(&K, 0, sizeof K);
+  for (int w = 0; w + 1 < hw.wins; w++) {
+    int b = hw.c * w + hw.c - 1;
+    K.k[b >> 5] |= 1u << (b & 31);
+  }
+  DevTmp t_dg(ctx), t_part(ctx), t_S(ctx);
+  SPG_CUDA(t_dg.alloc(slab * wins * R * sizeof(uint32_t)));
+  SPG_CUDA(t_part.alloc(slab * wins * nchunks * sizeof(ge8)));
+  SPG_CUDA(t_S.alloc(L * wins * sizeof(ge8)));
+  uint32_t *dg = t_dg.as<uint32_t>();
+  ge8 *partial = t_part.as<ge8>(), *S = t_S.as<ge8>();
+  for (size_t r0 = 0; r0 < L; r0 += slab) {
+    size_t n = L - r0 < slab ? L - r0 : slab;
+    size_t ntasks = n * wins;
+    SPG_LAUNCH(ctx, k_hrecode, (unsigned)((n * R + 255) / 256), 256, 0, scalars + r0 * row_stride, n, R, row_stride, hw, K, dg);
+    dim3 grid((unsigned)((ntasks + 127) / 128), (unsigned)nchunks);
+    double adds = (double)wins * nonzero_frac * (double)n * (double)R;
+    if (ctx->profiling) {  // the work units of the launch: one addition per non-zero digit (small scalars have few)
+      DevTmp t_cnt(ctx);
+      unsigned long long h_cnt = 0;
+      if (t_cnt.alloc(sizeof(h_cnt)) == cudaSuccess) {
+        cudaMemsetAsync(t_cnt.p, 0, sizeof(h_cnt), ctx->stream);
+        k_count_nonzero_u32<<<grid_for(ctx, ntasks * R, 256), 256, 0, ctx->stream>>>(dg, ntasks * R, t_cnt.as<unsigned long long>());
+        cudaMemcpyAsync(&h_cnt, t_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) adds = (double)h_cnt;
+      }
+    }
+    ctx->next_units = adds;
+    if (minb == 4) SPG_LAUNCH(ctx, k_msm_hrows<4>, grid, 128, 0, dg, ntasks, R, g->htab, hw.ent, chunk, nchunks, partial);
+    else SPG_LAUNCH(ctx, k_msm_hrows<3>, grid, 128, 0, dg, ntasks, R, g->htab, hw.ent, chunk, nchunks, partial);
+    SPG_LAUNCH(ctx, k_hsum, (unsigned)((ntasks + 127) / 128), 128, 0, partial, n, wins, nchunks, S + r0 * wins);
+  }
+  SPG_LAUNCH(ctx, k_hfinish, (unsigned)((L + 63) / 64), 64, 0, S, L, hw, d_blinds, g->table, g->tab_R, g->win, d_out);
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}
+
 int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
             uint8_t *d_out) {
   spg_ctx *ctx = g->ctx;
   const Win win = g->win;
   // work units of the launch = point additions: windows per scalar x non-zero scalars (counted
   // only while profiling; otherwise every scalar is assumed non-zero)
-  double adds = (double)win.wins;
+  double nonzero = 1.0;
   if (ctx->profiling && L * R >= 4096) {
     unsigned long long *d_cnt = nullptr, h_cnt = 0;
     if (dev_alloc(ctx, &d_cnt, sizeof(*d_cnt)) == cudaSuccess) {
       cudaMemsetAsync(d_cnt, 0, sizeof(*d_cnt), ctx->stream);
       k_count_nonzero<<<grid_for(ctx, L * R, 256), 256, 0, ctx->stream>>>(scalars, L, R, row_stride, d_cnt);
       cudaMemcpyAsync(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream);
-      if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) adds *= (double)h_cnt / ((double)L * (double)R);
+      if (cudaStreamSynchronize(ctx->stream) == cudaSuccess) nonzero = (double)h_cnt / ((double)L * (double)R);
       dev_free(ctx, d_cnt);
     }
   }
+  if (g->htab && g->htab_R >= R && horner_wanted(L, R))
+    return run_msm_horner(g, scalars, L, R, row_stride, d_blinds, d_out, nonzero);
+  double adds = (double)win.wins * nonzero;
   if (L <= 16 && R >= 256) {
     size_t nblk = (R + WIDE_BASES - 1) / WIDE_BASES;
     ge8 *partial = nullptr;
@@ -572,6 +877,7 @@ int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stri
              uint8_t *host_out) {
   SPG_CHECK(R <= g->n, "commit: %zu scalars per row but only %zu generators", R, g->n);
   SPG_TRY(ensure_table(g, R));
+  if (horner_wanted(L, R)) SPG_TRY(ensure_htab(g, R));
   uint8_t *d_out = nullptr;
   spg_ctx *ctx = g->ctx;
   // a handful of points: the finish kernel writes them straight into the context's mapped result
@@ -769,6 +1075,10 @@ void spg_gens_destroy(spg_gens *g) {
     cudaFree(g->table);
     g_table_bytes -= g->table_bytes;
   }
+  if (g->htab) {
+    cudaFree(g->htab);
+    g_table_bytes -= g->htab_bytes;
+  }
   delete g;
 }
 
@@ -794,6 +1104,24 @@ int spg_gens_prepare(spg_ctx *ctx, spg_gens *gens, size_t R) {
   SPG_CHECK(ctx && gens, "spg_gens_prepare: null argument");
   SPG_CHECK(R >= 1 && R <= gens->n, "spg_gens_prepare: %zu bases requested, %zu generators", R, gens->n);
   return ensure_table(gens, R);
+}
+
+int spg_gens_prepare_rows(spg_ctx *ctx, spg_gens *gens, size_t L, size_t R) {
+  spg::DeviceGuard _dev(spg::ctx_of(ctx));
+  SPG_CHECK(ctx && gens, "spg_gens_prepare_rows: null argument");
+  SPG_CHECK(R >= 1 && R <= gens->n, "spg_gens_prepare_rows: %zu bases requested, %zu generators", R, gens->n);
+  SPG_TRY(ensure_table(gens, R));
+  if (horner_wanted(L, R)) SPG_TRY(ensure_htab(gens, R));
+  return SPG_OK;
+}
+
+int spg_gens_info_rows(const spg_gens *gens, size_t out[4]) {
+  SPG_CHECK(gens && out, "spg_gens_info_rows: null argument");
+  out[0] = gens->htab ? (size_t)gens->hwin.c : 0;
+  out[1] = gens->htab ? (size_t)gens->hwin.wins : 0;
+  out[2] = gens->htab_bytes;
+  out[3] = gens->htab_R;
+  return SPG_OK;
 }
 
 int spg_gens_info(const spg_gens *gens, size_t out[4]) {

@@ -189,9 +189,10 @@ void *sph_sparse_gens_new(spg_ctx *ctx, const char *label, size_t num_vars_x, si
                           size_t batch) {
   try {
     std::unique_ptr<SparseGens> g(new SparseGens(ctx, label, num_vars_x, num_vars_y, max_nz, batch));
-    check(spg_gens_prepare(ctx, g->d_ops, g->ops.n), "spg_gens_prepare");
-    check(spg_gens_prepare(ctx, g->d_mem, g->mem.n), "spg_gens_prepare");
-    check(spg_gens_prepare(ctx, g->d_derefs, g->derefs.n), "spg_gens_prepare");
+    // tables for a commitment of 2^(nv / 2) rows over the 2^(nv - nv / 2) bases (DensePolynomial::commit)
+    check(spg_gens_prepare_rows(ctx, g->d_ops, (size_t)1 << (g->nv_ops / 2), g->ops.n), "spg_gens_prepare_rows");
+    check(spg_gens_prepare_rows(ctx, g->d_mem, (size_t)1 << (g->nv_mem / 2), g->mem.n), "spg_gens_prepare_rows");
+    check(spg_gens_prepare_rows(ctx, g->d_derefs, (size_t)1 << (g->nv_derefs / 2), g->derefs.n), "spg_gens_prepare_rows");
     return g.release();
   } catch (const std::exception &e) {
     g_err = e.what();

@@ -33,6 +33,7 @@ inline std::vector<spg_fq> to_fqv(const std::vector<Scalar> &v) {
 struct SparseGens {
   DotProductProofGens ops, mem, derefs;
   spg_gens *d_ops = nullptr, *d_mem = nullptr, *d_derefs = nullptr;
+  size_t nv_ops = 0, nv_mem = 0, nv_derefs = 0;  // variables of the polynomials committed under each
   SparseGens(spg_ctx *ctx, const std::string &label, size_t nvx, size_t nvy, size_t num_nz, size_t batch) {
     auto pcg = [&](size_t nv, spg_gens **d) {
       size_t n = (size_t)1 << (nv - nv / 2);
@@ -44,9 +45,12 @@ struct SparseGens {
       return g;
     };
     size_t lg = log2z(next_pow2(num_nz));
-    ops = pcg(lg + log2z(next_pow2(batch * 5)), &d_ops);
-    mem = pcg((nvx > nvy ? nvx : nvy) + 1, &d_mem);
-    derefs = pcg(lg + log2z(next_pow2(batch * 2)), &d_derefs);
+    nv_ops = lg + log2z(next_pow2(batch * 5));
+    nv_mem = (nvx > nvy ? nvx : nvy) + 1;
+    nv_derefs = lg + log2z(next_pow2(batch * 2));
+    ops = pcg(nv_ops, &d_ops);
+    mem = pcg(nv_mem, &d_mem);
+    derefs = pcg(nv_derefs, &d_derefs);
     ops.gens_1.precompute();
     mem.gens_1.precompute();
     derefs.gens_1.precompute();

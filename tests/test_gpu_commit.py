@@ -145,6 +145,56 @@ def test_window_widths(ctx, c, monkeypatch):
     dg.free()
 
 
+@pytest.mark.parametrize("c,slab", [(9, None), (13, 50), (16, None), (17, 1)])
+def test_many_rows_single_window_table(ctx, gens16, c, slab, monkeypatch):
+    """the many-row path (one window table per base, Horner over the windows; csrc/msm.cu k_msm_hrows)
+    forced at a size the python oracle reaches: 128 rows x 16 bases, every table width, one and several
+    slabs, edge scalars (0, 1, q-1, 2^252, digits at +-half in every window), blinds; bytes against the
+    oracle on chosen rows and against the per-window path on all rows"""
+    import spartan_parallel_b200 as sp
+
+    q = (1 << 252) + 27742317777372353535851937790883648493
+    L, R = 128, 16
+    half = 1 << (c - 1)
+    nw = -(-254 // c)
+    pats = [0, 1, q - 1, 1 << 252, (1 << 253) % q, half, half - 1, half + 1, (1 << c) - 1, 1 << c,
+            sum(half << (c * w) for w in range(nw - 1)) % q,          # every digit becomes -half ... with carries
+            sum((half - 1) << (c * w) for w in range(nw - 1)) % q,    # every digit just below the sign change
+            sum(((1 << c) - 1) << (c * w) for w in range(nw - 1)) % q, q - 2, q // 2, (q + 1) // 2]
+    s = rand_scalars(L * R, 70 + c).reshape(L, R, 4)
+    s[0] = np.stack([O.from_int(v) for v in pats])
+    s[1] = 0                                                          # identity
+    s[2] = 0
+    s[2, 15] = O.ONE
+    s[3, ::2] = 0
+    blinds = rand_scalars(L, 71 + c)
+    blinds[0] = O.from_int(q - 1)
+    blinds[5] = 0
+    monkeypatch.setenv("SPG_MSM_HORNER_MIN", str(1 << 60))            # per-window path
+    dg0 = sp.MultiCommitGens(ctx, gens16.compressed())
+    want_all = dg0.commit_batch(s, blinds)
+    assert dg0.info()["rows_table"]["table_bytes"] == 0
+    dg0.free()
+    monkeypatch.setenv("SPG_MSM_HORNER_MIN", "1")
+    monkeypatch.setenv("SPG_MSM_HWINDOW", str(c))
+    if slab is not None:
+        monkeypatch.setenv("SPG_MSM_SLAB_BYTES", str(slab * nw * R * 4))
+    dg = sp.MultiCommitGens(ctx, gens16.compressed())
+    got = dg.commit_batch(s, blinds)
+    info = dg.info()["rows_table"]
+    assert info["window_bits"] == c and info["adds_per_scalar"] == nw and info["table_bases"] == R
+    assert got == want_all
+    for i in [0, 1, 2, 3, 5, 64, 127]:
+        want = G.commit_vec([O.to_int(x) for x in s[i]], O.to_int(blinds[i]), gens16).compress()
+        assert got[i] == want, (c, i)
+    # the same rows without blinds through DensePolynomial::commit
+    poly = sp.DensePolynomial.new(ctx, s.reshape(L * R, 4))
+    rows = dg.commit_poly(poly, L)
+    assert rows[1] == bytes(32)
+    assert rows[64] == G.commit_vec([O.to_int(x) for x in s[64]], 0, gens16).compress()
+    dg.free()
+
+
 def test_commit_rows_slices(ctx, gens16):
     """spg_poly_commit_rows: any slice of rows equals the same rows of the full commitment
     (the multi-GPU sharding of a commitment relies on it)"""
@@ -185,6 +235,7 @@ def test_witness_commit_at_config_size(ctx, monkeypatch):
     poly = sp.DensePolynomial.new(ctx, Z)
     rows = dg.commit_poly(poly, Lr)
     assert dg.info()["table_bases"] >= R
+    assert dg.info()["rows_table"]["table_bases"] >= R  # 8192 rows: the single-window table + Horner path
     # (a) oracle on the sparse rows: the same generators derived by the oracle's own hash-to-group
     og = {c: G.from_uniform_bytes(uniform[64 * c: 64 * (c + 1)]) for c in cols + [R]}
     for r in sparse_rows:
