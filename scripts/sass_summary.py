@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "spartan_parallel_b200", "libspgpu.so")
-HOT = ["k_rows_rolled", "k_rows_spmv<2, true>", "k_z_bind_rq", "k_msm_rows", "k_msm_wide", "k_quad_bind_eval<1>", "k_cubic_eval_rlc"]
+HOT = ["k_rows_rolled", "k_rows_spmv<2, true>", "k_z_bind_rq", "k_msm_hrows<4>", "k_msm_rows", "k_msm_wide", "k_quad_bind_eval<1>", "k_cubic_eval_rlc"]
 
 
 def main():

@@ -85,6 +85,78 @@ __global__ void k_eq_expand_small(const fq *__restrict__ r, int ell, fq *__restr
   for (size_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = buf[cur][i];
 }
 
+// K doubling steps in one launch: a thread takes entry i of the input level and produces its 2^K
+// descendants in registers (field arithmetic is exact, so the values are those of K separate steps).
+// ALL = false writes only the last level to out[i 2^K + t]; ALL = true also the levels in between, each at
+// the place the suffix tables of the sumcheck keep it (level m at buf + 2^m, sc1.cu): out = buf, the
+// input level is m0. One launch per level above the first 2^9 entries cost ~8 us of mostly launch overhead
+// for a few microseconds of work, eleven times per table and two tables per proof.
+struct EqSteps {
+  fq r[3];
+};
+template <int K, bool ALL>
+__global__ void __launch_bounds__(256)
+k_eq_expand_multi(const fq *__restrict__ prev, size_t n, fq *__restrict__ out, unsigned int m0, const __grid_constant__ EqSteps rs) {
+  static_assert(K >= 1 && K <= 3, "k_eq_expand_multi: 1..3 steps");
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // one array per level (statically indexed: they stay in registers)
+    fq l1[2], l2[4], l3[8];
+    {
+      fq s = fq_load(prev + i);
+      fq hi = fq_mul(s, rs.r[0]);
+      l1[0] = fq_sub(s, hi);
+      l1[1] = hi;
+    }
+    if (K == 1 || ALL) {
+      fq *lv = ALL ? out + ((size_t)1 << (m0 + 1)) + (i << 1) : out + (i << 1);
+#pragma unroll
+      for (int t = 0; t < 2; t++) fq_store(lv + t, l1[t]);
+    }
+    if (K >= 2) {
+#pragma unroll
+      for (int t = 0; t < 2; t++) {
+        fq hi = fq_mul(l1[t], rs.r[1]);
+        l2[2 * t] = fq_sub(l1[t], hi);
+        l2[2 * t + 1] = hi;
+      }
+      if (K == 2 || ALL) {
+        fq *lv = ALL ? out + ((size_t)1 << (m0 + 2)) + (i << 2) : out + (i << 2);
+#pragma unroll
+        for (int t = 0; t < 4; t++) fq_store(lv + t, l2[t]);
+      }
+    }
+    if (K >= 3) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        fq hi = fq_mul(l2[t], rs.r[2]);
+        l3[2 * t] = fq_sub(l2[t], hi);
+        l3[2 * t + 1] = hi;
+      }
+      fq *lv = ALL ? out + ((size_t)1 << (m0 + 3)) + (i << 3) : out + (i << 3);
+#pragma unroll
+      for (int t = 0; t < 8; t++) fq_store(lv + t, l3[t]);
+    }
+  }
+}
+
+// `steps` (1..3) doubling steps from the n-entry level at prev; see k_eq_expand_multi
+int eq_expand_steps(spg_ctx *ctx, const fq *prev, size_t n, fq *out, unsigned int m0, const spg_fq *r, int steps, bool all) {
+  EqSteps rs;
+  memset(&rs, 0, sizeof rs);
+  for (int k = 0; k < steps; k++) memcpy(&rs.r[k], &r[k], sizeof(fq));
+  int grid = grid_for(ctx, n, 256);
+  if (all) {
+    if (steps == 3) SPG_LAUNCH(ctx, (k_eq_expand_multi<3, true>), grid, 256, 0, prev, n, out, m0, rs);
+    else if (steps == 2) SPG_LAUNCH(ctx, (k_eq_expand_multi<2, true>), grid, 256, 0, prev, n, out, m0, rs);
+    else SPG_LAUNCH(ctx, (k_eq_expand_multi<1, true>), grid, 256, 0, prev, n, out, m0, rs);
+  } else {
+    if (steps == 3) SPG_LAUNCH(ctx, (k_eq_expand_multi<3, false>), grid, 256, 0, prev, n, out, m0, rs);
+    else if (steps == 2) SPG_LAUNCH(ctx, (k_eq_expand_multi<2, false>), grid, 256, 0, prev, n, out, m0, rs);
+    else SPG_LAUNCH(ctx, (k_eq_expand_multi<1, false>), grid, 256, 0, prev, n, out, m0, rs);
+  }
+  return SPG_OK;
+}
+
 constexpr int EQ_SMALL_LV = 9;
 
 // evals of eq(r, .) with MSB <-> r[0]; r on device (ell scalars). out has 2^ell entries.
@@ -95,17 +167,17 @@ int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, 
     SPG_LAUNCH(ctx, k_eq_expand_small<EQ_SMALL_LV>, 1, 256, 0, d_r, small, out);
     return SPG_OK;
   }
-  // ping-pong so that the last level lands in `out`
+  // ping-pong, three levels per launch, so that the last level lands in `out`
   size_t remaining = ell - small;
+  size_t launches = (remaining + 2) / 3;
   fq *bufs[2] = {out, scratch};
-  int which = (remaining % 2 == 0) ? 0 : 1;
+  int which = (launches % 2 == 0) ? 0 : 1;
   SPG_LAUNCH(ctx, k_eq_expand_small<EQ_SMALL_LV>, 1, 256, 0, d_r, small, bufs[which]);
-  for (size_t j = small; j < ell; j++) {
-    size_t n = (size_t)1 << j;
-    fq rj;
-    memcpy(&rj, &h_r[j], sizeof(fq));
-    SPG_LAUNCH(ctx, k_eq_expand, grid_for(ctx, n, 256), 256, 0, bufs[which], bufs[which ^ 1], n, rj);
+  for (size_t j = small; j < ell;) {
+    int steps = (int)(ell - j < 3 ? ell - j : 3);
+    SPG_TRY(eq_expand_steps(ctx, bufs[which], (size_t)1 << j, bufs[which ^ 1], 0, h_r + j, steps, false));
     which ^= 1;
+    j += steps;
   }
   return SPG_OK;
 }

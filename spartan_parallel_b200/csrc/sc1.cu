@@ -15,6 +15,7 @@ namespace spg {
 
 int eq_evals_device(spg_ctx *ctx, const fq *d_r, const spg_fq *h_r, size_t ell, fq *out, fq *scratch);
 __global__ void k_eq_expand(const fq *__restrict__ prev, fq *__restrict__ out, size_t n, fq r);
+int eq_expand_steps(spg_ctx *ctx, const fq *prev, size_t n, fq *out, unsigned int m0, const spg_fq *r, int steps, bool all);
 
 // 128-thread blocks capped at 128 registers: four blocks (16 warps) per SM. Measured on
 // B200 for the 2^20 x 64 batch: 256 threads x 1 block 11.5 ms, 128 x 3 (160 regs) 10.16 ms,
@@ -478,11 +479,13 @@ int build_suffix_tables(spg_ctx *ctx, const std::vector<hfq> &tau, size_t max_le
   int small = (int)(max_level < (size_t)SUFFIX_SMALL ? max_level : SUFFIX_SMALL);
   for (int m = 1; m <= small; m++) memcpy(&st.t[m - 1], &tau[n - m], sizeof(fq));
   SPG_LAUNCH(ctx, k_suffix_small, 1, 256, 0, buf, st, small);
-  for (size_t m = small + 1; m <= max_level; m++) {
-    fq r;
-    memcpy(&r, &tau[n - m], sizeof r);
-    size_t cnt = (size_t)1 << (m - 1);
-    SPG_LAUNCH(ctx, k_eq_expand, grid_for(ctx, cnt, 256), 256, 0, buf + cnt, buf + 2 * cnt, cnt, r);
+  // the larger levels three per launch (k_eq_expand_multi, field_ops.cu): level m0 -> m0 + 1 .. m0 + steps
+  for (size_t m0 = small; m0 < max_level;) {
+    int steps = (int)(max_level - m0 < 3 ? max_level - m0 : 3);
+    spg_fq r[3];
+    for (int k = 0; k < steps; k++) memcpy(&r[k], &tau[n - (m0 + 1 + k)], sizeof(spg_fq));
+    SPG_TRY(eq_expand_steps(ctx, buf + ((size_t)1 << m0), (size_t)1 << m0, buf, (unsigned int)m0, r, steps, true));
+    m0 += steps;
   }
   return SPG_OK;
 }

@@ -192,6 +192,8 @@ def test_many_rows_single_window_table(ctx, gens16, c, slab, monkeypatch):
     rows = dg.commit_poly(poly, L)
     assert rows[1] == bytes(32)
     assert rows[64] == G.commit_vec([O.to_int(x) for x in s[64]], 0, gens16).compress()
+    # a slice of rows (one rank's share of a sharded commitment) through the same path
+    assert dg.commit_poly_rows(poly, L, 0, L) == b"".join(rows)
     dg.free()
 
 
