@@ -499,6 +499,14 @@ def run_gpu(args):
         except Exception as e:
             witness_gen = {"error": str(e)[:200]}
 
+    # ---- the general row path of the fused SpMV + first round: 3 non-unit entries per row and matrix
+    general_rows = None
+    if world == 1 and not args.no_general_rows:
+        try:
+            general_rows = general_rows_leg(sp, ctx, args.log_x, min(args.proofs, 16), args.steps, args.warmup)
+        except Exception as e:
+            general_rows = {"error": str(e)[:200]}
+
     # ---- N > 1 in strong mode: the weak figure (proofs per GPU fixed) as an extra
     weak = None
     if world > 1 and scaling == "strong" and not args.no_weak:
@@ -607,7 +615,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * main.N * 32 * world), "d2h_bytes_per_step": int(96 * (2 * nx + main.nq + ng + 1) + 7 * 32)},
         "gpu_launches": res["launches"], "full_proof": full_proof, "wall_ms_per_step": res["wall_ms"],
-        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse, "witness_gen": witness_gen,
+        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse, "witness_gen": witness_gen, "general_rows": general_rows,
         "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
         "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s, "host_affinity": numa,
     }
@@ -706,6 +714,107 @@ def sharded_equals_unsharded(sp, parallel, ctx, comm, rank, world, log_x, Q):
           and np.array_equal(gotc2, wantc2) and ok_y)
     return {"ok": bool(ok), "config": f"C3: X=2^{log_x} x Q={Q} sharded over {world} ranks vs unsharded on each rank's GPU",
             "compared": f"{len(want1)} + {len(want2)} round polynomials, 4 + 3 final claims, bit for bit"}
+
+
+def general_rows_leg(sp, ctx, log_x, Q, steps, warmup):
+    """The table pass on an instance whose rows have THREE entries per matrix with non-unit coefficients
+    (the synthetic north-star instance has one unit entry per row, which the fused SpMV + first round
+    serves from its fast path; real block circuits do not). Constraint x:
+      (a1 u_x + a2 u_{x+1} + a3 u_{x+2}) * (b1 u_{x+3} + b2 u_{x+4} + b3 u_{x+5}) = v_x + c2 u_x + c3 u_{x+7}
+    with v solved for on the device. Timed like the main leg and against the unit instance at the same size."""
+    X, nx, nq = 1 << log_x, log_x, log2(Q)
+    N = X * Q
+    rng = np.random.default_rng(0x6E7A1)
+    coef = random_canonical(rng, 8)  # a1 a2 a3 b1 b2 b3 c2 c3
+    rows = np.arange(X, dtype=np.uint32)
+
+    def mat(entries):
+        r = np.concatenate([rows for _ in entries])
+        c = np.concatenate([((rows + sh) % X + base).astype(np.uint32) for sh, base, _ in entries])
+        v = np.concatenate([np.tile(val, (X, 1)) for _, _, val in entries])
+        return r, c, v
+
+    A = mat([(0, 0, coef[0]), (1, 0, coef[1]), (2, 0, coef[2])])
+    B = mat([(3, 0, coef[3]), (4, 0, coef[4]), (5, 0, coef[5])])
+    Cm = mat([(0, X, ONE), (0, 0, coef[6]), (7, 0, coef[7])])
+    inst3 = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A], [B], [Cm])
+    A1, B1, C1 = synthetic_matrices(X, ONE)
+    inst1 = sp.R1CSInstance(ctx, 1, X, [X], 2 * X, [A1], [B1], [C1])
+    u = random_canonical(rng, N)
+    du = sp.DensePolynomial.new(ctx, u)
+
+    def shifted(sh):
+        return sp.DensePolynomial.new(ctx, np.ascontiguousarray(np.roll(u.reshape(Q, X, 4), -sh, axis=1).reshape(N, 4)))
+
+    def lin(terms):  # sum of coefficient * shifted u, on the device
+        acc = None
+        for sh, c in terms:
+            t = sp.vec_op(ctx, "mul", shifted(sh), sp.DensePolynomial.new(ctx, np.tile(c, (N, 1))))
+            acc = t if acc is None else sp.vec_op(ctx, "add", acc, t)
+        return acc
+
+    az = lin([(0, coef[0]), (1, coef[1]), (2, coef[2])])
+    bz = lin([(3, coef[3]), (4, coef[4]), (5, coef[5])])
+    v3 = sp.vec_op(ctx, "sub", sp.vec_op(ctx, "mul", az, bz), lin([(0, coef[6]), (7, coef[7])])).to_host()
+    v1 = sp.vec_op(ctx, "mul", du, shifted(1)).to_host()
+    del az, bz, du
+    crng = np.random.default_rng(0xC4A11E46E)
+    tau_q, tau_x = challenges(crng, nq), challenges(crng, nx)
+    ch1, ch2, r_abc = challenges(crng, nx + nq), challenges(crng, 1 + nx), challenges(crng, 3)
+
+    def run(inst, v, checked):
+        secs = [sp.ProverWitnessSecInfo(ctx, [Q], [X], u), sp.ProverWitnessSecInfo(ctx, [Q], [X], v)]
+
+        def one_pass(check=False):
+            z = sp.ZMat(ctx, [Q], [X], secs)
+            sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
+            if check:
+                sc1.set_claim_checked(ZERO)  # round 0 recomputes the sum: an unsatisfied witness is an error
+            else:
+                sc1.set_claim(ZERO)
+            sc1.run_rounds(ch1)
+            c1 = sc1.final()
+            sc1.free()
+            sc2 = sp.SumcheckPhase2(ctx, inst, z, [Q], Q, [X], X, 2, ch1[:nx][::-1].copy(), ch1[nx:], ch1[:0], *r_abc)
+            sc2.run_rounds(ch2)
+            c2 = sc2.final()
+            sc2.free()
+            z.free()
+            return c1, c2
+
+        first = one_pass(checked)
+        for _ in range(max(warmup - 1, 1)):
+            again = one_pass()
+        assert all(np.array_equal(a, b) for a, b in zip(first, again)), "checked and unchecked passes differ"
+        ctx.profile_begin()
+        ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one_pass()
+        ctx.sync()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        prof = ctx.profile_end()
+        for s_ in secs:
+            s_.free()
+        spmv = [r for r in prof if "spmv" in r["kernel"]]
+        return ms, (sum(r["total_ms"] for r in spmv) / steps if spmv else None), [r["kernel"] for r in spmv]
+
+    ms3, spmv3, names3 = run(inst3, v3, True)
+    ms1, spmv1, _ = run(inst1, v1, True)
+    # products of the fused SpMV + first round: one per non-unit entry and proof, plus 4 per pair of rows
+    modmul = Q * X * 8 + 4 * (N // 2)
+    int_peak = None
+    try:
+        int_peak = json.load(open(os.path.join(ROOT, "profiles", "r1_imad_peak.json")))["modmul_lazy_ilp2_t256_per_s"]
+    except Exception:
+        pass
+    return {"ms_per_pass": ms3, "constraints_per_s": N / (ms3 * 1e-3), "spmv_first_round_ms": spmv3, "kernels": names3,
+            "spmv_first_round_modmul_per_s": modmul / (spmv3 * 1e-3) if spmv3 else None,
+            "spmv_first_round_int_frac": (modmul / (spmv3 * 1e-3) / int_peak) if spmv3 and int_peak else None,
+            "unit_instance_ms_per_pass": ms1, "unit_instance_spmv_first_round_ms": spmv1, "ratio": ms3 / ms1,
+            "workload": f"X=2^{log_x} x Q={Q}, 3 entries per row and matrix, random coefficients (8 of 9 non-unit), witness satisfying; "
+                        "the first pass verifies the claim against the tables (spg_sc1_set_claim_checked)",
+            "what": "table pass (z_mat, SpMV + round 0, phase-1 rounds, ABC / Z tables, phase-2 rounds), wall clock, witness resident"}
 
 
 def witness_gen_leg(sp, ctx, log_rows=18, n=16, phy=4, vir=2):
@@ -942,6 +1051,7 @@ def main():
     ap.add_argument("--no-sparse", dest="with_sparse", action="store_false", help="skip the sparse-polynomial evaluation proof leg")
     ap.add_argument("--sparse-log-nnz", type=int, default=20)
     ap.add_argument("--no-witness-gen", action="store_true", help="skip the derived-witness-section leg")
+    ap.add_argument("--no-general-rows", action="store_true", help="skip the leg with 3 non-unit entries per row and matrix")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded == unsharded check (C3)")
     ap.add_argument("--replicated-phase2", action="store_true", help="N > 1: run phase 2 replicated on every rank instead of sharded over y")
     ap.add_argument("--no-weak", action="store_true", help="N > 1, strong mode: skip the extra weak-scaling figure")
