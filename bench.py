@@ -381,14 +381,19 @@ def run_gpu(args):
         e2e_ms, last = main.measure_e2e(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     assert np.array_equal(res["first"][0], last[0]) and np.array_equal(res["first"][1], last[1])
-    if args.trace_phases:  # wall clock per phase of one more pass, every rank, to stderr (syncs between phases)
+    phase_trace = None
+    if args.trace_phases or world > 1:
+        # wall clock per phase of one more pass (a device sync between the phases, so the sum is a little above
+        # ms_per_step): at N > 1 it goes into the line as `phase_trace_ms` -- what limits the strong scaling
         secs = main.upload()
         barrier()
         del trace[:]
         tracing[0] = True
         main.one_pass(secs)
         tracing[0] = False
-        print(f"[rank {rank}] " + ", ".join(f"{n}: {(t - trace[i][1]) * 1e3:.2f} ms" for i, (n, t) in enumerate(trace[1:])), file=sys.stderr, flush=True)
+        phase_trace = {n: round((t - trace[i][1]) * 1e3, 3) for i, (n, t) in enumerate(trace[1:])}
+        if args.trace_phases:
+            print(f"[rank {rank}] " + ", ".join(f"{n}: {v:.2f} ms" for n, v in phase_trace.items()), file=sys.stderr, flush=True)
         for s_ in secs:
             s_.free()
 
@@ -615,7 +620,7 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * main.N * 32 * world), "d2h_bytes_per_step": int(96 * (2 * nx + main.nq + ng + 1) + 7 * 32)},
         "gpu_launches": res["launches"], "full_proof": full_proof, "wall_ms_per_step": res["wall_ms"],
-        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse, "witness_gen": witness_gen, "general_rows": general_rows,
+        "prove_time_s": prove_time_s, "prove_time": prove_time, "polycommit": commit, "sparse_proof": sparse, "witness_gen": witness_gen, "general_rows": general_rows, "phase_trace_ms": phase_trace,
         "clocks": clocks, "roofline": roofline, "roofline_by_kernel": by_kernel, "cpu_baseline": cpu,
         "kernels": sorted(prof, key=lambda r: -r["total_ms"])[:8], "setup_s": setup_s, "host_affinity": numa,
     }
@@ -624,6 +629,13 @@ def run_gpu(args):
         line["parity_check"] = parity
     if weak is not None:
         line["weak"] = weak
+    if world > 1 and phase_trace:
+        fixed = sum(v for n, v in phase_trace.items() if "rounds" not in n)
+        line["scaling_limiter"] = (
+            f"per-round latency: a pass is {2 * nx + main.nq + ng + 1} sequential rounds, each a kernel + 96 bytes to the host + a "
+            f"{world}-rank exchange before the next challenge (~20 us on the late rounds whose tables are a few thousand scalars), plus "
+            f"{fixed:.2f} ms per pass outside the round loops (prover set-up, Z bind + peer reduce-scatter with two host barriers); "
+            "see phase_trace_ms and DESIGN.md section 5")
     emit(line)
 
 
