@@ -621,5 +621,15 @@ extern "C" {
     ) -> c_int;
     pub fn spg_bullet_fold(b: *mut spg_bullet, nk: usize, u: *const spg_fq, u_inv: *const spg_fq) -> c_int;
     pub fn spg_bullet_final(b: *mut spg_bullet, out_G: *mut u8) -> c_int;
+    pub fn spg_bullet_set_ab(b: *mut spg_bullet, a: *const spg_fq, bvec: *const spg_fq) -> c_int;
+    pub fn spg_bullet_lr_resident(
+        b: *mut spg_bullet,
+        nk: usize,
+        blinds: *const spg_fq,
+        ext: c_int,
+        out_LR: *mut u8,
+        out_c: *mut spg_fq,
+    ) -> c_int;
+    pub fn spg_bullet_final_ab(b: *mut spg_bullet, out_G: *mut u8, out_ab: *mut spg_fq) -> c_int;
     pub fn spg_bullet_destroy(b: *mut spg_bullet);
 }

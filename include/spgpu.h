@@ -477,6 +477,17 @@ int spg_bullet_create(spg_ctx *ctx, const spg_gens *gens, size_t n, spg_bullet *
 int spg_bullet_lr(spg_bullet *b, size_t nk, const spg_fq *a, const spg_fq blinds[2], uint8_t out_LR[64]);
 int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_inv);
 int spg_bullet_final(spg_bullet *b, uint8_t out_G[32]);
+/* The same rounds with a and b resident on the device (the O(nk) host loops of bullet.rs:83-84 and
+ * :113-116 move with them): spg_bullet_set_ab uploads both vectors (n scalars each) once;
+ * spg_bullet_lr_resident returns the round's L and R as above plus c_L = <a_L, b_R>, c_R = <a_R, b_L>;
+ * spg_bullet_fold then folds s, a and b; spg_bullet_final_ab returns G_hat and the folded a[0], b[0].
+ * ext = 0: out_LR = two ristretto encodings (64 bytes). ext = 1: the two points in extended coordinates,
+ * X, Y, Z, T as canonical little-endian field elements (2 x 128 bytes): the caller adds c Q and encodes
+ * the sum anyway, so the encoding here (an inversion and a square root on one thread) and the decoding
+ * there are skipped. */
+int spg_bullet_set_ab(spg_bullet *b, const spg_fq *a, const spg_fq *bvec);
+int spg_bullet_lr_resident(spg_bullet *b, size_t nk, const spg_fq blinds[2], int ext, uint8_t *out_LR, spg_fq out_c[2]);
+int spg_bullet_final_ab(spg_bullet *b, uint8_t out_G[32], spg_fq out_ab[2]);
 void spg_bullet_destroy(spg_bullet *b);
 
 #ifdef __cplusplus

@@ -123,6 +123,9 @@ def _proto(L):
         "spg_bullet_lr": [P, SZ, P, P, P],
         "spg_bullet_fold": [P, SZ, P, P],
         "spg_bullet_final": [P, P],
+        "spg_bullet_set_ab": [P, P, P],
+        "spg_bullet_lr_resident": [P, SZ, P, INT, P, P],
+        "spg_bullet_final_ab": [P, P, P],
         "spg_gens_upload": [P, P, SZ, PP],
         "spg_gens_from_uniform": [P, P, SZ, PP],
         "spg_poly_commit": [P, P, P, SZ, P],

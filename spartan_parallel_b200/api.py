@@ -785,6 +785,29 @@ class BulletReduction:
         check(self.ctx.L.spg_bullet_final(self.h, _ptr(out)), "spg_bullet_final")
         return out.tobytes()
 
+    # a and b resident on the device: the host loops over them (bullet.rs:83-84, 113-116) move along
+    def set_ab(self, a, b):
+        a, b = _fq(a), _fq(b)
+        assert a.shape[0] == self.n and b.shape[0] == self.n
+        check(self.ctx.L.spg_bullet_set_ab(self.h, _ptr(a), _ptr(b)), "spg_bullet_set_ab")
+
+    def lr_resident(self, nk: int, blind_L, blind_R, ext: bool = False):
+        """(L, R, c_L, c_R) of the round over the device's a and b; L and R as ristretto encodings, or with
+        ``ext`` as 128 bytes of extended coordinates X, Y, Z, T each"""
+        bl = np.stack([_fq(blind_L).reshape(4), _fq(blind_R).reshape(4)])
+        per = 128 if ext else 32
+        out = np.empty(2 * per, dtype=np.uint8)
+        c = np.empty((2, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_bullet_lr_resident(self.h, nk, _ptr(bl), int(ext), _ptr(out), _ptr(c)), "spg_bullet_lr_resident")
+        return out[:per].tobytes(), out[per:].tobytes(), c[0], c[1]
+
+    def final_ab(self):
+        """(G_hat, a[0], b[0]) after the last fold"""
+        out = np.empty(32, dtype=np.uint8)
+        ab = np.empty((2, 4), dtype=np.uint64)
+        check(self.ctx.L.spg_bullet_final_ab(self.h, _ptr(out), _ptr(ab)), "spg_bullet_final_ab")
+        return out.tobytes(), ab[0], ab[1]
+
     def free(self):
         if getattr(self, "h", None) is not None and self.h.value:
             self.ctx.L.spg_bullet_destroy(self.h)

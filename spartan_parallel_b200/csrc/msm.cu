@@ -413,17 +413,33 @@ __device__ __forceinline__ void store_compressed(const ge8 &acc, uint8_t *__rest
   for (int k = 0; k < 32; k++) out[k] = enc[k];
 }
 
+// the point itself instead of its encoding: X, Y, Z, T as four canonical 32-byte field elements. A caller
+// that goes on adding to the point (a bullet round adds c Q on the host) skips the inversion + square root
+// inside the ristretto encoding here (one thread, ~0.1 ms) and the decoding on its side.
+__device__ __forceinline__ void store_ext(const ge8 &acc, uint8_t *__restrict__ out) {
+  const fe8 *c[4] = {&acc.X, &acc.Y, &acc.Z, &acc.T};
+  for (int k = 0; k < 4; k++) {
+    uint8_t enc[32];
+    fe_tobytes(fe8_to_fe(*c[k]), enc);
+    for (int j = 0; j < 32; j++) out[32 * k + j] = enc[j];
+  }
+}
+__device__ __forceinline__ void store_point(const ge8 &acc, uint8_t *__restrict__ out, size_t i, int ext) {
+  if (ext) store_ext(acc, out + 128 * i);
+  else store_compressed(acc, out + 32 * i);
+}
+
 // out[i] = compress(sum_k partial[i][k] + blind[i] * h)
 __global__ void k_msm_finish(const ge8 *__restrict__ partial, size_t L, size_t nchunks,
                              const fq *__restrict__ blinds, const niels8 *__restrict__ table, size_t hslot, Win win,
-                             uint8_t *__restrict__ out) {
+                             uint8_t *__restrict__ out, int ext) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L) return;
   ge8 acc = partial[i * nchunks];
 #pragma unroll 1
   for (size_t k = 1; k < nchunks; k++) acc = ge8_add(acc, partial[i * nchunks + k]);
   if (blinds) add_blind(acc, blinds[i], table, hslot, win);
-  store_compressed(acc, out + 32 * i);
+  store_point(acc, out, i, ext);
 }
 
 // out[i] = compress(sum_w 2^(c w) S[i][w] + blind[i] * h): the Horner chain of one row, top window first
@@ -451,7 +467,7 @@ k_hfinish(const ge8 *__restrict__ S, size_t L, Win hwin, const fq *__restrict__ 
 // k_msm_finish would do, which is what a round of the opening proof waits for.
 __global__ void __launch_bounds__(128)
 k_msm_finish_tree(const ge8 *__restrict__ partial, size_t nblk, const fq *__restrict__ blinds,
-                  const niels8 *__restrict__ table, size_t hslot, Win win, uint8_t *__restrict__ out) {
+                  const niels8 *__restrict__ table, size_t hslot, Win win, uint8_t *__restrict__ out, int ext) {
   __shared__ ge8 sm[64];
   const size_t i = blockIdx.x;
   ge8 acc = ge8_identity();
@@ -470,7 +486,7 @@ k_msm_finish_tree(const ge8 *__restrict__ partial, size_t nblk, const fq *__rest
     if ((int)threadIdx.x < half) acc = ge8_add(acc, sm[threadIdx.x]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) store_compressed(acc, out + 32 * i);
+  if (threadIdx.x == 0) store_point(acc, out, i, ext);
 }
 
 // profiling only: the number of non-zero scalars (zero scalars cost no additions)
@@ -819,7 +835,7 @@ int run_msm_horner(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t ro
 }
 
 int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
-            uint8_t *d_out) {
+            uint8_t *d_out, int ext) {
   spg_ctx *ctx = g->ctx;
   const Win win = g->win;
   // work units of the launch = point additions: windows per scalar x non-zero scalars (counted
@@ -835,7 +851,7 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
       dev_free(ctx, d_cnt);
     }
   }
-  if (g->htab && g->htab_R >= R && horner_wanted(L, R))
+  if (!ext && g->htab && g->htab_R >= R && horner_wanted(L, R))
     return run_msm_horner(g, scalars, L, R, row_stride, d_blinds, d_out, nonzero);
   double adds = (double)win.wins * nonzero;
   if (L <= 16 && R >= 256) {
@@ -847,7 +863,7 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
     int rc = [&]() -> int {
       SPG_LAUNCH(ctx, k_msm_wide, grid, 128, 0, scalars, R, row_stride, g->table, win, partial);
       SPG_CHECK(win.wins <= 128, "one thread per window of the blind");
-      SPG_LAUNCH(ctx, k_msm_finish_tree, (unsigned)L, 128, 0, partial, nblk, d_blinds, g->table, g->tab_R, win, d_out);
+      SPG_LAUNCH(ctx, k_msm_finish_tree, (unsigned)L, 128, 0, partial, nblk, d_blinds, g->table, g->tab_R, win, d_out, ext);
       SPG_CUDA(cudaStreamSynchronize(ctx->stream));
       return SPG_OK;
     }();
@@ -865,7 +881,7 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
   int rc = [&]() -> int {
     SPG_LAUNCH(ctx, k_msm_rows, grid, 128, 0, scalars, L, R, row_stride, g->table, win, chunk, nchunks, partial);
     SPG_LAUNCH(ctx, k_msm_finish, (unsigned)((L + 63) / 64), 64, 0, partial, L, nchunks, d_blinds, g->table, g->tab_R, win,
-               d_out);
+               d_out, ext);
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
     return SPG_OK;
   }();
@@ -874,23 +890,24 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
 }
 
 int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
-             uint8_t *host_out) {
+             uint8_t *host_out, int ext = 0) {
   SPG_CHECK(R <= g->n, "commit: %zu scalars per row but only %zu generators", R, g->n);
   SPG_TRY(ensure_table(g, R));
-  if (horner_wanted(L, R)) SPG_TRY(ensure_htab(g, R));
+  if (!ext && horner_wanted(L, R)) SPG_TRY(ensure_htab(g, R));
   uint8_t *d_out = nullptr;
   spg_ctx *ctx = g->ctx;
+  const size_t per = ext ? 128 : 32;  // extended coordinates (store_ext) or the ristretto encoding
   // a handful of points: the finish kernel writes them straight into the context's mapped result
   // page (run_msm ends with a stream synchronise), no device buffer and no copy call
-  const bool mapped = L * 32 <= 48 * sizeof(fq);
+  const bool mapped = L * per <= 48 * sizeof(fq);
   if (mapped) d_out = reinterpret_cast<uint8_t *>(ctx->d_result);
-  else SPG_CUDA(dev_alloc(ctx, &d_out, L * 32));
-  int rc = run_msm(g, scalars, L, R, row_stride, d_blinds, d_out);
+  else SPG_CUDA(dev_alloc(ctx, &d_out, L * per));
+  int rc = run_msm(g, scalars, L, R, row_stride, d_blinds, d_out, ext);
   if (rc == SPG_OK) {
     if (mapped) {
-      memcpy(host_out, ctx->h_result, L * 32);
+      memcpy(host_out, ctx->h_result, L * per);
     } else {
-      cudaError_t e = cudaMemcpy(host_out, d_out, L * 32, cudaMemcpyDeviceToHost);
+      cudaError_t e = cudaMemcpy(host_out, d_out, L * per, cudaMemcpyDeviceToHost);
       if (e != cudaSuccess) rc = cuda_fail(e, "commit download", __FILE__, __LINE__);
     }
   }
@@ -923,6 +940,41 @@ __global__ void k_bullet_fold(fq *__restrict__ s, size_t n, size_t nk, fq u, fq 
   if (m >= n) return;
   fq_store(s + m, fq_mul(fq_load(s + m), (m & (nk - 1)) >= (nk >> 1) ? u : u_inv));
 }
+// the same round with the vectors a and b resident on the device (spg_bullet_set_ab): the fold of s and,
+// for the first nk / 2 entries, of a and b (bullet.rs:113-116); reads come from [nk/2, nk) and the thread's
+// own entry, writes go to [0, nk/2)
+__global__ void k_bullet_fold_ab(fq *__restrict__ s, fq *__restrict__ a, fq *__restrict__ b, size_t n, size_t nk, fq u,
+                                 fq u_inv) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  size_t nh = nk >> 1;
+  fq_store(s + m, fq_mul(fq_load(s + m), (m & (nk - 1)) >= nh ? u : u_inv));
+  if (m < nh) {
+    fq_store(a + m, fq_add(fq_mul(fq_load(a + m), u), fq_mul(u_inv, fq_load(a + nh + m))));
+    fq_store(b + m, fq_add(fq_mul(fq_load(b + m), u_inv), fq_mul(u, fq_load(b + nh + m))));
+  }
+}
+// c_L = <a_L, b_R>, c_R = <a_R, b_L> (bullet.rs:83-84) -> out[0], out[1]; one block
+__global__ void __launch_bounds__(256)
+k_bullet_inner(const fq *__restrict__ a, const fq *__restrict__ b, size_t nh, fq *__restrict__ out) {
+  __shared__ fq sm[2 * 32];
+  fq acc[2] = {fq_zero(), fq_zero()};
+  for (size_t i = threadIdx.x; i < nh; i += blockDim.x) {
+    acc[0] = fq_add(acc[0], fq_mul(fq_load(a + i), fq_load(b + nh + i)));
+    acc[1] = fq_add(acc[1], fq_mul(fq_load(a + nh + i), fq_load(b + i)));
+  }
+  block_sum<2>(acc, sm);
+  if (threadIdx.x == 0) {
+    fq_store(out, acc[0]);
+    fq_store(out + 1, acc[1]);
+  }
+}
+__global__ void k_bullet_heads(const fq *__restrict__ a, const fq *__restrict__ b, fq *__restrict__ out) {
+  if (threadIdx.x == 0) {
+    fq_store(out, fq_load(a));
+    fq_store(out + 1, fq_load(b));
+  }
+}
 __global__ void k_fill_one(fq *__restrict__ s, size_t n) {
   size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m < n) fq_store(s + m, fq_one());
@@ -937,6 +989,7 @@ struct spg_bullet {
   fq *s = nullptr, *rows = nullptr;
   fq *in = nullptr;       // device: [blind_L, blind_R, a_0 .. a_{nk-1}]
   fq *h_in = nullptr;     // pinned staging of the same layout: one copy per round
+  fq *a = nullptr, *bv = nullptr;  // spg_bullet_set_ab: the vectors themselves, folded in place on the device
 };
 
 extern "C" {
@@ -984,7 +1037,61 @@ int spg_bullet_fold(spg_bullet *b, size_t nk, const spg_fq *u, const spg_fq *u_i
   fq fu, fi;
   memcpy(&fu, u, sizeof(fq));
   memcpy(&fi, u_inv, sizeof(fq));
-  SPG_LAUNCH(b->ctx, k_bullet_fold, (unsigned)((b->n + 255) / 256), 256, 0, b->s, b->n, nk, fu, fi);
+  if (b->a)
+    SPG_LAUNCH(b->ctx, k_bullet_fold_ab, (unsigned)((b->n + 255) / 256), 256, 0, b->s, b->a, b->bv, b->n, nk, fu, fi);
+  else
+    SPG_LAUNCH(b->ctx, k_bullet_fold, (unsigned)((b->n + 255) / 256), 256, 0, b->s, b->n, nk, fu, fi);
+  return SPG_OK;
+}
+
+int spg_bullet_set_ab(spg_bullet *b, const spg_fq *a, const spg_fq *bvec) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
+  SPG_CHECK(b && a && bvec, "spg_bullet_set_ab: null argument");
+  spg_ctx *ctx = b->ctx;
+  if (!b->a) {
+    cudaError_t e = dev_alloc(ctx, &b->a, b->n * sizeof(fq));
+    if (e == cudaSuccess) e = dev_alloc(ctx, &b->bv, b->n * sizeof(fq));
+    if (e != cudaSuccess) {
+      if (b->a) dev_free(ctx, b->a);
+      b->a = b->bv = nullptr;
+      return cuda_fail(e, "spg_bullet_set_ab", __FILE__, __LINE__);
+    }
+  }
+  // through the pinned staging buffer (n + 2 scalars), one vector at a time
+  memcpy(b->h_in, a, b->n * sizeof(fq));
+  SPG_CUDA(cudaMemcpyAsync(b->a, b->h_in, b->n * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(b->h_in, bvec, b->n * sizeof(fq));
+  SPG_CUDA(cudaMemcpyAsync(b->bv, b->h_in, b->n * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPG_OK;
+}
+
+int spg_bullet_lr_resident(spg_bullet *b, size_t nk, const spg_fq blinds[2], int ext, uint8_t *out_LR, spg_fq out_c[2]) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
+  SPG_CHECK(b && blinds && out_LR && out_c, "spg_bullet_lr_resident: null argument");
+  SPG_CHECK(b->a, "spg_bullet_lr_resident: call spg_bullet_set_ab first");
+  SPG_CHECK(nk >= 2 && nk <= b->n && (nk & (nk - 1)) == 0, "spg_bullet_lr_resident: bad round size %zu", nk);
+  spg_ctx *ctx = b->ctx;
+  memcpy(b->h_in, blinds, 2 * sizeof(fq));
+  SPG_CUDA(cudaMemcpyAsync(b->in, b->h_in, 2 * sizeof(fq), cudaMemcpyHostToDevice, ctx->stream));
+  // c_L, c_R into slots 48 and 49 of the mapped result page (56 scalars): msm_rows uses the first 48 at most
+  // -- here 2 or 8 for the two points -- and ends with a stream synchronise, so one wait serves both
+  SPG_LAUNCH(ctx, k_bullet_inner, 1, 256, 0, b->a, b->bv, nk / 2, ctx->d_result + 48);
+  SPG_LAUNCH(ctx, k_bullet_rows, (unsigned)((b->n + 255) / 256), 256, 0, b->a, b->s, b->n, nk, b->rows);
+  SPG_TRY(msm_rows(b->gens, b->rows, 2, b->n, b->n, b->in, out_LR, ext ? 1 : 0));
+  memcpy(out_c, ctx->h_result + 48, 2 * sizeof(fq));
+  return SPG_OK;
+}
+
+int spg_bullet_final_ab(spg_bullet *b, uint8_t out_G[32], spg_fq out_ab[2]) {
+  spg::DeviceGuard _dev(spg::ctx_of(b));
+  SPG_CHECK(b && out_G && out_ab, "spg_bullet_final_ab: null argument");
+  SPG_CHECK(b->a, "spg_bullet_final_ab: call spg_bullet_set_ab first");
+  spg_ctx *ctx = b->ctx;
+  SPG_LAUNCH(ctx, k_bullet_heads, 1, 32, 0, b->a, b->bv, ctx->d_result + 48);
+  SPG_TRY(msm_rows(b->gens, b->s, 1, b->n, b->n, nullptr, out_G));
+  memcpy(out_ab, ctx->h_result + 48, 2 * sizeof(fq));
   return SPG_OK;
 }
 
@@ -1000,6 +1107,8 @@ void spg_bullet_destroy(spg_bullet *b) {
   dev_free(b->ctx, b->s);
   dev_free(b->ctx, b->rows);
   dev_free(b->ctx, b->in);
+  if (b->a) dev_free(b->ctx, b->a);
+  if (b->bv) dev_free(b->ctx, b->bv);
   if (b->h_in) cudaFreeHost(b->h_in);
   delete b;
 }

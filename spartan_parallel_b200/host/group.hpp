@@ -87,6 +87,15 @@ struct Point {
     spg::ristretto_compress(p, c.b);
     return c;
   }
+  // extended coordinates X, Y, Z, T as four canonical 32-byte field elements (spg_bullet_lr_resident, ext = 1)
+  static Point from_ext_bytes(const uint8_t b[128]) {
+    spg::ge g;
+    g.X = spg::fe_frombytes(b);
+    g.Y = spg::fe_frombytes(b + 32);
+    g.Z = spg::fe_frombytes(b + 64);
+    g.T = spg::fe_frombytes(b + 96);
+    return Point(g);
+  }
   static Point decompress(const Compressed &c) {
     spg::ge g;
     if (!spg::ristretto_decompress(c.b, &g)) throw std::runtime_error("invalid ristretto255 encoding");

@@ -357,14 +357,23 @@ struct BulletReductionProof {
     BulletReductionProof p;
     Scalar blind_fin = blind;
     // the per-base scalars s[m] and the L / R scalar rows (O(n) per round) live on the device
-    // (spg_bullet_*); the host keeps a, b (O(nk) per round) and the transcript
+    // (spg_bullet_*), and so do a and b; the host keeps the transcript
     spg_bullet *st = nullptr;
     check(spg_bullet_create(gens.ctx, gens.dev, n, &st), "spg_bullet_create");
     struct Guard {
       spg_bullet *s;
       ~Guard() { spg_bullet_destroy(s); }
     } guard{st};
-    std::vector<spg_fq> a_fq(n);
+    // a and b go to the device once; a round's inner products c_L, c_R come back with its L and R, and the
+    // fold of a and b rides in the kernel that folds s (spg_bullet_set_ab / _lr_resident / _final_ab)
+    {
+      std::vector<spg_fq> a_fq(n), b_fq(n);
+      for (size_t i = 0; i < n; i++) {
+        a_fq[i] = a[i].to_fq();
+        b_fq[i] = b[i].to_fq();
+      }
+      check(spg_bullet_set_ab(st, a_fq.data(), b_fq.data()), "spg_bullet_set_ab");
+    }
     size_t nk = n, round = 0;
     static const bool trace = getenv("SPH_TRACE") != nullptr;
     double t_dev = 0, t_grp = 0, t_fold = 0;
@@ -374,21 +383,15 @@ struct BulletReductionProof {
     };
     while (nk != 1) {
       size_t nh = nk / 2;
-      auto t0 = now();
-      Scalar c_L, c_R;
-      for (size_t i = 0; i < nh; i++) {
-        c_L += a[i] * b[nh + i];
-        c_R += a[nh + i] * b[i];
-      }
       const Scalar &blind_L = blinds[round].first, &blind_R = blinds[round].second;
       round++;
-      for (size_t i = 0; i < nk; i++) a_fq[i] = a[i].to_fq();
-      spg_fq bl[2] = {blind_L.to_fq(), blind_R.to_fq()};
-      Compressed lr[2];
+      spg_fq bl[2] = {blind_L.to_fq(), blind_R.to_fq()}, cc[2];
+      uint8_t lr[256];  // the two points in extended coordinates: c Q is added before anything is encoded
       auto t1 = now();
-      check(spg_bullet_lr(st, nk, a_fq.data(), bl, (uint8_t *)lr), "spg_bullet_lr");
+      check(spg_bullet_lr_resident(st, nk, bl, 1, lr, cc), "spg_bullet_lr_resident");
       auto t2 = now();
-      Compressed Lc = (Point::decompress(lr[0]) + q_mul(c_L)).compress(), Rc = (Point::decompress(lr[1]) + q_mul(c_R)).compress();
+      Scalar c_L = Scalar::from_fq(cc[0]), c_R = Scalar::from_fq(cc[1]);
+      Compressed Lc = (Point::from_ext_bytes(lr) + q_mul(c_L)).compress(), Rc = (Point::from_ext_bytes(lr + 128) + q_mul(c_R)).compress();
       t.append_point("L", Lc);
       t.append_point("R", Rc);
       Scalar u = t.challenge_scalar("u");
@@ -396,26 +399,23 @@ struct BulletReductionProof {
       auto t3 = now();
       spg_fq fu = u.to_fq(), fi = u_inv.to_fq();
       check(spg_bullet_fold(st, nk, &fu, &fi), "spg_bullet_fold");
-      for (size_t i = 0; i < nh; i++) {
-        a[i] = a[i] * u + u_inv * a[nh + i];
-        b[i] = b[i] * u_inv + u * b[nh + i];
-      }
       blind_fin = blind_fin + blind_L * u * u + blind_R * u_inv * u_inv;
       p.L_vec.push_back(Lc);
       p.R_vec.push_back(Rc);
       nk = nh;
       auto t4 = now();
-      t_fold += ms(t0, t1) + ms(t3, t4);
+      t_fold += ms(t3, t4);
       t_dev += ms(t1, t2);
       t_grp += ms(t2, t3);
     }
     Compressed gh;
+    spg_fq ab[2];
     auto t5 = now();
-    check(spg_bullet_final(st, gh.b), "spg_bullet_final");
+    check(spg_bullet_final_ab(st, gh.b, ab), "spg_bullet_final_ab");
     if (trace)
-      fprintf(stderr, "[sph]   bullet n=%zu: device L/R %.3f ms, host group+transcript %.3f ms, host scalar folds %.3f ms, G_hat %.3f ms\n",
+      fprintf(stderr, "[sph]   bullet n=%zu: device L/R + inner products %.3f ms, host group+transcript %.3f ms, fold launches %.3f ms, G_hat %.3f ms\n",
               n, t_dev, t_grp, t_fold, ms(t5, now()));
-    Out o{a[0], b[0], blind_fin, Point::decompress(gh)};
+    Out o{Scalar::from_fq(ab[0]), Scalar::from_fq(ab[1]), blind_fin, Point::decompress(gh)};
     return {p, o};
   }
   void write(Writer &w) const {

@@ -51,6 +51,54 @@ def test_bullet_rounds_match_folded_generators(ctx, n):
     br.free()
 
 
+@pytest.mark.parametrize("n", [2, 16, 512])
+def test_bullet_rounds_with_resident_vectors(ctx, n):
+    """a and b on the device (spg_bullet_set_ab / _lr_resident / _final_ab): every round's L and R equal those
+    of the host-fed rounds, c_L, c_R and the folded a, b equal python integers (src/nizk/bullet.rs:83-84,
+    113-116); n = 512 goes through the few-row MSM kernels"""
+    import spartan_parallel_b200 as sp
+
+    gens = G.MultiCommitGens(n, b"bullet-test")
+    dg = sp.MultiCommitGens(ctx, gens.compressed())
+    ref, br = sp.BulletReduction(ctx, dg, n), sp.BulletReduction(ctx, dg, n)
+    a = [O.to_int(s) for s in rand_scalars(n, 50 + n)]
+    b = [O.to_int(s) for s in rand_scalars(n, 51 + n)]
+    if n >= 16:
+        a[1] = 0
+        b[3] = 0
+    br.set_ab(np.stack([O.from_int(x) for x in a]), np.stack([O.from_int(x) for x in b]))
+    with pytest.raises(sp.SpgError):
+        ref.lr_resident(n, O.from_int(1), O.from_int(2))  # no vectors uploaded
+    nk, rnd = n, 0
+    while nk != 1:
+        nh = nk // 2
+        bl = [O.to_int(s) for s in rand_scalars(2, 1900 + 10 * n + rnd)]
+        want = ref.lr(np.stack([O.from_int(x) for x in a[:nk]]), O.from_int(bl[0]), O.from_int(bl[1]))
+        L, R, cL, cR = br.lr_resident(nk, O.from_int(bl[0]), O.from_int(bl[1]))
+        assert (L, R) == want, (n, nk)
+        # the same two points as extended coordinates: canonical field elements on the curve's equivalence class
+        Le, Re, cL2, cR2 = br.lr_resident(nk, O.from_int(bl[0]), O.from_int(bl[1]), ext=True)
+        for enc, pt in ((L, Le), (R, Re)):
+            co = [int.from_bytes(pt[32 * k: 32 * (k + 1)], "little") for k in range(4)]
+            assert all(c < G.P for c in co)
+            assert G.Point(*co).compress() == enc
+        assert np.array_equal(cL, cL2) and np.array_equal(cR, cR2)
+        assert O.to_int(cL) == sum(a[i] * b[nh + i] for i in range(nh)) % Q
+        assert O.to_int(cR) == sum(a[nh + i] * b[i] for i in range(nh)) % Q
+        u = O.to_int(rand_scalars(1, 8000 + 10 * n + rnd)[0]) or 1
+        u_inv = pow(u, -1, Q)
+        for x in (ref, br):
+            x.fold(nk, O.from_int(u), O.from_int(u_inv))
+        a = [(a[i] * u + u_inv * a[nh + i]) % Q for i in range(nh)]
+        b = [(b[i] * u_inv + u * b[nh + i]) % Q for i in range(nh)]
+        nk, rnd = nh, rnd + 1
+    g_hat, a0, b0 = br.final_ab()
+    assert g_hat == ref.final()
+    assert O.to_int(a0) == a[0] and O.to_int(b0) == b[0]
+    ref.free()
+    br.free()
+
+
 def test_bullet_rejects_bad_sizes(ctx):
     import spartan_parallel_b200 as sp
 
