@@ -55,6 +55,7 @@ if not args.no_commit:
     L, R = 1 << (ell // 2), 1 << (ell - ell // 2)
     base = bytes.fromhex("e2f2ae0a6abc4e71a884a961c500515f58e30b6aa582dd8db6a65945e08d2d76")
     gens = sp.MultiCommitGens.from_uniform(ctx, hashlib.shake_256(b"gens_r1cs_sat" + base).digest(64 * (R + 1)))
+    gens.prepare(R, L)  # setup-time tables (the widest window), as SNARKGens would hold them
     rows_c = gens.commit_poly(secs[0].poly_w(0), L)
     print("commit rows", len(rows_c), gens.info())
 ctx.sync()

@@ -21,6 +21,7 @@
 // table entry is fetched before the current addition is computed (its address depends only on
 // the scalar's digits).
 #include <atomic>
+#include <chrono>
 
 #include "common.cuh"
 #include "ed25519.cuh"
@@ -593,6 +594,8 @@ struct spg_gens {
   Win hwin = make_win(8);
   size_t htab_bytes = 0;
   bool htab_failed = false;  // no budget / allocation failed once: do not try again for the same R
+  bool htab_ahead = false;   // built by spg_gens_prepare_rows (widest window), not inside a commitment
+  bool table_ahead = false;  // the same for the per-window table (spg_gens_prepare / _prepare_rows)
 };
 
 namespace {
@@ -607,6 +610,14 @@ size_t table_bytes_for(size_t slots, const Win &w) { return slots * (size_t)w.wi
 // and at most 60 % of what is left of the process-wide allowance for tables (60 % of the device's
 // memory) and of the memory free right now.
 std::atomic<size_t> g_table_bytes{0};
+// SPG_MSM_TRACE=1: one line per table build and per MSM call on stderr (which path, which window, how long)
+bool msm_trace() {
+  static const bool on = getenv("SPG_MSM_TRACE") != nullptr;
+  return on;
+}
+double msm_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 size_t clamp_table_budget(size_t budget) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
@@ -617,7 +628,11 @@ size_t clamp_table_budget(size_t budget) {
   }
   return budget;
 }
-Win pick_window(size_t slots) {
+// L_lazy = rows of the call that builds the table inside itself (0 = built ahead by spg_gens_prepare*, setup):
+// a lazily built table has to pay for itself in that call, so its width minimises, per base,
+// 43 * wins * 2^(c-1) products to build + 7 * L * wins to use (an entry costs ~43 field products, an addition 7)
+// -- c = 8 for the two rows of a bullet round, where the widest table would cost 50 x the MSMs it serves.
+Win pick_window(size_t slots, size_t L_lazy) {
   if (const char *e = getenv("SPG_MSM_WINDOW")) {  // development / tests: force a width
     int c = atoi(e);
     if (c >= 5 && c <= 16) return make_win(c);
@@ -626,17 +641,29 @@ Win pick_window(size_t slots) {
   if (const char *e = getenv("SPG_MSM_TABLE_GIB")) gib = atof(e);
   size_t budget = clamp_table_budget((size_t)(gib * 1073741824.0));
   Win best = make_win(8);
+  double best_cost = (43.0 * best.ent + 7.0 * (double)L_lazy) * best.wins;
   for (int c = 9; c <= 13; c++) {
     Win w = make_win(c);
-    if (table_bytes_for(slots, w) <= budget && w.wins < best.wins) best = w;
+    if (table_bytes_for(slots, w) > budget) continue;
+    if (L_lazy) {
+      double cost = (43.0 * w.ent + 7.0 * (double)L_lazy) * w.wins;
+      if (cost < best_cost) {
+        best = w;
+        best_cost = cost;
+      }
+    } else if (w.wins < best.wins) {
+      best = w;
+    }
   }
   return best;
 }
 
-int build_table(spg_gens *g, size_t R) {
+int build_table(spg_gens *g, size_t R, size_t L_lazy) {
   spg_ctx *ctx = g->ctx;
   size_t slots = R + 1;
-  Win win = pick_window(slots);
+  Win win = pick_window(slots, L_lazy);
+  if (g->table && g->tab_R >= R && g->win.c >= win.c) return SPG_OK;  // what exists is at least as wide
+  const double t_start = msm_trace() ? msm_now_ms() : 0;
   niels8 *t = nullptr;
   ge8 *wb = nullptr;
   size_t bytes = table_bytes_for(slots, win);
@@ -669,20 +696,31 @@ int build_table(spg_gens *g, size_t R) {
   g->win = win;
   g->table_bytes = bytes;
   g_table_bytes += bytes;
+  if (msm_trace())
+    fprintf(stderr, "[spg msm] per-window table: %zu bases, c = %d (%d windows), %.2f GiB, %s, %.2f ms\n", R, win.c, win.wins,
+            (double)bytes / 1073741824.0, L_lazy ? "built inside a call" : "built ahead", msm_now_ms() - t_start);
   return SPG_OK;
 }
 
-int ensure_table(spg_gens *g, size_t R) {
-  if (g->table && g->tab_R >= R) return SPG_OK;
-  return build_table(g, R);
+// L_lazy as in pick_window; a table built ahead replaces a lazily built (narrower) one
+int ensure_table(spg_gens *g, size_t R, size_t L_lazy) {
+  if (g->table && g->tab_R >= R && (L_lazy || g->table_ahead)) return SPG_OK;
+  SPG_TRY(build_table(g, R, L_lazy));
+  if (!L_lazy) g->table_ahead = true;
+  return SPG_OK;
 }
 
 // ---- the single-window table of the many-row path
 // Width: the largest c in [9, 17] whose table (R * 2^(c-1) entries of 96 bytes: 48 GiB for 8192 bases at
 // c = 17, 15 additions per scalar; 24 GiB at c = 16, 16 additions) fits SPG_MSM_HTABLE_GIB (default 48)
 // and the same allowance rules as above; 0 if none gives fewer additions than the per-window table.
+// A table built ahead (spg_gens_prepare_rows: setup, like the generators themselves) takes the widest window
+// the budget allows. A table built lazily inside the first commitment that wants it has to earn its
+// cost in that call: an entry costs ~43 field products to build (k_build_table), an addition 7, so the
+// width then minimises 43 * 2^(c-1) + 7 * L * ceil(254 / c) per base -- c = 12 or 13 for 4096 - 8192 rows,
+// where the widest table would cost several times the commitment it serves.
 size_t htab_bytes_for(size_t R, int c) { return R * ((size_t)1 << (c - 1)) * sizeof(niels8); }
-int pick_hwindow(size_t R, int perwindow_wins) {
+int pick_hwindow(size_t R, int perwindow_wins, size_t L_lazy /* 0: built ahead */) {
   if (const char *e = getenv("SPG_MSM_HWINDOW")) {  // development / tests: force a width
     int c = atoi(e);
     if (c >= 5 && c <= 17) return c;
@@ -691,9 +729,17 @@ int pick_hwindow(size_t R, int perwindow_wins) {
   if (const char *e = getenv("SPG_MSM_HTABLE_GIB")) gib = atof(e);
   size_t budget = clamp_table_budget((size_t)(gib * 1073741824.0));
   int best = 0, best_wins = perwindow_wins;
+  double best_cost = 0;
   for (int c = 9; c <= 17; c++) {
     int wins = make_win(c).wins;
-    if (htab_bytes_for(R, c) <= budget && wins < best_wins) {
+    if (htab_bytes_for(R, c) > budget || wins >= perwindow_wins) continue;
+    if (L_lazy) {
+      double cost = 43.0 * (double)((size_t)1 << (c - 1)) + 7.0 * (double)L_lazy * wins;
+      if (best == 0 || cost < best_cost) {
+        best = c;
+        best_cost = cost;
+      }
+    } else if (wins < best_wins) {
       best = c;
       best_wins = wins;
     }
@@ -714,15 +760,16 @@ bool horner_wanted(size_t L, size_t R) {
   return L * R >= min_scalars;
 }
 
-int build_htab(spg_gens *g, size_t R) {
+int build_htab(spg_gens *g, size_t R, size_t L_lazy) {
   spg_ctx *ctx = g->ctx;
-  int c = pick_hwindow(R, g->table ? g->win.wins : 1 << 30);
-  if (c == 0) {
-    g->htab_failed = true;
-    return SPG_OK;  // not an error: the per-window path serves the call
+  int c = pick_hwindow(R, g->table ? g->win.wins : 1 << 30, L_lazy);
+  if (c == 0 || (g->htab && g->htab_R >= R && g->hwin.c >= c)) {
+    if (!g->htab) g->htab_failed = true;
+    return SPG_OK;  // not an error: the per-window path (or the table that exists) serves the call
   }
   Win hw = make_win(c), one = hw;
   one.wins = 1;  // table geometry: one window per base
+  const double t_start = msm_trace() ? msm_now_ms() : 0;
   niels8 *t = nullptr;
   ge8 *wb = nullptr;
   size_t bytes = htab_bytes_for(R, c);
@@ -757,14 +804,19 @@ int build_htab(spg_gens *g, size_t R) {
   g->hwin = hw;
   g->htab_bytes = bytes;
   g->htab_failed = false;
+  g->htab_ahead = L_lazy == 0;
   g_table_bytes += bytes;
+  if (msm_trace())
+    fprintf(stderr, "[spg msm] single-window table: %zu bases, c = %d (%d additions per scalar), %.2f GiB, %s, %.2f ms\n", R, hw.c,
+            hw.wins, (double)bytes / 1073741824.0, L_lazy ? "built inside a call" : "built ahead", msm_now_ms() - t_start);
   return SPG_OK;
 }
 
-int ensure_htab(spg_gens *g, size_t R) {
-  if (g->htab && g->htab_R >= R) return SPG_OK;
+// L_lazy = rows of the commitment that asks (the table is built inside it), 0 = built ahead at setup time
+int ensure_htab(spg_gens *g, size_t R, size_t L_lazy) {
+  if (g->htab && g->htab_R >= R && (L_lazy || g->htab_ahead)) return SPG_OK;
   if (g->htab_failed && !g->htab) return SPG_OK;
-  return build_htab(g, R);
+  return build_htab(g, R, L_lazy);
 }
 
 // the many-row path: slabs of rows (the digits of a slab take at most ~1 GiB), see k_msm_hrows
@@ -892,8 +944,13 @@ int run_msm(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_strid
 int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stride, const fq *d_blinds,
              uint8_t *host_out, int ext = 0) {
   SPG_CHECK(R <= g->n, "commit: %zu scalars per row but only %zu generators", R, g->n);
-  SPG_TRY(ensure_table(g, R));
-  if (!ext && horner_wanted(L, R)) SPG_TRY(ensure_htab(g, R));
+  // many rows: the single-window table serves the sums; the per-window table is then only needed for blinds
+  bool horner = !ext && horner_wanted(L, R);
+  if (horner) {
+    SPG_TRY(ensure_htab(g, R, L));
+    horner = g->htab && g->htab_R >= R;
+  }
+  if (!horner || d_blinds) SPG_TRY(ensure_table(g, R, L));
   uint8_t *d_out = nullptr;
   spg_ctx *ctx = g->ctx;
   const size_t per = ext ? 128 : 32;  // extended coordinates (store_ext) or the ristretto encoding
@@ -902,7 +959,12 @@ int msm_rows(spg_gens *g, const fq *scalars, size_t L, size_t R, size_t row_stri
   const bool mapped = L * per <= 48 * sizeof(fq);
   if (mapped) d_out = reinterpret_cast<uint8_t *>(ctx->d_result);
   else SPG_CUDA(dev_alloc(ctx, &d_out, L * per));
+  const double t_start = msm_trace() ? msm_now_ms() : 0;
   int rc = run_msm(g, scalars, L, R, row_stride, d_blinds, d_out, ext);
+  if (msm_trace())
+    fprintf(stderr, "[spg msm] %zu rows x %zu bases%s: %s, %.3f ms\n", L, R, d_blinds ? " + blinds" : "",
+            horner ? "single-window table + Horner" : (L <= 16 && R >= 256 ? "per-window table, few-row kernels" : "per-window table"),
+            msm_now_ms() - t_start);
   if (rc == SPG_OK) {
     if (mapped) {
       memcpy(host_out, ctx->h_result, L * per);
@@ -1212,15 +1274,15 @@ int spg_gens_prepare(spg_ctx *ctx, spg_gens *gens, size_t R) {
   spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens, "spg_gens_prepare: null argument");
   SPG_CHECK(R >= 1 && R <= gens->n, "spg_gens_prepare: %zu bases requested, %zu generators", R, gens->n);
-  return ensure_table(gens, R);
+  return ensure_table(gens, R, 0);
 }
 
 int spg_gens_prepare_rows(spg_ctx *ctx, spg_gens *gens, size_t L, size_t R) {
   spg::DeviceGuard _dev(spg::ctx_of(ctx));
   SPG_CHECK(ctx && gens, "spg_gens_prepare_rows: null argument");
   SPG_CHECK(R >= 1 && R <= gens->n, "spg_gens_prepare_rows: %zu bases requested, %zu generators", R, gens->n);
-  SPG_TRY(ensure_table(gens, R));
-  if (horner_wanted(L, R)) SPG_TRY(ensure_htab(gens, R));
+  SPG_TRY(ensure_table(gens, R, 0));
+  if (horner_wanted(L, R)) SPG_TRY(ensure_htab(gens, R, 0));
   return SPG_OK;
 }
 

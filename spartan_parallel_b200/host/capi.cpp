@@ -59,7 +59,15 @@ int sph_transcript_kat(const char *label, const char *l, const char *m, const ch
 // context the opening-proof generators also live on the device (fixed-base tables built on first use)
 void *sph_r1cs_gens_new(spg_ctx *ctx, const char *label, size_t num_vars) {
   try {
-    return new R1CSGens(label, num_vars, ctx);
+    std::unique_ptr<R1CSGens> g(new R1CSGens(label, num_vars, ctx));
+    // a generator set that is created once and reused (the reference's SNARKGens): its tables are setup too --
+    // the per-window table of the openings' few-row MSMs and, for a polynomial of num_vars scalars, the
+    // single-window table of its row commitments (spg_gens_prepare_rows decides whether that one pays)
+    if (ctx && g->d_pc) {
+      size_t ell = log2z(num_vars);
+      check(spg_gens_prepare_rows(ctx, g->d_pc, (size_t)1 << (ell / 2), g->pc.n), "spg_gens_prepare_rows");
+    }
+    return g.release();
   } catch (const std::exception &e) {
     g_err = e.what();
     return nullptr;

@@ -236,8 +236,13 @@ def test_witness_commit_at_config_size(ctx, monkeypatch):
         Z[r * R + np.array(cols)] = keep
     poly = sp.DensePolynomial.new(ctx, Z)
     rows = dg.commit_poly(poly, Lr)
-    assert dg.info()["table_bases"] >= R
-    assert dg.info()["rows_table"]["table_bases"] >= R  # 8192 rows: the single-window table + Horner path
+    info = dg.info()
+    assert info["rows_table"]["table_bases"] >= R  # 8192 rows: the single-window table + Horner path
+    assert info["table_bases"] == 0                # no blinds: the per-window table was not needed (yet)
+    assert info["rows_table"]["window_bits"] <= 14  # built inside the call: sized to pay for itself in one commitment
+    dg.prepare(R, Lr)                               # setup-time tables: the widest window the budget allows
+    assert dg.info()["rows_table"]["window_bits"] >= 16 and dg.info()["table_bases"] >= R
+    assert dg.commit_poly(poly, Lr) == rows
     # (a) oracle on the sparse rows: the same generators derived by the oracle's own hash-to-group
     og = {c: G.from_uniform_bytes(uniform[64 * c: 64 * (c + 1)]) for c in cols + [R]}
     for r in sparse_rows:
