@@ -143,6 +143,8 @@ KERNEL_MODEL = {
     "k_z_bind_rq": (32.0, 74.0 / 104.0),  # one product per witness scalar read, as four-term dot products: 296 wide multiplies per 4 instead of 4 x 104
     "k_cubic_eval_rlc": (192.0, 6.0),
     "k_cubic_eval_split": (192.0, 6.0),
+    "k_cubic_bind_eval_rlc": (288.0, 12.0),    # fused bind_j + eval_{j+1}: 12 scalars read, 6 written, 6 binds + 6 products per item and triple
+    "k_cubic_bind_eval_split": (288.0, 12.0),
     "k_multi_bind_top": (96.0, 1.0),
     "k_prod_layer": (96.0, 1.0),
     "k_hash_layer_fq": (128.0, 2.0),

@@ -105,6 +105,113 @@ k_cubic_eval_split(const __grid_constant__ CubicPtrs P, const __grid_constant__ 
   finish_block_lanes3(fa, mine, sm);
 }
 
+// Fused bind_j + eval_{j+1} (sumcheck.rs:373-407 then :297-371 of the next round): an item binds the four
+// entries i, i + q, i + 2q, i + 3q (q = a quarter of the current length) of each table of its triple with
+// r_j -- the bound pair (i, i + q) is exactly what round j + 1 evaluates -- stores the pair and evaluates
+// it. A, B (and a sequential triple's own C) are bound in place: an item reads and writes only its own
+// four / two positions. The C table SHARED by the parallel triples is read by every one of them, so its
+// bound form goes to a second buffer (Cout of the first parallel triple, null for the others, which bind
+// their copy of the pair in registers only); the two buffers swap roles every round. One launch per round
+// instead of a bind launch and an evaluation launch.
+struct CubicBindPtrs {
+  fq *A[24];
+  fq *B[24];
+  const fq *C[24];
+  fq *Cout[24];
+};
+__device__ __forceinline__ fq cbind(const fq &lo, const fq &hi, const fq &r) { return fq_add(lo, fq_mul(r, fq_sub(hi, lo))); }
+
+__global__ void __launch_bounds__(CB)
+k_cubic_bind_eval_rlc(const __grid_constant__ CubicBindPtrs P, const __grid_constant__ CubicCoeffs K, int gx, size_t quarter, fq r,
+                      FinishArgs fa) {
+  __shared__ fq sm[3 * 32];
+  const int k = blockIdx.x / gx, bx = blockIdx.x % gx;
+  fq *A = P.A[k], *B = P.B[k], *Co = P.Cout[k];
+  const fq *C = P.C[k];
+  const size_t half = 2 * quarter;
+  fq acc[3] = {fq_zero(), fq_zero(), fq_zero()};
+  for (size_t i = (size_t)bx * CB + threadIdx.x; i < quarter; i += (size_t)gx * CB) {
+    fq a0 = cbind(fq_load(A + i), fq_load(A + i + half), r), a1 = cbind(fq_load(A + i + quarter), fq_load(A + i + quarter + half), r);
+    fq b0 = cbind(fq_load(B + i), fq_load(B + i + half), r), b1 = cbind(fq_load(B + i + quarter), fq_load(B + i + quarter + half), r);
+    fq c0 = cbind(fq_load(C + i), fq_load(C + i + half), r), c1 = cbind(fq_load(C + i + quarter), fq_load(C + i + quarter + half), r);
+    fq_store(A + i, a0);
+    fq_store(A + i + quarter, a1);
+    fq_store(B + i, b0);
+    fq_store(B + i + quarter, b1);
+    if (Co) {
+      fq_store(Co + i, c0);
+      fq_store(Co + i + quarter, c1);
+    }
+    fq a2, a3, b2, b3, c2, c3;
+    cline23(a0, a1, a2, a3);
+    cline23(b0, b1, b2, b3);
+    cline23(c0, c1, c2, c3);
+    acc[0] = fq_add(acc[0], fq_mul(fq_mul(a0, b0), c0));
+    acc[1] = fq_add(acc[1], fq_mul(fq_mul(a2, b2), c2));
+    acc[2] = fq_add(acc[2], fq_mul(fq_mul(a3, b3), c3));
+  }
+  block_sum<3>(acc, sm);
+  if (threadIdx.x == 0) {
+    fq ck = K.c[k];
+#pragma unroll
+    for (int t = 0; t < 3; t++) acc[t] = fq_mul(ck, acc[t]);
+  }
+  finish_block<3>(fa, acc, sm);
+}
+
+// the same on small tables (k_cubic_eval_split's layout: four lanes per item, lanes 0..2 on t = 0, 2, 3). Each of
+// the three lanes binds all six scalars itself -- the products are independent and the round is a dependent
+// chain, not throughput -- and lane 0 / 1 / 2 stores the A / B / C pair after the warp has finished reading.
+__global__ void __launch_bounds__(128)
+k_cubic_bind_eval_split(const __grid_constant__ CubicBindPtrs P, const __grid_constant__ CubicCoeffs K, int gx, size_t quarter, fq r,
+                        FinishArgs fa) {
+  __shared__ fq sm[4 * 4];
+  const unsigned int lane = threadIdx.x & 31, l = lane & 3, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x / gx, bx = blockIdx.x % gx;
+  fq *A = P.A[k], *B = P.B[k], *Co = P.Cout[k];
+  const fq *C = P.C[k];
+  const size_t half = 2 * quarter;
+  const size_t i = (size_t)bx * CUBIC_SPLIT_ITEMS + (threadIdx.x >> 2);
+  const bool act = i < quarter && l < 3;
+  fq acc = fq_zero(), s0 = fq_zero(), s1 = fq_zero();
+  if (act) {
+    fq a0 = cbind(fq_load(A + i), fq_load(A + i + half), r), a1 = cbind(fq_load(A + i + quarter), fq_load(A + i + quarter + half), r);
+    fq b0 = cbind(fq_load(B + i), fq_load(B + i + half), r), b1 = cbind(fq_load(B + i + quarter), fq_load(B + i + quarter + half), r);
+    fq c0 = cbind(fq_load(C + i), fq_load(C + i + half), r), c1 = cbind(fq_load(C + i + quarter), fq_load(C + i + quarter + half), r);
+    acc = fq_mul(fq_mul(split_point(a0, a1, l), split_point(b0, b1, l)), split_point(c0, c1, l));
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      s0.v[w] = l == 0 ? a0.v[w] : (l == 1 ? b0.v[w] : c0.v[w]);
+      s1.v[w] = l == 0 ? a1.v[w] : (l == 1 ? b1.v[w] : c1.v[w]);
+    }
+  }
+  __syncwarp();  // every lane of the item has read the unbound entries before one of them overwrites them
+  if (act) {
+    fq *T = l == 0 ? A : (l == 1 ? B : Co);
+    if (T) {
+      fq_store(T + i, s0);
+      fq_store(T + i + quarter, s1);
+    }
+  }
+  // lanes 4 j + l hold point l of item j
+  acc = fq_add(acc, fq_shfl_down(acc, 4));
+  acc = fq_add(acc, fq_shfl_down(acc, 8));
+  acc = fq_add(acc, fq_shfl_down(acc, 16));
+  if (lane < 3) sm[warp * 4 + lane] = acc;
+  __syncthreads();
+  fq mine[3] = {fq_zero(), fq_zero(), fq_zero()};
+  if (warp == 0) {
+    fq t = (lane < 16 && l < 3) ? sm[(lane >> 2) * 4 + l] : fq_zero();
+    t = fq_add(t, fq_shfl_down(t, 4));
+    t = fq_add(t, fq_shfl_down(t, 8));
+    t = fq_mul(K.c[k], t);  // lanes 0 .. 2: the three sums of this block, scaled by the triple's coefficient
+    mine[0] = t;
+    mine[1] = fq_shfl(t, 1);
+    mine[2] = fq_shfl(t, 2);
+  }
+  finish_block_lanes3(fa, mine, sm);
+}
+
 struct BindPtrs {
   fq *T[64];
 };
@@ -196,6 +303,13 @@ struct spg_cubic {
   std::vector<hfq> coeffs;
   size_t len = 0;
   bool evaluated = false;
+  // fused bind + evaluation (k_cubic_bind_eval_*): the shared C table alternates between C_par's own buffer
+  // and C_alt; the evaluations of the round that follows a fused bind are cached here
+  fq *C_alt = nullptr;
+  bool c_in_alt = false, have_cached = false;
+  spg_fq cached[3];
+  const fq *c_cur() const { return c_in_alt ? C_alt : C_par->d; }
+  fq *c_cur() { return c_in_alt ? C_alt : C_par->d; }
 };
 
 extern "C" {
@@ -320,13 +434,19 @@ int spg_cubic_round_eval(spg_cubic *s, spg_fq e[3]) {
     set_error(s->evaluated ? "spg_cubic_round_eval: round already evaluated" : "spg_cubic_round_eval: all rounds are done");
     return SPG_ESTATE;
   }
+  if (s->have_cached) {  // evaluated by the fused kernel of the previous bind
+    memcpy(e, s->cached, sizeof s->cached);
+    s->have_cached = false;
+    s->evaluated = true;
+    return SPG_OK;
+  }
   spg_ctx *ctx = s->ctx;
   size_t nt = s->npar + s->nseq, half = s->len / 2;
   CubicPtrs P;
   for (size_t k = 0; k < s->npar; k++) {
     P.A[k] = s->A_par[k]->d;
     P.B[k] = s->B_par[k]->d;
-    P.C[k] = s->C_par->d;
+    P.C[k] = s->c_cur();
   }
   for (size_t k = 0; k < s->nseq; k++) {
     P.A[s->npar + k] = s->A_seq[k]->d;
@@ -375,10 +495,60 @@ int spg_cubic_round_bind(spg_cubic *s, const spg_fq *r) {
   for (auto v : s->A_seq) all.push_back(v);
   for (auto v : s->B_seq) all.push_back(v);
   for (auto v : s->C_seq) all.push_back(v);
+  static const bool fuse = [] {
+    const char *e = getenv("SPG_CUBIC_FUSE");  // SPG_CUBIC_FUSE=0: separate bind and evaluation launches (A/B switch)
+    return !(e && *e == '0');
+  }();
+  if (fuse && s->len >= 4) {
+    // another round follows: bind and evaluate it in one launch
+    const size_t nt = s->npar + s->nseq, quarter = s->len / 4;
+    if (s->npar && !s->C_alt) SPG_CUDA(dev_alloc(ctx, &s->C_alt, (s->len / 2) * sizeof(fq)));
+    CubicBindPtrs P;
+    memset(&P, 0, sizeof P);
+    fq *c_next = s->npar ? (s->c_in_alt ? s->C_par->d : s->C_alt) : nullptr;
+    for (size_t k = 0; k < s->npar; k++) {
+      P.A[k] = s->A_par[k]->d;
+      P.B[k] = s->B_par[k]->d;
+      P.C[k] = s->c_cur();
+      P.Cout[k] = k == 0 ? c_next : nullptr;
+    }
+    for (size_t k = 0; k < s->nseq; k++) {
+      P.A[s->npar + k] = s->A_seq[k]->d;
+      P.B[s->npar + k] = s->B_seq[k]->d;
+      P.C[s->npar + k] = s->C_seq[k]->d;
+      P.Cout[s->npar + k] = s->C_seq[k]->d;
+    }
+    int gx = grid_for(ctx, quarter, CB, 2);
+    if (gx > 1024) gx = 1024;
+    if ((size_t)gx * nt > 4096) gx = (int)(4096 / nt);  // keep the in-kernel final reduction (finish_args)
+    const size_t gx_split = (quarter + CUBIC_SPLIT_ITEMS - 1) / CUBIC_SPLIT_ITEMS;
+    const bool split = gx_split * nt <= 512;
+    if (split) gx = (int)gx_split;
+    size_t nblocks = (size_t)gx * nt;
+    SPG_TRY(ensure_partials(ctx, nblocks * 3));
+    CubicCoeffs K;
+    for (size_t k = 0; k < nt; k++) {
+      spg_fq c = hfq_to(s->coeffs[k]);
+      memcpy(&K.c[k], &c, sizeof(fq));
+    }
+    ctx->next_units = 288.0 * (double)quarter * (double)nt;  // per item and triple: 12 scalars read (C shared), 6 written
+    FinishArgs fa = finish_args(ctx, nblocks);
+    if (split)
+      SPG_LAUNCH(ctx, k_cubic_bind_eval_split, (unsigned)nblocks, 128, 0, P, K, gx, quarter, rr, fa);
+    else
+      SPG_LAUNCH(ctx, k_cubic_bind_eval_rlc, (unsigned)nblocks, CB, 0, P, K, gx, quarter, rr, fa);
+    if (s->npar) s->c_in_alt = !s->c_in_alt;
+    for (auto v : all) v->n = half;
+    s->len = half;
+    s->evaluated = false;
+    SPG_TRY(finish_result(ctx, fa, nblocks, 3, s->cached));
+    s->have_cached = true;
+    return SPG_OK;
+  }
   for (size_t base = 0; base < all.size(); base += 64) {
     size_t cnt = all.size() - base < 64 ? all.size() - base : 64;
     BindPtrs P;
-    for (size_t i = 0; i < cnt; i++) P.T[i] = all[base + i]->d;
+    for (size_t i = 0; i < cnt; i++) P.T[i] = (all[base + i] == s->C_par && s->npar) ? s->c_cur() : all[base + i]->d;
     int gx = grid_for(ctx, half, 128, 2);
     dim3 grid(gx, (unsigned)cnt);
     ctx->next_units = 96.0 * (double)half * (double)cnt;
@@ -405,6 +575,11 @@ int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
   for (auto v : s->A_seq) all.push_back(v);
   for (auto v : s->B_seq) all.push_back(v);
   for (auto v : s->C_seq) all.push_back(v);
+  if (s->npar && s->c_in_alt) {
+    // the caller's vector holds the bound scalar too, like every other table
+    SPG_CUDA(cudaMemcpyAsync(s->C_par->d, s->C_alt, sizeof(fq), cudaMemcpyDeviceToDevice, ctx->stream));
+    s->c_in_alt = false;
+  }
   std::vector<const fq *> heads;
   for (auto v : all) heads.push_back(v->d);
   return gather_heads(ctx, heads.data(), heads.size(), claims);
@@ -413,6 +588,7 @@ int spg_cubic_final(spg_cubic *s, spg_fq *claims) {
 void spg_cubic_destroy(spg_cubic *s) {
   spg::DeviceGuard _dev(spg::ctx_of(s));
   if (!s) return;
+  if (s->C_alt) dev_free(s->ctx, s->C_alt);
   delete s;
 }
 

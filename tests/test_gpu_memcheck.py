@@ -71,7 +71,7 @@ def test_hash_layer_and_deref(ctx):
         sp.deref(ctx, np.array([n], dtype=np.uint64), dmem)
 
 
-@pytest.mark.parametrize("logn,npar,nseq", [(1, 1, 0), (6, 3, 0), (9, 4, 2), (12, 12, 6), (4, 0, 2)])
+@pytest.mark.parametrize("logn,npar,nseq", [(1, 1, 0), (2, 2, 1), (6, 3, 0), (9, 4, 2), (12, 12, 6), (4, 0, 2), (15, 3, 1)])
 def test_cubic_batched(ctx, logn, npar, nseq):
     import spartan_parallel_b200 as sp
 
@@ -104,6 +104,10 @@ def test_cubic_batched(ctx, logn, npar, nseq):
     got = sc.final()
     want = [x[0] for x in oa] + [x[0] for x in ob] + ([oc[0]] if npar else []) + [x[0] for x in oas] + [x[0] for x in obs] + [x[0] for x in ocs]
     assert np.array_equal(got, np.stack(want))
+    # the caller's vectors were bound in place (the shared C table alternates between two buffers on the way):
+    # each now holds its one bound scalar
+    for vec, w in zip(dA + dB + ([dC] if npar else []) + dAs + dBs + dCs, want):
+        assert np.array_equal(vec.to_host()[0], w)
 
 
 def test_addr_timestamps_on_device(ctx):
