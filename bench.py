@@ -134,7 +134,7 @@ class ClockSampler:
 # per item); DESIGN.md section 4 states both per kernel. MSM kernels count point additions instead.
 KERNEL_MODEL = {
     "k_rows_rolled": (576.0, 10.0),      # fused bind_j + eval_{j+1}: 4 read + 2 written scalars x 3 tables, 6 binds + 4
-    "k_rows_spmv": (288.0, 4.0),         # SpMV + round 0: z read + 3 tables written per pair, 2 products + 2 weighted sums
+    "k_rows_spmv": (288.0, 2.0),         # SpMV + round 0 for a satisfying witness (spg_sc1_set_satisfied): z read + 3 tables written per pair, the point t = 2 only: 1 product + 1 weighted sum (4 with spg_sc1_set_claim)
     "k_rows": (192.0, 4.0),
     "k_quad_bind_eval": (576.0, 13.0),
     "k_quad_split": (576.0, 13.0),       # the same round with one item over eight lanes (late rounds: latency, not throughput)
@@ -289,7 +289,7 @@ def run_gpu(args):
             rx = ch1[:nx][::-1].copy()
             if world == 1:
                 sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, self.tau_q[:0], self.tau_q, self.tau_x)
-                sc1.set_claim(ZERO)  # claim_phase1 = 0 (src/r1csproof.rs:330); the synthetic witness satisfies the instance
+                sc1.set_satisfied()  # claim_phase1 = 0 (src/r1csproof.rs:330) and the witness satisfies the instance row by row
                 sc1.run_rounds(ch1[:sc1.num_rounds])  # C loop: eval -> host -> bind per round, no Python in between
                 c1 = sc1.final()
                 sc1.free()
@@ -617,7 +617,7 @@ def run_gpu(args):
                    "constraints_per_step": total_units, "sharding": shard_note,
                    "e2e_pipeline": "double-buffered: the H2D copy of batch i+1 overlaps the proving of batch i; all copies are inside the timed region",
                    "l2": f"inputs ({2 * main.N * 32 / 2**30:.2f} GiB per GPU per step) exceed the 126 MB L2; no flush needed",
-                   "challenges": "precomputed per-round challenges replayed by a C loop (spg_sc1_run_rounds / spg_sc2_run_rounds); every round still returns its 3 evaluations to the host (96 B) before the bind with that round's challenge (32 B) is issued; `value` is therefore the rate of the table work, `prove_time` the whole protocol",
+                   "first_round": "spg_sc1_set_satisfied: claim 0 and Az Bz - Cz = 0 row by row (a satisfying witness, what R1CSProof::prove is called with), so the fused SpMV + first round evaluates t = 2 only", "challenges": "precomputed per-round challenges replayed by a C loop (spg_sc1_run_rounds / spg_sc2_run_rounds); every round still returns its 3 evaluations to the host (96 B) before the bind with that round's challenge (32 B) is issued; `value` is therefore the rate of the table work, `prove_time` the whole protocol",
                    "phases": "z_mat + SpMV + phase-1 rounds + ABC/Z tables + phase-2 rounds"},
         "e2e": {"value": e2e_value, "unit": "constraints/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(2 * main.N * 32 * world), "d2h_bytes_per_step": int(96 * (2 * nx + main.nq + ng + 1) + 7 * 32)},

@@ -226,6 +226,7 @@ extern "C" {
     pub fn spg_sc1_set_scale(s: *mut spg_sc1, c: *const spg_fq) -> c_int;
     pub fn spg_sc1_set_claim(s: *mut spg_sc1, claim: *const spg_fq) -> c_int;
     pub fn spg_sc1_set_claim_checked(s: *mut spg_sc1, claim: *const spg_fq) -> c_int;
+    pub fn spg_sc1_set_satisfied(s: *mut spg_sc1) -> c_int;
     pub fn spg_sc1_num_rounds(s: *const spg_sc1) -> usize;
     pub fn spg_sc1_round_eval(s: *mut spg_sc1, e: *mut spg_fq) -> c_int;
     pub fn spg_sc1_round_bind(s: *mut spg_sc1, r: *const spg_fq) -> c_int;

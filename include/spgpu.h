@@ -187,6 +187,12 @@ int spg_sc1_set_claim(spg_sc1 *s, const spg_fq *claim);
  * (every row of at least 2^8 constraints); smaller tables evaluate three points anyway and ignore
  * the supplied claim's value. */
 int spg_sc1_set_claim_checked(spg_sc1 *s, const spg_fq *claim);
+/* spg_sc1_set_claim(0) plus the statement that the witness satisfies the instance row by row:
+ * Az Bz - Cz is then zero at every (p, q, x), e(0) = e(1) = 0 in the first round are sums of zeros, and the
+ * kernel that fuses the SpMV with that round evaluates the single point t = 2 (half its products). This is
+ * what R1CSProof::prove knows about its inputs (src/r1csproof.rs:330 passes the zero claim for that reason).
+ * Bit-identical to the reference for a satisfying witness; for any other input use _set_claim_checked. */
+int spg_sc1_set_satisfied(spg_sc1 *s);
 size_t spg_sc1_num_rounds(const spg_sc1 *s);
 /* e = (eval_point_0, eval_point_2, eval_point_3) of the current round, :1166-1245 */
 int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]);

@@ -142,6 +142,7 @@ def _proto(L):
         "spg_peer_reduce_scatter": [P, P, INT, INT, SZ],
         "spg_zmat_bind_rq_sharded": [P, P, P, SZ, SZ, P, INT, INT, SZ, INT, P, SZ, P],
         "spg_sc1_set_claim_checked": [P, P],
+        "spg_sc1_set_satisfied": [P],
         "spg_zmat_bind_weights": [P, P, P, SZ, P, P],
         "spg_vec_zero": [P, P],
         "spg_wit_perm_w0": [P, P, P, SZ, SZ, PP],

@@ -303,6 +303,11 @@ class SumcheckPhase1:
         c = _fq(np.asarray(claim, dtype=np.uint64).reshape(4))
         check(self.ctx.L.spg_sc1_set_claim_checked(self.h, _ptr(c)), "spg_sc1_set_claim_checked")
 
+    def set_satisfied(self):
+        """set_claim(0) plus: the witness satisfies the instance row by row, so the first round (fused with
+        the SpMV) evaluates one point per pair instead of two. Exact for a satisfying witness."""
+        check(self.ctx.L.spg_sc1_set_satisfied(self.h), "spg_sc1_set_satisfied")
+
     def set_claim(self, claim):
         """The prover's `claim` argument (src/sumcheck.rs:1069; zero in R1CSProof::prove): lets round 0
         use e(1) = claim - e(0) like the reference does. Exact iff the claim is the true sum."""

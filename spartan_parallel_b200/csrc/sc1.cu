@@ -328,7 +328,7 @@ template <int NE, bool COLD = false>
 __global__ void __launch_bounds__(RB, SPG_MINB)
 k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__restrict__ O0, fq *__restrict__ O1,
             fq *__restrict__ O2, int nseg, const __grid_constant__ SegPack pk, const fq *__restrict__ RW,
-            const fq *__restrict__ S, fq *__restrict__ partials) {
+            const fq *__restrict__ S, fq *__restrict__ partials, int skip_t0) {
   __shared__ fq sm[NE * 32];
   unsigned long long tile = blockIdx.x;
   int si = 0;
@@ -377,7 +377,10 @@ k_rows_spmv(const __grid_constant__ SpmvSegs SP, unsigned int log_ymax, fq *__re
     fq_store_stream(O2 + idx, lo3[2]); fq_store_stream(O2 + idx + 1, hi3[2]);
     fq w = fq_load(S + it);
     // wide-range forms (fq.cuh), bounds as in k_rows_rolled; lo3 / hi3 are canonical
-    acc[0] = fq_fold2q(fq_raw_add(acc[0], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(lo3[0], lo3[1]), lo3[2]))));
+    // skip_t0: the caller vouches that the witness satisfies the instance (spg_sc1_set_satisfied), so
+    // Az Bz - Cz vanishes at every row and only the point t = 2 carries information (a run-time flag, uniform
+    // over the grid: a separate instantiation without the t = 0 sum crashes ptxas 12.9)
+    if (!skip_t0) acc[0] = fq_fold2q(fq_raw_add(acc[0], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(lo3[0], lo3[1]), lo3[2]))));
     if (NE == 3) acc[1] = fq_fold2q(fq_raw_add(acc[1], fq_mul_lazy(w, fq_sub_plus2q(fq_mul_lazy(hi3[0], hi3[1]), hi3[2]))));
     fq a2 = fq_raw_add(hi3[0], fq_sub_plus2q(hi3[0], lo3[0]));
     fq b2 = fq_raw_add(hi3[1], fq_sub_plus2q(hi3[1], lo3[1]));
@@ -521,6 +524,7 @@ struct spg_sc1 {
   size_t tab_lazy_n = 0;
   bool claim_known = false;
   bool check_claim = false;  // verify a supplied claim against the tables in the first round (spg_sc1_set_claim_checked)
+  bool satisfied = false;    // spg_sc1_set_satisfied: every row of Az Bz - Cz is zero, the first round needs only t = 2
   hfq supplied_claim;
   hfq claim;
   hfq last_e[3];
@@ -841,6 +845,21 @@ int spg_sc1_set_claim(spg_sc1 *s, const spg_fq *claim) {
   return SPG_OK;
 }
 
+// The caller vouches that the witness satisfies the instance: (Az Bz - Cz)[p][q][x] = 0 for EVERY row, not only
+// in the weighted sum (for random tau the two are the same statement up to negligible probability, and the
+// prover of a correct execution knows it outright). Implies spg_sc1_set_claim(0); in addition the first
+// round -- the one fused with the SpMV -- then evaluates ONE point per pair, t = 2: e(0) and e(1) are sums of
+// zeros. Half the products of that kernel. Exact (bit-identical to the reference, which computes the zeros)
+// iff the statement holds; spg_sc1_set_claim_checked is the variant that verifies instead of trusting.
+int spg_sc1_set_satisfied(spg_sc1 *s) {
+  SPG_CHECK(s, "spg_sc1_set_satisfied: null argument");
+  spg_fq zero;
+  memset(&zero, 0, sizeof zero);
+  SPG_TRY(spg_sc1_set_claim(s, &zero));
+  s->satisfied = true;
+  return SPG_OK;
+}
+
 // Replaces the row weights RW[p][q] = eq_p[p] * eq_q[q] of the x rounds by caller-supplied ones (one
 // per (instance, proof) row, in table order). A rank of a sharded proof that owns an arbitrary subset of
 // the batch's rows passes the GLOBAL eq weights of its rows here; the q and p rounds of such a
@@ -996,12 +1015,13 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
         // tables do not exist yet: compute them in the same pass (read z once, write 96 N bytes once)
         ctx->next_units = 288.0 * pairs;
         static const bool cold = spmv_cold_enabled();
+        const int skip_t0 = s->satisfied && s->round == 0;
         if (cold)
           SPG_LAUNCH(ctx, (k_rows_spmv<2, true>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
-                     s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+                     s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials, skip_t0);
         else
           SPG_LAUNCH(ctx, (k_rows_spmv<2>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
-                     s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+                     s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials, skip_t0);
         s->pend_inst = nullptr;
         s->pend_z = nullptr;
       } else {
@@ -1010,7 +1030,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
                    s->d_segs, (int)s->P, make_pack(s->segs), RW, S, fa);
       }
       spg_fq tmp[2];
-      SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));
+      SPG_TRY(finish_result(ctx, fa, tiles, 2, tmp));  // (with skip_t0 the first sum is a sum of zeros)
       s->cached[0] = hfq_from(tmp[0]);
       s->cached[1] = hfq_from(tmp[1]);
       s->cached_kind = 2;
@@ -1054,7 +1074,7 @@ int spg_sc1_round_eval(spg_sc1 *s, spg_fq e[3]) {
       if (s->pend_inst) {
         ctx->next_units = 288.0 * pairs;
         SPG_LAUNCH(ctx, (k_rows_spmv<3>), (unsigned)tiles, RB, 0, make_spmv_segs(s), log2u(s->pend_max_num_inputs),
-                   s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials);
+                   s->tab[0][0], s->tab[0][1], s->tab[0][2], (int)s->P, make_pack(s->segs), RW, S, ctx->d_partials, 0);
         s->pend_inst = nullptr;
         s->pend_z = nullptr;
       } else {

@@ -856,10 +856,9 @@ inline R1CSProofOut r1cs_prove(spg_ctx *ctx, size_t num_instances, size_t max_nu
   check(spg_sc1_create(ctx, inst, z, P, num_proofs.data(), max_num_proofs, block_num_cons.data(), num_cons,
                        max_num_inputs, fqv(tau_p).data(), fqv(tau_q).data(), fqv(tau_x).data(), &sc1),
         "spg_sc1_create");
-  {
-    spg_fq zero = Scalar::zero().to_fq();  // claim_phase1 (:330)
-    check(spg_sc1_set_claim(sc1, &zero), "spg_sc1_set_claim");
-  }
+  // claim_phase1 = 0 (:330): the prover's witness satisfies the instance row by row, which also lets the
+  // fused SpMV + first round skip the evaluation at 0
+  check(spg_sc1_set_satisfied(sc1), "spg_sc1_set_satisfied");
   tr.lap("z_mat + SpMV + sc1 setup");
   std::vector<Scalar> r1;
   Scalar blind_claim_postsc1;

@@ -493,13 +493,14 @@ def gpu_phase2_sharded(ctx, comm, inst, zrq, max_num_inputs: int, W: int, rx, r_
 def gpu_phase1(ctx, comm, inst, z, Q_local, X, max_num_inputs, tau_q, tau_x, satisfied: bool = False) -> ShardedPhase1:
     """ShardedPhase1 on this rank's GPU. satisfied=True asserts that the witness satisfies the
     instance: Az*Bz - Cz then vanishes entry by entry, so every shard's own sum is zero and the
-    shard may take e(1) from that claim (spg_sc1_set_claim) exactly like the unsharded prover."""
+    shard may take e(1) from that claim and skip e(0) in the first round (spg_sc1_set_satisfied) exactly like
+    the unsharded prover."""
     empty = np.zeros((0, 4), dtype=np.uint64)
 
     def make_engine(tau_q_local):
         sc = api.sumcheck_phase1(ctx, inst, z, [Q_local], Q_local, [X], X, max_num_inputs, empty, tau_q_local, tau_x)
         if satisfied:
-            sc.set_claim(np.zeros(4, dtype=np.uint64))
+            sc.set_satisfied()
         return sc
 
     def make_tail(Az, Bz, Cz, tau_high):
@@ -735,7 +736,7 @@ def gpu_phase1_rows(ctx, comm, mats, num_cons, max_num_cons, num_vars, secs, num
                                  max_num_inputs, np.tile(api.ONE, (log2(next_pow2(len(ps))), 1)), np.tile(api.ONE, (log2(max(Ql)), 1)), tau_x)
         sc.set_row_weights(weights)
         if satisfied:
-            sc.set_claim(np.zeros(4, dtype=np.uint64))
+            sc.set_satisfied()
         state.update(z=z, inst=inst, secs=dsecs)
         return sc
 

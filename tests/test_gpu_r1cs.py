@@ -19,7 +19,8 @@ def ctx():
     return sp.Context(0)
 
 
-def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2, claim=None):
+def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2, claim=None,
+                 satisfied=False):
     import spartan_parallel_b200 as sp
 
     A = [inst.mats[3 * i] for i in range(inst.num_instances)]
@@ -34,7 +35,9 @@ def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p
     z = sp.ZMat(ctx, num_proofs, num_inputs, dsecs)
     block_cons = [inst.num_cons[0]] * P if inst.num_instances == 1 else inst.num_cons
     sc1 = sp.sumcheck_phase1(ctx, dinst, z, num_proofs, max_q, block_cons, inst.max_num_cons, max_y, tau_p, tau_q, tau_x)
-    if claim is not None:
+    if satisfied:
+        sc1.set_satisfied()
+    elif claim is not None:
         sc1.set_claim(claim)
     e1 = []
     for j in range(sc1.num_rounds):
@@ -54,7 +57,7 @@ def gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p
     return e1, c1, e2, c2, dinst, dsecs
 
 
-def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, claim=None):
+def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, claim=None, satisfied=False):
     max_q = max(num_proofs)
     Pp = 1 if P == 1 else 1 << (P - 1).bit_length()
     W = len(secs)
@@ -66,7 +69,8 @@ def run_case(ctx, inst, P, num_proofs, num_inputs, max_y, secs, seed, claim=None
     ch2 = rand_scalars(max(np_ + nw + ny, 1), seed + 2)
     r_abc = rand_scalars(3, seed + 3)
     want = R.prove_tables(inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
-    e1, c1, e2, c2, dinst, _ = gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2, claim)
+    e1, c1, e2, c2, dinst, _ = gpu_pipeline(ctx, inst, P, max_q, num_proofs, max_y, num_inputs, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2, claim,
+                                            satisfied)
     assert len(e1) == len(want.evals1) and len(e2) == len(want.evals2)
     for j, (g, w) in enumerate(zip(e1, want.evals1)):
         assert np.array_equal(g, w), f"phase 1 round {j}"
@@ -96,6 +100,17 @@ def test_supplied_claim_two_point_first_round(ctx, log_x, Q, P):
     inst = R.synthetic_instance(X, num_instances=P, unit=(P == 1), seed=7)
     secs = R.synthetic_witness(X, [Q] * P, seed=15)
     run_case(ctx, inst, P, [Q] * P, [X] * P, X, secs, seed=105, claim=O.ZERO)
+
+
+@pytest.mark.parametrize("log_x,Q,P", [(10, 4, 1), (9, 8, 1), (8, 4, 3), (12, 16, 1)])
+def test_satisfied_one_point_first_round(ctx, log_x, Q, P):
+    """spg_sc1_set_satisfied: the witness satisfies the instance row by row, so the fused SpMV + first round
+    evaluates t = 2 only (e(0) = e(1) = 0 are sums of zeros); every round and claim still equals the oracle's,
+    which computes the zeros like the reference does. Unit rows (P = 1) and general rows (P = 3)."""
+    X = 1 << log_x
+    inst = R.synthetic_instance(X, num_instances=P, unit=(P == 1), seed=7)
+    secs = R.synthetic_witness(X, [Q] * P, seed=15)
+    run_case(ctx, inst, P, [Q] * P, [X] * P, X, secs, seed=106, satisfied=True)
 
 
 def test_set_claim_after_first_round_is_refused(ctx):
