@@ -657,10 +657,13 @@ def ncu_traffic(kernel_name):
                         break
                     seen = kernel_name.split("<")[0] in ln
                     rd = wr = None
-                elif seen and ln.startswith("dram__bytes_read.sum ="):
-                    rd = float(ln.split("=")[1].split()[0]) * 1e9
-                elif seen and ln.startswith("dram__bytes_write.sum ="):
-                    wr = float(ln.split("=")[1].split()[0]) * 1e9
+                elif seen and (ln.startswith("dram__bytes_read.sum =") or ln.startswith("dram__bytes_write.sum =")):
+                    val, unit = ln.split("=")[1].split()[:2]
+                    b = float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[unit]
+                    if "read" in ln.split("=")[0]:
+                        rd = b
+                    else:
+                        wr = b
             if seen and rd and wr:
                 best = (rd + wr, f"largest launch of {kernel_name.split('<')[0]} in {os.path.basename(path)} (ncu --set full, captured separately)")
                 break

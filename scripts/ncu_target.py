@@ -42,7 +42,7 @@ secs = [sp.ProverWitnessSecInfo(ctx, [Q], [X], u), sp.ProverWitnessSecInfo(ctx, 
 z = sp.ZMat(ctx, [Q], [X], secs)
 tau_q, tau_x, ch1, ch2, r_abc = canon(nq), canon(nx), canon(nx + nq), canon(1 + nx), canon(3)
 sc1 = sp.sumcheck_phase1(ctx, inst, z, [Q], Q, [X], X, X, tau_q[:0], tau_q, tau_x)
-sc1.set_claim(np.zeros(4, dtype=np.uint64))
+sc1.set_satisfied()  # claim 0, witness satisfying row by row: what bench.py times
 sc1.run_rounds(ch1)
 c1 = sc1.final()
 sc1.free()
