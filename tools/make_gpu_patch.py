@@ -148,7 +148,9 @@ pub(crate) fn phase1_begin(
       sys::spg_sc1_create(c, s.r1cs, s.zmat, num_instances, num_proofs.as_ptr(), max_num_proofs,
         block_num_cons.as_ptr(), num_cons, max_num_inputs, fq_ptr(tau_p), fq_ptr(tau_q), fq_ptr(tau_x), &mut s.sc1)
     });
-    check(unsafe { sys::spg_sc1_set_claim(s.sc1, &fq(&Scalar::zero())) });
+    // claim_phase1 = 0 and the witness satisfies the instance row by row (what R1CSProof::prove is called with):
+    // the first round, fused with the SpMV, then skips the evaluation at 0
+    check(unsafe { sys::spg_sc1_set_satisfied(s.sc1) });
   });
 }
 
