@@ -39,6 +39,21 @@ def test_kernel_roofline_table():
     assert out["k_unknown"]["bound"] == "hbm" and "int_frac" not in out["k_unknown"]
 
 
+def test_ncu_traffic_reads_the_committed_summary_with_units():
+    """roofline.traffic comes from the committed `ncu --set full` summary: DRAM reads + writes of the kernel's
+    launch, whatever unit ncu printed them in (the commitment kernel reads gigabytes and writes megabytes)"""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    t, note = bench.ncu_traffic("k_rows_rolled<true>")
+    assert 9.0e9 < t < 1.1e10 and "r2_ncu_full.txt" in note            # 9.66 GB algorithmic, 1.00x
+    t, _ = bench.ncu_traffic("k_msm_hrows<4>")
+    assert 1.5e11 < t < 1.7e11                                          # 160.1 Gbyte + 509 Mbyte
+    t, _ = bench.ncu_traffic("k_rows_spmv<2, true>")
+    assert 1.05e10 < t < 1.15e10                                        # the shipped one-point first round comes first in the file
+    assert bench.ncu_traffic("k_no_such_kernel") is None
+
+
 def test_reference_arm_other_ranks_do_nothing():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
