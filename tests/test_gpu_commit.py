@@ -239,9 +239,11 @@ def test_witness_commit_at_config_size(ctx, monkeypatch):
     info = dg.info()
     assert info["rows_table"]["table_bases"] >= R  # 8192 rows: the single-window table + Horner path
     assert info["table_bases"] == 0                # no blinds: the per-window table was not needed (yet)
-    assert info["rows_table"]["window_bits"] <= 14  # built inside the call: sized to pay for itself in one commitment
+    lazy_bits = info["rows_table"]["window_bits"]
+    assert lazy_bits <= 14                          # built inside the call: sized to pay for itself in one commitment
     dg.prepare(R, Lr)                               # setup-time tables: the widest window the budget allows
-    assert dg.info()["rows_table"]["window_bits"] >= 16 and dg.info()["table_bases"] >= R
+    ahead = dg.info()                               # (17 bits on an otherwise empty B200; the allowance shrinks it when
+    assert ahead["rows_table"]["window_bits"] > lazy_bits and ahead["table_bases"] >= R  # other tables are alive)
     assert dg.commit_poly(poly, Lr) == rows
     # (a) oracle on the sparse rows: the same generators derived by the oracle's own hash-to-group
     og = {c: G.from_uniform_bytes(uniform[64 * c: 64 * (c + 1)]) for c in cols + [R]}
