@@ -110,3 +110,37 @@ def test_sc1_oracle_is_a_valid_sumcheck(num_proofs, num_cons):
         if len(t):
             want = O.mul(want, O.eq_evaluate(t, r))
     assert np.array_equal(tau_claim, want)
+
+
+@pytest.mark.parametrize("unit,P", [(True, 1), (False, 1), (False, 3)])
+def test_first_round_of_a_satisfying_witness_vanishes_at_0_and_1(unit, P):
+    """What spg_sc1_set_satisfied relies on (csrc/sc1.cu): for a witness that satisfies the instance
+    Az * Bz - Cz is zero at EVERY row, so the first round polynomial of the phase-1 sumcheck
+    (src/sumcheck.rs:1166-1245) is zero at 0 and at 1 -- the reference computes those zeros -- and, being
+    l(t) * G(t) with G quadratic and G(0) = G(1) = 0, it is fixed by its value at 2: e(3) l(2) = 3 e(2) l(3)
+    with l(t) = eq(tau, t) for the variable bound first. Unit and general coefficients, several instances."""
+    from oracle import r1cs as R
+
+    X, Q = 1 << 6, 4
+    inst = R.synthetic_instance(X, num_instances=P, unit=unit, seed=3)
+    secs = R.synthetic_witness(X, [Q] * P, seed=9)
+    Pp = 1 if P == 1 else 1 << (P - 1).bit_length()
+    np_, nq, nx = log2(Pp), log2(Q), log2(X)
+    big = rand_scalars(64, 77)
+    tau_p, tau_q, tau_x = big[:np_], big[8:8 + nq], big[16:16 + nx]
+    ch1, ch2, r_abc = rand_scalars(np_ + nq + nx, 78), rand_scalars(np_ + 1 + nx, 79), rand_scalars(3, 80)
+    t = R.prove_tables(inst, P, Q, [Q] * P, X, [X] * P, secs, tau_p, tau_q, tau_x, ch1, r_abc, ch2)
+    # every row satisfied
+    assert np.array_equal(O.vec_sub(O.vec_mul(t.Az.reshape(-1, 4), t.Bz.reshape(-1, 4)), t.Cz.reshape(-1, 4)),
+                          np.zeros((t.Az.size // 4, 4), dtype=np.uint64))
+    e0, e2, e3 = t.evals1[0]
+    assert O.to_int(e0) == 0                      # e(1) = claim - e(0) = 0 as well: the claim of phase 1 is zero
+    q = (1 << 252) + 27742317777372353535851937790883648493
+    e2i, e3i = O.to_int(e2), O.to_int(e3)
+    assert e2i != 0
+    # the variable bound first pairs entries (2i, 2i + 1) of x: its eq factor is one of the tau_x -- the relation
+    # holds for exactly that one
+    def line(tau, tt):
+        return ((1 - tau) * (1 - tt) + tau * tt) % q
+    hits = [k for k in range(nx) if (e3i * line(O.to_int(tau_x[k]), 2) - 3 * e2i * line(O.to_int(tau_x[k]), 3)) % q == 0]
+    assert len(hits) == 1
