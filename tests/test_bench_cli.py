@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -52,6 +54,32 @@ def test_ncu_traffic_reads_the_committed_summary_with_units():
     t, _ = bench.ncu_traffic("k_rows_spmv<2, true>")
     assert 1.05e10 < t < 1.15e10                                        # the shipped one-point first round comes first in the file
     assert bench.ncu_traffic("k_no_such_kernel") is None
+
+
+def test_committed_bench_lines_keep_the_contract():
+    """the bench lines under profiles/ (written by bench.py on the pool's B200s) carry every key the driver
+    and the roofline bookkeeping read"""
+    def last_line(name):
+        return json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
+
+    d = last_line("r2_bench_plain.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "prove_time_s"):
+        assert k in d, k
+    assert d["metric"] == "sumcheck_constraints_per_sec" and d["n_gpus"] == 1 and d["higher_is_better"] is True
+    assert d["config"]["constraints_per_step"] == 1 << 26 and "workload" in d["config"]
+    assert abs(d["value"] - d["config"]["constraints_per_step"] / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] == 4 << 30 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] and 0.9 < r["traffic"] / (r["algorithmic_bytes_per_launch"] * 5.5) < 1.2   # the largest launch is 5.5 x the average
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["prove_time"]["polycommit"] + d["prove_time"]["R1CSProof::prove"] + d["prove_time"]["SparseMatPolyEvalProof::prove"] == pytest.approx(d["prove_time_s"])
+    for n in (2, 4, 8):
+        s_ = last_line(f"r2_scale{n}_strong.json")
+        assert s_["n_gpus"] == n and s_["scaling"] == "strong" and s_["parity"] is True
+        assert s_["config"]["constraints_per_step"] == 1 << 26 and s_["weak"]["value"] > s_["value"]
 
 
 def test_reference_arm_other_ranks_do_nothing():
